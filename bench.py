@@ -1,0 +1,457 @@
+#!/usr/bin/env python
+"""bench.py — RK steps/sec and stage-combine HBM GB/s (fp64) of the explicit-RK hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
+    python bench.py --sweep [--out FILE]                     # BASELINE.json config 5: kernel bandwidth sweep
+
+A "step" is one accepted Runge–Kutta step of the adaptive driver loop (ode.nim:511-541): S-1 right-hand
+side launches, S-1 fused stage-accumulate launches, one fused combine+error-norm launch and an 8-byte
+read-back per attempt (plus one ncclAllReduce of a scalar when sharded).
+
+Workload at every N: BASELINE.json configs[1] per GPU — DOPRI54, diag-linear IVP y' = -lambda .* y,
+2^23 fp64 state elements PER GPU (weak scaling: N_global = n_gpus * 2^23, contiguous shards), absTol =
+relTol = 1e-6, dtMax = 1, dtMin = 1e-8. `value` counts shard-steps: K accepted steps x n_gpus shards / time.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SHARD_LOG2 = 23
+OPTS = dict(absTol=1e-6, relTol=1e-6, dtMax=1.0, dtMin=1e-8)
+WORKLOADS = {
+    # name: (integrator, rhs, log2 elements per GPU)
+    "cfg2_dopri54_diag_8M": ("dopri54", "diag", 23),
+    "cfg3_tsit54_lorenz96_16M": ("tsit54", "l96", 24),
+    "cfg4_vern65_diag_16M_per_gpu": ("vern65", "diag", 24),
+    "rk4_diag_8M": ("rk4", "diag", 23),
+}
+# algorithmic bytes per element per ATTEMPT of the RK kernels (RHS excluded), zero weights skipped
+ALG_BYTES_PER_ELEM = {"dopri54": 8 * (32 + 7), "tsit54": 8 * (33 + 8), "vern65": 8 * (45 + 9), "rk4": 8 * 15}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def problem_arrays(n_global: int, off: int, ln: int):
+    """lambda[i] = 0.1 + 9.9 i/(N-1); y0[i] = 1 + 0.5 sin(2 pi i/N), local slice."""
+    i = np.arange(off, off + ln, dtype=np.float64)
+    lam = 0.1 + 9.9 * i / float(n_global - 1)
+    y0 = 1.0 + 0.5 * np.sin(2.0 * np.pi * i / float(n_global))
+    return lam, y0
+
+
+def l96_y0(n_global: int, off: int, ln: int, F: float = 8.0):
+    i = np.arange(off, off + ln, dtype=np.float64)
+    return F + 0.01 * np.sin(2.0 * np.pi * 37.0 * i / float(n_global))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+# ======================================================================================================
+# our arm
+# ======================================================================================================
+def run_ours(args):
+    import torch
+
+    import numericalnim_b200 as nn
+    from numericalnim_b200 import _capi
+
+    rank, local_rank, world = dist_env()
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N bench.py --gpus N ...")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    nccl_id = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        box = [nn.Context.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        nccl_id = box[0]
+    ctx = nn.Context(local_rank, rank, world, nccl_id)
+    nn.set_default_context(ctx)
+    integrator, rhs_kind, lg = WORKLOADS[args.workload]
+    if args.log2n:
+        lg = args.log2n
+    n_shard = 1 << lg
+    n_global = n_shard * world
+    probe = nn.GpuVector.empty(n_global, ctx)
+    off, ln = probe.local_offset, probe.local_len
+    probe.free()
+    opts = nn.newODEoptions(**OPTS)
+    if rhs_kind == "diag":
+        lam_h, y0_h = problem_arrays(n_global, off, ln)
+        glam = nn.GpuVector.from_local(n_global, lam_h, ctx)
+        rhs = nn.rhsDiagLinear(glam)
+    else:
+        if world > 1:
+            raise SystemExit("lorenz96 workload is single-GPU (sharded halo exchange is a 'next' row)")
+        y0_h = l96_y0(n_global, off, ln)
+        lam_h = None
+        rhs = nn.rhsLorenz96(8.0, ctx)
+    gy0 = nn.GpuVector.from_local(n_global, y0_h, ctx)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timed region: exactly K accepted steps of the driver loop --------------------
+    solver = nn.Solver(integrator, rhs, gy0, 1e12, opts)
+    solver.advance(args.warmup)
+    ctx.set("profile", 1)
+    ctx.profile_reset()
+    st0, cs0 = solver.stats(), ctx.stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        with torch.cuda.stream(stream):
+            e0.record()
+        done, _ = solver.advance(args.steps)
+        with torch.cuda.stream(stream):
+            e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    prof = ctx.profile_read()
+    ctx.set("profile", 0)
+    st1, cs1 = solver.stats(), ctx.stats()
+    t_now, dt_next, _, _ = solver.state()
+    solver.close()
+    assert done == args.steps, (done, args.steps)
+    ms_t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_max = float(ms_t.item())
+    attempts = st1["attempts"] - st0["attempts"]
+    launches = cs1["launches"] - cs0["launches"]
+
+    # ---- end to end: solveODE over [0, 2] from pinned HOST buffers (H2D y0 + lambda, solve, D2H states) ----
+    L = _capi.lib()
+    y0_pin = torch.from_numpy(y0_h).pin_memory()
+    lam_pin = torch.from_numpy(lam_h).pin_memory() if lam_h is not None else None
+    out_pin = torch.empty((2, ln), dtype=torch.float64).pin_memory()
+    ts = np.array([0.0, 2.0] if rhs_kind == "diag" else [0.0, 1.0])
+    t_out = np.empty(2)
+    n_out = C.c_size_t(0)
+    method = nn.ode.method_id(integrator)
+    e2e_steps, e2e_ms, h2d, d2h = 0, 0.0, 0, 0
+    reps = max(1, args.e2e_reps)
+    for rep in range(reps + 1):  # first repetition is warm-up
+        st = _capi.Stats()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        with torch.cuda.stream(stream):
+            a0.record()
+        if lam_pin is not None:
+            _capi.check(L.b200rk_vec_upload_local(glam._h, lam_pin.data_ptr()), ctx.handle)
+        _capi.check(L.b200rk_solve_host(ctx.handle, method, rhs.fn, rhs.user, n_global, y0_pin.data_ptr(), ts.ctypes.data, 2,
+                                        C.byref(opts), t_out.ctypes.data, out_pin.data_ptr(), C.byref(n_out), C.byref(st)), ctx.handle)
+        with torch.cuda.stream(stream):
+            a1.record()
+        barrier()
+        if rep == 0:
+            continue
+        e2e_ms += a0.elapsed_time(a1)
+        e2e_steps += st.steps
+        h2d += y0_pin.numel() * 8 + (lam_pin.numel() * 8 if lam_pin is not None else 0)
+        d2h += int(n_out.value) * ln * 8
+    e2e_t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_ms_max = float(e2e_t.item())
+
+    # ---- CPU baseline (rank 0, N = 1 only): the oracle port on a bounded sample -----------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and rhs_kind == "diag":
+        cpu = cpu_baseline_sample(integrator, n_shard, steps=2)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        stage = prof["stage"]
+        ach = stage["bytes"] / (stage["ms"] * 1e-3) / 1e9 if stage["ms"] > 0 else 0.0
+        fin = prof["finish"]
+        ach_fin = fin["bytes"] / (fin["ms"] * 1e-3) / 1e9 if fin["ms"] > 0 else 0.0
+        rhsp = prof["rhs"]
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "stage_kernel_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as fh:
+                traffic = json.load(fh).get("dram_bytes_per_launch")
+        kernel_ms = stage["ms"] + fin["ms"] + rhsp["ms"] + prof["other"]["ms"]
+        line = {
+            "metric": "rk_steps_per_sec", "value": args.steps * world / (ms_max * 1e-3), "unit": "RK steps/s (x 2^%d-element shard, summed over GPUs)" % lg,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "integrator": integrator, "rhs": rhs_kind, "elems_per_gpu": n_shard, "elems_global": n_global,
+                       "options": OPTS, "l2": "working set (>= 10 vectors x %d MiB per GPU) exceeds the 126 MB L2; no flush" % (n_shard * 8 >> 20),
+                       "sharding": "contiguous, 1 ncclAllReduce(1 x f64) per attempt" if world > 1 else "single GPU, no collective",
+                       "vec_width": ctx.get("vec_width"), "ctas_per_sm": ctx.get("ctas_per_sm")},
+            "attempts": attempts, "attempts_per_sec": attempts * world / (ms_max * 1e-3), "rejected": st1["rejected"] - st0["rejected"],
+            "t_reached": t_now, "dt_next": dt_next,
+            "gpu_launches": launches, "collectives": cs1["collectives"] - cs0["collectives"],
+            "hbm_gbs_step": ALG_BYTES_PER_ELEM.get(integrator, 0) * n_shard * attempts / (ms * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "kernel": "stage_kernel<M,W,U> (fused stage accumulate, all %d launches of the timed region)" % stage["launches"],
+                         "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak, "frac_of_nominal_8000": ach / 8000.0,
+                         "traffic": traffic, "launches": stage["launches"], "avg_launch_us": 1e3 * stage["ms"] / max(1, stage["launches"]),
+                         "algorithmic_bytes_per_launch": stage["bytes"] / max(1, stage["launches"]),
+                         "finish_kernel": {"achieved": ach_fin, "frac": ach_fin / peak, "launches": fin["launches"], "avg_launch_us": 1e3 * fin["ms"] / max(1, fin["launches"])},
+                         "rhs_kernel": {"achieved": (rhsp["bytes"] / (rhsp["ms"] * 1e-3) / 1e9) if rhsp["ms"] > 0 else 0.0, "launches": rhsp["launches"]},
+                         "kernel_time_share_of_step": kernel_ms / ms if ms > 0 else None},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_steps * world / (e2e_ms_max * 1e-3), "unit": "RK steps/s (solveODE on host buffers: H2D y0+lambda, solve, D2H states)",
+                    "h2d_bytes_per_step": h2d / max(1, e2e_steps), "d2h_bytes_per_step": d2h / max(1, e2e_steps), "steps_per_solve": e2e_steps / reps,
+                    "ms_per_solve": e2e_ms_max / reps},
+            "clocks": clocks.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ======================================================================================================
+# CPU: oracle port (the reference cannot be built: Nim, no toolchain) — bench.py's only use of oracle/
+# ======================================================================================================
+def cpu_baseline_sample(integrator: str, n: int, steps: int):
+    import oracle as O
+
+    lam, y0 = problem_arrays(n, 0, n)
+    t0 = time.time()
+    s = O.solve_vector(integrator, O.rhs_diag_linear(lam), y0, [0.0, 1e12], O.new_options(**OPTS), max_steps=steps)
+    wall = time.time() - t0
+    return {"value": s.stats.steps / s.stats.seconds, "unit": "RK steps/s at 2^%d elements" % int(np.log2(n)), "cores": 1, "kind": "port",
+            "sample": "%d accepted %s steps (+2 start-up RHS evaluations) at N=2^%d on 1 of %d host cores; %.1f s" % (
+                s.stats.steps, integrator, int(np.log2(n)), os.cpu_count() or 0, wall)}
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path, as faithfully as it can be had here: the C++
+    oracle port (allocating one-pass-per-operator Vectors, sequential sum, -O2, no FMA). Single thread because
+    numericalnim's ode.nim / utils.nim have no threading construct — that is every thread the reference uses."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    import oracle as O
+
+    integrator, rhs_kind, lg = WORKLOADS[args.workload]
+    if rhs_kind != "diag":
+        raise SystemExit("reference arm implements the diag-linear workloads")
+    n_full = 1 << (args.log2n or lg)
+    # calibrate on a small sample, then pick the largest power-of-two N_s whose K+W steps fit the budget
+    lam, y0 = problem_arrays(1 << 18, 0, 1 << 18)
+    c = O.solve_vector(integrator, O.rhs_diag_linear(lam), y0, [0.0, 1e12], O.new_options(**OPTS), max_steps=2)
+    per_elem_step = c.stats.seconds / 2 / (1 << 18) * 3.0  # large vectors are ~3x slower per element (page faults)
+    budget = args.cpu_budget_s
+    n_s = n_full
+    while n_s > (1 << 16) and per_elem_step * n_s * (args.steps + args.warmup) > budget:
+        n_s >>= 1
+    lam, y0 = problem_arrays(n_s, 0, n_s)
+    O.solve_vector(integrator, O.rhs_diag_linear(lam), y0, [0.0, 1e12], O.new_options(**OPTS), max_steps=max(1, args.warmup))
+    t0 = time.time()
+    s = O.solve_vector(integrator, O.rhs_diag_linear(lam), y0, [0.0, 1e12], O.new_options(**OPTS), max_steps=args.steps)
+    wall = time.time() - t0
+    scale = n_full / n_s  # time assumed linear in N (bandwidth-bound) — favours the CPU, see DESIGN.md §6
+    secs = s.stats.seconds * scale
+    value = s.stats.steps / secs
+    sample = "%d accepted %s steps at N_s=2^%d (%s of the 2^%d workload, time scaled x%g), 1 of %d host cores, %.1f s wall" % (
+        s.stats.steps, integrator, int(np.log2(n_s)), "all" if n_s == n_full else "1/%d" % int(scale), int(np.log2(n_full)), scale, os.cpu_count() or 0, wall)
+    line = {"impl": "reference", "metric": "rk_steps_per_sec", "value": value,
+            "unit": "RK steps/s (x 2^%d-element shard, summed over GPUs)" % int(np.log2(n_full)), "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, s.stats.steps), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "integrator": integrator, "rhs": rhs_kind, "elems_per_gpu": n_full, "options": OPTS,
+                       "note": "CPU arm: one shard on one host thread (the reference is single-threaded); not multiplied by n_gpus"},
+            "cpu_baseline": {"value": value, "unit": "RK steps/s", "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "RK steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ======================================================================================================
+# config 5: kernel bandwidth sweep
+# ======================================================================================================
+def run_sweep(args):
+    import numericalnim_b200 as nn
+    import oracle as O
+
+    ctx = nn.default_context()
+    peak, peak_src = peaks()
+    rows = []
+    l2_bytes = 126e6
+    rng = np.random.default_rng(1234)
+    for lg in range(args.sweep_min, args.sweep_max + 1, args.sweep_step):
+        n = 1 << lg
+        base = rng.uniform(-1.0, 1.0, n)
+        vecs = [nn.newVector(np.roll(base, 17 * j), ctx) for j in range(10)]
+        out = nn.GpuVector.empty(n, ctx)
+        cases = []
+        for m in (1, 5, 8):
+            w = O.pair_tableau("vern65")["a"][9][:8] if m == 8 else O.pair_tableau("dopri54")["a"][6][:m]
+            cases.append((f"stage_m{m}", "stage", lambda m=m, w=w: nn.stageAccum(w[:m], 0.01, vecs[0], vecs[1:1 + m], out=out), 8.0 * n * (m + 2)))
+        for meth, S in (("dopri54", 7), ("tsit54", 7), ("vern65", 9)):
+            cases.append((f"finish_{meth}", "finish", lambda meth=meth, S=S: nn.combineErr(meth, 0.01, 1e-6, 1e-6, vecs[0], vecs[1:1 + S]), None))
+        for name, cls, fn, nbytes in cases:
+            for _ in range(args.sweep_warm):
+                fn()
+            ctx.set("profile", 1)
+            ctx.profile_reset()
+            for _ in range(args.sweep_iters):
+                fn()
+            p = ctx.profile_read()
+            ctx.set("profile", 0)
+            ms, b, ln = p[cls]["ms"], p[cls]["bytes"], p[cls]["launches"]
+            if name == "finish_tsit54":  # the raw API adds a stage launch for yNew; keep the finish class only
+                pass
+            gbs = b / (ms * 1e-3) / 1e9
+            ws = (b / ln)
+            rows.append({"log2n": lg, "kernel": name, "us_per_launch": 1e3 * ms / ln, "GBps": gbs, "frac_of_peak": gbs / peak,
+                         "l2_resident": bool(ws < l2_bytes), "alg_bytes_per_launch": ws})
+            print(json.dumps(rows[-1]), flush=True)
+        for v in vecs:
+            v.free()
+        out.free()
+        ctx.set("pool_budget_mb", 0)
+        ctx.set("pool_budget_mb", 48 << 10)
+    if args.out:
+        with open(args.out, "w") as fh:
+            json.dump({"peak_gbs": peak, "peak_source": peak_src, "rows": rows}, fh, indent=1)
+
+
+def run_tune(args):
+    """Launch-geometry matrix at one size: vec_width x ctas_per_sm for stage m=1,5,8 and the DOPRI54 finish."""
+    import numericalnim_b200 as nn
+    import oracle as O
+
+    ctx = nn.default_context()
+    peak, _ = peaks()
+    n = 1 << (args.log2n or 23)
+    rng = np.random.default_rng(1234)
+    base = rng.uniform(-1.0, 1.0, n)
+    vecs = [nn.newVector(np.roll(base, 17 * j), ctx) for j in range(10)]
+    out = nn.GpuVector.empty(n, ctx)
+    w8 = O.pair_tableau("vern65")["a"][9][:8]
+    for vw in (2, 4):
+        for cps in (0, 2, 4, 8, 16):
+            ctx.set("vec_width", vw)
+            ctx.set("ctas_per_sm", cps)
+            res = {}
+            for name, cls, fn in (("stage_m1", "stage", lambda: nn.stageAccum(w8[:1], 0.01, vecs[0], vecs[1:2], out=out)),
+                                  ("stage_m5", "stage", lambda: nn.stageAccum(w8[:5], 0.01, vecs[0], vecs[1:6], out=out)),
+                                  ("stage_m8", "stage", lambda: nn.stageAccum(w8, 0.01, vecs[0], vecs[1:9], out=out)),
+                                  ("finish_dopri54", "finish", lambda: nn.combineErr("dopri54", 0.01, 1e-6, 1e-6, vecs[0], vecs[1:8])),
+                                  ("finish_vern65", "finish", lambda: nn.combineErr("vern65", 0.01, 1e-6, 1e-6, vecs[0], vecs[1:10]))):
+                for _ in range(10):
+                    fn()
+                ctx.set("profile", 1)
+                ctx.profile_reset()
+                for _ in range(50):
+                    fn()
+                p = ctx.profile_read()
+                ctx.set("profile", 0)
+                res[name] = round(p[cls]["bytes"] / (p[cls]["ms"] * 1e-3) / 1e9, 1)
+            print(json.dumps({"log2n": int(np.log2(n)), "vec_width": vw, "ctas_per_sm": cps, "GBps": res,
+                              "frac": {k: round(v / peak, 3) for k, v in res.items()}}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2_dopri54_diag_8M", choices=sorted(WORKLOADS))
+    ap.add_argument("--log2n", type=int, default=0, help="override log2 of elements per GPU")
+    ap.add_argument("--e2e-reps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=120.0)
+    ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--tune", action="store_true")
+    ap.add_argument("--sweep-min", type=int, default=16)
+    ap.add_argument("--sweep-max", type=int, default=26)
+    ap.add_argument("--sweep-step", type=int, default=1)
+    ap.add_argument("--sweep-warm", type=int, default=20)
+    ap.add_argument("--sweep-iters", type=int, default=100)
+    ap.add_argument("--out", default="")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.tune:
+        return run_tune(args)
+    if args.sweep:
+        return run_sweep(args)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

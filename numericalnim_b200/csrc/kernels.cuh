@@ -1,0 +1,503 @@
+// kernels.cuh — hand-written sm_100a kernels of the explicit Runge–Kutta hot path (fp64, BLAS-1,
+// HBM-bandwidth-bound; no tensor cores on purpose).
+//
+// What each kernel replaces in the reference (numericalnim, src/numericalnim/):
+//   stage_kernel    y + c*(w1*k1 + ... + wm*km)            ode.nim:185-187, 294-299, 364-369, 455-462
+//                   (2m-1 allocating Vector passes there: `*` utils.nim:176-180, `+` utils.nim:59-64)
+//   finish_kernel   yNew, yLow/error_y, tolerance, scaled square and its sum
+//                   ode.nim:301-303, 371-372, 464-466 + ode.nim:61-65 (34..41 Vector passes there)
+//   rk4_final       y + dt/6*(k1 + 2*(k2+k3) + k4)         ode.nim:188
+//   hermite_kernel  hermiteSpline                           utils.nim:273-279
+//   ewise kernels   the Vector[T] operators themselves      utils.nim:59-223
+//
+// Parity: every product / sum uses __dmul_rn / __dadd_rn (never contracted into FMA) in exactly the
+// reference's left-to-right association, so element-wise results are bit-identical to the CPU path.
+// Only the error-norm reduction differs in summation order (deterministic tree vs sequential).
+//
+// Memory access: W doubles per thread per access (W = 2 -> 128-bit LDG/STG, W = 4 -> 256-bit
+// LDG.E.256 / STG.E.256, new on sm_100), U independent accesses per input stream issued back to back
+// before first use, fully coalesced, read-only non-coherent path with L1 no-allocate (every element is
+// touched exactly once per launch). The Butcher row travels as kernel parameters, i.e. in the constant
+// bank: one uniform broadcast read per weight, no shared-memory staging or barrier needed.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200rk {
+
+constexpr int kMaxTerms = 9;  // Vern65 has 9 stages
+
+// ---------------------------------------------------------------------------------------------------
+// W-wide global memory access
+// ---------------------------------------------------------------------------------------------------
+template <int W>
+struct Pk {
+  double v[W];
+};
+
+template <int W>
+__device__ __forceinline__ Pk<W> ld_stream(const double* p);
+template <>
+__device__ __forceinline__ Pk<1> ld_stream<1>(const double* p) {
+  Pk<1> r;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r.v[0]) : "l"(p));
+  return r;
+}
+template <>
+__device__ __forceinline__ Pk<2> ld_stream<2>(const double* p) {
+  Pk<2> r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.v[0]), "=d"(r.v[1]) : "l"(p));
+  return r;
+}
+template <>
+__device__ __forceinline__ Pk<4> ld_stream<4>(const double* p) {
+  Pk<4> r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3])
+               : "l"(p));
+  return r;
+}
+// coherent variant for kernels whose output may alias an input (in-place Vector ops)
+template <int W>
+__device__ __forceinline__ Pk<W> ld_plain(const double* p) {
+  Pk<W> r;
+  if (W == 2) {
+    const double2 t = *reinterpret_cast<const double2*>(p);
+    r.v[0] = t.x; r.v[W > 1 ? 1 : 0] = t.y;
+  } else {
+#pragma unroll
+    for (int e = 0; e < W; ++e) r.v[e] = p[e];
+  }
+  return r;
+}
+template <int W>
+__device__ __forceinline__ void st_stream(double* p, const Pk<W>& x);
+template <>
+__device__ __forceinline__ void st_stream<1>(double* p, const Pk<1>& x) {
+  asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(x.v[0]) : "memory");
+}
+template <>
+__device__ __forceinline__ void st_stream<2>(double* p, const Pk<2>& x) {
+  asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(x.v[0]), "d"(x.v[1]) : "memory");
+}
+template <>
+__device__ __forceinline__ void st_stream<4>(double* p, const Pk<4>& x) {
+  asm volatile("st.global.L1::no_allocate.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(x.v[0]), "d"(x.v[1]),
+               "d"(x.v[2]), "d"(x.v[3])
+               : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Stage accumulate:  out = y + c * (w0*k0 + w1*k1 + ... )      (left-associated, no FMA)
+//   CHAIN form (Kutta3's third stage, ode.nim:128):  out = ((y + w0*k0) + w1*k1) + ...   (c unused)
+// ---------------------------------------------------------------------------------------------------
+template <int M>
+struct StageArgs {
+  const double* y;
+  const double* k[M];
+  double w[M];
+  double c;
+  double* out;
+  size_t n;
+};
+
+template <int M, bool CHAIN>
+__device__ __forceinline__ double stage_elem(double y, const double (&k)[M], const double (&w)[M], double c) {
+  if (CHAIN) {
+    double acc = y;
+#pragma unroll
+    for (int j = 0; j < M; ++j) acc = __dadd_rn(acc, __dmul_rn(k[j], w[j]));
+    return acc;
+  }
+  double acc = __dmul_rn(k[0], w[0]);
+#pragma unroll
+  for (int j = 1; j < M; ++j) acc = __dadd_rn(acc, __dmul_rn(k[j], w[j]));
+  return __dadd_rn(y, __dmul_rn(acc, c));
+}
+
+template <int M, int W, int U, bool CHAIN, int THREADS>
+__global__ void __launch_bounds__(THREADS) stage_kernel(const StageArgs<M> a) {
+  const size_t nvec = a.n / W;
+  const size_t tile = (size_t)THREADS * U;
+  for (size_t base = (size_t)blockIdx.x * tile; base < nvec; base += (size_t)gridDim.x * tile) {
+    Pk<W> yv[U], kv[U][M];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t v = base + (size_t)u * THREADS + threadIdx.x;
+      if (v < nvec) {
+        yv[u] = ld_stream<W>(a.y + v * W);
+#pragma unroll
+        for (int j = 0; j < M; ++j) kv[u][j] = ld_stream<W>(a.k[j] + v * W);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t v = base + (size_t)u * THREADS + threadIdx.x;
+      if (v < nvec) {
+        Pk<W> o;
+#pragma unroll
+        for (int e = 0; e < W; ++e) {
+          double ke[M];
+#pragma unroll
+          for (int j = 0; j < M; ++j) ke[j] = kv[u][j].v[e];
+          o.v[e] = stage_elem<M, CHAIN>(yv[u].v[e], ke, a.w, a.c);
+        }
+        st_stream<W>(a.out + v * W, o);
+      }
+    }
+  }
+  // ragged tail (n % W elements)
+  if (blockIdx.x == 0) {
+    const size_t i = nvec * W + threadIdx.x;
+    if (i < a.n) {
+      double ke[M];
+#pragma unroll
+      for (int j = 0; j < M; ++j) ke[j] = a.k[j][i];
+      a.out[i] = stage_elem<M, CHAIN>(a.y[i], ke, a.w, a.c);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// RK4 final combine (ode.nim:188):  y + (dt/6) * ((k1 + 2*(k2 + k3)) + k4), c6 = dt/6.0 from the host
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double rk4_elem(double y, double k1, double k2, double k3, double k4, double c6) {
+  const double s = __dadd_rn(__dadd_rn(k1, __dmul_rn(__dadd_rn(k2, k3), 2.0)), k4);
+  return __dadd_rn(y, __dmul_rn(s, c6));
+}
+template <int W, int U, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+    rk4_final_kernel(const double* __restrict__ y, const double* __restrict__ k1, const double* __restrict__ k2,
+                     const double* __restrict__ k3, const double* __restrict__ k4, double c6, double* __restrict__ out,
+                     size_t n) {
+  const size_t nvec = n / W;
+  const size_t tile = (size_t)THREADS * U;
+  for (size_t base = (size_t)blockIdx.x * tile; base < nvec; base += (size_t)gridDim.x * tile) {
+    Pk<W> a[U][5];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t v = base + (size_t)u * THREADS + threadIdx.x;
+      if (v < nvec) {
+        a[u][0] = ld_stream<W>(y + v * W);
+        a[u][1] = ld_stream<W>(k1 + v * W);
+        a[u][2] = ld_stream<W>(k2 + v * W);
+        a[u][3] = ld_stream<W>(k3 + v * W);
+        a[u][4] = ld_stream<W>(k4 + v * W);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t v = base + (size_t)u * THREADS + threadIdx.x;
+      if (v < nvec) {
+        Pk<W> o;
+#pragma unroll
+        for (int e = 0; e < W; ++e)
+          o.v[e] = rk4_elem(a[u][0].v[e], a[u][1].v[e], a[u][2].v[e], a[u][3].v[e], a[u][4].v[e], c6);
+        st_stream<W>(out + v * W, o);
+      }
+    }
+  }
+  if (blockIdx.x == 0) {
+    const size_t i = nvec * W + threadIdx.x;
+    if (i < n) out[i] = rk4_elem(y[i], k1[i], k2[i], k3[i], k4[i], c6);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Deterministic sum reduction: warp shuffle -> shared -> one partial per block -> the last block to
+// finish (atomic ticket) adds the partials in index order. No floating-point atomics anywhere.
+// ---------------------------------------------------------------------------------------------------
+struct ReduceScratch {
+  double* partials;        // gridDim.x doubles
+  unsigned int* ticket;    // zero before launch; reset to zero by the last block
+  double* result;          // device scalar
+  double* result_host;     // optional zero-copy mirror (mapped pinned host memory), may be null
+};
+
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double v) {
+  __shared__ double warp_part[THREADS / 32];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, off));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();  // protect warp_part against a previous use
+  if (lane == 0) warp_part[warp] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (warp == 0) {
+    r = (lane < THREADS / 32) ? warp_part[lane] : 0.0;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) r = __dadd_rn(r, __shfl_down_sync(0xffffffffu, r, off));
+  }
+  return r;  // valid in thread 0
+}
+
+template <int THREADS>
+__device__ __forceinline__ void grid_sum_finish(double thread_val, const ReduceScratch& rs) {
+  __shared__ bool is_last;
+  const double bsum = block_sum<THREADS>(thread_val);
+  if (threadIdx.x == 0) {
+    rs.partials[blockIdx.x] = bsum;
+    __threadfence();
+    const unsigned int t = atomicAdd(rs.ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    double acc = 0.0;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += THREADS) acc = __dadd_rn(acc, __ldcg(rs.partials + i));
+    const double total = block_sum<THREADS>(acc);
+    if (threadIdx.x == 0) {
+      *rs.result = total;
+      if (rs.result_host) *rs.result_host = total;
+      *rs.ticket = 0u;
+      __threadfence_system();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Finish: solution combine + embedded error + scaled RMS accumulation of one adaptive attempt.
+//   yNew  = y + cb  * (Σ_{j in mask_b}  wb[j]*k[j])                         ode.nim:301/371/464
+//   e     = DIRECT ? cbh * (Σ wbh[j]*k[j])                                   ode.nim:372
+//                  : yNew - (y + cbh * (Σ_{j in mask_bh} wbh[j]*k[j]))       ode.nim:302-303/465-466
+//   tol   = absTol + relTol*|yNew| ; r = e/tol ; S += r*r                    ode.nim:61-65
+// NK = number of distinct k streams loaded. YNEW_MODE: 0 = recompute in registers, do not store (the
+// stage-S input buffer already holds the identical bits: DOPRI54/Tsit54/BS32), 1 = compute and store
+// (Vern65, RK21), 2 = load yNew instead of y (Tsit54: y itself is not needed once yNew is known).
+// ---------------------------------------------------------------------------------------------------
+template <int NK>
+struct FinishArgs {
+  const double* y;       // y, or yNew when YNEW_MODE == 2
+  const double* k[NK];
+  double wb[NK], wbh[NK];
+  uint32_t mask_b, mask_bh;
+  double cb, cbh, absTol, relTol;
+  double* ynew_out;      // YNEW_MODE == 1
+  double* err_out;       // optional: element-wise error_y for tests (may be null)
+  size_t n;
+  ReduceScratch rs;
+};
+
+template <int NK>
+__device__ __forceinline__ double masked_wsum(const double (&k)[NK], const double (&w)[NK], uint32_t mask) {
+  double acc = 0.0;
+  bool have = false;
+#pragma unroll
+  for (int j = 0; j < NK; ++j) {
+    if ((mask >> j) & 1u) {
+      const double p = __dmul_rn(k[j], w[j]);
+      acc = have ? __dadd_rn(acc, p) : p;
+      have = true;
+    }
+  }
+  return acc;
+}
+
+template <int NK, bool DIRECT, int YNEW_MODE>
+__device__ __forceinline__ double finish_elem(double y, const double (&k)[NK], const FinishArgs<NK>& a,
+                                              double& ynew, double& e) {
+  if (YNEW_MODE == 2) ynew = y;
+  else ynew = __dadd_rn(y, __dmul_rn(masked_wsum<NK>(k, a.wb, a.mask_b), a.cb));
+  const double lo = __dmul_rn(masked_wsum<NK>(k, a.wbh, a.mask_bh), a.cbh);
+  if (DIRECT) e = lo;
+  else e = __dadd_rn(ynew, -__dadd_rn(y, lo));  // a - b == a + (-b) exactly
+  const double tol = __dadd_rn(a.absTol, __dmul_rn(fabs(ynew), a.relTol));
+  const double r = __ddiv_rn(e, tol);
+  return __dmul_rn(r, r);
+}
+
+template <int NK, int W, int U, bool DIRECT, int YNEW_MODE, int THREADS>
+__global__ void __launch_bounds__(THREADS) finish_kernel(const FinishArgs<NK> a) {
+  const size_t nvec = a.n / W;
+  const size_t tile = (size_t)THREADS * U;
+  double acc = 0.0;
+  for (size_t base = (size_t)blockIdx.x * tile; base < nvec; base += (size_t)gridDim.x * tile) {
+    Pk<W> yv[U], kv[U][NK];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t v = base + (size_t)u * THREADS + threadIdx.x;
+      if (v < nvec) {
+        yv[u] = ld_stream<W>(a.y + v * W);
+#pragma unroll
+        for (int j = 0; j < NK; ++j) kv[u][j] = ld_stream<W>(a.k[j] + v * W);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t v = base + (size_t)u * THREADS + threadIdx.x;
+      if (v < nvec) {
+        Pk<W> yo, eo;
+#pragma unroll
+        for (int e = 0; e < W; ++e) {
+          double ke[NK];
+#pragma unroll
+          for (int j = 0; j < NK; ++j) ke[j] = kv[u][j].v[e];
+          acc = __dadd_rn(acc, finish_elem<NK, DIRECT, YNEW_MODE>(yv[u].v[e], ke, a, yo.v[e], eo.v[e]));
+        }
+        if (YNEW_MODE == 1) st_stream<W>(a.ynew_out + v * W, yo);
+        if (a.err_out) st_stream<W>(a.err_out + v * W, eo);
+      }
+    }
+  }
+  if (blockIdx.x == 0) {
+    const size_t i = nvec * W + threadIdx.x;
+    if (i < a.n) {
+      double ke[NK], yn, ee;
+#pragma unroll
+      for (int j = 0; j < NK; ++j) ke[j] = a.k[j][i];
+      acc = __dadd_rn(acc, finish_elem<NK, DIRECT, YNEW_MODE>(a.y[i], ke, a, yn, ee));
+      if (YNEW_MODE == 1) a.ynew_out[i] = yn;
+      if (a.err_out) a.err_out[i] = ee;
+    }
+  }
+  grid_sum_finish<THREADS>(acc, a.rs);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Dense output: hermiteSpline (utils.nim:273-279) with host-side scalars
+//   out = ((h00*y1 + hA*dy1) + h01*y2) + hB*dy2,   hA = h10*(x2-x1), hB = h11*(x2-x1)
+// ---------------------------------------------------------------------------------------------------
+template <int W, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+    hermite_kernel(const double* __restrict__ y1, const double* __restrict__ dy1, const double* __restrict__ y2,
+                   const double* __restrict__ dy2, double h00, double hA, double h01, double hB,
+                   double* __restrict__ out, size_t n) {
+  const size_t nvec = n / W;
+  for (size_t v = (size_t)blockIdx.x * THREADS + threadIdx.x; v < nvec; v += (size_t)gridDim.x * THREADS) {
+    const Pk<W> a = ld_stream<W>(y1 + v * W), b = ld_stream<W>(dy1 + v * W), c = ld_stream<W>(y2 + v * W),
+                d = ld_stream<W>(dy2 + v * W);
+    Pk<W> o;
+#pragma unroll
+    for (int e = 0; e < W; ++e)
+      o.v[e] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(a.v[e], h00), __dmul_rn(b.v[e], hA)), __dmul_rn(c.v[e], h01)),
+                         __dmul_rn(d.v[e], hB));
+    st_stream<W>(out + v * W, o);
+  }
+  if (blockIdx.x == 0) {
+    const size_t i = nvec * W + threadIdx.x;
+    if (i < n)
+      out[i] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(y1[i], h00), __dmul_rn(dy1[i], hA)), __dmul_rn(y2[i], h01)),
+                         __dmul_rn(dy2[i], hB));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Element-wise Vector[T] operators (utils.nim:59-223) and built-in right-hand sides
+// ---------------------------------------------------------------------------------------------------
+enum EwiseOp : int {
+  EW_ADD = 0,        // a + b                 utils.nim:59-64
+  EW_SUB = 1,        // a - b                 utils.nim:113-118
+  EW_HMUL = 2,       // a *. b                utils.nim:186-191
+  EW_HDIV = 3,       // a /. b                utils.nim:192-197
+  EW_SCALE = 4,      // s * a                 utils.nim:176-180
+  EW_ADD_SCALAR = 5, // s +. a                utils.nim:78-82
+  EW_NEG = 6,        // -a                    utils.nim:214-218
+  EW_ABS = 7,        // abs(a)                utils.nim:219-223
+  EW_DIV_SCALAR = 8, // a / s                 utils.nim:166-170
+  EW_NEG_HMUL = 9,   // -(a *. b)             diag-linear right-hand side k = -(lambda .* y)
+  EW_FILL = 10,      // s
+};
+
+template <int OP>
+__device__ __forceinline__ double ewise_elem(double a, double b, double s) {
+  switch (OP) {
+    case EW_ADD: return __dadd_rn(a, b);
+    case EW_SUB: return __dadd_rn(a, -b);
+    case EW_HMUL: return __dmul_rn(a, b);
+    case EW_HDIV: return __ddiv_rn(a, b);
+    case EW_SCALE: return __dmul_rn(a, s);
+    case EW_ADD_SCALAR: return __dadd_rn(a, s);
+    case EW_NEG: return -a;
+    case EW_ABS: return fabs(a);
+    case EW_DIV_SCALAR: return __ddiv_rn(a, s);
+    case EW_NEG_HMUL: return -__dmul_rn(a, b);
+    case EW_FILL: return s;
+    default: return a;
+  }
+}
+template <int OP>
+struct EwiseArity { static constexpr bool binary = (OP == EW_ADD || OP == EW_SUB || OP == EW_HMUL || OP == EW_HDIV || OP == EW_NEG_HMUL); };
+
+template <int OP, int W, int U, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+    ewise_kernel(const double* a, const double* b, double s, double* out, size_t n) {
+  constexpr bool BIN = EwiseArity<OP>::binary;
+  const size_t nvec = n / W;
+  const size_t tile = (size_t)THREADS * U;
+  for (size_t base = (size_t)blockIdx.x * tile; base < nvec; base += (size_t)gridDim.x * tile) {
+    Pk<W> av[U], bv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t v = base + (size_t)u * THREADS + threadIdx.x;
+      if (v < nvec) {
+        av[u] = ld_plain<W>(a + v * W);
+        if (BIN) bv[u] = ld_plain<W>(b + v * W);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t v = base + (size_t)u * THREADS + threadIdx.x;
+      if (v < nvec) {
+        Pk<W> o;
+#pragma unroll
+        for (int e = 0; e < W; ++e) o.v[e] = ewise_elem<OP>(av[u].v[e], BIN ? bv[u].v[e] : 0.0, s);
+        st_stream<W>(out + v * W, o);
+      }
+    }
+  }
+  if (blockIdx.x == 0) {
+    const size_t i = nvec * W + threadIdx.x;
+    if (i < n) out[i] = ewise_elem<OP>(a[i], BIN ? b[i] : 0.0, s);
+  }
+}
+
+// Plain sum(v) (utils.nim:243-250) — deterministic tree instead of the sequential CPU order.
+template <int W, int THREADS>
+__global__ void __launch_bounds__(THREADS) sum_kernel(const double* __restrict__ a, size_t n, ReduceScratch rs) {
+  const size_t nvec = n / W;
+  double acc = 0.0;
+  for (size_t v = (size_t)blockIdx.x * THREADS + threadIdx.x; v < nvec; v += (size_t)gridDim.x * THREADS) {
+    const Pk<W> x = ld_stream<W>(a + v * W);
+#pragma unroll
+    for (int e = 0; e < W; ++e) acc = __dadd_rn(acc, x.v[e]);
+  }
+  if (blockIdx.x == 0) {
+    const size_t i = nvec * W + threadIdx.x;
+    if (i < n) acc = __dadd_rn(acc, a[i]);
+  }
+  grid_sum_finish<THREADS>(acc, rs);
+}
+
+// Lorenz-96 right-hand side, cyclic: k[i] = ((y[i+1] - y[i-2]) * y[i-1] - y[i]) + F.
+// `y` is the local block [lo, lo+n) of a cyclic global vector; left2[0..1] = y[lo-2], y[lo-1] and
+// right1[0] = y[lo+n] (for a single GPU these are &y[n-2] and &y[0]: no copies). Two outputs per thread from three
+// aligned 128-bit loads; the neighbour loads hit L1/L2, DRAM traffic stays at one read + one write.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+    lorenz96_kernel(const double* __restrict__ y, const double* __restrict__ left2, const double* __restrict__ right1,
+                    double F, double* __restrict__ out, size_t n) {
+  const size_t npair = n / 2;
+  for (size_t p = (size_t)blockIdx.x * THREADS + threadIdx.x; p < npair; p += (size_t)gridDim.x * THREADS) {
+    const size_t i = 2 * p;
+    const double2 c = __ldg(reinterpret_cast<const double2*>(y + i));
+    double2 l, r;
+    if (p > 0) l = __ldg(reinterpret_cast<const double2*>(y + i - 2));
+    else l = make_double2(left2[0], left2[1]);
+    double rx;
+    if (i + 2 < n) rx = __ldg(y + i + 2);
+    else rx = right1[0];
+    r.x = rx;
+    double2 o;
+    o.x = __dadd_rn(__dadd_rn(__dmul_rn(__dadd_rn(c.y, -l.x), l.y), -c.x), F);
+    o.y = __dadd_rn(__dadd_rn(__dmul_rn(__dadd_rn(r.x, -l.y), c.x), -c.y), F);
+    *reinterpret_cast<double2*>(out + i) = o;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {  // odd n: last element
+    const size_t i = n - 1;
+    out[i] = __dadd_rn(__dadd_rn(__dmul_rn(__dadd_rn(right1[0], -y[i - 2]), y[i - 1]), -y[i]), F);  // n >= 4
+  }
+}
+
+}  // namespace b200rk

@@ -145,7 +145,8 @@ class Solve:
     trace: list
 
 
-def solve_vector(integrator: str, rhs: Rhs, y0, tspan, options: OracleOptions | None = None, trace: bool = False, trace_cap: int = 1 << 20) -> Solve:
+def solve_vector(integrator: str, rhs: Rhs, y0, tspan, options: OracleOptions | None = None, trace: bool = False, trace_cap: int = 1 << 20,
+                 max_steps: int = 0) -> Solve:
     y0 = _f64(y0)
     tspan = _f64(tspan)
     n = y0.size
@@ -160,7 +161,7 @@ def solve_vector(integrator: str, rhs: Rhs, y0, tspan, options: OracleOptions | 
     rc = lib().oracle_solve_vector(
         integrator.encode(), C.c_int(rhs.kind), _p(rhs.param) if rhs.param is not None else None, C.c_double(rhs.scalar),
         cb, None, C.c_size_t(n), _p(y0), _p(tspan), C.c_size_t(tspan.size), C.byref(options), _p(t_out), _p(y_out),
-        C.c_size_t(tspan.size), C.byref(n_y), C.byref(st), tr, C.c_size_t(trace_cap if trace else 0), C.byref(n_tr))
+        C.c_size_t(tspan.size), C.byref(n_y), C.byref(st), tr, C.c_size_t(trace_cap if trace else 0), C.byref(n_tr), C.c_long(max_steps))
     del keep
     _check(rc)
     recs = [(tr[i].t, tr[i].dt_used, tr[i].error, tr[i].attempts) for i in range(min(n_tr.value, trace_cap))] if trace else []

@@ -75,10 +75,11 @@ int oracle_solve_vector(const char* integrator, int rhs_kind, const double* rhs_
                         oracle_rhs_cb cb, void* user, size_t n, const double* y0, const double* tspan,
                         size_t n_tspan, const oracle_options* opt, double* t_out, double* y_out,
                         size_t y_out_cap, size_t* n_y_out, oracle_stats* stats,
-                        oracle_step_record* trace, size_t trace_cap, size_t* n_trace) {
+                        oracle_step_record* trace, size_t trace_cap, size_t* n_trace, long max_steps) {
   try {
     OdeProc<Vector> f = make_rhs(rhs_kind, rhs_param, n, rhs_scalar, cb, user);
     Context<Vector> ctx;
+    ctx.max_steps = max_steps;
     std::vector<Context<Vector>::StepRecord> tr;
     if (trace) ctx.trace = &tr;
     auto t0 = std::chrono::steady_clock::now();

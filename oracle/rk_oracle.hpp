@@ -204,6 +204,7 @@ struct Context {
   std::map<std::string, T> tValues;
   // instrumentation (not in the reference)
   long rhs_evals = 0, attempts = 0, rejected = 0, limiter_hits = 0, steps = 0;
+  long max_steps = 0;  // > 0: stop the driver loop after this many accepted steps (bounded CPU timing)
   bool nan_guard_tripped = false;
   struct StepRecord { double t, dt_used, error; int attempts; };
   std::vector<StepRecord>* trace = nullptr;
@@ -598,6 +599,7 @@ Solution<T> ode_solver(const OdeProc<T>& f, const T& y0, const std::vector<doubl
       record(t_before, dt, a0);
       if (adaptive) controller(dt);
       if (ctx && ctx->nan_guard_tripped) break;
+      if (ctx && ctx->max_steps > 0 && ctx->steps >= ctx->max_steps) break;
     }
     yPositive.push_back(y);                                            // ode.nim:542
   }
@@ -637,6 +639,7 @@ Solution<T> ode_solver(const OdeProc<T>& f, const T& y0, const std::vector<doubl
       record(-t_before, dt, a0);
       if (adaptive) controller(dt);
       if (ctx && ctx->nan_guard_tripped) break;
+      if (ctx && ctx->max_steps > 0 && ctx->steps >= ctx->max_steps) break;
     }
     yNegative.push_back(y);
   }

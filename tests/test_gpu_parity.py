@@ -1,0 +1,479 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu). Every test calls the CUDA path through the C-ABI
+(numericalnim_b200 is a ctypes shim) and compares with the CPU oracle on the same inputs.
+
+Bar: element-wise results BIT-EXACT (the kernels keep the reference's association and never use FMA);
+quantities that pass through the error-norm reduction (sum order differs: tree vs sequential) within
+RTOL_NORM = 1e-13 on the norm, RTOL_DT = 1e-10 on each dt of the step sequence, RTOL_Y = 1e-9 on states.
+"""
+import math
+
+import numpy as np
+import pytest
+from conftest import assert_bitwise_equal, unhex
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL_NORM = 1e-13
+RTOL_DT = 1e-10
+RTOL_Y = 1e-9
+
+
+@pytest.fixture(scope="module")
+def nn():
+    import numericalnim_b200 as nn
+    nn.default_context()  # raises loudly if the CUDA library / device is missing
+    return nn
+
+
+def rng_vec(rng, n, scale=1.0):
+    return (rng.uniform(-1.0, 1.0, n) * scale).astype(np.float64)
+
+
+SIZES = [1, 2, 3, 4, 5, 7, 255, 256, 1000, 4097, (1 << 16) + 3, (1 << 20) + 1]
+
+
+# ---------------------------------------------------------------------------------------------------
+# K1 stage accumulate
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("vec_width", [2, 4])
+@pytest.mark.parametrize("m", range(1, 10))
+def test_stage_accum_bitwise(nn, m, vec_width):
+    ctx = nn.default_context()
+    ctx.set("vec_width", vec_width)
+    rng = np.random.default_rng(100 + m)
+    try:
+        for n in SIZES:
+            y = rng_vec(rng, n, 3.0)
+            ks = [rng_vec(rng, n, 10.0 ** rng.integers(-3, 3)) for _ in range(m)]
+            w = rng_vec(rng, m, 5.0)
+            c = float(rng.uniform(1e-4, 0.5))
+            ref = O.weighted_stage(w, c, y, ks)
+            gy = nn.newVector(y)
+            gk = [nn.newVector(k) for k in ks]
+            out = nn.stageAccum(w, c, gy, gk)
+            assert_bitwise_equal(out.to_numpy(), ref, f"stage m={m} n={n} W={vec_width}")
+    finally:
+        ctx.set("vec_width", 4)
+
+
+def test_stage_accum_special_values(nn):
+    """±0, subnormals, inf, NaN travel through the kernel exactly as through the CPU operators."""
+    specials = np.array([0.0, -0.0, 5e-324, -5e-324, 2.2250738585072014e-308, 1e308, -1e308, np.inf, -np.inf, np.nan, 1.0, -1.0])
+    rng = np.random.default_rng(7)
+    n = 4096
+    y = rng.choice(specials, n)
+    ks = [rng.choice(specials, n) for _ in range(3)]
+    w = np.array([0.5, -2.0, 0.0])
+    ref = O.weighted_stage(w, 0.25, y, ks)
+    out = nn.stageAccum(w, 0.25, nn.newVector(y), [nn.newVector(k) for k in ks])
+    got = out.to_numpy()
+    nan_ref, nan_got = np.isnan(ref), np.isnan(got)
+    assert np.array_equal(nan_ref, nan_got)
+    assert_bitwise_equal(got[~nan_ref], ref[~nan_ref], "special values")
+
+
+def test_stage_chain_form_kutta3(nn):
+    """ode.nim:128: y - dt*k1 + 2*dt*k2 == ((y + (-dt)*k1) + (2*dt)*k2) bit for bit."""
+    rng = np.random.default_rng(11)
+    n, dt = 10007, 0.0371
+    y, k1, k2 = rng_vec(rng, n), rng_vec(rng, n, 4.0), rng_vec(rng, n, 4.0)
+    ref = (y - dt * k1) + (2 * dt) * k2  # numpy: one rounding per op, no FMA
+    out = nn.stageAccum([-1.0 * dt, 2.0 * dt], 0.0, nn.newVector(y), [nn.newVector(k1), nn.newVector(k2)], chain=True)
+    assert_bitwise_equal(out.to_numpy(), ref, "kutta3 chain")
+
+
+@pytest.mark.parametrize("method,stages", [("dopri54", 7), ("tsit54", 7), ("vern65", 9)])
+def test_pair_stage_rows_via_step(nn, method, stages):
+    """Each stage-input row of the product's tableau, applied by the kernel, equals the oracle's row."""
+    import ctypes as C
+    from numericalnim_b200 import _capi
+    rng = np.random.default_rng(5)
+    n, dt = 3001, 0.0123
+    y = rng_vec(rng, n, 2.0)
+    ks = [rng_vec(rng, n, 3.0) for _ in range(stages)]
+    c, a, b, bh = np.zeros(10), np.zeros((10, 9)), np.zeros(9), np.zeros(9)
+    _capi.lib().b200rk_method_tableau(nn.ode.method_id(method), c.ctypes.data, a.ctypes.data, b.ctypes.data, bh.ctypes.data)
+    gy = nn.newVector(y)
+    gk = [nn.newVector(k) for k in ks]
+    ctx = nn.default_context()
+    for strict in (1, 0):
+        ctx.set("strict_zeros", strict)
+        for s in range(2, stages + 1):
+            row = a[s][: s - 1]
+            idx = [j for j in range(s - 1) if strict or row[j] != 0.0 or s == 2]
+            out = nn.stageAccum(row[idx], dt, gy, [gk[j] for j in idx])
+            ref = O.pair_stage_input(method, s, dt, y, ks[: s - 1])
+            assert_bitwise_equal(out.to_numpy(), ref, f"{method} stage {s} strict={strict}")
+    ctx.set("strict_zeros", 0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# K2 combine + error norm
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("vec_width", [2, 4])
+@pytest.mark.parametrize("method,stages", [("dopri54", 7), ("tsit54", 7), ("vern65", 9)])
+def test_combine_err_parity(nn, method, stages, vec_width):
+    ctx = nn.default_context()
+    ctx.set("vec_width", vec_width)
+    rng = np.random.default_rng(21)
+    try:
+        for n in [1, 3, 8, 1001, 65536, (1 << 20) + 5]:
+            y = rng_vec(rng, n, 2.0)
+            ks = [rng_vec(rng, n, 3.0) for _ in range(stages)]
+            dt, atol, rtol = 0.0173, 1e-6, 1e-5
+            yn_ref, ey_ref, S_ref, E_ref = O.pair_finish(method, dt, atol, rtol, y, ks)
+            yn, ey, S, E = nn.combineErr(method, dt, atol, rtol, nn.newVector(y), [nn.newVector(k) for k in ks], want_err_y=True)
+            assert_bitwise_equal(yn.to_numpy(), yn_ref, f"{method} yNew n={n}")
+            assert_bitwise_equal(ey.to_numpy(), ey_ref, f"{method} error_y n={n}")
+            assert abs(S - S_ref) <= RTOL_NORM * abs(S_ref), (method, n, S, S_ref)
+            assert abs(E - E_ref) <= RTOL_NORM * abs(E_ref), (method, n, E, E_ref)
+    finally:
+        ctx.set("vec_width", 4)
+
+
+def test_error_norm_is_deterministic(nn):
+    rng = np.random.default_rng(3)
+    n = (1 << 21) + 17
+    y = nn.newVector(rng_vec(rng, n))
+    ks = [nn.newVector(rng_vec(rng, n, 2.0)) for _ in range(7)]
+    vals = {nn.combineErr("dopri54", 0.01, 1e-6, 1e-6, y, ks)[2].hex() for _ in range(5)}
+    assert len(vals) == 1, vals
+
+
+def test_rk4_combine_bitwise(nn):
+    rng = np.random.default_rng(9)
+    for n in SIZES:
+        y, k1, k2, k3, k4 = (rng_vec(rng, n, 2.0) for _ in range(5))
+        ref = O.rk4_combine(0.0137, y, k1, k2, k3, k4)
+        out = nn.rk4Combine(0.0137, *(nn.newVector(v) for v in (y, k1, k2, k3, k4)))
+        assert_bitwise_equal(out.to_numpy(), ref, f"rk4 combine n={n}")
+
+
+def test_hermite_bitwise(nn):
+    rng = np.random.default_rng(13)
+    for n in [1, 5, 1000, 65537]:
+        y1, y2, d1, d2 = (rng_vec(rng, n, 2.0) for _ in range(4))
+        for x in (0.3, 0.55, 1.0, 0.2):
+            ref = O.hermite(x, 0.2, 1.0, y1, y2, d1, d2)
+            out = nn.hermiteSpline(x, 0.2, 1.0, *(nn.newVector(v) for v in (y1, y2, d1, d2)))
+            assert_bitwise_equal(out.to_numpy(), ref, f"hermite n={n} x={x}")
+    # at x == x2 the spline returns y2 exactly
+    assert_bitwise_equal(nn.hermiteSpline(1.0, 0.2, 1.0, *(nn.newVector(v) for v in (y1, y2, d1, d2))).to_numpy(), y2)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Vector operators and right-hand sides
+# ---------------------------------------------------------------------------------------------------
+def test_vector_operators_bitwise(nn):
+    rng = np.random.default_rng(17)
+    for n in [1, 3, 1000, 65539]:
+        a, b = rng_vec(rng, n, 5.0), rng_vec(rng, n, 5.0) + 7.0
+        ga, gb = nn.newVector(a), nn.newVector(b)
+        assert_bitwise_equal((ga + gb).to_numpy(), O.vector_binop(0, a, b), "+")
+        assert_bitwise_equal((ga - gb).to_numpy(), O.vector_binop(1, a, b), "-")
+        assert_bitwise_equal(ga.hmul(gb).to_numpy(), O.vector_binop(2, a, b), "*.")
+        assert_bitwise_equal(ga.hdiv(gb).to_numpy(), O.vector_binop(3, a, b), "/.")
+        assert_bitwise_equal((8.98 * ga).to_numpy(), O.vector_unop(0, 8.98, a), "scalar *")
+        assert_bitwise_equal((ga / 8.98).to_numpy(), O.vector_unop(1, 8.98, a), "/ scalar")
+        assert_bitwise_equal((-ga).to_numpy(), O.vector_unop(2, 0.0, a), "neg")
+        assert_bitwise_equal(abs(ga).to_numpy(), O.vector_unop(3, 0.0, a), "abs")
+        assert_bitwise_equal((8.98 + ga).to_numpy(), O.vector_unop(4, 8.98, a), "+.")
+        assert_bitwise_equal(ga.clone().to_numpy(), a, "clone")
+        s_ref = O.vector_sum(a)
+        assert abs(ga.sum() - s_ref) <= 1e-12 * np.abs(a).sum()
+    with pytest.raises(ValueError, match="same size"):  # utils.nim:22-26, tests/test_vector.nim:41-45
+        nn.newVector([1.0, 2.0, 4.0, 1.34, 9.9]) + nn.newVector([3.3, 2.2, 1.1, 5.67])
+
+
+def test_vector_known_answers_from_reference_tests(nn):  # tests/test_vector.nim:26-30, 120-132, 289-293
+    v1, v2 = nn.newVector([1.1, 2.2, 3.3]), nn.newVector([3.3, 2.2, 1.0])
+    assert (v1 + v2).to_numpy().tolist() == [1.1 + 3.3, 2.2 + 2.2, 3.3 + 1.0]
+    assert (v1 - v2).to_numpy().tolist() == [1.1 - 3.3, 2.2 - 2.2, 3.3 - 1.0]
+    assert v1.hmul(v2).to_numpy().tolist() == [1.1 * 3.3, 2.2 * 2.2, 3.3 * 1.0]
+    assert nn.newVector([1.0, 2.0, 3.0, 4.5]).sum() == 10.5
+
+
+@pytest.mark.parametrize("n", [4, 5, 6, 7, 40, 41, 1000, 65536, 65537])
+def test_lorenz96_rhs_bitwise(nn, n):
+    rng = np.random.default_rng(n)
+    y = 8.0 + rng_vec(rng, n)
+    ref = O.rhs_eval(O.rhs_lorenz96(8.0), 0.0, y)
+    gy = nn.newVector(y)
+    # one explicit Euler-like stage through the step API would hide the RHS; call it through solve of 0 steps:
+    out = _eval_builtin(nn, nn.rhsLorenz96(8.0), gy)
+    assert_bitwise_equal(out, ref, f"lorenz96 n={n}")
+
+
+def test_diag_linear_and_scale_rhs_bitwise(nn):
+    rng = np.random.default_rng(23)
+    n = 10001
+    y, lam = rng_vec(rng, n, 3.0), rng.uniform(0.1, 10.0, n)
+    glam = nn.newVector(lam)
+    assert_bitwise_equal(_eval_builtin(nn, nn.rhsDiagLinear(glam), nn.newVector(y)), O.rhs_eval(O.rhs_diag_linear(lam), 0.0, y))
+    assert_bitwise_equal(_eval_builtin(nn, nn.rhsScale(-0.1), nn.newVector(y)), O.rhs_eval(O.rhs_scale(-0.1), 0.0, y))
+
+
+def _eval_builtin(nn, rhs, gy):
+    """Evaluate a built-in right-hand side once, through the same callback pointer the solver uses."""
+    import ctypes as C
+    out = gy._new_like()
+    rc = rhs.fn(0.0, gy._h, out._h, rhs.user)
+    assert rc == 0
+    return out.to_numpy()
+
+
+# ---------------------------------------------------------------------------------------------------
+# IntegratorProc: one step of every method
+# ---------------------------------------------------------------------------------------------------
+ALL = ["dopri54", "tsit54", "vern65", "rk4", "rk21", "bs32", "heun2", "ralston2", "kutta3", "heun3", "ralston3", "ssprk3", "ralston4", "kutta4"]
+
+
+@pytest.mark.parametrize("method", ALL)
+def test_single_step_matches_oracle(nn, method):
+    rng = np.random.default_rng(31)
+    n = 2049
+    lam = rng.uniform(0.1, 5.0, n)
+    y = 1.0 + rng_vec(rng, n, 0.5)
+    fsal = O.rhs_eval(O.rhs_diag_linear(lam), 0.3, y)
+    opts = dict(absTol=1e-3, relTol=1e-3, dtMax=1.0, dtMin=1e-8)  # loose: the first attempt is accepted
+    dt = 0.005
+    yn_ref, fn_ref, dt_ref, err_ref, st = O.step_vector(method, O.rhs_diag_linear(lam), 0.3, y, fsal, dt, O.new_options(**opts))
+    assert st.rejected == 0
+    glam = nn.newVector(lam)
+    yn, fn, dt_used, err = nn.integratorStep(method, nn.rhsDiagLinear(glam), 0.3, nn.newVector(y), nn.newVector(fsal), dt, nn.newODEoptions(**opts))
+    assert dt_used == dt_ref
+    assert_bitwise_equal(yn.to_numpy(), yn_ref, f"{method} yNew")
+    assert_bitwise_equal(fn.to_numpy(), fn_ref, f"{method} FSAL out")
+    if err_ref == 0.0:
+        assert err == 0.0
+    else:
+        assert abs(err - err_ref) <= RTOL_NORM * err_ref
+
+
+@pytest.mark.parametrize("method", ["dopri54", "tsit54", "vern65", "rk21", "bs32"])
+def test_single_step_with_rejections_matches_oracle(nn, method):
+    """Tight tolerance and a big first dt: the retry loop (ode.nim:57-76) runs several attempts."""
+    rng = np.random.default_rng(37)
+    n = 1025
+    lam = rng.uniform(1.0, 50.0, n)
+    y = 1.0 + rng_vec(rng, n, 0.5)
+    fsal = O.rhs_eval(O.rhs_diag_linear(lam), 0.0, y)
+    opts = dict(absTol=1e-10, relTol=1e-10, dtMax=1.0, dtMin=1e-9)
+    yn_ref, fn_ref, dt_ref, err_ref, st = O.step_vector(method, O.rhs_diag_linear(lam), 0.0, y, fsal, 0.2, O.new_options(**opts))
+    assert st.rejected >= 1
+    yn, fn, dt_used, err = nn.integratorStep(method, nn.rhsDiagLinear(nn.newVector(lam)), 0.0, nn.newVector(y), nn.newVector(fsal), 0.2, nn.newODEoptions(**opts))
+    assert abs(dt_used - dt_ref) <= RTOL_DT * dt_ref
+    assert np.allclose(yn.to_numpy(), yn_ref, rtol=RTOL_Y, atol=0)
+    assert abs(err - err_ref) <= 1e-8 * err_ref
+
+
+def test_step_rejects_aliasing_and_size_mismatch(nn):
+    y = nn.newVector(np.ones(8))
+    f = nn.newVector(np.ones(8))
+    rhs = nn.rhsScale(-1.0)
+    import ctypes as C
+    from numericalnim_b200 import _capi
+    du, er = C.c_double(), C.c_double()
+    o = nn.newODEoptions()
+    rc = _capi.lib().b200rk_step(y.ctx.handle, 0, rhs.fn, rhs.user, 0.0, y._h, f._h, 0.1, C.byref(o), y._h, f._h, C.byref(du), C.byref(er))
+    assert rc == _capi.EINVAL
+    with pytest.raises(ValueError, match="same size"):
+        nn.integratorStep("dopri54", rhs, 0.0, y, nn.newVector(np.ones(9)), 0.1)
+
+
+def test_nan_error_is_reported_not_looped(nn):
+    """ode.nim:69-76 would spin forever on a NaN norm; the library returns B200RK_ENONFINITE instead."""
+    from numericalnim_b200 import B200rkError
+    y = nn.newVector(np.array([1.0, np.nan, 2.0, 3.0]))
+    rhs = nn.rhsScale(-1.0)
+    fsal = nn.newVector(np.array([-1.0, np.nan, -2.0, -3.0]))
+    with pytest.raises(B200rkError) as ei:
+        nn.integratorStep("tsit54", rhs, 0.0, y, fsal, 0.1)
+    assert ei.value.code == 6
+
+
+# ---------------------------------------------------------------------------------------------------
+# solveODE: golden fixtures (tests/golden/trajectories.json) and the reference's own test cases
+# ---------------------------------------------------------------------------------------------------
+def _builtin_from(nn, desc):
+    if desc["kind"] == "scale":
+        return nn.rhsScale(desc["c"])
+    if desc["kind"] == "diag":
+        return nn.rhsDiagLinear(nn.newVector(unhex(desc["lam"])))
+    if desc["kind"] == "l96":
+        return nn.rhsLorenz96(desc["F"])
+    raise KeyError(desc)
+
+
+def test_solve_matches_golden_fixtures(nn, golden_trajectories):
+    checked = 0
+    for name, g in golden_trajectories.items():
+        y0, ts = unhex(g["y0"]), unhex(g["tspan"])
+        opts = nn.newODEoptions(**g["options"])
+        rhs = _builtin_from(nn, g["rhs"])
+        gy = np.array([unhex(r) for r in g["y"]])
+        t, ys = nn.solveODE(rhs, nn.newVector(y0), ts, opts, integrator=g["integrator"])
+        st = dict(nn.ode.last_stats)
+        assert_bitwise_equal(np.array(t), unhex(g["t"]), name + " t")
+        got = np.array([v.to_numpy() for v in ys])
+        assert got.shape == gy.shape, name
+        assert (st["steps"], st["attempts"], st["rejected"], st["limiter_hits"]) == (g["steps"], g["attempts"], g["rejected"], g["limiter_hits"]), name
+        if g["integrator"] == "rk4":
+            assert_bitwise_equal(got, gy, name + " (fixed step: identical trajectory)")
+        else:
+            scale = np.maximum(np.abs(gy), 1e-300)
+            lim = 1e-6 if name.startswith(("l96", "limiter")) else RTOL_Y  # chaotic / limiter-accepted steps amplify ulps
+            assert np.max(np.abs(got - gy) / scale) <= lim, (name, np.max(np.abs(got - gy) / scale))
+        checked += 1
+    assert checked >= 20
+
+
+def test_step_sequence_matches_oracle(nn):
+    """Same number of steps and the same dt sequence (rtol 1e-10) as the CPU oracle on a vector IVP."""
+    n = 4096
+    lam = 0.1 + 9.9 * np.arange(n) / (n - 1)
+    y0 = 1.0 + 0.5 * np.sin(2 * np.pi * np.arange(n) / n)
+    kw = dict(absTol=1e-6, relTol=1e-6, dtMax=1.0, dtMin=1e-8)
+    for method in ("dopri54", "tsit54", "vern65"):
+        ref = O.solve_vector(method, O.rhs_diag_linear(lam), y0, [0.0, 2.0], O.new_options(**kw), trace=True)
+        s = nn.Solver(method, nn.rhsDiagLinear(nn.newVector(lam)), nn.newVector(y0), 2.0, nn.newODEoptions(**kw))
+        dts = []
+        while True:
+            t_before = s.state()[0]
+            done, fin = s.advance(1)
+            if done:
+                dts.append(s.state()[0] - t_before)
+            if fin:
+                break
+        st = s.stats()
+        assert st["steps"] == ref.stats.steps and st["rejected"] == ref.stats.rejected, method
+        ref_dts = np.array([r[1] for r in ref.trace])
+        t_acc = np.cumsum(ref_dts)
+        assert np.allclose(np.cumsum(dts), t_acc, rtol=1e-9, atol=0), method
+        y_end = s.state()[3].to_numpy()
+        assert np.allclose(y_end, ref.y[-1], rtol=RTOL_Y, atol=1e-300), method
+        exact = y0 * np.exp(-lam * 2.0)
+        assert np.max(np.abs(y_end - exact)) < 1e-5
+        s.close()
+
+
+OOV = dict(relTol=1e-8, dt=1e-2)  # tests/test_ode.nim:10
+
+
+@pytest.mark.parametrize("integrator,opts,tol", [
+    ("dopri54", None, 1e-4), ("dopri54", OOV, 1e-8), ("rk4", OOV, 1e-8), ("heun2", OOV, 1e-5),
+    ("tsit54", None, 1e-4), ("tsit54", OOV, 1e-8), ("vern65", None, 1e-4), ("vern65", OOV, 1e-8)])
+def test_reference_vector_cases_on_gpu(nn, integrator, opts, tol):
+    """tests/test_ode.nim:139-197 with the right-hand side written as in the reference: -0.1 * y."""
+    tspan = nn.linspace(-10.0, 10.0, 100)
+
+    def fVector(x, y, ctx):  # tests/test_ode.nim:6
+        return -0.1 * y
+
+    o = nn.newODEoptions(**opts) if opts else None
+    t, ys = nn.solveODE(fVector, nn.newVector([1.0, 1.0, 1.0]), tspan, o, integrator=integrator) if o else \
+        nn.solveODE(fVector, nn.newVector([1.0, 1.0, 1.0]), tspan, integrator=integrator)
+    assert t == tspan  # `check t == tspan`
+    assert len(ys) == 100
+    for ti, v in zip(t, ys):
+        c = math.exp(-0.1 * ti)
+        assert O.is_close(v.to_numpy(), np.array([c, c, c]), tol)
+
+
+@pytest.mark.parametrize("integrator", ["dopri54", "tsit54", "vern65", "rk21", "bs32", "kutta4"])
+def test_reference_scalar_cases_on_gpu(nn, integrator):
+    """tests/test_ode.nim:24-136 (scalar T): a Python float travels as a length-1 vector; host-buffer path."""
+    tspan = nn.linspace(-10.0, 10.0, 100)
+    kw = {} if integrator != "kutta4" else dict(dt=1e-2)  # fixed-step default dt=1e-4 is 200k launches x4
+    t, y = nn.solveODE(nn.rhsScale(-0.1), 1.0, tspan, nn.newODEoptions(**kw), integrator=integrator)
+    assert t == tspan
+    ref_t, ref_y, _ = O.solve_scalar(integrator, 1.0, tspan, O.new_options(**kw))
+    assert len(y) == len(ref_y) == 100
+    if integrator == "kutta4":
+        assert_bitwise_equal(np.array(y), ref_y, "fixed-step scalar trajectory")
+    else:
+        assert np.allclose(y, ref_y, rtol=RTOL_Y, atol=0)
+    for ti, v in zip(t, y):
+        assert O.is_close(float(v), math.exp(-0.1 * ti), 1e-6 if integrator in ("rk21", "bs32") else 1e-4)
+
+
+def test_rk4_trajectory_is_bit_identical(nn):
+    """Fixed step: identical step sequence and bit-identical states, dense output and backward time included."""
+    rng = np.random.default_rng(41)
+    n = 257
+    lam = rng.uniform(0.1, 3.0, n)
+    y0 = 1.0 + rng_vec(rng, n, 0.3)
+    ts = nn.linspace(-0.5, 1.0, 7)
+    kw = dict(dt=1e-2)
+    ref = O.solve_vector("rk4", O.rhs_diag_linear(lam), y0, ts, O.new_options(**kw))
+    t, ys = nn.solveODE(nn.rhsDiagLinear(nn.newVector(lam)), nn.newVector(y0), ts, nn.newODEoptions(**kw), integrator="rk4")
+    assert_bitwise_equal(np.array(t), ref.t)
+    assert_bitwise_equal(np.array([v.to_numpy() for v in ys]), ref.y, "rk4 dense+backward trajectory")
+    assert nn.ode.last_stats["steps"] == ref.stats.steps
+    assert nn.ode.last_stats["rhs_evals"] == ref.stats.rhs_evals
+
+
+@pytest.mark.parametrize("method", ["heun2", "ralston2", "kutta3", "heun3", "ralston3", "ssprk3", "ralston4", "kutta4"])
+def test_other_fixed_methods_bit_identical(nn, method):
+    n = 33
+    lam = np.linspace(0.1, 2.0, n)
+    y0 = np.linspace(1.0, 2.0, n)
+    kw = dict(dt=5e-3)
+    ref = O.solve_vector(method, O.rhs_diag_linear(lam), y0, [0.0, 0.25], O.new_options(**kw))
+    t, ys = nn.solveODE(nn.rhsDiagLinear(nn.newVector(lam)), nn.newVector(y0), [0.0, 0.25], nn.newODEoptions(**kw), integrator=method)
+    assert_bitwise_equal(np.array([v.to_numpy() for v in ys]), ref.y, method)
+
+
+def test_tspan_quirks_match_reference(nn):
+    """tspan of length 2 without tStart returns two times but one state; unsorted tspan is sorted."""
+    rhs = nn.rhsScale(-0.1)
+    t, ys = nn.solveODE(rhs, nn.newVector([1.0, 2.0]), [2.0, 1.0], nn.newODEoptions(dtMax=0.5), integrator="tsit54")
+    ref = O.solve_vector("tsit54", O.rhs_scale(-0.1), [1.0, 2.0], [2.0, 1.0], O.new_options(dtMax=0.5))
+    assert t == [1.0, 2.0] and len(ys) == ref.y.shape[0] == 1
+    assert np.allclose(ys[0].to_numpy(), ref.y[0], rtol=RTOL_Y)
+    with pytest.raises(ValueError, match="not a valid integrator"):
+        nn.solveODE(rhs, nn.newVector([1.0]), [0.0, 1.0], integrator="rk5")
+
+
+def test_host_buffer_path_equals_device_path(nn):
+    n = 1000
+    lam = np.linspace(0.1, 4.0, n)
+    y0 = np.linspace(1.0, 2.0, n)
+    kw = dict(absTol=1e-7, relTol=1e-7, dtMax=0.5, dtMin=1e-8)
+    rhs = nn.rhsDiagLinear(nn.newVector(lam))
+    ts = nn.linspace(0.0, 1.0, 5)
+    t1, y1 = nn.solveODE(rhs, y0, ts, nn.newODEoptions(**kw), integrator="dopri54")
+    t2, y2 = nn.solveODE(rhs, nn.newVector(y0), ts, nn.newODEoptions(**kw), integrator="dopri54")
+    assert t1 == t2
+    assert_bitwise_equal(np.array(y1), np.array([v.to_numpy() for v in y2]), "host vs device path")
+
+
+# ---------------------------------------------------------------------------------------------------
+# Full-size properties (BASELINE.json sizes): bitwise vs the oracle on one launch, and invariants
+# ---------------------------------------------------------------------------------------------------
+def test_full_size_stage_and_finish(nn):
+    n = 1 << 23
+    rng = np.random.default_rng(2023)
+    y = rng_vec(rng, n)
+    ks = [rng_vec(rng, n, 2.0) for _ in range(7)]
+    gy = nn.newVector(y)
+    gk = [nn.newVector(k) for k in ks]
+    T = O.pair_tableau("dopri54")
+    # stage 6 (ode.nim:298): bitwise vs numpy evaluated with the reference's association (no FMA in numpy)
+    w = T["a"][6][:5]
+    acc = w[0] * ks[0]
+    for j in range(1, 5):
+        acc = acc + w[j] * ks[j]
+    ref = y + 0.01 * acc
+    out = nn.stageAccum(w, 0.01, gy, gk[:5])
+    assert_bitwise_equal(out.to_numpy(), ref, "stage 6 at N=2^23")
+    yn_ref, _, S_ref, E_ref = O.pair_finish("dopri54", 0.01, 1e-6, 1e-6, y, ks)
+    yn, _, S, E = nn.combineErr("dopri54", 0.01, 1e-6, 1e-6, gy, gk)
+    assert_bitwise_equal(yn.to_numpy(), yn_ref, "yNew at N=2^23")
+    assert abs(S - S_ref) <= RTOL_NORM * S_ref
+    # linearity in the derivative streams: stage(y, 2k) - y == 2*(stage(y, k) - y) is NOT exact in floating
+    # point, but scaling all k by a power of two is: stage(y; 2k, c/2) == stage(y; k, c) bit for bit.
+    out2 = nn.stageAccum(w, 0.005, gy, [2.0 * k for k in gk[:5]])
+    assert_bitwise_equal(out2.to_numpy(), ref, "power-of-two scaling invariance")

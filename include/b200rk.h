@@ -111,6 +111,10 @@ B200RK_API int b200rk_method_info(int method, int* stages, int* use_fsal, double
 /* dense tableau of the three FSAL pairs for cross-checks: c[10], a[10*9] (a[s*9+j-1] = a_sj), b[9], bhat[9] */
 B200RK_API int b200rk_method_tableau(int method, double* c, double* a, double* b, double* bhat);
 
+/* Contiguous shard of rank `rank` of `world` for a vector of n_global elements: [offset, offset+len).
+ * chunk = ceil(n_global/world) rounded up to a multiple of 4 elements (32-byte aligned boundaries). Host-only. */
+B200RK_API int b200rk_shard_range(size_t n_global, int rank, int world, size_t* offset, size_t* len);
+
 /* ---- vectors (Vector[float], utils.nim:14-271) ------------------------------------------------ */
 B200RK_API int b200rk_vec_new(b200rk_ctx* ctx, size_t n_global, b200rk_vec** out); /* newVector; contents undefined */
 B200RK_API int b200rk_vec_free(b200rk_vec* v);

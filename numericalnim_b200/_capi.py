@@ -61,6 +61,7 @@ _DECLS = {
     "b200rk_method_name": (C.c_char_p, [C.c_int]),
     "b200rk_method_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "b200rk_method_tableau": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200rk_shard_range": (C.c_int, [C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "b200rk_vec_new": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "b200rk_vec_free": (C.c_int, [C.c_void_p]),
     "b200rk_vec_len": (C.c_size_t, [C.c_void_p]),

@@ -4,7 +4,8 @@
 // in include/b200rk.h. Host control flow restates numericalnim's ode.nim:57-76 (retry loop),
 // ode.nim:471-586 (driver) and ode.nim:589-651 (dispatch); all O(N) arithmetic runs in kernels.cuh.
 #include <cuda_runtime.h>
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is bound at run time, see NcclApi below
 
 #include <algorithm>
 #include <cctype>
@@ -50,7 +51,8 @@ struct b200rk_ctx {
   size_t pool_budget_bytes = (size_t)48 << 30;
   // knobs
   int vec_width = 4;
-  int ctas_per_sm = 0;
+  int ctas_per_sm = 0;         // stage/element-wise kernels: 0 = one tile per CTA (measured best, profiles/)
+  int finish_ctas_per_sm = 2;  // reducing kernels: persistent grid, one partial per CTA (measured best)
   bool strict_zeros = false;
   bool profile = false;
   // counters
@@ -81,7 +83,7 @@ static int fail(const b200rk_ctx* ctx, int code, const std::string& msg) {
   do {                                                                                              \
     ncclResult_t _e = (expr);                                                                       \
     if (_e != ncclSuccess)                                                                          \
-      return fail(ctx, B200RK_ENCCL, std::string(#expr) + ": " + ncclGetErrorString(_e));           \
+      return fail(ctx, B200RK_ENCCL, std::string(#expr) + ": " + g_nccl.GetErrorString(_e));        \
   } while (0)
 #define TRY(expr)                      \
   do {                                 \
@@ -91,6 +93,46 @@ static int fail(const b200rk_ctx* ctx, int code, const std::string& msg) {
 
 static inline double nim_min(double x, double y) { return (x <= y) ? x : y; }  // Nim system.min
 static inline double nim_max(double x, double y) { return (y <= x) ? x : y; }  // Nim system.max
+
+// ---- NCCL, bound lazily ------------------------------------------------------------------------------
+// libb200rk.so does not link libnccl: a process may already hold a libnccl.so.2 (PyTorch bundles its own,
+// newer than the system one, and resolves symbols against whichever copy was loaded first). The first
+// distributed call binds, in order: a copy already in the process, $B200RK_NCCL_LIB, then the default
+// search path. Single-GPU use never touches NCCL.
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*GetVersion)(int*) = nullptr;
+  std::string where;
+};
+static NcclApi g_nccl;
+
+static int nccl_bind(const b200rk_ctx* ctx) {
+  if (g_nccl.handle) return B200RK_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  std::string where = "already loaded in the process";
+  if (!h) {
+    if (const char* p = getenv("B200RK_NCCL_LIB")) { h = dlopen(p, RTLD_NOW | RTLD_GLOBAL); where = p; }
+  }
+  if (!h) { h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL); where = "libnccl.so.2 (default search path)"; }
+  if (!h) return fail(ctx, B200RK_ENCCL, std::string("cannot load libnccl.so.2: ") + dlerror());
+  NcclApi a;
+  a.handle = h; a.where = where;
+  a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+  a.CommInitRank = (decltype(a.CommInitRank))dlsym(h, "ncclCommInitRank");
+  a.CommDestroy = (decltype(a.CommDestroy))dlsym(h, "ncclCommDestroy");
+  a.AllReduce = (decltype(a.AllReduce))dlsym(h, "ncclAllReduce");
+  a.GetErrorString = (decltype(a.GetErrorString))dlsym(h, "ncclGetErrorString");
+  a.GetVersion = (decltype(a.GetVersion))dlsym(h, "ncclGetVersion");
+  if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce || !a.GetErrorString)
+    return fail(ctx, B200RK_ENCCL, "libnccl.so.2 lacks a required symbol");
+  g_nccl = a;
+  return B200RK_OK;
+}
 
 // ---- profiling: one CUDA-event pair per launch on the context stream --------------------------------
 struct ProfScope {
@@ -129,10 +171,11 @@ struct StageUnroll {  // keep ~16 doubles of loads in flight per thread
   static constexpr int value = raw < 1 ? 1 : (raw > 4 ? 4 : raw);
 };
 
-static inline unsigned grid_for(const b200rk_ctx* c, size_t nvec, int per_block) {
+static inline unsigned grid_for(const b200rk_ctx* c, size_t nvec, int per_block, int ctas_per_sm = -1) {
   size_t tiles = (nvec + per_block - 1) / per_block;
   if (tiles == 0) tiles = 1;
-  if (c->ctas_per_sm > 0) tiles = std::min(tiles, (size_t)c->ctas_per_sm * c->sm_count);
+  if (ctas_per_sm < 0) ctas_per_sm = c->ctas_per_sm;
+  if (ctas_per_sm > 0) tiles = std::min(tiles, (size_t)ctas_per_sm * c->sm_count);
   return (unsigned)std::min(tiles, (size_t)0x7fffffff);
 }
 
@@ -218,7 +261,7 @@ static int launch_finish_cfg(b200rk_ctx* c, const FinishPlan& p) {
   for (int j = 0; j < NK; ++j) { a.k[j] = p.k[j]; a.wb[j] = p.wb[j]; a.wbh[j] = p.wbh[j]; }
   a.mask_b = p.mask_b; a.mask_bh = p.mask_bh; a.cb = p.cb; a.cbh = p.cbh; a.absTol = p.absTol; a.relTol = p.relTol;
   a.ynew_out = p.ynew_out; a.err_out = p.err_out; a.n = p.n;
-  unsigned grid = grid_for(c, p.n / W, kThreads * U);
+  unsigned grid = grid_for(c, p.n / W, kThreads * U, c->finish_ctas_per_sm);
   TRY(ensure_partials(c, grid));
   a.rs = reduce_scratch(c);
   finish_kernel<NK, W, U, DIRECT, MODE, kThreads><<<grid, kThreads, 0, c->stream>>>(a);
@@ -254,7 +297,7 @@ static int launch_finish(b200rk_ctx* c, const FinishPlan& p) {
 // After a reducing kernel: (allreduce across shards) and bring the scalar to the host.
 static int fetch_global_sum(b200rk_ctx* c, double* out) {
   if (c->world > 1) {
-    NCCL_TRY(c, ncclAllReduce(c->d_result, c->d_result, 1, ncclDouble, ncclSum, c->comm, c->stream));
+    NCCL_TRY(c, g_nccl.AllReduce(c->d_result, c->d_result, 1, ncclDouble, ncclSum, c->comm, c->stream));
     c->collectives++;
     CUDA_TRY(c, cudaMemcpyAsync(c->h_result, c->d_result, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   }
@@ -750,6 +793,7 @@ static int ctx_common_init(b200rk_ctx* c) {
   TRY(ensure_partials(c, 1));
   if (const char* e = getenv("B200RK_VEC_WIDTH")) c->vec_width = (atoi(e) == 2) ? 2 : 4;
   if (const char* e = getenv("B200RK_CTAS_PER_SM")) c->ctas_per_sm = std::max(0, atoi(e));
+  if (const char* e = getenv("B200RK_FINISH_CTAS_PER_SM")) c->finish_ctas_per_sm = std::max(0, atoi(e));
   if (const char* e = getenv("B200RK_STRICT_ZEROS")) c->strict_zeros = atoi(e) != 0;
   CUDA_TRY(c, cudaDeviceSynchronize());
   return B200RK_OK;
@@ -767,8 +811,9 @@ int b200rk_init(b200rk_ctx** out, int device) {
 
 int b200rk_nccl_unique_id(void* out128) {
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  TRY(nccl_bind(nullptr));
   ncclUniqueId id;
-  NCCL_TRY(nullptr, ncclGetUniqueId(&id));
+  NCCL_TRY(nullptr, g_nccl.GetUniqueId(&id));
   std::memcpy(out128, &id, sizeof(id));
   return B200RK_OK;
 }
@@ -781,8 +826,11 @@ int b200rk_init_distributed(b200rk_ctx** out, int device, int rank, int world, c
   if (rc == B200RK_OK && world > 1) {
     ncclUniqueId id;
     std::memcpy(&id, id128, sizeof(id));
-    ncclResult_t e = ncclCommInitRank(&c->comm, world, id, rank);
-    if (e != ncclSuccess) rc = fail(c, B200RK_ENCCL, std::string("ncclCommInitRank: ") + ncclGetErrorString(e));
+    rc = nccl_bind(c);
+    if (rc == B200RK_OK) {
+      ncclResult_t e = g_nccl.CommInitRank(&c->comm, world, id, rank);
+      if (e != ncclSuccess) rc = fail(c, B200RK_ENCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(e));
+    }
   }
   if (rc != B200RK_OK) { g_thread_err = c->err; delete c; return rc; }
   *out = c;
@@ -796,7 +844,7 @@ void b200rk_destroy(b200rk_ctx* c) {
   for (auto* v : c->pool) { cudaFree(v->d); delete v; }
   for (auto& r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : c->ev_free) cudaEventDestroy(e);
-  if (c->comm) ncclCommDestroy(c->comm);
+  if (c->comm) g_nccl.CommDestroy(c->comm);
   cudaFree(c->d_partials); cudaFree(c->d_ticket); cudaFree(c->d_result); cudaFreeHost(c->h_result);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -812,6 +860,7 @@ int b200rk_set(b200rk_ctx* c, const char* key, int64_t v) {
   if (k == "strict_zeros") c->strict_zeros = v != 0;
   else if (k == "vec_width") { if (v != 2 && v != 4) return fail(c, B200RK_EINVAL, "vec_width must be 2 or 4"); c->vec_width = (int)v; }
   else if (k == "ctas_per_sm") { if (v < 0) return fail(c, B200RK_EINVAL, "ctas_per_sm must be >= 0"); c->ctas_per_sm = (int)v; }
+  else if (k == "finish_ctas_per_sm") { if (v < 0) return fail(c, B200RK_EINVAL, "finish_ctas_per_sm must be >= 0"); c->finish_ctas_per_sm = (int)v; }
   else if (k == "profile") c->profile = v != 0;
   else if (k == "pool_budget_mb") {
     c->pool_budget_bytes = (size_t)std::max<int64_t>(0, v) << 20;
@@ -829,6 +878,7 @@ int b200rk_get(const b200rk_ctx* c, const char* key, int64_t* v) {
   if (k == "strict_zeros") *v = c->strict_zeros;
   else if (k == "vec_width") *v = c->vec_width;
   else if (k == "ctas_per_sm") *v = c->ctas_per_sm;
+  else if (k == "finish_ctas_per_sm") *v = c->finish_ctas_per_sm;
   else if (k == "profile") *v = c->profile;
   else if (k == "sm_count") *v = c->sm_count;
   else if (k == "pool_budget_mb") *v = (int64_t)(c->pool_budget_bytes >> 20);
@@ -904,6 +954,12 @@ int b200rk_method_tableau(int method, double* c, double* a, double* b, double* b
   }
   for (int j = 0; j < m.b.m; ++j) b[m.b.idx[j] - 1] = m.b.w[j];
   for (int j = 0; j < m.bhat.m; ++j) bhat[m.bhat.idx[j] - 1] = m.bhat.w[j];
+  return B200RK_OK;
+}
+
+int b200rk_shard_range(size_t n_global, int rank, int world, size_t* offset, size_t* len) {
+  if (world < 1 || rank < 0 || rank >= world || !offset || !len) return fail(nullptr, B200RK_EINVAL, "bad rank/world");
+  shard_range(n_global, rank, world, offset, len);
   return B200RK_OK;
 }
 

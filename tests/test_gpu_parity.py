@@ -1,9 +1,17 @@
 """GPU parity tests (run on the B200 box: pytest -m gpu). Every test calls the CUDA path through the C-ABI
 (numericalnim_b200 is a ctypes shim) and compares with the CPU oracle on the same inputs.
 
-Bar: element-wise results BIT-EXACT (the kernels keep the reference's association and never use FMA);
-quantities that pass through the error-norm reduction (sum order differs: tree vs sequential) within
-RTOL_NORM = 1e-13 on the norm, RTOL_DT = 1e-10 on each dt of the step sequence, RTOL_Y = 1e-9 on states.
+Bar: element-wise results BIT-EXACT (the kernels keep the reference's association and never use FMA).
+Quantities that pass through the error-norm reduction differ in summation order (deterministic tree on
+the GPU, sequential on the CPU), so they are compared within stated tolerances:
+  * the norm itself: norm_rtol(n) = max(1e-13, 4*sqrt(n)*2.2e-16) — the sequential CPU sum is itself only
+    accurate to ~sqrt(n) ulps, which exceeds 1e-13 once n > ~10^5;
+  * each dt of the step sequence: RTOL_DT = 1e-10;
+  * states of adaptive solves: |dy| <= RTOL_Y*|y| + ATOL_Y*max|y|, RTOL_Y = 1e-9, ATOL_Y = 1e-13. The
+    absolute term is needed because a 1-ulp change of dt re-draws every rounding error of the step, and
+    Vern65's tableau (|a_8j|, |b_7|, |b_8| up to 208) amplifies that noise to ~1e-9 RELATIVE on components
+    that have decayed far below the solver's own absTol (absolute size ~1e-17, 11 orders under absTol).
+Fixed-step trajectories are bit-identical.
 """
 import math
 
@@ -18,6 +26,22 @@ pytestmark = pytest.mark.gpu
 RTOL_NORM = 1e-13
 RTOL_DT = 1e-10
 RTOL_Y = 1e-9
+ATOL_Y = 1e-13
+
+
+def norm_rtol(n):
+    return max(RTOL_NORM, 4.0 * math.sqrt(n) * 2.2e-16)
+
+
+def assert_states_close(got, ref, what="", rtol=RTOL_Y):
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    bound = rtol * np.abs(ref) + ATOL_Y * np.max(np.abs(ref))
+    bad = np.abs(got - ref) > bound
+    if bad.any():
+        i = np.flatnonzero(bad.ravel())[:5]
+        raise AssertionError(f"{what}: {bad.sum()} of {got.size} outside tolerance; idx {i}: got {got.ravel()[i]} ref {ref.ravel()[i]} "
+                             f"max rel {np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)):.3e}")
 
 
 @pytest.fixture(scope="module")
@@ -127,8 +151,8 @@ def test_combine_err_parity(nn, method, stages, vec_width):
             yn, ey, S, E = nn.combineErr(method, dt, atol, rtol, nn.newVector(y), [nn.newVector(k) for k in ks], want_err_y=True)
             assert_bitwise_equal(yn.to_numpy(), yn_ref, f"{method} yNew n={n}")
             assert_bitwise_equal(ey.to_numpy(), ey_ref, f"{method} error_y n={n}")
-            assert abs(S - S_ref) <= RTOL_NORM * abs(S_ref), (method, n, S, S_ref)
-            assert abs(E - E_ref) <= RTOL_NORM * abs(E_ref), (method, n, E, E_ref)
+            assert abs(S - S_ref) <= norm_rtol(n) * abs(S_ref), (method, n, S, S_ref)
+            assert abs(E - E_ref) <= norm_rtol(n) * abs(E_ref), (method, n, E, E_ref)
     finally:
         ctx.set("vec_width", 4)
 
@@ -265,7 +289,7 @@ def test_single_step_with_rejections_matches_oracle(nn, method):
     assert st.rejected >= 1
     yn, fn, dt_used, err = nn.integratorStep(method, nn.rhsDiagLinear(nn.newVector(lam)), 0.0, nn.newVector(y), nn.newVector(fsal), 0.2, nn.newODEoptions(**opts))
     assert abs(dt_used - dt_ref) <= RTOL_DT * dt_ref
-    assert np.allclose(yn.to_numpy(), yn_ref, rtol=RTOL_Y, atol=0)
+    assert_states_close(yn.to_numpy(), yn_ref, method)
     assert abs(err - err_ref) <= 1e-8 * err_ref
 
 
@@ -323,9 +347,8 @@ def test_solve_matches_golden_fixtures(nn, golden_trajectories):
         if g["integrator"] == "rk4":
             assert_bitwise_equal(got, gy, name + " (fixed step: identical trajectory)")
         else:
-            scale = np.maximum(np.abs(gy), 1e-300)
-            lim = 1e-6 if name.startswith(("l96", "limiter")) else RTOL_Y  # chaotic / limiter-accepted steps amplify ulps
-            assert np.max(np.abs(got - gy) / scale) <= lim, (name, np.max(np.abs(got - gy) / scale))
+            # chaotic (Lorenz-96) and limiter-accepted (error > 1, stiff) trajectories amplify ulp differences
+            assert_states_close(got, gy, name, rtol=1e-6 if name.startswith(("l96", "limiter")) else RTOL_Y)
         checked += 1
     assert checked >= 20
 
@@ -351,9 +374,10 @@ def test_step_sequence_matches_oracle(nn):
         assert st["steps"] == ref.stats.steps and st["rejected"] == ref.stats.rejected, method
         ref_dts = np.array([r[1] for r in ref.trace])
         t_acc = np.cumsum(ref_dts)
-        assert np.allclose(np.cumsum(dts), t_acc, rtol=1e-9, atol=0), method
+        assert np.allclose(np.cumsum(dts), t_acc, rtol=1e-12, atol=0), method
+        assert np.allclose(dts[:-1], ref_dts[:-1], rtol=RTOL_DT, atol=0), method  # last dt = tEnd - t (difference of near-equal numbers)
         y_end = s.state()[3].to_numpy()
-        assert np.allclose(y_end, ref.y[-1], rtol=RTOL_Y, atol=1e-300), method
+        assert_states_close(y_end, ref.y[-1], method)
         exact = y0 * np.exp(-lam * 2.0)
         assert np.max(np.abs(y_end - exact)) < 1e-5
         s.close()
@@ -394,7 +418,7 @@ def test_reference_scalar_cases_on_gpu(nn, integrator):
     if integrator == "kutta4":
         assert_bitwise_equal(np.array(y), ref_y, "fixed-step scalar trajectory")
     else:
-        assert np.allclose(y, ref_y, rtol=RTOL_Y, atol=0)
+        assert_states_close(np.array(y), ref_y, integrator)
     for ti, v in zip(t, y):
         assert O.is_close(float(v), math.exp(-0.1 * ti), 1e-6 if integrator in ("rk21", "bs32") else 1e-4)
 
@@ -432,7 +456,7 @@ def test_tspan_quirks_match_reference(nn):
     t, ys = nn.solveODE(rhs, nn.newVector([1.0, 2.0]), [2.0, 1.0], nn.newODEoptions(dtMax=0.5), integrator="tsit54")
     ref = O.solve_vector("tsit54", O.rhs_scale(-0.1), [1.0, 2.0], [2.0, 1.0], O.new_options(dtMax=0.5))
     assert t == [1.0, 2.0] and len(ys) == ref.y.shape[0] == 1
-    assert np.allclose(ys[0].to_numpy(), ref.y[0], rtol=RTOL_Y)
+    assert_states_close(ys[0].to_numpy(), ref.y[0], "len-2 tspan")
     with pytest.raises(ValueError, match="not a valid integrator"):
         nn.solveODE(rhs, nn.newVector([1.0]), [0.0, 1.0], integrator="rk5")
 
@@ -472,7 +496,7 @@ def test_full_size_stage_and_finish(nn):
     yn_ref, _, S_ref, E_ref = O.pair_finish("dopri54", 0.01, 1e-6, 1e-6, y, ks)
     yn, _, S, E = nn.combineErr("dopri54", 0.01, 1e-6, 1e-6, gy, gk)
     assert_bitwise_equal(yn.to_numpy(), yn_ref, "yNew at N=2^23")
-    assert abs(S - S_ref) <= RTOL_NORM * S_ref
+    assert abs(S - S_ref) <= norm_rtol(n) * S_ref, (S, S_ref)
     # linearity in the derivative streams: stage(y, 2k) - y == 2*(stage(y, k) - y) is NOT exact in floating
     # point, but scaling all k by a power of two is: stage(y; 2k, c/2) == stage(y; k, c) bit for bit.
     out2 = nn.stageAccum(w, 0.005, gy, [2.0 * k for k in gk[:5]])

@@ -1,0 +1,191 @@
+## b200rk.nim — thin {.importc, cdecl.} shim over libb200rk.so (include/b200rk.h), re-exposing
+## numericalnim's `solveODE` / `newODEoptions` / `IntegratorProc` for a device-resident vector type.
+##
+## STATUS: written against the C header, NOT compiled — this image has no Nim toolchain (nim, nimble and
+## choosenim are absent; see DESIGN.md §2). Every proc below is a 1:1 declaration of a symbol whose
+## behaviour is exercised through the same ABI by the pytest suite (ctypes). Usage from reference code:
+##
+##   import numericalnim            # for ODEoptions, NumContext, linspace, ...
+##   import b200rk                  # adds the GpuVector overloads
+##   proc f(t: float, y: GpuVector, ctx: NumContext[GpuVector, float]): GpuVector = -0.1 * y
+##   let (ts, ys) = solveODE(f, newGpuVector(@[1.0, 1.0, 1.0]), linspace(-10.0, 10.0, 100), integrator = "tsit54")
+##
+## Nim's overload resolution prefers this non-generic `solveODE` over the reference's generic
+## `solveODE*[T]` (ode.nim:589) when `y0` is a GpuVector, so existing call sites switch by changing the
+## type of `y0` only.
+import std/[strutils]
+import numericalnim/ode            # ODEoptions, newODEoptions, ODEProc, IntegratorProc (ode.nim:26-38)
+import numericalnim/common/commonTypes   # NumContext (commonTypes.nim:3-15)
+
+const lib = "libb200rk.so"
+
+type
+  CtxObj {.incompleteStruct.} = object
+  VecObj {.incompleteStruct.} = object
+  B200rkCtx* = ptr CtxObj
+  VecHandle = ptr VecObj
+  COptions {.bycopy.} = object       ## b200rk_options == ODEoptions field for field (ode.nim:26-34)
+    dt, dtMax, dtMin, tStart, absTol, relTol, scaleMax, scaleMin: cdouble
+  CStats {.bycopy.} = object
+    steps, attempts, rejected, limiterHits, rhsEvals, launches, collectives: int64
+  RhsFn = proc(t: cdouble, y: VecHandle, dydt: VecHandle, user: pointer): cint {.cdecl.}
+
+  GpuVector* = object                ## stands where Vector[float] stands in the reference (utils.nim:14-17)
+    h: VecHandle
+    ctx: B200rkCtx
+    borrowed: bool                   ## handles lent by the library inside a callback are not freed
+
+const
+  B200RK_OK = 0.cint
+  B200RK_EINVAL = 1.cint
+
+# ---- 1:1 declarations (include/b200rk.h) ------------------------------------------------------------
+proc b200rk_init(outCtx: ptr B200rkCtx, device: cint): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_nccl_unique_id(out128: pointer): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_init_distributed(outCtx: ptr B200rkCtx, device, rank, world: cint, id128: pointer): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_destroy(ctx: B200rkCtx) {.importc, cdecl, dynlib: lib.}
+proc b200rk_last_error(ctx: B200rkCtx): cstring {.importc, cdecl, dynlib: lib.}
+proc b200rk_stream(ctx: B200rkCtx): pointer {.importc, cdecl, dynlib: lib.}
+proc b200rk_method_from_name(name: cstring, methodId: ptr cint): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_vec_new(ctx: B200rkCtx, n: csize_t, outVec: ptr VecHandle): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_vec_free(v: VecHandle): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_vec_len(v: VecHandle): csize_t {.importc, cdecl, dynlib: lib.}
+proc b200rk_vec_data(v: VecHandle): ptr cdouble {.importc, cdecl, dynlib: lib.}
+proc b200rk_vec_upload(v: VecHandle, host: ptr cdouble): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_vec_download(v: VecHandle, host: ptr cdouble): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_vec_copy(dst, src: VecHandle): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_vec_add(o, a, b: VecHandle): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_vec_sub(o, a, b: VecHandle): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_vec_hmul(o, a, b: VecHandle): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_vec_hdiv(o, a, b: VecHandle): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_vec_scale(o: VecHandle, s: cdouble, a: VecHandle): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_vec_div_scalar(o, a: VecHandle, s: cdouble): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_vec_add_scalar(o: VecHandle, s: cdouble, a: VecHandle): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_vec_neg(o, a: VecHandle): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_vec_abs(o, a: VecHandle): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_vec_sum(a: VecHandle, outSum: ptr cdouble): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_hermite(o: VecHandle, x, x1, x2: cdouble, y1, y2, dy1, dy2: VecHandle): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_step(ctx: B200rkCtx, methodId: cint, f: RhsFn, user: pointer, t: cdouble, y, fsal: VecHandle, dt: cdouble,
+                 options: ptr COptions, yNew, fsalNew: VecHandle, dtUsed, error: ptr cdouble): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_solve(ctx: B200rkCtx, methodId: cint, f: RhsFn, user: pointer, y0: VecHandle, tspan: ptr cdouble, nTspan: csize_t,
+                  options: ptr COptions, tOut: ptr cdouble, yOut: ptr VecHandle, nYOut: ptr csize_t, stats: ptr CStats): cint {.importc, cdecl, dynlib: lib.}
+
+# ---- error convention: status code -> Nim exception (SURVEY.md §8b) ---------------------------------
+proc check(rc: cint, ctx: B200rkCtx = nil) =
+  if rc == B200RK_OK: return
+  let msg = $b200rk_last_error(ctx)
+  if rc == B200RK_EINVAL: raise newException(ValueError, msg)     # what the reference raises
+  raise newException(IOError, "b200rk: " & msg)
+
+# ---- context ----------------------------------------------------------------------------------------
+var defaultCtx: B200rkCtx
+proc b200rkContext*(device = 0): B200rkCtx =
+  if defaultCtx.isNil: check b200rk_init(addr defaultCtx, device.cint)
+  defaultCtx
+
+# ---- GpuVector: value semantics like Vector[T] (every operator returns a fresh vector) --------------
+proc `=destroy`*(v: var GpuVector) =
+  if not v.h.isNil and not v.borrowed: discard b200rk_vec_free(v.h)
+  v.h = nil
+proc `=copy`*(dst: var GpuVector, src: GpuVector) =
+  if dst.h == src.h: return
+  `=destroy`(dst)
+  if src.h.isNil: return
+  dst.ctx = src.ctx; dst.borrowed = false
+  check(b200rk_vec_new(src.ctx, b200rk_vec_len(src.h), addr dst.h), src.ctx)
+  check(b200rk_vec_copy(dst.h, src.h), src.ctx)
+
+proc newLike(v: GpuVector): GpuVector =
+  result.ctx = v.ctx
+  check(b200rk_vec_new(v.ctx, b200rk_vec_len(v.h), addr result.h), v.ctx)
+
+proc newGpuVector*(components: openArray[float], ctx: B200rkCtx = b200rkContext()): GpuVector =
+  ## newVector (utils.nim:19-20): copies the host data to the device.
+  result.ctx = ctx
+  check(b200rk_vec_new(ctx, components.len.csize_t, addr result.h), ctx)
+  if components.len > 0: check(b200rk_vec_upload(result.h, cast[ptr cdouble](unsafeAddr components[0])), ctx)
+
+proc toSeq*(v: GpuVector): seq[float] =
+  result = newSeq[float](b200rk_vec_len(v.h).int)
+  if result.len > 0: check(b200rk_vec_download(v.h, cast[ptr cdouble](addr result[0])), v.ctx)
+
+proc len*(v: GpuVector): int = b200rk_vec_len(v.h).int
+proc size*(v: GpuVector): int = v.len                                         # utils.nim:57
+proc clone*(v: GpuVector): GpuVector = (result = newLike(v); check(b200rk_vec_copy(result.h, v.h), v.ctx))  # utils.nim:269
+proc `+`*(a, b: GpuVector): GpuVector = (result = newLike(a); check(b200rk_vec_add(result.h, a.h, b.h), a.ctx))   # utils.nim:59-64
+proc `-`*(a, b: GpuVector): GpuVector = (result = newLike(a); check(b200rk_vec_sub(result.h, a.h, b.h), a.ctx))   # utils.nim:113-118
+proc `*`*(d: float, a: GpuVector): GpuVector = (result = newLike(a); check(b200rk_vec_scale(result.h, d, a.h), a.ctx))  # utils.nim:176-180
+proc `*`*(a: GpuVector, d: float): GpuVector = d * a                                                              # utils.nim:171-175
+proc `/`*(a: GpuVector, d: float): GpuVector = (result = newLike(a); check(b200rk_vec_div_scalar(result.h, a.h, d), a.ctx))  # utils.nim:166-170
+proc `-`*(a: GpuVector): GpuVector = (result = newLike(a); check(b200rk_vec_neg(result.h, a.h), a.ctx))          # utils.nim:214-218
+proc abs*(a: GpuVector): GpuVector = (result = newLike(a); check(b200rk_vec_abs(result.h, a.h), a.ctx))          # utils.nim:219-223
+proc `+.`*(d: float, a: GpuVector): GpuVector = (result = newLike(a); check(b200rk_vec_add_scalar(result.h, d, a.h), a.ctx))  # utils.nim:78-82
+proc `*.`*(a, b: GpuVector): GpuVector = (result = newLike(a); check(b200rk_vec_hmul(result.h, a.h, b.h), a.ctx))  # utils.nim:186-191
+proc `/.`*(a, b: GpuVector): GpuVector = (result = newLike(a); check(b200rk_vec_hdiv(result.h, a.h, b.h), a.ctx))  # utils.nim:192-197
+proc sum*(a: GpuVector): float = check(b200rk_vec_sum(a.h, addr result), a.ctx)                                  # utils.nim:243-250
+proc hermiteSpline*(x, x1, x2: float, y1, y2, dy1, dy2: GpuVector): GpuVector =                                  # utils.nim:273-279
+  result = newLike(y1)
+  check(b200rk_hermite(result.h, x, x1, x2, y1.h, y2.h, dy1.h, dy2.h), y1.ctx)
+
+# ---- ODEProc[GpuVector] closure -> b200rk_rhs_fn ------------------------------------------------------
+type RhsEnv = object
+  f: ODEProc[GpuVector]
+  ctx: NumContext[GpuVector, float]
+  dev: B200rkCtx
+  err: ref Exception
+
+proc rhsTrampoline(t: cdouble, y: VecHandle, dydt: VecHandle, user: pointer): cint {.cdecl.} =
+  ## Calls the user's Nim closure with borrowed handles; the closure's GpuVector operators enqueue their
+  ## kernels on the context stream; the result is copied into `dydt`. Exceptions never cross the ABI.
+  let env = cast[ptr RhsEnv](user)
+  try:
+    let yv = GpuVector(h: y, ctx: env.dev, borrowed: true)
+    let r = env.f(t.float, yv, env.ctx)
+    if r.h != dydt: check(b200rk_vec_copy(dydt, r.h), env.dev)
+    return 0
+  except CatchableError as e:
+    env.err = e
+    return 1
+
+proc toC(o: ODEoptions): COptions =
+  COptions(dt: o.dt, dtMax: o.dtMax, dtMin: o.dtMin, tStart: o.tStart, absTol: o.absTol, relTol: o.relTol,
+           scaleMax: o.scaleMax, scaleMin: o.scaleMin)
+
+proc methodId(integrator: string): cint =
+  check b200rk_method_from_name(integrator.cstring, addr result)   # ValueError "<name> is not a valid integrator" (ode.nim:651)
+
+# ---- IntegratorProc[GpuVector] (ode.nim:38): one step of the named integrator ------------------------
+proc gpuIntegrator*(integrator: string): IntegratorProc[GpuVector] =
+  let mid = methodId(integrator)
+  result = proc(f: ODEProc[GpuVector], t: float, y, FSAL: GpuVector, dt: float, options: ODEoptions,
+                ctx: NumContext[GpuVector, float]): (GpuVector, GpuVector, float, float) =
+    var env = RhsEnv(f: f, ctx: ctx, dev: y.ctx)
+    var yNew = newLike(y)
+    var fsalNew = newLike(y)
+    var co = toC(options)
+    var dtUsed, error: cdouble
+    let rc = b200rk_step(y.ctx, mid, rhsTrampoline, addr env, t, y.h, FSAL.h, dt, addr co, yNew.h, fsalNew.h, addr dtUsed, addr error)
+    if not env.err.isNil: raise env.err
+    check(rc, y.ctx)
+    (yNew, fsalNew, dtUsed.float, error.float)
+
+# ---- solveODE (ode.nim:589-651) for T = GpuVector -----------------------------------------------------
+proc solveODE*(f: ODEProc[GpuVector], y0: GpuVector, tspan: openArray[float],
+               options: ODEoptions = newODEoptions(), ctx: NumContext[GpuVector, float] = nil,
+               integrator = "dopri54"): (seq[float], seq[GpuVector]) =
+  var nctx = ctx
+  if nctx.isNil: nctx = newNumContext[GpuVector, float]()          # ode.nim:604-606
+  let mid = methodId(integrator.toLower())
+  var env = RhsEnv(f: f, ctx: nctx, dev: y0.ctx)
+  var co = toC(options)
+  var ts = @tspan
+  var tOut = newSeq[cdouble](ts.len)
+  var slots = newSeq[VecHandle](max(ts.len, 1))
+  var nOut: csize_t
+  let rc = b200rk_solve(y0.ctx, mid, rhsTrampoline, addr env, y0.h, cast[ptr cdouble](addr ts[0]), ts.len.csize_t, addr co,
+                        cast[ptr cdouble](addr tOut[0]), addr slots[0], addr nOut, nil)
+  if not env.err.isNil: raise env.err
+  check(rc, y0.ctx)
+  var ys = newSeq[GpuVector](nOut.int)
+  for i in 0 ..< nOut.int: ys[i] = GpuVector(h: slots[i], ctx: y0.ctx, borrowed: false)
+  result = (@tOut, ys)

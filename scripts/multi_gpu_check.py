@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""Sharded-path check, one process per GPU (torchrun): the state is split contiguously across ranks, the
+only collective is the library's own ncclAllReduce of the squared error norm. Compares every rank's shard
+with the unsharded CPU oracle: same step count, states within the adaptive tolerance; RK4 bit-identical."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    import numericalnim_b200 as nn
+    import oracle as O
+    from numericalnim_b200 import distributed as D
+
+    rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = D.init_context(local)
+    assert (ctx.rank, ctx.world) == (rank, world)
+    n = 100003
+    lam = 0.1 + 9.9 * np.arange(n) / (n - 1)
+    y0 = 1.0 + 0.5 * np.sin(2 * np.pi * np.arange(n) / n)
+    kw = dict(absTol=1e-6, relTol=1e-6, dtMax=1.0, dtMin=1e-8)
+    glam, gy0 = nn.newVector(lam, ctx), nn.newVector(y0, ctx)
+    off, ln = gy0.local_offset, gy0.local_len
+    assert (off, ln) == D.shard_range(n, rank, world)
+    fails = []
+    for method in ("dopri54", "tsit54", "vern65", "rk4"):
+        okw = dict(kw, dt=5e-3)
+        ts = [0.0, 2.0] if method != "rk4" else [0.0, 0.5]
+        ref = O.solve_vector(method, O.rhs_diag_linear(lam), y0, ts, O.new_options(**okw))
+        t, ys = nn.solveODE(nn.rhsDiagLinear(glam), gy0, ts, nn.newODEoptions(**okw), integrator=method)
+        st = dict(nn.ode.last_stats)
+        got = ys[-1].local_numpy()
+        exp = ref.y[-1][off:off + ln]
+        if method == "rk4":
+            ok = np.array_equal(got.view(np.uint64), exp.view(np.uint64)) and st["collectives"] == 0
+        else:
+            ok = bool(np.all(np.abs(got - exp) <= 1e-9 * np.abs(exp) + 1e-13 * np.max(np.abs(ref.y[-1])))) and st["collectives"] == st["attempts"]
+        ok = ok and st["steps"] == ref.stats.steps and st["rejected"] == ref.stats.rejected
+        if not ok:
+            fails.append((method, st, ref.stats.steps, float(np.max(np.abs(got - exp)))))
+        if rank == 0:
+            print(f"[multi-gpu world={world}] {method}: steps={st['steps']} attempts={st['attempts']} collectives={st['collectives']} ok={ok}", flush=True)
+    # sharded sum(v) goes through the same allreduce
+    s = gy0.sum()
+    assert abs(s - O.vector_sum(y0)) <= 1e-12 * np.abs(y0).sum(), (s, O.vector_sum(y0))
+    flag = torch.tensor([len(fails)], device="cuda")
+    dist.all_reduce(flag)
+    dist.barrier()
+    dist.destroy_process_group()
+    if fails:
+        print("FAILS", rank, fails, flush=True)
+    sys.exit(1 if int(flag.item()) else 0)
+
+
+if __name__ == "__main__":
+    main()

@@ -166,34 +166,46 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timed region: exactly K accepted steps of the driver loop --------------------
-    solver = nn.Solver(integrator, rhs, gy0, 1e12, opts)
     clocks = ClockSampler(local_rank)
-    clocks.__enter__()  # sampled from the warm-up through the timed region and the end-to-end solves
-    solver.advance(args.warmup)
-    ctx.set("profile", 1)
-    ctx.profile_reset()
-    st0, cs0 = solver.stats(), ctx.stats()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    with torch.cuda.stream(stream):
-        e0.record()
-    done, _ = solver.advance(args.steps)
-    with torch.cuda.stream(stream):
-        e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    prof = ctx.profile_read()
-    ctx.set("profile", 0)
-    st1, cs1 = solver.stats(), ctx.stats()
-    t_now, dt_next, _, _ = solver.state()
-    solver.close()
-    assert done == args.steps, (done, args.steps)
-    ms_t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-    ms_max = float(ms_t.item())
-    attempts = st1["attempts"] - st0["attempts"]
-    launches = cs1["launches"] - cs0["launches"]
+    clocks.__enter__()  # sampled from the warm-up through the timed regions and the end-to-end solves
+
+    def timed_steps(fuse: int) -> dict:
+        """W untimed + K timed accepted steps with the given fuse_pointwise setting; device time (CUDA events on
+        the library stream), max over ranks; per-kernel-class event times from the library's profiler."""
+        ctx.set("fuse_pointwise", fuse)
+        solver = nn.Solver(integrator, rhs, gy0, 1e12, opts)
+        solver.advance(args.warmup)
+        ctx.set("profile", 1)
+        ctx.profile_reset()
+        st0, cs0 = solver.stats(), ctx.stats()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        with torch.cuda.stream(stream):
+            e0.record()
+        done, _ = solver.advance(args.steps)
+        with torch.cuda.stream(stream):
+            e1.record()
+        barrier()
+        ms_loc = e0.elapsed_time(e1)
+        prof_ = ctx.profile_read()
+        ctx.set("profile", 0)
+        st1, cs1 = solver.stats(), ctx.stats()
+        t_now_, dt_next_, _, _ = solver.state()
+        solver.close()
+        assert done == args.steps, (done, args.steps)
+        ms_t = torch.tensor([ms_loc], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+        return dict(ms=ms_loc, ms_max=float(ms_t.item()), prof=prof_, attempts=st1["attempts"] - st0["attempts"],
+                    rejected=st1["rejected"] - st0["rejected"], launches=cs1["launches"] - cs0["launches"],
+                    collectives=cs1["collectives"] - cs0["collectives"], t=t_now_, dt_next=dt_next_)
+
+    fusable = rhs_kind == "diag" and not args.no_fuse
+    pipe = timed_steps(0)                       # stage / RHS / finish pipeline (what any user closure gets)
+    head = timed_steps(1) if fusable else pipe  # headline: the library's default path for this workload
+    ctx.set("fuse_pointwise", 1 if fusable else 0)
+    ms, ms_max, prof = head["ms"], head["ms_max"], head["prof"]
+    attempts, launches, t_now, dt_next = head["attempts"], head["launches"], head["t"], head["dt_next"]
 
     # ---- end to end: solveODE over [0, 2] from pinned HOST buffers (H2D y0 + lambda, solve, D2H states) ----
     L = _capi.lib()
@@ -238,17 +250,44 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = peaks()
-        stage = prof["stage"]
-        ach = stage["bytes"] / (stage["ms"] * 1e-3) / 1e9 if stage["ms"] > 0 else 0.0
-        fin = prof["finish"]
-        ach_fin = fin["bytes"] / (fin["ms"] * 1e-3) / 1e9 if fin["ms"] > 0 else 0.0
-        rhsp = prof["rhs"]
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "stage_kernel_traffic.json")
+        traffic_db = {}
+        tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
         if os.path.exists(tp):
             with open(tp) as fh:
-                traffic = json.load(fh).get("dram_bytes_per_launch")
-        kernel_ms = stage["ms"] + fin["ms"] + rhsp["ms"] + prof["other"]["ms"]
+                traffic_db = json.load(fh)
+
+        def gbs(p):
+            return p["bytes"] / (p["ms"] * 1e-3) / 1e9 if p["ms"] > 0 else 0.0
+
+        def stage_roofline(r):
+            """Roofline object of the stage / RHS / finish pipeline: the dominant kernel family is stage_kernel."""
+            st, fn_, rh = r["prof"]["stage"], r["prof"]["finish"], r["prof"]["rhs"]
+            kms = st["ms"] + fn_["ms"] + rh["ms"] + r["prof"]["other"]["ms"]
+            a = gbs(st)
+            return {"bound": "hbm", "kernel": "stage_kernel<M,W,U> (fused stage accumulate y + dt*sum(a_sj k_j); all %d launches of the timed region)" % st["launches"],
+                    "achieved": a, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": a / peak, "frac_of_nominal_8000": a / 8000.0,
+                    "traffic": traffic_db.get("stage_kernel_%s_2p%d" % (integrator, lg)), "launches": st["launches"],
+                    "avg_launch_us": 1e3 * st["ms"] / max(1, st["launches"]), "algorithmic_bytes_per_launch": st["bytes"] / max(1, st["launches"]),
+                    "finish_kernel": {"achieved": gbs(fn_), "frac": gbs(fn_) / peak, "launches": fn_["launches"], "avg_launch_us": 1e3 * fn_["ms"] / max(1, fn_["launches"])},
+                    "rhs_kernel": {"achieved": gbs(rh), "launches": rh["launches"]},
+                    "kernel_time_share_of_step": kms / r["ms"] if r["ms"] > 0 else None}
+
+        if head is pipe:
+            roofline = stage_roofline(pipe)
+            pipeline_obj = None
+        else:
+            fu = prof["fused"]
+            a = gbs(fu)
+            roofline = {"bound": "hbm", "kernel": "fused_attempt_kernel<S,RHS> (whole attempt of an element-local IVP in one kernel: all stages, RHS, yNew, error norm)",
+                        "achieved": a, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": a / peak, "frac_of_nominal_8000": a / 8000.0,
+                        "traffic": traffic_db.get("fused_attempt_kernel_%s_2p%d" % (integrator, lg)), "launches": fu["launches"],
+                        "avg_launch_us": 1e3 * fu["ms"] / max(1, fu["launches"]), "algorithmic_bytes_per_launch": fu["bytes"] / max(1, fu["launches"]),
+                        "kernel_time_share_of_step": fu["ms"] / ms if ms > 0 else None}
+            pipeline_obj = {"note": "same K steps with fuse_pointwise=0: the stage / RHS / finish pipeline every user-supplied right-hand side runs through",
+                            "value": args.steps * world / (pipe["ms_max"] * 1e-3), "ms_per_step": pipe["ms_max"] / args.steps, "attempts": pipe["attempts"],
+                            "gpu_launches": pipe["launches"],
+                            "hbm_gbs_step": ALG_BYTES_PER_ELEM.get(integrator, 0) * n_shard * pipe["attempts"] / (pipe["ms"] * 1e-3) / 1e9,
+                            "roofline": stage_roofline(pipe)}
         line = {
             "metric": "rk_steps_per_sec", "value": args.steps * world / (ms_max * 1e-3), "unit": "RK steps/s (x 2^%d-element shard, summed over GPUs)" % lg,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
@@ -256,18 +295,14 @@ def run_ours(args):
             "config": {"workload": args.workload, "integrator": integrator, "rhs": rhs_kind, "elems_per_gpu": n_shard, "elems_global": n_global,
                        "options": OPTS, "l2": "working set (>= 10 vectors x %d MiB per GPU) exceeds the 126 MB L2; no flush" % (n_shard * 8 >> 20),
                        "sharding": "contiguous, 1 ncclAllReduce(1 x f64) per attempt" if world > 1 else "single GPU, no collective",
-                       "vec_width": ctx.get("vec_width"), "ctas_per_sm": ctx.get("ctas_per_sm"), "finish_ctas_per_sm": ctx.get("finish_ctas_per_sm")},
-            "attempts": attempts, "attempts_per_sec": attempts * world / (ms_max * 1e-3), "rejected": st1["rejected"] - st0["rejected"],
+                       "vec_width": ctx.get("vec_width"), "ctas_per_sm": ctx.get("ctas_per_sm"), "finish_ctas_per_sm": ctx.get("finish_ctas_per_sm"),
+                       "fuse_pointwise": ctx.get("fuse_pointwise"), "fused_ctas_per_sm": ctx.get("fused_ctas_per_sm")},
+            "attempts": attempts, "attempts_per_sec": attempts * world / (ms_max * 1e-3), "rejected": head["rejected"],
             "t_reached": t_now, "dt_next": dt_next,
-            "gpu_launches": launches, "collectives": cs1["collectives"] - cs0["collectives"],
-            "hbm_gbs_step": ALG_BYTES_PER_ELEM.get(integrator, 0) * n_shard * attempts / (ms * 1e-3) / 1e9,
-            "roofline": {"bound": "hbm", "kernel": "stage_kernel<M,W,U> (fused stage accumulate, all %d launches of the timed region)" % stage["launches"],
-                         "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak, "frac_of_nominal_8000": ach / 8000.0,
-                         "traffic": traffic, "launches": stage["launches"], "avg_launch_us": 1e3 * stage["ms"] / max(1, stage["launches"]),
-                         "algorithmic_bytes_per_launch": stage["bytes"] / max(1, stage["launches"]),
-                         "finish_kernel": {"achieved": ach_fin, "frac": ach_fin / peak, "launches": fin["launches"], "avg_launch_us": 1e3 * fin["ms"] / max(1, fin["launches"])},
-                         "rhs_kernel": {"achieved": (rhsp["bytes"] / (rhsp["ms"] * 1e-3) / 1e9) if rhsp["ms"] > 0 else 0.0, "launches": rhsp["launches"]},
-                         "kernel_time_share_of_step": kernel_ms / ms if ms > 0 else None},
+            "gpu_launches": launches, "collectives": head["collectives"],
+            "path": "fused_attempt (element-local built-in RHS)" if head is not pipe else "stage/RHS/finish pipeline",
+            "roofline": roofline,
+            "pipeline": pipeline_obj,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_steps * world / (e2e_ms_max * 1e-3), "unit": "RK steps/s (solveODE on host buffers: H2D y0+lambda, solve, D2H states)",
                     "h2d_bytes_per_step": h2d / max(1, e2e_steps), "d2h_bytes_per_step": d2h / max(1, e2e_steps), "steps_per_solve": e2e_steps / reps,
@@ -423,6 +458,31 @@ def run_tune(args):
                 res[name] = round(p[cls]["bytes"] / (p[cls]["ms"] * 1e-3) / 1e9, 1)
             print(json.dumps({"log2n": int(np.log2(n)), "vec_width": vw, "ctas_per_sm": cps, "GBps": res,
                               "frac": {k: round(v / peak, 3) for k, v in res.items()}}), flush=True)
+    # fused attempt kernel (element-local RHS): persistent-grid width x vector width
+    ctx.set("ctas_per_sm", 0)
+    ctx.set("finish_ctas_per_sm", 2)
+    ctx.set("fuse_pointwise", 1)
+    lam = nn.newVector(0.1 + 9.9 * np.arange(n) / (n - 1), ctx)
+    rhs = nn.rhsDiagLinear(lam)
+    o = nn.newODEoptions(absTol=1e-3, relTol=1e-3, dtMax=1.0, dtMin=1e-8)
+    for vw in (2, 4):
+        for cps in (1, 2, 3, 4, 6, 8, 0):
+            ctx.set("vec_width", vw)
+            ctx.set("fused_ctas_per_sm", cps)
+            res = {}
+            for meth in ("dopri54", "tsit54", "vern65", "rk4"):
+                for _ in range(5):
+                    nn.integratorStep(meth, rhs, 0.0, vecs[0], vecs[1], 1e-3, o)
+                ctx.set("profile", 1)
+                ctx.profile_reset()
+                for _ in range(30):
+                    nn.integratorStep(meth, rhs, 0.0, vecs[0], vecs[1], 1e-3, o)
+                p = ctx.profile_read()
+                ctx.set("profile", 0)
+                res[meth] = {"GBps": round(p["fused"]["bytes"] / (p["fused"]["ms"] * 1e-3) / 1e9, 1), "us": round(1e3 * p["fused"]["ms"] / p["fused"]["launches"], 1)}
+            print(json.dumps({"log2n": int(np.log2(n)), "kernel": "fused_attempt", "vec_width": vw, "fused_ctas_per_sm": cps, "res": res}), flush=True)
+    ctx.set("vec_width", 4)
+    ctx.set("fused_ctas_per_sm", 2)
 
 
 def main():
@@ -435,6 +495,7 @@ def main():
     ap.add_argument("--log2n", type=int, default=0, help="override log2 of elements per GPU")
     ap.add_argument("--e2e-reps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true", help="headline = the stage/RHS/finish pipeline even for element-local built-in RHS")
     ap.add_argument("--cpu-budget-s", type=float, default=120.0)
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--tune", action="store_true")

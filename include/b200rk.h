@@ -70,7 +70,7 @@ typedef struct b200rk_stats {
 } b200rk_stats;
 
 /* Per-kernel-class device timing (CUDA events on the context stream) for the roofline report. */
-enum b200rk_kernel_class { B200RK_K_STAGE = 0, B200RK_K_FINISH = 1, B200RK_K_RHS = 2, B200RK_K_OTHER = 3, B200RK_K_COUNT = 4 };
+enum b200rk_kernel_class { B200RK_K_STAGE = 0, B200RK_K_FINISH = 1, B200RK_K_RHS = 2, B200RK_K_OTHER = 3, B200RK_K_FUSED = 4, B200RK_K_COUNT = 5 };
 typedef struct b200rk_profile {
   int64_t launches[B200RK_K_COUNT];
   double ms[B200RK_K_COUNT];              /* summed event time */
@@ -90,7 +90,9 @@ B200RK_API int b200rk_rank(const b200rk_ctx* ctx);
 B200RK_API int b200rk_world(const b200rk_ctx* ctx);
 /* knobs: "strict_zeros" (1 = multiply zero Butcher weights through like the reference instead of
  * skipping the read), "vec_width" (2|4 doubles per access), "ctas_per_sm" (0 = one tile per CTA,
- * k = persistent grid of k*SMs CTAs), "profile" (0|1), "pool_budget_mb" (bytes of freed vectors the
+ * k = persistent grid of k*SMs CTAs), "finish_ctas_per_sm" / "fused_ctas_per_sm" (same for the reducing
+ * kernels), "fuse_pointwise" (1 = element-local built-in right-hand sides run a whole attempt as one
+ * kernel; 0 = always the stage / RHS / finish pipeline), "profile" (0|1), "pool_budget_mb" (bytes of freed vectors the
  * context keeps for reuse; 0 = release everything now) */
 B200RK_API int b200rk_set(b200rk_ctx* ctx, const char* key, int64_t value);
 B200RK_API int b200rk_get(const b200rk_ctx* ctx, const char* key, int64_t* value);

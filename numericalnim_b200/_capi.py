@@ -15,7 +15,7 @@ OK, EINVAL, ECUDA, ENCCL, ENOMEM, ECALLBACK, ENONFINITE = range(7)
 METHODS = ("dopri54", "tsit54", "vern65", "rk4", "rk21", "bs32", "heun2", "ralston2", "kutta3", "heun3",
            "ralston3", "ssprk3", "ralston4", "kutta4")  # enum b200rk_method order
 RHS_SCALE, RHS_DIAG_LINEAR, RHS_LORENZ96 = 0, 1, 2
-K_STAGE, K_FINISH, K_RHS, K_OTHER, K_COUNT = 0, 1, 2, 3, 4
+K_STAGE, K_FINISH, K_RHS, K_OTHER, K_FUSED, K_COUNT = 0, 1, 2, 3, 4, 5
 
 
 class Options(C.Structure):

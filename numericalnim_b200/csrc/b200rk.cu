@@ -53,6 +53,8 @@ struct b200rk_ctx {
   int vec_width = 4;
   int ctas_per_sm = 0;         // stage/element-wise kernels: 0 = one tile per CTA (measured best, profiles/)
   int finish_ctas_per_sm = 2;  // reducing kernels: persistent grid, one partial per CTA (measured best)
+  int fused_ctas_per_sm = 2;   // fused pointwise attempt kernel
+  bool fuse_pointwise = true;  // element-local built-in RHS: whole attempt in one kernel
   bool strict_zeros = false;
   bool profile = false;
   // counters
@@ -506,6 +508,99 @@ struct Workspace {
 
 struct StepCounters { int64_t attempts = 0, rejected = 0, limiter_hits = 0; };
 
+// ---- fused attempt for element-local built-in right-hand sides (kernels.cuh: fused_attempt_kernel) ----
+static bool pointwise_kind(const RhsCall& rhs, int* pw_kind, const BuiltinRhs** br) {
+  if (rhs.f != &builtin_rhs_fn) return false;
+  const BuiltinRhs* r = static_cast<const BuiltinRhs*>(rhs.user);
+  if (r->kind == B200RK_RHS_SCALE) *pw_kind = PW_SCALE;
+  else if (r->kind == B200RK_RHS_DIAG_LINEAR) *pw_kind = PW_DIAG;
+  else return false;
+  *br = r;
+  return true;
+}
+static bool method_fusable(const MethodDef& md) {
+  if (md.rk4_final) return true;
+  if (!(md.adaptive && md.k1_from_fsal && md.fsal_out == md.stages && (md.stages == 7 || md.stages == 9))) return false;
+  for (int s = 2; s <= md.stages; ++s)
+    if (md.a_cfac[s] != 1.0 || md.a_chain[s] || md.a[s].m != s - 1) return false;
+  return md.b_cfac == 1.0 && md.bhat_cfac == 1.0;
+}
+
+static uint32_t row_mask(const b200rk_ctx* c, const Row& row, double* w_dense, int width) {
+  uint32_t mask = 0;
+  for (int j = 0; j < width; ++j) w_dense[j] = 0.0;
+  int kept = 0;
+  for (int j = 0; j < row.m; ++j) {
+    w_dense[row.idx[j] - 1] = row.w[j];
+    if (row.w[j] == 0.0 && !c->strict_zeros && row.m > 1) continue;
+    mask |= 1u << (row.idx[j] - 1);
+    ++kept;
+  }
+  if (!kept) mask |= 1u << (row.idx[0] - 1);  // same rule as gather_row: an all-zero row keeps its first term
+  return mask;
+}
+
+template <int S, int KIND, bool DIRECT, bool LAST>
+static int launch_fused_cfg(b200rk_ctx* c, const FusedArgs<S>& a) {
+  const size_t n = a.n;
+  if (c->vec_width == 4) {
+    unsigned grid = grid_for(c, n / 4, kThreads, c->fused_ctas_per_sm);
+    TRY(ensure_partials(c, grid));
+    fused_attempt_kernel<S, KIND, DIRECT, LAST, 4, kThreads><<<grid, kThreads, 0, c->stream>>>(a);
+  } else {
+    unsigned grid = grid_for(c, n / 2, kThreads, c->fused_ctas_per_sm);
+    TRY(ensure_partials(c, grid));
+    fused_attempt_kernel<S, KIND, DIRECT, LAST, 2, kThreads><<<grid, kThreads, 0, c->stream>>>(a);
+  }
+  CUDA_TRY(c, cudaGetLastError());
+  return B200RK_OK;
+}
+
+template <int S>
+static int launch_fused_pair(b200rk_ctx* c, const MethodDef& md, int pw_kind, const BuiltinRhs* br, bool negate, double dt,
+                             const b200rk_options& o, const b200rk_vec* y, const b200rk_vec* fsal, b200rk_vec* y_new,
+                             b200rk_vec* fsal_new) {
+  FusedArgs<S> a;
+  std::memset(&a, 0, sizeof(a));
+  a.y = y->d; a.k1 = fsal->d; a.lam = br->lambda ? br->lambda->d : nullptr; a.rhs_scalar = br->scalar; a.negate = negate ? 1 : 0;
+  for (int s = 2; s <= S; ++s) a.amask[s - 2] = row_mask(c, md.a[s], a.a[s - 2], S - 1);
+  a.bmask = row_mask(c, md.b, a.b, S);
+  a.bhmask = row_mask(c, md.bhat, a.bh, S);
+  if (!c->strict_zeros) {  // finish rows: plan_finish drops every zero weight (no keep-first rule needed: rows are never all-zero)
+    a.bmask = 0; a.bhmask = 0;
+    for (int j = 0; j < md.b.m; ++j) if (md.b.w[j] != 0.0) a.bmask |= 1u << (md.b.idx[j] - 1);
+    for (int j = 0; j < md.bhat.m; ++j) if (md.bhat.w[j] != 0.0) a.bhmask |= 1u << (md.bhat.idx[j] - 1);
+  }
+  a.dt = dt; a.cb = dt; a.cbh = dt; a.absTol = o.absTol; a.relTol = o.relTol;
+  a.ynew = y_new->d; a.ks_out = fsal_new->d; a.n = y->n_local;
+  a.rs = reduce_scratch(c);
+  const int streams = 4 + (pw_kind == PW_DIAG ? 1 : 0);  // y, k1 (+ lambda) read; yNew, k_S written
+  ProfScope ps(c, B200RK_K_FUSED, 8.0 * double(y->n_local) * streams);
+  const bool direct = md.err_direct, last = md.ynew_is_last_stage_input;
+#define B200RK_FUSED_CASE(KIND)                                                               \
+  if (direct && last) return launch_fused_cfg<S, KIND, true, true>(c, a);                     \
+  if (!direct && last) return launch_fused_cfg<S, KIND, false, true>(c, a);                   \
+  if (!direct && !last) return launch_fused_cfg<S, KIND, false, false>(c, a);
+  if (pw_kind == PW_SCALE) { B200RK_FUSED_CASE(PW_SCALE) }
+  else { B200RK_FUSED_CASE(PW_DIAG) }
+#undef B200RK_FUSED_CASE
+  return fail(c, B200RK_EINVAL, "fused attempt: unsupported method shape");
+}
+
+static int launch_fused_rk4(b200rk_ctx* c, int pw_kind, const BuiltinRhs* br, bool negate, double dt, const b200rk_vec* y,
+                            b200rk_vec* y_new) {
+  const size_t n = y->n_local;
+  if (!n) return B200RK_OK;
+  ProfScope ps(c, B200RK_K_FUSED, 8.0 * double(n) * (2 + (pw_kind == PW_DIAG ? 1 : 0)));
+  const double hdt = 0.5 * dt, c6 = dt / 6.0;
+  const double* lam = br->lambda ? br->lambda->d : nullptr;
+  unsigned grid = grid_for(c, n / 4, kThreads, c->ctas_per_sm);
+  if (pw_kind == PW_SCALE) fused_rk4_kernel<PW_SCALE, 4, kThreads><<<grid, kThreads, 0, c->stream>>>(y->d, lam, br->scalar, negate, hdt, dt, c6, y_new->d, n);
+  else fused_rk4_kernel<PW_DIAG, 4, kThreads><<<grid, kThreads, 0, c->stream>>>(y->d, lam, br->scalar, negate, hdt, dt, c6, y_new->d, n);
+  CUDA_TRY(c, cudaGetLastError());
+  return B200RK_OK;
+}
+
 // One IntegratorProc call. y, fsal read-only; y_new, fsal_new written.
 static int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, double t, const b200rk_vec* y,
                    const b200rk_vec* fsal, double dt_in, const b200rk_options& o, b200rk_vec* y_new,
@@ -515,24 +610,39 @@ static int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, doubl
   Workspace ws(c);
   b200rk_vec* k[kMaxStages + 1] = {nullptr};
   b200rk_vec* tmp = nullptr;
+  int pw_kind = 0;
+  const BuiltinRhs* br = nullptr;
+  const bool fused = c->fuse_pointwise && pointwise_kind(rhs, &pw_kind, &br) && method_fusable(md) &&
+                     (md.rk4_final || (fsal && fsal_new));
+  if (fused && pw_kind == PW_DIAG) TRY(check_same(c, y, br->lambda));
   if (md.k1_from_fsal) {
     if (!fsal) return fail(c, B200RK_EINVAL, std::string(md.name) + ": FSAL vector required");
     TRY(check_same(c, y, fsal));
     k[1] = const_cast<b200rk_vec*>(fsal);
-  } else {
+  } else if (!fused) {
     TRY(ws.get(N, &k[1]));
   }
-  for (int s = 2; s <= S; ++s) {
-    if (s == md.fsal_out && fsal_new) k[s] = fsal_new;
-    else TRY(ws.get(N, &k[s]));
-  }
   const bool last_input_is_ynew = md.ynew_is_last_stage_input;
-  if (!(last_input_is_ynew && S == 2)) TRY(ws.get(N, &tmp));
+  if (!fused) {
+    for (int s = 2; s <= S; ++s) {
+      if (s == md.fsal_out && fsal_new) k[s] = fsal_new;
+      else TRY(ws.get(N, &k[s]));
+    }
+    if (!(last_input_is_ynew && S == 2)) TRY(ws.get(N, &tmp));
+  }
 
   double dt = dt_in, error = 0.0;
   int limitCounter = 0;
   while (true) {
     if (cnt) cnt->attempts++;
+    if (fused) {
+      // element-local right-hand side: the whole attempt is one kernel (the callbacks it stands for are
+      // still counted so rhs_evals matches the unfused path)
+      if (rhs.evals) *rhs.evals += md.rk4_final ? 4 : (S - 1);
+      if (md.rk4_final) { TRY(launch_fused_rk4(c, pw_kind, br, rhs.negate_time, dt, y, y_new)); break; }
+      if (S == 7) TRY(launch_fused_pair<7>(c, md, pw_kind, br, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new));
+      else TRY(launch_fused_pair<9>(c, md, pw_kind, br, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new));
+    } else {
     if (!md.k1_from_fsal) TRY(eval_rhs(c, rhs, t, y, k[1]));
     for (int s = 2; s <= S; ++s) {
       b200rk_vec* in = (s == S && last_input_is_ynew) ? y_new : tmp;
@@ -561,6 +671,7 @@ static int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, doubl
     FinishPlan p;
     TRY(plan_finish(c, md, dt, o.absTol, o.relTol, y, k, y_new, last_input_is_ynew, nullptr, &p));
     TRY(launch_finish(c, p));
+    }  // !fused
     double S2 = 0.0;
     TRY(fetch_global_sum(c, &S2));
     error = std::sqrt(1.0 / double(N) * S2);                                     // ode.nim:64-65
@@ -795,6 +906,7 @@ static int ctx_common_init(b200rk_ctx* c) {
   if (const char* e = getenv("B200RK_CTAS_PER_SM")) c->ctas_per_sm = std::max(0, atoi(e));
   if (const char* e = getenv("B200RK_FINISH_CTAS_PER_SM")) c->finish_ctas_per_sm = std::max(0, atoi(e));
   if (const char* e = getenv("B200RK_STRICT_ZEROS")) c->strict_zeros = atoi(e) != 0;
+  if (const char* e = getenv("B200RK_FUSE_POINTWISE")) c->fuse_pointwise = atoi(e) != 0;
   CUDA_TRY(c, cudaDeviceSynchronize());
   return B200RK_OK;
 }
@@ -862,6 +974,8 @@ int b200rk_set(b200rk_ctx* c, const char* key, int64_t v) {
   else if (k == "ctas_per_sm") { if (v < 0) return fail(c, B200RK_EINVAL, "ctas_per_sm must be >= 0"); c->ctas_per_sm = (int)v; }
   else if (k == "finish_ctas_per_sm") { if (v < 0) return fail(c, B200RK_EINVAL, "finish_ctas_per_sm must be >= 0"); c->finish_ctas_per_sm = (int)v; }
   else if (k == "profile") c->profile = v != 0;
+  else if (k == "fuse_pointwise") c->fuse_pointwise = v != 0;
+  else if (k == "fused_ctas_per_sm") { if (v < 0) return fail(c, B200RK_EINVAL, "fused_ctas_per_sm must be >= 0"); c->fused_ctas_per_sm = (int)v; }
   else if (k == "pool_budget_mb") {
     c->pool_budget_bytes = (size_t)std::max<int64_t>(0, v) << 20;
     if (v == 0) {  // trim now
@@ -879,6 +993,8 @@ int b200rk_get(const b200rk_ctx* c, const char* key, int64_t* v) {
   else if (k == "vec_width") *v = c->vec_width;
   else if (k == "ctas_per_sm") *v = c->ctas_per_sm;
   else if (k == "finish_ctas_per_sm") *v = c->finish_ctas_per_sm;
+  else if (k == "fuse_pointwise") *v = c->fuse_pointwise;
+  else if (k == "fused_ctas_per_sm") *v = c->fused_ctas_per_sm;
   else if (k == "profile") *v = c->profile;
   else if (k == "sm_count") *v = c->sm_count;
   else if (k == "pool_budget_mb") *v = (int64_t)(c->pool_budget_bytes >> 20);

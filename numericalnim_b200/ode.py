@@ -78,7 +78,7 @@ class Context:
     def profile_read(self) -> dict:
         p = capi.Profile()
         capi.check(capi.lib().b200rk_profile_read(self._h, C.byref(p)), self._h)
-        names = ("stage", "finish", "rhs", "other")
+        names = ("stage", "finish", "rhs", "other", "fused")
         return {n: dict(launches=int(p.launches[i]), ms=float(p.ms[i]), bytes=float(p.algorithmic_bytes[i])) for i, n in enumerate(names)}
 
     def stats(self) -> dict:

@@ -51,6 +51,17 @@ def nn():
     return nn
 
 
+@pytest.fixture(params=[1, 0], ids=["fused", "unfused"])
+def fuse_mode(nn, request):
+    """Element-local built-in right-hand sides run a whole attempt as ONE kernel by default
+    (fuse_pointwise=1); 0 forces the stage / RHS / finish pipeline every user closure goes through.
+    Solver-level tests run in both modes."""
+    ctx = nn.default_context()
+    ctx.set("fuse_pointwise", request.param)
+    yield request.param
+    ctx.set("fuse_pointwise", 1)
+
+
 def rng_vec(rng, n, scale=1.0):
     return (rng.uniform(-1.0, 1.0, n) * scale).astype(np.float64)
 
@@ -255,7 +266,7 @@ ALL = ["dopri54", "tsit54", "vern65", "rk4", "rk21", "bs32", "heun2", "ralston2"
 
 
 @pytest.mark.parametrize("method", ALL)
-def test_single_step_matches_oracle(nn, method):
+def test_single_step_matches_oracle(nn, method, fuse_mode):
     rng = np.random.default_rng(31)
     n = 2049
     lam = rng.uniform(0.1, 5.0, n)
@@ -277,7 +288,7 @@ def test_single_step_matches_oracle(nn, method):
 
 
 @pytest.mark.parametrize("method", ["dopri54", "tsit54", "vern65", "rk21", "bs32"])
-def test_single_step_with_rejections_matches_oracle(nn, method):
+def test_single_step_with_rejections_matches_oracle(nn, method, fuse_mode):
     """Tight tolerance and a big first dt: the retry loop (ode.nim:57-76) runs several attempts."""
     rng = np.random.default_rng(37)
     n = 1025
@@ -307,7 +318,7 @@ def test_step_rejects_aliasing_and_size_mismatch(nn):
         nn.integratorStep("dopri54", rhs, 0.0, y, nn.newVector(np.ones(9)), 0.1)
 
 
-def test_nan_error_is_reported_not_looped(nn):
+def test_nan_error_is_reported_not_looped(nn, fuse_mode):
     """ode.nim:69-76 would spin forever on a NaN norm; the library returns B200RK_ENONFINITE instead."""
     from numericalnim_b200 import B200rkError
     y = nn.newVector(np.array([1.0, np.nan, 2.0, 3.0]))
@@ -331,7 +342,7 @@ def _builtin_from(nn, desc):
     raise KeyError(desc)
 
 
-def test_solve_matches_golden_fixtures(nn, golden_trajectories):
+def test_solve_matches_golden_fixtures(nn, golden_trajectories, fuse_mode):
     checked = 0
     for name, g in golden_trajectories.items():
         y0, ts = unhex(g["y0"]), unhex(g["tspan"])
@@ -355,7 +366,7 @@ def test_solve_matches_golden_fixtures(nn, golden_trajectories):
     assert checked >= 20
 
 
-def test_step_sequence_matches_oracle(nn):
+def test_step_sequence_matches_oracle(nn, fuse_mode):
     """Same number of steps and the same dt sequence (rtol 1e-10) as the CPU oracle on a vector IVP."""
     n = 4096
     lam = 0.1 + 9.9 * np.arange(n) / (n - 1)
@@ -412,7 +423,7 @@ def test_reference_vector_cases_on_gpu(nn, integrator, opts, tol):
 
 
 @pytest.mark.parametrize("integrator", ["dopri54", "tsit54", "vern65", "rk21", "bs32", "kutta4"])
-def test_reference_scalar_cases_on_gpu(nn, integrator):
+def test_reference_scalar_cases_on_gpu(nn, integrator, fuse_mode):
     """tests/test_ode.nim:24-136 (scalar T): a Python float travels as a length-1 vector; host-buffer path."""
     tspan = nn.linspace(-10.0, 10.0, 100)
     kw = {} if integrator != "kutta4" else dict(dt=1e-2)  # fixed-step default dt=1e-4 is 200k launches x4
@@ -428,7 +439,7 @@ def test_reference_scalar_cases_on_gpu(nn, integrator):
         assert O.is_close(float(v), math.exp(-0.1 * ti), 1e-6 if integrator in ("rk21", "bs32") else 1e-4)
 
 
-def test_rk4_trajectory_is_bit_identical(nn):
+def test_rk4_trajectory_is_bit_identical(nn, fuse_mode):
     """Fixed step: identical step sequence and bit-identical states, dense output and backward time included."""
     rng = np.random.default_rng(41)
     n = 257
@@ -466,7 +477,7 @@ def test_tspan_quirks_match_reference(nn):
         nn.solveODE(rhs, nn.newVector([1.0]), [0.0, 1.0], integrator="rk5")
 
 
-def test_host_buffer_path_equals_device_path(nn):
+def test_host_buffer_path_equals_device_path(nn, fuse_mode):
     n = 1000
     lam = np.linspace(0.1, 4.0, n)
     y0 = np.linspace(1.0, 2.0, n)
@@ -506,3 +517,57 @@ def test_full_size_stage_and_finish(nn):
     # point, but scaling all k by a power of two is: stage(y; 2k, c/2) == stage(y; k, c) bit for bit.
     out2 = nn.stageAccum(w, 0.005, gy, [2.0 * k for k in gk[:5]])
     assert_bitwise_equal(out2.to_numpy(), ref, "power-of-two scaling invariance")
+
+
+# ---------------------------------------------------------------------------------------------------
+# Fused attempt (element-local right-hand sides): same bits as the stage / RHS / finish pipeline
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("strict", [0, 1])
+@pytest.mark.parametrize("rhs_kind", ["scale", "diag"])
+@pytest.mark.parametrize("method", ["dopri54", "tsit54", "vern65", "rk4"])
+def test_fused_attempt_bitwise_equals_pipeline(nn, method, rhs_kind, strict):
+    ctx = nn.default_context()
+    rng = np.random.default_rng(77)
+    out = {}
+    try:
+        ctx.set("strict_zeros", strict)
+        for n in [1, 3, 4, 5, 1023, 65536 + 7]:
+            lam = rng.uniform(0.1, 5.0, n)
+            y = 1.0 + rng_vec(rng, n, 0.5)
+            glam, gy = nn.newVector(lam), nn.newVector(y)
+            rhs = nn.rhsDiagLinear(glam) if rhs_kind == "diag" else nn.rhsScale(-0.37)
+            fsal = nn.newVector(_eval_builtin(nn, rhs, gy))
+            o = nn.newODEoptions(absTol=1e-4, relTol=1e-4, dtMax=1.0, dtMin=1e-8, dt=0.01)
+            for fuse in (1, 0):
+                ctx.set("fuse_pointwise", fuse)
+                l0 = ctx.stats()["launches"]
+                yn, fn, dt_used, err = nn.integratorStep(method, rhs, 0.25, gy, fsal, 0.01, o)
+                out[fuse] = (yn.to_numpy(), fn.to_numpy(), dt_used, err, ctx.stats()["launches"] - l0)
+            assert_bitwise_equal(out[1][0], out[0][0], f"{method}/{rhs_kind} yNew n={n}")
+            assert_bitwise_equal(out[1][1], out[0][1], f"{method}/{rhs_kind} FSAL n={n}")
+            assert out[1][2] == out[0][2]
+            assert abs(out[1][3] - out[0][3]) <= norm_rtol(n) * abs(out[0][3])
+            assert out[1][4] == 1 and out[0][4] >= 8  # one kernel instead of >= 8
+    finally:
+        ctx.set("strict_zeros", 0)
+        ctx.set("fuse_pointwise", 1)
+
+
+def test_fused_backward_time_bitwise(nn):
+    """Backward pass g(t, y) = -f(-t, y) (ode.nim:545) inside the fused kernel vs the pipeline + negate kernel."""
+    ctx = nn.default_context()
+    n = 513
+    lam = np.linspace(0.1, 3.0, n)
+    y0 = np.linspace(1.0, 2.0, n)
+    ts = nn.linspace(-1.0, 0.5, 6)
+    res = {}
+    try:
+        for fuse in (1, 0):
+            ctx.set("fuse_pointwise", fuse)
+            t, ys = nn.solveODE(nn.rhsDiagLinear(nn.newVector(lam)), nn.newVector(y0), ts, nn.newODEoptions(dt=1e-2), integrator="rk4")
+            res[fuse] = np.array([v.to_numpy() for v in ys])
+        assert_bitwise_equal(res[1], res[0], "rk4 fused vs pipeline, dense + backward")
+        ref = O.solve_vector("rk4", O.rhs_diag_linear(lam), y0, ts, O.new_options(dt=1e-2))
+        assert_bitwise_equal(res[1], ref.y, "rk4 fused vs oracle")
+    finally:
+        ctx.set("fuse_pointwise", 1)

@@ -377,26 +377,49 @@ def run_reference(args):
 # config 5: kernel bandwidth sweep
 # ======================================================================================================
 def run_sweep(args):
+    """BASELINE.json config 5: fused stage-combine / combine+norm bandwidth and solver steps/s for N = 2^min..2^max
+    (N is the GLOBAL length; under torchrun it is sharded over the ranks), next to the oracle port's CPU time for the
+    same expressions on one host core (rank 0, N <= 2^cpu_max)."""
+    import torch
+
     import numericalnim_b200 as nn
     import oracle as O
+    from numericalnim_b200 import distributed as D
 
-    ctx = nn.default_context()
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = D.init_context(local_rank)
+    nn.set_default_context(ctx)
     peak, peak_src = peaks()
     rows = []
     l2_bytes = 126e6
     rng = np.random.default_rng(1234)
+    w5 = O.pair_tableau("dopri54")["a"][6][:5]
+    w8 = O.pair_tableau("vern65")["a"][9][:8]
+
+    def allmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     for lg in range(args.sweep_min, args.sweep_max + 1, args.sweep_step):
         n = 1 << lg
-        base = rng.uniform(-1.0, 1.0, n)
-        vecs = [nn.newVector(np.roll(base, 17 * j), ctx) for j in range(10)]
+        off, ln = D.shard_range(n, rank, world)
+        base = rng.uniform(-1.0, 1.0, ln)
+        vecs = [nn.GpuVector.from_local(n, np.roll(base, 17 * j), ctx) for j in range(10)]
         out = nn.GpuVector.empty(n, ctx)
         cases = []
-        for m in (1, 5, 8):
-            w = O.pair_tableau("vern65")["a"][9][:8] if m == 8 else O.pair_tableau("dopri54")["a"][6][:m]
-            cases.append((f"stage_m{m}", "stage", lambda m=m, w=w: nn.stageAccum(w[:m], 0.01, vecs[0], vecs[1:1 + m], out=out), 8.0 * n * (m + 2)))
+        for m, w in ((1, w5), (5, w5), (8, w8)):
+            cases.append((f"stage_m{m}", "stage", lambda m=m, w=w: nn.stageAccum(w[:m], 0.01, vecs[0], vecs[1:1 + m], out=out)))
         for meth, S in (("dopri54", 7), ("tsit54", 7), ("vern65", 9)):
-            cases.append((f"finish_{meth}", "finish", lambda meth=meth, S=S: nn.combineErr(meth, 0.01, 1e-6, 1e-6, vecs[0], vecs[1:1 + S]), None))
-        for name, cls, fn, nbytes in cases:
+            cases.append((f"finish_{meth}", "finish", lambda meth=meth, S=S: nn.combineErr(meth, 0.01, 1e-6, 1e-6, vecs[0], vecs[1:1 + S])))
+        for name, cls, fn in cases:
             for _ in range(args.sweep_warm):
                 fn()
             ctx.set("profile", 1)
@@ -405,22 +428,58 @@ def run_sweep(args):
                 fn()
             p = ctx.profile_read()
             ctx.set("profile", 0)
-            ms, b, ln = p[cls]["ms"], p[cls]["bytes"], p[cls]["launches"]
-            if name == "finish_tsit54":  # the raw API adds a stage launch for yNew; keep the finish class only
-                pass
-            gbs = b / (ms * 1e-3) / 1e9
-            ws = (b / ln)
-            rows.append({"log2n": lg, "kernel": name, "us_per_launch": 1e3 * ms / ln, "GBps": gbs, "frac_of_peak": gbs / peak,
-                         "l2_resident": bool(ws < l2_bytes), "alg_bytes_per_launch": ws})
-            print(json.dumps(rows[-1]), flush=True)
-        for v in vecs:
+            ms, b, nl = allmax(p[cls]["ms"]), p[cls]["bytes"], p[cls]["launches"]
+            gbs = world * b / (ms * 1e-3) / 1e9  # every rank moves the same bytes; slowest rank's time
+            row = {"log2n": lg, "n_gpus": world, "kernel": name, "us_per_launch": 1e3 * ms / nl, "GBps": gbs, "GBps_per_gpu": gbs / world,
+                   "frac_of_peak_per_gpu": gbs / world / peak, "l2_resident": bool(b / nl < l2_bytes), "alg_bytes_per_launch_per_gpu": b / nl}
+            if rank == 0 and world == 1 and lg <= args.sweep_cpu_max and name in ("stage_m5", "finish_dopri54"):
+                hv = [v.local_numpy() for v in vecs[:8]]
+                best = 1e30
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    if name == "stage_m5":
+                        O.weighted_stage(w5, 0.01, hv[0], hv[1:6])
+                    else:
+                        O.pair_finish("dopri54", 0.01, 1e-6, 1e-6, hv[0], hv[1:8])
+                    best = min(best, time.perf_counter() - t0)
+                # same algorithmic-byte formula as the GPU column (the reference really moves ~5-6x more)
+                row["cpu_ms"] = 1e3 * best
+                row["cpu_GBps"] = (b / nl) / best / 1e9
+                row["gpu_over_cpu"] = best / (1e-3 * ms / nl)
+            rows.append(row)
+            if rank == 0:
+                print(json.dumps(row), flush=True)
+        # solver steps/s at this N (DOPRI54, diag-linear), pipeline and fused element-local path
+        i = np.arange(off, off + ln, dtype=np.float64)
+        glam = nn.GpuVector.from_local(n, 0.1 + 9.9 * i / float(max(n - 1, 1)), ctx)
+        gy0 = nn.GpuVector.from_local(n, 1.0 + 0.5 * np.sin(2.0 * np.pi * i / float(n)), ctx)
+        rhs = nn.rhsDiagLinear(glam)
+        for fuse in (0, 1):
+            ctx.set("fuse_pointwise", fuse)
+            sv = nn.Solver("dopri54", rhs, gy0, 1e12, nn.newODEoptions(**OPTS))
+            sv.advance(8)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            sv.advance(args.sweep_solver_steps)
+            torch.cuda.synchronize()
+            dt_s = allmax(time.perf_counter() - t0)
+            sv.close()
+            row = {"log2n": lg, "n_gpus": world, "kernel": "solver_dopri54_" + ("fused" if fuse else "pipeline"),
+                   "steps_per_sec": args.sweep_solver_steps / dt_s, "us_per_step": 1e6 * dt_s / args.sweep_solver_steps}
+            rows.append(row)
+            if rank == 0:
+                print(json.dumps(row), flush=True)
+        ctx.set("fuse_pointwise", 1)
+        for v in vecs + [out, glam, gy0]:
             v.free()
-        out.free()
         ctx.set("pool_budget_mb", 0)
         ctx.set("pool_budget_mb", 48 << 10)
-    if args.out:
+    if args.out and rank == 0:
         with open(args.out, "w") as fh:
-            json.dump({"peak_gbs": peak, "peak_source": peak_src, "rows": rows}, fh, indent=1)
+            json.dump({"peak_gbs": peak, "peak_source": peak_src, "n_gpus": world, "host_cores": os.cpu_count(), "rows": rows}, fh, indent=1)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def run_tune(args):
@@ -504,6 +563,8 @@ def main():
     ap.add_argument("--sweep-step", type=int, default=1)
     ap.add_argument("--sweep-warm", type=int, default=20)
     ap.add_argument("--sweep-iters", type=int, default=100)
+    ap.add_argument("--sweep-cpu-max", type=int, default=23)
+    ap.add_argument("--sweep-solver-steps", type=int, default=40)
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -540,51 +540,67 @@ static uint32_t row_mask(const b200rk_ctx* c, const Row& row, double* w_dense, i
   return mask;
 }
 
-template <int S, int KIND, bool DIRECT, bool LAST>
-static int launch_fused_cfg(b200rk_ctx* c, const FusedArgs<S>& a) {
+template <int PAT, int KIND>
+static int launch_fused_cfg(b200rk_ctx* c, const FusedArgs<Pattern<PAT>::S>& a) {
   const size_t n = a.n;
   if (c->vec_width == 4) {
     unsigned grid = grid_for(c, n / 4, kThreads, c->fused_ctas_per_sm);
     TRY(ensure_partials(c, grid));
-    fused_attempt_kernel<S, KIND, DIRECT, LAST, 4, kThreads><<<grid, kThreads, 0, c->stream>>>(a);
+    fused_attempt_kernel<PAT, KIND, 4, kThreads><<<grid, kThreads, 0, c->stream>>>(a);
   } else {
     unsigned grid = grid_for(c, n / 2, kThreads, c->fused_ctas_per_sm);
     TRY(ensure_partials(c, grid));
-    fused_attempt_kernel<S, KIND, DIRECT, LAST, 2, kThreads><<<grid, kThreads, 0, c->stream>>>(a);
+    fused_attempt_kernel<PAT, KIND, 2, kThreads><<<grid, kThreads, 0, c->stream>>>(a);
   }
   CUDA_TRY(c, cudaGetLastError());
   return B200RK_OK;
 }
 
-template <int S>
+// Runtime masks of the method (same dropping rules as gather_row / plan_finish) must equal the kernel's
+// compile-time pattern; otherwise the caller falls back to the pipeline.
+template <int PAT>
+static bool pattern_matches(const b200rk_ctx* c, const MethodDef& md) {
+  constexpr int S = Pattern<PAT>::S;
+  if (md.stages != S || md.err_direct != Pattern<PAT>::direct || md.ynew_is_last_stage_input != Pattern<PAT>::last) return false;
+  double scratch[kMaxStages];
+  for (int s = 2; s <= S; ++s)
+    if (row_mask(c, md.a[s], scratch, S - 1) != Pattern<PAT>::a(s - 2)) return false;
+  uint32_t bm = 0, bhm = 0;
+  for (int j = 0; j < md.b.m; ++j) if (md.b.w[j] != 0.0 || c->strict_zeros) bm |= 1u << (md.b.idx[j] - 1);
+  for (int j = 0; j < md.bhat.m; ++j) if (md.bhat.w[j] != 0.0 || c->strict_zeros) bhm |= 1u << (md.bhat.idx[j] - 1);
+  if (!Pattern<PAT>::last && bm != Pattern<PAT>::b()) return false;
+  return bhm == Pattern<PAT>::bh();
+}
+
+static int fused_pattern_of(const b200rk_ctx* c, const MethodDef& md) {
+  if (pattern_matches<PAT_DOPRI54>(c, md) && !std::strcmp(md.name, "dopri54")) return PAT_DOPRI54;
+  if (pattern_matches<PAT_DOPRI54_STRICT>(c, md) && !std::strcmp(md.name, "dopri54")) return PAT_DOPRI54_STRICT;
+  if (pattern_matches<PAT_TSIT54>(c, md) && !std::strcmp(md.name, "tsit54")) return PAT_TSIT54;
+  if (pattern_matches<PAT_VERN65>(c, md)) return PAT_VERN65;
+  if (pattern_matches<PAT_VERN65_STRICT>(c, md)) return PAT_VERN65_STRICT;
+  return -1;
+}
+
+template <int PAT>
 static int launch_fused_pair(b200rk_ctx* c, const MethodDef& md, int pw_kind, const BuiltinRhs* br, bool negate, double dt,
                              const b200rk_options& o, const b200rk_vec* y, const b200rk_vec* fsal, b200rk_vec* y_new,
                              b200rk_vec* fsal_new) {
+  constexpr int S = Pattern<PAT>::S;
   FusedArgs<S> a;
   std::memset(&a, 0, sizeof(a));
-  a.y = y->d; a.k1 = fsal->d; a.lam = br->lambda ? br->lambda->d : nullptr; a.rhs_scalar = br->scalar; a.negate = negate ? 1 : 0;
-  for (int s = 2; s <= S; ++s) a.amask[s - 2] = row_mask(c, md.a[s], a.a[s - 2], S - 1);
-  a.bmask = row_mask(c, md.b, a.b, S);
-  a.bhmask = row_mask(c, md.bhat, a.bh, S);
-  if (!c->strict_zeros) {  // finish rows: plan_finish drops every zero weight (no keep-first rule needed: rows are never all-zero)
-    a.bmask = 0; a.bhmask = 0;
-    for (int j = 0; j < md.b.m; ++j) if (md.b.w[j] != 0.0) a.bmask |= 1u << (md.b.idx[j] - 1);
-    for (int j = 0; j < md.bhat.m; ++j) if (md.bhat.w[j] != 0.0) a.bhmask |= 1u << (md.bhat.idx[j] - 1);
-  }
+  a.y = y->d; a.k1 = fsal->d; a.lam = br->lambda ? br->lambda->d : nullptr;
+  a.rhs_scalar = negate ? -br->scalar : br->scalar;   // -(y*c) == y*(-c) exactly
+  a.rhs_sign = negate ? 1.0 : -1.0;                   // k = (lam*y)*sign
+  for (int s = 2; s <= S; ++s) row_mask(c, md.a[s], a.a[s - 2], S - 1);
+  row_mask(c, md.b, a.b, S);
+  row_mask(c, md.bhat, a.bh, S);
   a.dt = dt; a.cb = dt; a.cbh = dt; a.absTol = o.absTol; a.relTol = o.relTol;
   a.ynew = y_new->d; a.ks_out = fsal_new->d; a.n = y->n_local;
   a.rs = reduce_scratch(c);
   const int streams = 4 + (pw_kind == PW_DIAG ? 1 : 0);  // y, k1 (+ lambda) read; yNew, k_S written
   ProfScope ps(c, B200RK_K_FUSED, 8.0 * double(y->n_local) * streams);
-  const bool direct = md.err_direct, last = md.ynew_is_last_stage_input;
-#define B200RK_FUSED_CASE(KIND)                                                               \
-  if (direct && last) return launch_fused_cfg<S, KIND, true, true>(c, a);                     \
-  if (!direct && last) return launch_fused_cfg<S, KIND, false, true>(c, a);                   \
-  if (!direct && !last) return launch_fused_cfg<S, KIND, false, false>(c, a);
-  if (pw_kind == PW_SCALE) { B200RK_FUSED_CASE(PW_SCALE) }
-  else { B200RK_FUSED_CASE(PW_DIAG) }
-#undef B200RK_FUSED_CASE
-  return fail(c, B200RK_EINVAL, "fused attempt: unsupported method shape");
+  if (pw_kind == PW_SCALE) return launch_fused_cfg<PAT, PW_SCALE>(c, a);
+  return launch_fused_cfg<PAT, PW_DIAG>(c, a);
 }
 
 static int launch_fused_rk4(b200rk_ctx* c, int pw_kind, const BuiltinRhs* br, bool negate, double dt, const b200rk_vec* y,
@@ -595,8 +611,9 @@ static int launch_fused_rk4(b200rk_ctx* c, int pw_kind, const BuiltinRhs* br, bo
   const double hdt = 0.5 * dt, c6 = dt / 6.0;
   const double* lam = br->lambda ? br->lambda->d : nullptr;
   unsigned grid = grid_for(c, n / 4, kThreads, c->ctas_per_sm);
-  if (pw_kind == PW_SCALE) fused_rk4_kernel<PW_SCALE, 4, kThreads><<<grid, kThreads, 0, c->stream>>>(y->d, lam, br->scalar, negate, hdt, dt, c6, y_new->d, n);
-  else fused_rk4_kernel<PW_DIAG, 4, kThreads><<<grid, kThreads, 0, c->stream>>>(y->d, lam, br->scalar, negate, hdt, dt, c6, y_new->d, n);
+  const double cs = negate ? -br->scalar : br->scalar, sgn = negate ? 1.0 : -1.0;
+  if (pw_kind == PW_SCALE) fused_rk4_kernel<PW_SCALE, 4, kThreads><<<grid, kThreads, 0, c->stream>>>(y->d, lam, cs, sgn, hdt, dt, c6, y_new->d, n);
+  else fused_rk4_kernel<PW_DIAG, 4, kThreads><<<grid, kThreads, 0, c->stream>>>(y->d, lam, cs, sgn, hdt, dt, c6, y_new->d, n);
   CUDA_TRY(c, cudaGetLastError());
   return B200RK_OK;
 }
@@ -612,8 +629,10 @@ static int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, doubl
   b200rk_vec* tmp = nullptr;
   int pw_kind = 0;
   const BuiltinRhs* br = nullptr;
-  const bool fused = c->fuse_pointwise && pointwise_kind(rhs, &pw_kind, &br) && method_fusable(md) &&
-                     (md.rk4_final || (fsal && fsal_new));
+  int fused_pat = -1;
+  bool fused = c->fuse_pointwise && pointwise_kind(rhs, &pw_kind, &br) && method_fusable(md) &&
+               (md.rk4_final || (fsal && fsal_new));
+  if (fused && !md.rk4_final) { fused_pat = fused_pattern_of(c, md); fused = fused_pat >= 0; }
   if (fused && pw_kind == PW_DIAG) TRY(check_same(c, y, br->lambda));
   if (md.k1_from_fsal) {
     if (!fsal) return fail(c, B200RK_EINVAL, std::string(md.name) + ": FSAL vector required");
@@ -640,8 +659,13 @@ static int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, doubl
       // still counted so rhs_evals matches the unfused path)
       if (rhs.evals) *rhs.evals += md.rk4_final ? 4 : (S - 1);
       if (md.rk4_final) { TRY(launch_fused_rk4(c, pw_kind, br, rhs.negate_time, dt, y, y_new)); break; }
-      if (S == 7) TRY(launch_fused_pair<7>(c, md, pw_kind, br, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new));
-      else TRY(launch_fused_pair<9>(c, md, pw_kind, br, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new));
+      switch (fused_pat) {
+        case PAT_DOPRI54: TRY(launch_fused_pair<PAT_DOPRI54>(c, md, pw_kind, br, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new)); break;
+        case PAT_DOPRI54_STRICT: TRY(launch_fused_pair<PAT_DOPRI54_STRICT>(c, md, pw_kind, br, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new)); break;
+        case PAT_TSIT54: TRY(launch_fused_pair<PAT_TSIT54>(c, md, pw_kind, br, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new)); break;
+        case PAT_VERN65: TRY(launch_fused_pair<PAT_VERN65>(c, md, pw_kind, br, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new)); break;
+        default: TRY(launch_fused_pair<PAT_VERN65_STRICT>(c, md, pw_kind, br, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new)); break;
+      }
     } else {
     if (!md.k1_from_fsal) TRY(eval_rhs(c, rhs, t, y, k[1]));
     for (int s = 2; s <= S; ++s) {

@@ -366,25 +366,76 @@ __global__ void __launch_bounds__(THREADS) finish_kernel(const FinishArgs<NK> a)
 // ---------------------------------------------------------------------------------------------------
 enum PointwiseRhs : int { PW_SCALE = 0, PW_DIAG = 1 };
 
+// `sgn`: PW_SCALE folds the backward-pass negation (g = -f(-t, y), ode.nim:545) into the scalar on the
+// host (-(y*c) == y*(-c) exactly); PW_DIAG multiplies by -1 (forward: -(lam*y)) or +1 (backward), also
+// exact. No select instructions on the fp64 path.
 template <int KIND>
-__device__ __forceinline__ double pointwise_rhs(double y, double lam, double c, bool negate) {
-  double k;
-  if (KIND == PW_SCALE) k = __dmul_rn(y, c);       // EW_SCALE
-  else k = -__dmul_rn(lam, y);                     // EW_NEG_HMUL
-  return negate ? -k : k;                          // backward pass g = -f(-t, y) (ode.nim:545)
+__device__ __forceinline__ double pointwise_rhs(double y, double lam, double c, double sgn) {
+  if (KIND == PW_SCALE) return __dmul_rn(y, c);           // EW_SCALE
+  return __dmul_rn(__dmul_rn(lam, y), sgn);               // EW_NEG_HMUL (sgn = -1)
 }
+
+// Sparsity patterns of the three FSAL pairs, as COMPILE-TIME constants: which terms of each row are kept
+// (bit j <-> k_{j+1}). With runtime masks every term costs shifts, predicates and 64-bit selects and the
+// kernel becomes ALU-bound (measured: 354 instructions per element, alu pipe 71 %); with constexpr masks the
+// unrolled loops fold to exactly the reference's multiply/add sequence. The host checks that the masks it
+// derives from the tableau (methods.h) equal the pattern before taking this path.
+enum FusedPattern : int { PAT_DOPRI54 = 0, PAT_DOPRI54_STRICT = 1, PAT_TSIT54 = 2, PAT_VERN65 = 3, PAT_VERN65_STRICT = 4 };
+
+template <int PAT>
+struct Pattern;
+template <>
+struct Pattern<PAT_DOPRI54> {  // a72 = bHat2 = 0 dropped (ode.nim:263, 277)
+  static constexpr int S = 7;
+  static constexpr bool direct = false, last = true;
+  __host__ __device__ static constexpr uint32_t a(int r) { return r == 0 ? 0x1u : r == 1 ? 0x3u : r == 2 ? 0x7u : r == 3 ? 0xFu : r == 4 ? 0x1Fu : 0x3Du; }
+  __host__ __device__ static constexpr uint32_t b() { return 0x3Du; }
+  __host__ __device__ static constexpr uint32_t bh() { return 0x7Du; }
+};
+template <>
+struct Pattern<PAT_DOPRI54_STRICT> {
+  static constexpr int S = 7;
+  static constexpr bool direct = false, last = true;
+  __host__ __device__ static constexpr uint32_t a(int r) { return (2u << r) - 1u; }
+  __host__ __device__ static constexpr uint32_t b() { return 0x3Fu; }
+  __host__ __device__ static constexpr uint32_t bh() { return 0x7Fu; }
+};
+template <>
+struct Pattern<PAT_TSIT54> {  // dense: no zero weights (ode.nim:317-352); error row is direct (ode.nim:372)
+  static constexpr int S = 7;
+  static constexpr bool direct = true, last = true;
+  __host__ __device__ static constexpr uint32_t a(int r) { return (2u << r) - 1u; }
+  __host__ __device__ static constexpr uint32_t b() { return 0x3Fu; }
+  __host__ __device__ static constexpr uint32_t bh() { return 0x7Fu; }
+};
+template <>
+struct Pattern<PAT_VERN65> {  // zeros a42 a52 a62 a72 a82 a92 a93 b2 b3 bHat2 bHat3 bHat7 dropped (ode.nim:393-441)
+  static constexpr int S = 9;
+  static constexpr bool direct = false, last = false;
+  __host__ __device__ static constexpr uint32_t a(int r) {
+    return r == 0 ? 0x1u : r == 1 ? 0x3u : r == 2 ? 0x5u : r == 3 ? 0xDu : r == 4 ? 0x1Du : r == 5 ? 0x3Du : r == 6 ? 0x7Du : 0xF9u;
+  }
+  __host__ __device__ static constexpr uint32_t b() { return 0xF9u; }
+  __host__ __device__ static constexpr uint32_t bh() { return 0x1B9u; }
+};
+template <>
+struct Pattern<PAT_VERN65_STRICT> {
+  static constexpr int S = 9;
+  static constexpr bool direct = false, last = false;
+  __host__ __device__ static constexpr uint32_t a(int r) { return (2u << r) - 1u; }
+  __host__ __device__ static constexpr uint32_t b() { return 0xFFu; }
+  __host__ __device__ static constexpr uint32_t bh() { return 0x1FFu; }
+};
 
 template <int S>
 struct FusedArgs {
   const double* y;
   const double* k1;    // FSAL
   const double* lam;   // PW_DIAG
-  double rhs_scalar;   // PW_SCALE
-  int negate;
+  double rhs_scalar;   // PW_SCALE (already negated for the backward pass)
+  double rhs_sign;     // PW_DIAG: -1 forward, +1 backward
   double a[S - 1][S - 1];   // a[s-2][j] = a_{s,j+1}
-  uint32_t amask[S - 1];    // terms kept (zero weights dropped unless strict)
   double b[S], bh[S];
-  uint32_t bmask, bhmask;
   double dt, cb, cbh, absTol, relTol;
   double* ynew;
   double* ks_out;
@@ -392,41 +443,57 @@ struct FusedArgs {
   ReduceScratch rs;
 };
 
-template <int S, int KIND, bool DIRECT, bool YNEW_IS_LAST>
-__device__ __forceinline__ double fused_elem(double y, double k1, double lam, const FusedArgs<S>& a, double& ynew,
-                                             double& ks) {
+// left-associated sum of the kept terms; MASK is a compile-time constant after unrolling
+template <int NK, uint32_t MASK>
+__device__ __forceinline__ double const_wsum(const double (&k)[NK], const double* w) {
+  double acc = 0.0;
+  bool have = false;
+#pragma unroll
+  for (int j = 0; j < NK; ++j) {
+    if ((MASK >> j) & 1u) {
+      const double p = __dmul_rn(k[j], w[j]);
+      acc = have ? __dadd_rn(acc, p) : p;
+      have = true;
+    }
+  }
+  return acc;
+}
+
+template <int PAT, int KIND, int s>
+struct FusedStages {  // stages 2..s, recursively, so that every row mask is a template constant
+  template <int S>
+  __device__ __forceinline__ static double run(double y, double lam, const FusedArgs<S>& a, double (&k)[S]) {
+    if constexpr (s > 2) FusedStages<PAT, KIND, s - 1>::run(y, lam, a, k);
+    const double acc = const_wsum<S, Pattern<PAT>::a(s - 2)>(k, a.a[s - 2]);
+    const double in = __dadd_rn(y, __dmul_rn(acc, a.dt));
+    k[s - 1] = pointwise_rhs<KIND>(in, lam, a.rhs_scalar, a.rhs_sign);
+    return in;
+  }
+};
+
+template <int PAT, int KIND>
+__device__ __forceinline__ double fused_elem(double y, double k1, double lam, const FusedArgs<Pattern<PAT>::S>& a,
+                                             double& ynew, double& ks) {
+  constexpr int S = Pattern<PAT>::S;
   double k[S];
   k[0] = k1;
-  double in = y;
 #pragma unroll
-  for (int s = 2; s <= S; ++s) {
-    double acc = 0.0;
-    bool have = false;
-#pragma unroll
-    for (int j = 0; j < s - 1; ++j) {
-      if ((a.amask[s - 2] >> j) & 1u) {
-        const double p = __dmul_rn(k[j], a.a[s - 2][j]);
-        acc = have ? __dadd_rn(acc, p) : p;
-        have = true;
-      }
-    }
-    in = __dadd_rn(y, __dmul_rn(acc, a.dt));
-    k[s - 1] = pointwise_rhs<KIND>(in, lam, a.rhs_scalar, a.negate != 0);
-  }
+  for (int j = 1; j < S; ++j) k[j] = 0.0;
+  const double in = FusedStages<PAT, KIND, S>::run(y, lam, a, k);
   ks = k[S - 1];
-  if (YNEW_IS_LAST) ynew = in;
-  else ynew = __dadd_rn(y, __dmul_rn(masked_wsum<S>(k, a.b, a.bmask), a.cb));
-  const double lo = __dmul_rn(masked_wsum<S>(k, a.bh, a.bhmask), a.cbh);
+  if (Pattern<PAT>::last) ynew = in;
+  else ynew = __dadd_rn(y, __dmul_rn(const_wsum<S, Pattern<PAT>::b()>(k, a.b), a.cb));
+  const double lo = __dmul_rn(const_wsum<S, Pattern<PAT>::bh()>(k, a.bh), a.cbh);
   double e;
-  if (DIRECT) e = lo;
+  if (Pattern<PAT>::direct) e = lo;
   else e = __dadd_rn(ynew, -__dadd_rn(y, lo));
   const double tol = __dadd_rn(a.absTol, __dmul_rn(fabs(ynew), a.relTol));
   const double r = __ddiv_rn(e, tol);
   return __dmul_rn(r, r);
 }
 
-template <int S, int KIND, bool DIRECT, bool YNEW_IS_LAST, int W, int THREADS>
-__global__ void __launch_bounds__(THREADS) fused_attempt_kernel(const FusedArgs<S> a) {
+template <int PAT, int KIND, int W, int THREADS>
+__global__ void __launch_bounds__(THREADS) fused_attempt_kernel(const FusedArgs<Pattern<PAT>::S> a) {
   const size_t nvec = a.n / W;
   double acc = 0.0;
   for (size_t v = (size_t)blockIdx.x * THREADS + threadIdx.x; v < nvec; v += (size_t)gridDim.x * THREADS) {
@@ -436,8 +503,7 @@ __global__ void __launch_bounds__(THREADS) fused_attempt_kernel(const FusedArgs<
     Pk<W> yo, ko;
 #pragma unroll
     for (int e = 0; e < W; ++e)
-      acc = __dadd_rn(acc, fused_elem<S, KIND, DIRECT, YNEW_IS_LAST>(yv.v[e], kv.v[e], KIND == PW_DIAG ? lv.v[e] : 0.0, a,
-                                                                      yo.v[e], ko.v[e]));
+      acc = __dadd_rn(acc, fused_elem<PAT, KIND>(yv.v[e], kv.v[e], KIND == PW_DIAG ? lv.v[e] : 0.0, a, yo.v[e], ko.v[e]));
     st_stream<W>(a.ynew + v * W, yo);
     st_stream<W>(a.ks_out + v * W, ko);
   }
@@ -445,7 +511,7 @@ __global__ void __launch_bounds__(THREADS) fused_attempt_kernel(const FusedArgs<
     const size_t i = nvec * W + threadIdx.x;
     if (i < a.n) {
       double yn, ks;
-      acc = __dadd_rn(acc, fused_elem<S, KIND, DIRECT, YNEW_IS_LAST>(a.y[i], a.k1[i], KIND == PW_DIAG ? a.lam[i] : 0.0, a, yn, ks));
+      acc = __dadd_rn(acc, fused_elem<PAT, KIND>(a.y[i], a.k1[i], KIND == PW_DIAG ? a.lam[i] : 0.0, a, yn, ks));
       a.ynew[i] = yn;
       a.ks_out[i] = ks;
     }
@@ -455,7 +521,7 @@ __global__ void __launch_bounds__(THREADS) fused_attempt_kernel(const FusedArgs<
 
 // Fused RK4 step for element-local right-hand sides (ode.nim:180-189): reads y (+ lambda), writes yNew.
 template <int KIND>
-__device__ __forceinline__ double fused_rk4_elem(double y, double lam, double c, bool neg, double hdt, double dt, double c6) {
+__device__ __forceinline__ double fused_rk4_elem(double y, double lam, double c, double neg, double hdt, double dt, double c6) {
   const double k1 = pointwise_rhs<KIND>(y, lam, c, neg);
   const double k2 = pointwise_rhs<KIND>(__dadd_rn(y, __dmul_rn(k1, hdt)), lam, c, neg);
   const double k3 = pointwise_rhs<KIND>(__dadd_rn(y, __dmul_rn(k2, hdt)), lam, c, neg);
@@ -464,7 +530,7 @@ __device__ __forceinline__ double fused_rk4_elem(double y, double lam, double c,
 }
 template <int KIND, int W, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-    fused_rk4_kernel(const double* __restrict__ y, const double* __restrict__ lam, double c, int negate, double hdt,
+    fused_rk4_kernel(const double* __restrict__ y, const double* __restrict__ lam, double c, double sgn, double hdt,
                      double dt, double c6, double* __restrict__ out, size_t n) {
   const size_t nvec = n / W;
   for (size_t v = (size_t)blockIdx.x * THREADS + threadIdx.x; v < nvec; v += (size_t)gridDim.x * THREADS) {
@@ -473,12 +539,12 @@ __global__ void __launch_bounds__(THREADS)
     if (KIND == PW_DIAG) lv = ld_stream<W>(lam + v * W);
     Pk<W> o;
 #pragma unroll
-    for (int e = 0; e < W; ++e) o.v[e] = fused_rk4_elem<KIND>(yv.v[e], KIND == PW_DIAG ? lv.v[e] : 0.0, c, negate != 0, hdt, dt, c6);
+    for (int e = 0; e < W; ++e) o.v[e] = fused_rk4_elem<KIND>(yv.v[e], KIND == PW_DIAG ? lv.v[e] : 0.0, c, sgn, hdt, dt, c6);
     st_stream<W>(out + v * W, o);
   }
   if (blockIdx.x == 0) {
     const size_t i = nvec * W + threadIdx.x;
-    if (i < n) out[i] = fused_rk4_elem<KIND>(y[i], KIND == PW_DIAG ? lam[i] : 0.0, c, negate != 0, hdt, dt, c6);
+    if (i < n) out[i] = fused_rk4_elem<KIND>(y[i], KIND == PW_DIAG ? lam[i] : 0.0, c, sgn, hdt, dt, c6);
   }
 }
 

@@ -46,6 +46,11 @@ struct b200rk_ctx {
   double* d_result = nullptr;   // device scalar (allreduce buffer)
   double* h_result = nullptr;   // pinned + mapped host scalar
   double* h_result_dev = nullptr;  // device alias of h_result
+  double* d_halo = nullptr;        // 3 doubles: stencil halo of the sharded Lorenz-96 right-hand side
+  unsigned long long* h_seq = nullptr;      // pinned + mapped: sequence word of the last finished reduction
+  unsigned long long* h_seq_dev = nullptr;  // device alias
+  unsigned long long seq = 0;               // last sequence number handed to a reducing launch
+  bool spin_readback = true;                // poll h_seq instead of cudaStreamSynchronize (single GPU)
   // workspace pool (free vectors by global length)
   std::vector<b200rk_vec*> pool;
   size_t pool_budget_bytes = (size_t)48 << 30;
@@ -53,7 +58,7 @@ struct b200rk_ctx {
   int vec_width = 4;
   int ctas_per_sm = 0;         // stage/element-wise kernels: 0 = one tile per CTA (measured best, profiles/)
   int finish_ctas_per_sm = 2;  // reducing kernels: persistent grid, one partial per CTA (measured best)
-  int fused_ctas_per_sm = 2;   // fused pointwise attempt kernel
+  int fused_ctas_per_sm = 4;   // fused pointwise attempt kernel (54 registers -> 4 CTAs/SM resident; measured best)
   bool fuse_pointwise = true;  // element-local built-in RHS: whole attempt in one kernel
   bool strict_zeros = false;
   bool profile = false;
@@ -109,6 +114,10 @@ struct NcclApi {
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   ncclResult_t (*GetVersion)(int*) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   std::string where;
 };
 static NcclApi g_nccl;
@@ -130,7 +139,12 @@ static int nccl_bind(const b200rk_ctx* ctx) {
   a.AllReduce = (decltype(a.AllReduce))dlsym(h, "ncclAllReduce");
   a.GetErrorString = (decltype(a.GetErrorString))dlsym(h, "ncclGetErrorString");
   a.GetVersion = (decltype(a.GetVersion))dlsym(h, "ncclGetVersion");
-  if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce || !a.GetErrorString)
+  a.Send = (decltype(a.Send))dlsym(h, "ncclSend");
+  a.Recv = (decltype(a.Recv))dlsym(h, "ncclRecv");
+  a.GroupStart = (decltype(a.GroupStart))dlsym(h, "ncclGroupStart");
+  a.GroupEnd = (decltype(a.GroupEnd))dlsym(h, "ncclGroupEnd");
+  if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce || !a.GetErrorString || !a.Send || !a.Recv ||
+      !a.GroupStart || !a.GroupEnd)
     return fail(ctx, B200RK_ENCCL, "libnccl.so.2 lacks a required symbol");
   g_nccl = a;
   return B200RK_OK;
@@ -238,6 +252,8 @@ static ReduceScratch reduce_scratch(b200rk_ctx* c) {
   rs.ticket = c->d_ticket;
   rs.result = c->d_result;
   rs.result_host = (c->world == 1) ? c->h_result_dev : nullptr;
+  rs.seq_host = c->h_seq_dev;
+  rs.seq = ++c->seq;
   return rs;
 }
 
@@ -297,13 +313,33 @@ static int launch_finish(b200rk_ctx* c, const FinishPlan& p) {
 }
 
 // After a reducing kernel: (allreduce across shards) and bring the scalar to the host.
+// Single GPU: the last CTA of the kernel wrote the sum and then the launch's sequence number into mapped
+// pinned memory; the host polls that word (~2 us) instead of paying a stream synchronisation (~6-8 us) per
+// attempt. A stuck or faulted kernel is caught by the bounded spin falling back to cudaStreamSynchronize.
 static int fetch_global_sum(b200rk_ctx* c, double* out) {
   if (c->world > 1) {
     NCCL_TRY(c, g_nccl.AllReduce(c->d_result, c->d_result, 1, ncclDouble, ncclSum, c->comm, c->stream));
     c->collectives++;
     CUDA_TRY(c, cudaMemcpyAsync(c->h_result, c->d_result, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    *out = *(volatile double*)c->h_result;
+    return B200RK_OK;
   }
-  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (c->spin_readback) {
+    const unsigned long long want = c->seq;
+    volatile unsigned long long* flag = c->h_seq;
+    for (long spins = 0; *flag != want; ++spins) {
+      __builtin_ia32_pause();
+      if (spins > 2000000L) {  // ~10 ms: far beyond any kernel of this path at sane sizes -> blocking wait
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        if (*flag != want) return fail(c, B200RK_ECUDA, "reduction result never arrived");
+        break;
+      }
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+  } else {
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  }
   *out = *(volatile double*)c->h_result;
   return B200RK_OK;
 }
@@ -390,11 +426,27 @@ static int builtin_rhs_fn(double /*t*/, const b200rk_vec* y, b200rk_vec* dydt, v
       TRY(check_same(c, y, r->lambda));
       return launch_ewise<EW_NEG_HMUL>(c, r->lambda->d, y->d, 0.0, dydt->d, n, B200RK_K_RHS);
     case B200RK_RHS_LORENZ96: {
-      if (c->world != 1) return fail(c, B200RK_EINVAL, "lorenz96: sharded halo exchange is not implemented");
-      if (n < 4) return fail(c, B200RK_EINVAL, "lorenz96 needs n >= 4");
+      if (y->n_global < 4) return fail(c, B200RK_EINVAL, "lorenz96 needs n >= 4");
+      const double *left2 = y->d + n - 2, *right1 = y->d;  // single GPU: the cyclic neighbours are in the vector itself
+      if (c->world > 1) {
+        // Sharded stencil: 3-element halo per evaluation over NVLink. Each rank sends its
+        // first element to the left neighbour and its last two to the right neighbour (ring), on the
+        // context stream, so the exchange is ordered with the producing and consuming kernels.
+        if (n < 2) return fail(c, B200RK_EINVAL, "lorenz96: every shard needs at least 2 elements");
+        const int left = (c->rank + c->world - 1) % c->world, right = (c->rank + 1) % c->world;
+        NCCL_TRY(c, g_nccl.GroupStart());
+        NCCL_TRY(c, g_nccl.Send(y->d, 1, ncclDouble, left, c->comm, c->stream));
+        NCCL_TRY(c, g_nccl.Send(y->d + n - 2, 2, ncclDouble, right, c->comm, c->stream));
+        NCCL_TRY(c, g_nccl.Recv(c->d_halo + 2, 1, ncclDouble, right, c->comm, c->stream));
+        NCCL_TRY(c, g_nccl.Recv(c->d_halo, 2, ncclDouble, left, c->comm, c->stream));
+        NCCL_TRY(c, g_nccl.GroupEnd());
+        c->collectives++;
+        left2 = c->d_halo;
+        right1 = c->d_halo + 2;
+      }
       ProfScope ps(c, B200RK_K_RHS, 8.0 * double(n) * 2);
       unsigned grid = grid_for(c, n / 2, kThreads);
-      lorenz96_kernel<kThreads><<<grid, kThreads, 0, c->stream>>>(y->d, y->d + n - 2, y->d, r->scalar, dydt->d, n);
+      lorenz96_kernel<kThreads><<<grid, kThreads, 0, c->stream>>>(y->d, left2, right1, r->scalar, dydt->d, n);
       CUDA_TRY(c, cudaGetLastError());
       return B200RK_OK;
     }
@@ -923,8 +975,13 @@ static int ctx_common_init(b200rk_ctx* c) {
   CUDA_TRY(c, cudaMalloc(&c->d_ticket, sizeof(unsigned int)));
   CUDA_TRY(c, cudaMemset(c->d_ticket, 0, sizeof(unsigned int)));
   CUDA_TRY(c, cudaMalloc(&c->d_result, sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->d_halo, 4 * sizeof(double)));
   CUDA_TRY(c, cudaHostAlloc(&c->h_result, sizeof(double), cudaHostAllocMapped));
   CUDA_TRY(c, cudaHostGetDevicePointer(&c->h_result_dev, c->h_result, 0));
+  CUDA_TRY(c, cudaHostAlloc(&c->h_seq, sizeof(unsigned long long), cudaHostAllocMapped));
+  *c->h_seq = 0;
+  CUDA_TRY(c, cudaHostGetDevicePointer(&c->h_seq_dev, c->h_seq, 0));
+  if (const char* e = getenv("B200RK_SPIN_READBACK")) c->spin_readback = atoi(e) != 0;
   TRY(ensure_partials(c, 1));
   if (const char* e = getenv("B200RK_VEC_WIDTH")) c->vec_width = (atoi(e) == 2) ? 2 : 4;
   if (const char* e = getenv("B200RK_CTAS_PER_SM")) c->ctas_per_sm = std::max(0, atoi(e));
@@ -981,7 +1038,7 @@ void b200rk_destroy(b200rk_ctx* c) {
   for (auto& r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : c->ev_free) cudaEventDestroy(e);
   if (c->comm) g_nccl.CommDestroy(c->comm);
-  cudaFree(c->d_partials); cudaFree(c->d_ticket); cudaFree(c->d_result); cudaFreeHost(c->h_result);
+  cudaFree(c->d_partials); cudaFree(c->d_ticket); cudaFree(c->d_result); cudaFree(c->d_halo); cudaFreeHost(c->h_result); cudaFreeHost(c->h_seq);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -999,6 +1056,7 @@ int b200rk_set(b200rk_ctx* c, const char* key, int64_t v) {
   else if (k == "finish_ctas_per_sm") { if (v < 0) return fail(c, B200RK_EINVAL, "finish_ctas_per_sm must be >= 0"); c->finish_ctas_per_sm = (int)v; }
   else if (k == "profile") c->profile = v != 0;
   else if (k == "fuse_pointwise") c->fuse_pointwise = v != 0;
+  else if (k == "spin_readback") c->spin_readback = v != 0;
   else if (k == "fused_ctas_per_sm") { if (v < 0) return fail(c, B200RK_EINVAL, "fused_ctas_per_sm must be >= 0"); c->fused_ctas_per_sm = (int)v; }
   else if (k == "pool_budget_mb") {
     c->pool_budget_bytes = (size_t)std::max<int64_t>(0, v) << 20;
@@ -1018,6 +1076,7 @@ int b200rk_get(const b200rk_ctx* c, const char* key, int64_t* v) {
   else if (k == "ctas_per_sm") *v = c->ctas_per_sm;
   else if (k == "finish_ctas_per_sm") *v = c->finish_ctas_per_sm;
   else if (k == "fuse_pointwise") *v = c->fuse_pointwise;
+  else if (k == "spin_readback") *v = c->spin_readback;
   else if (k == "fused_ctas_per_sm") *v = c->fused_ctas_per_sm;
   else if (k == "profile") *v = c->profile;
   else if (k == "sm_count") *v = c->sm_count;

@@ -212,6 +212,8 @@ struct ReduceScratch {
   unsigned int* ticket;    // zero before launch; reset to zero by the last block
   double* result;          // device scalar
   double* result_host;     // optional zero-copy mirror (mapped pinned host memory), may be null
+  unsigned long long* seq_host;  // mapped pinned host word: set to `seq` after result_host is visible
+  unsigned long long seq;        // launch sequence number the host spins on (no cudaStreamSynchronize)
 };
 
 template <int THREADS>
@@ -250,8 +252,12 @@ __device__ __forceinline__ void grid_sum_finish(double thread_val, const ReduceS
     const double total = block_sum<THREADS>(acc);
     if (threadIdx.x == 0) {
       *rs.result = total;
-      if (rs.result_host) *rs.result_host = total;
       *rs.ticket = 0u;
+      if (rs.result_host) {
+        *(volatile double*)rs.result_host = total;
+        __threadfence_system();  // the value is visible to the host before the sequence word
+        *(volatile unsigned long long*)rs.seq_host = rs.seq;
+      }
       __threadfence_system();
     }
   }
@@ -495,17 +501,35 @@ __device__ __forceinline__ double fused_elem(double y, double k1, double lam, co
 template <int PAT, int KIND, int W, int THREADS>
 __global__ void __launch_bounds__(THREADS) fused_attempt_kernel(const FusedArgs<Pattern<PAT>::S> a) {
   const size_t nvec = a.n / W;
+  const size_t stride = (size_t)gridDim.x * THREADS;
   double acc = 0.0;
-  for (size_t v = (size_t)blockIdx.x * THREADS + threadIdx.x; v < nvec; v += (size_t)gridDim.x * THREADS) {
-    const Pk<W> yv = ld_stream<W>(a.y + v * W), kv = ld_stream<W>(a.k1 + v * W);
-    Pk<W> lv;
+  // Software-pipelined grid-stride loop: the loads of the next tile are issued before the ~100 dependent
+  // fp64 operations of the current one, so HBM latency hides under arithmetic even at 16-32 warps/SM
+  // (the kernel is close to balanced: ~46 us of fp64 pipe vs ~51 us of HBM traffic per 2^23 elements).
+  size_t v = (size_t)blockIdx.x * THREADS + threadIdx.x;
+  Pk<W> yv, kv, lv;
+  if (v < nvec) {
+    yv = ld_stream<W>(a.y + v * W);
+    kv = ld_stream<W>(a.k1 + v * W);
     if (KIND == PW_DIAG) lv = ld_stream<W>(a.lam + v * W);
+  }
+  while (v < nvec) {
+    const size_t vn = v + stride;
+    Pk<W> yn_, kn_, ln_;
+    if (vn < nvec) {
+      yn_ = ld_stream<W>(a.y + vn * W);
+      kn_ = ld_stream<W>(a.k1 + vn * W);
+      if (KIND == PW_DIAG) ln_ = ld_stream<W>(a.lam + vn * W);
+    }
     Pk<W> yo, ko;
 #pragma unroll
     for (int e = 0; e < W; ++e)
       acc = __dadd_rn(acc, fused_elem<PAT, KIND>(yv.v[e], kv.v[e], KIND == PW_DIAG ? lv.v[e] : 0.0, a, yo.v[e], ko.v[e]));
     st_stream<W>(a.ynew + v * W, yo);
     st_stream<W>(a.ks_out + v * W, ko);
+    yv = yn_; kv = kn_;
+    if (KIND == PW_DIAG) lv = ln_;
+    v = vn;
   }
   if (blockIdx.x == 0) {
     const size_t i = nvec * W + threadIdx.x;

@@ -48,6 +48,35 @@ def main():
             fails.append((method, st, ref.stats.steps, float(np.max(np.abs(got - exp)))))
         if rank == 0:
             print(f"[multi-gpu world={world}] {method}: steps={st['steps']} attempts={st['attempts']} collectives={st['collectives']} ok={ok}", flush=True)
+    # the fused element-local path and the pipeline must agree bit for bit on every shard (fixed step)
+    res = {}
+    for fuse in (1, 0):
+        ctx.set("fuse_pointwise", fuse)
+        t, ys = nn.solveODE(nn.rhsDiagLinear(glam), gy0, [0.0, 0.2], nn.newODEoptions(dt=5e-3), integrator="rk4")
+        res[fuse] = ys[-1].local_numpy()
+    ctx.set("fuse_pointwise", 1)
+    if not np.array_equal(res[0].view(np.uint64), res[1].view(np.uint64)):
+        fails.append(("rk4 fused vs pipeline",))
+    # sharded Lorenz-96: 3-element ring halo per right-hand-side evaluation (ncclSend/ncclRecv on the stream)
+    for nl in (1000, 100003):
+        yl = 8.0 + 0.01 * np.sin(2 * np.pi * 37 * np.arange(nl) / nl)
+        gl = nn.newVector(yl, ctx)
+        lo, ll = gl.local_offset, gl.local_len
+        rhs_l = nn.rhsLorenz96(8.0, ctx)
+        out = gl._new_like()
+        assert rhs_l.fn(0.0, gl._h, out._h, rhs_l.user) == 0
+        exp_k = O.rhs_eval(O.rhs_lorenz96(8.0), 0.0, yl)[lo:lo + ll]
+        if not np.array_equal(out.local_numpy().view(np.uint64), exp_k.view(np.uint64)):
+            fails.append(("lorenz96 rhs bitwise", nl))
+        refl = O.solve_vector("tsit54", O.rhs_lorenz96(8.0), yl, [0.0, 0.5], O.new_options(**kw))
+        t, ys = nn.solveODE(rhs_l, gl, [0.0, 0.5], nn.newODEoptions(**kw), integrator="tsit54")
+        st = dict(nn.ode.last_stats)
+        got, exp = ys[-1].local_numpy(), refl.y[-1][lo:lo + ll]
+        ok = bool(np.all(np.abs(got - exp) <= 1e-7 * np.abs(exp))) and st["steps"] == refl.stats.steps and st["rejected"] == refl.stats.rejected
+        if not ok:
+            fails.append(("lorenz96 tsit54", nl, st, refl.stats.steps, float(np.max(np.abs(got - exp)))))
+        if rank == 0:
+            print(f"[multi-gpu world={world}] lorenz96 n={nl} tsit54: steps={st['steps']} rejected={st['rejected']} collectives={st['collectives']} ok={ok}", flush=True)
     # sharded sum(v) goes through the same allreduce
     s = gy0.sum()
     assert abs(s - O.vector_sum(y0)) <= 1e-12 * np.abs(y0).sum(), (s, O.vector_sum(y0))

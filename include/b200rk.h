@@ -14,7 +14,10 @@
  *     host (step, solve, sum) synchronise that stream, the others do not.
  *   - one context = one GPU = one host thread. Multi-GPU = one process (rank) per GPU; a vector of
  *     global length N is sharded contiguously, rank r owning [r*chunk, min(N,(r+1)*chunk)), and the only
- *     collective on the path is one ncclAllReduce(sum, 1 x fp64) of the squared error norm per attempt.
+ *     collective on the path is one all-reduce(sum, 1 x fp64) of the squared error norm per attempt. It is
+ *     fused into the reducing kernel: the last CTA stores the shard's partial into every peer's mailbox over
+ *     NVLink (CUDA-IPC mapped peer memory) and adds the `world` partials in rank order. If the mailboxes
+ *     cannot be mapped (or B200RK_P2P=0) every rank falls back to one ncclAllReduce per attempt.
  *   - step functions never write their inputs; outputs must not alias inputs.
  */
 #ifndef B200RK_H

@@ -51,6 +51,12 @@ struct b200rk_ctx {
   unsigned long long* h_seq_dev = nullptr;  // device alias
   unsigned long long seq = 0;               // last sequence number handed to a reducing launch
   bool spin_readback = true;                // poll h_seq instead of cudaStreamSynchronize (single GPU)
+  // in-kernel all-reduce of the error norm over peer mailboxes (multi-GPU)
+  unsigned long long* d_mail = nullptr;     // this rank's mailbox
+  unsigned long long* peer_mail[kMaxPeers] = {nullptr};
+  bool peer_opened[kMaxPeers] = {false};
+  bool p2p = false;
+  std::string p2p_note;
   // workspace pool (free vectors by global length)
   std::vector<b200rk_vec*> pool;
   size_t pool_budget_bytes = (size_t)48 << 30;
@@ -118,6 +124,7 @@ struct NcclApi {
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   std::string where;
 };
 static NcclApi g_nccl;
@@ -143,8 +150,9 @@ static int nccl_bind(const b200rk_ctx* ctx) {
   a.Recv = (decltype(a.Recv))dlsym(h, "ncclRecv");
   a.GroupStart = (decltype(a.GroupStart))dlsym(h, "ncclGroupStart");
   a.GroupEnd = (decltype(a.GroupEnd))dlsym(h, "ncclGroupEnd");
+  a.AllGather = (decltype(a.AllGather))dlsym(h, "ncclAllGather");
   if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce || !a.GetErrorString || !a.Send || !a.Recv ||
-      !a.GroupStart || !a.GroupEnd)
+      !a.GroupStart || !a.GroupEnd || !a.AllGather)
     return fail(ctx, B200RK_ENCCL, "libnccl.so.2 lacks a required symbol");
   g_nccl = a;
   return B200RK_OK;
@@ -251,10 +259,64 @@ static ReduceScratch reduce_scratch(b200rk_ctx* c) {
   rs.partials = c->d_partials;
   rs.ticket = c->d_ticket;
   rs.result = c->d_result;
-  rs.result_host = (c->world == 1) ? c->h_result_dev : nullptr;
+  const bool in_kernel_collective = c->world > 1 && c->p2p;
+  rs.result_host = (c->world == 1 || in_kernel_collective) ? c->h_result_dev : nullptr;
   rs.seq_host = c->h_seq_dev;
   rs.seq = ++c->seq;
+  rs.mail.world = in_kernel_collective ? c->world : 1;
+  rs.mail.rank = c->rank;
+  for (int p = 0; p < kMaxPeers; ++p) rs.mail.box[p] = (in_kernel_collective && p < c->world) ? c->peer_mail[p] : nullptr;
+  if (in_kernel_collective) c->collectives++;
   return rs;
+}
+
+// Peer mailboxes for the in-kernel all-reduce of the error norm (kernels.cuh: peer_allreduce). Every rank
+// cudaMalloc's a 512-byte mailbox, the CUDA-IPC handles travel through one ncclAllGather on the
+// communicator we already have, and each rank maps its peers' mailboxes (NVLink/NVSwitch peer access). The
+// outcome is agreed by an ncclAllReduce(min): either every rank uses the mailboxes or every rank falls back to
+// ncclAllReduce per attempt.
+static int setup_p2p(b200rk_ctx* c) {
+  c->p2p = false;
+  if (const char* e = getenv("B200RK_P2P")) if (atoi(e) == 0) { c->p2p_note = "disabled by B200RK_P2P=0"; return B200RK_OK; }
+  if (c->world > kMaxPeers) { c->p2p_note = "world larger than kMaxPeers"; return B200RK_OK; }
+  const size_t mail_bytes = 2 * kMaxPeers * 2 * sizeof(unsigned long long);
+  CUDA_TRY(c, cudaMalloc(&c->d_mail, mail_bytes));
+  CUDA_TRY(c, cudaMemset(c->d_mail, 0, mail_bytes));
+  cudaIpcMemHandle_t mine;
+  int ok = 1;
+  if (cudaIpcGetMemHandle(&mine, c->d_mail) != cudaSuccess) { ok = 0; cudaGetLastError(); std::memset(&mine, 0, sizeof(mine)); }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+  char* d_handles = nullptr;
+  int* d_flag = nullptr;
+  CUDA_TRY(c, cudaMalloc(&d_handles, 64 * (size_t)c->world));
+  CUDA_TRY(c, cudaMalloc(&d_flag, sizeof(int)));
+  CUDA_TRY(c, cudaMemcpyAsync(d_handles + 64 * (size_t)c->rank, &mine, 64, cudaMemcpyHostToDevice, c->stream));
+  NCCL_TRY(c, g_nccl.AllGather(d_handles + 64 * (size_t)c->rank, d_handles, 64, ncclChar, c->comm, c->stream));
+  std::vector<cudaIpcMemHandle_t> all(c->world);
+  CUDA_TRY(c, cudaMemcpyAsync(all.data(), d_handles, 64 * (size_t)c->world, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  for (int p = 0; p < c->world && ok; ++p) {
+    if (p == c->rank) { c->peer_mail[p] = c->d_mail; continue; }
+    void* ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      c->p2p_note = std::string("cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(cudaGetLastError());
+      ok = 0;
+    } else {
+      c->peer_mail[p] = static_cast<unsigned long long*>(ptr);
+      c->peer_opened[p] = true;
+    }
+  }
+  CUDA_TRY(c, cudaMemcpyAsync(d_flag, &ok, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  NCCL_TRY(c, g_nccl.AllReduce(d_flag, d_flag, 1, ncclInt, ncclMin, c->comm, c->stream));
+  int agreed = 0;
+  CUDA_TRY(c, cudaMemcpyAsync(&agreed, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  cudaFree(d_handles);
+  cudaFree(d_flag);
+  c->p2p = agreed != 0;
+  if (c->p2p) c->p2p_note = "peer mailboxes mapped over CUDA IPC";
+  else if (c->p2p_note.empty()) c->p2p_note = "a peer could not map the mailboxes";
+  return B200RK_OK;
 }
 
 struct FinishPlan {
@@ -317,7 +379,7 @@ static int launch_finish(b200rk_ctx* c, const FinishPlan& p) {
 // pinned memory; the host polls that word (~2 us) instead of paying a stream synchronisation (~6-8 us) per
 // attempt. A stuck or faulted kernel is caught by the bounded spin falling back to cudaStreamSynchronize.
 static int fetch_global_sum(b200rk_ctx* c, double* out) {
-  if (c->world > 1) {
+  if (c->world > 1 && !c->p2p) {  // fallback: one ncclAllReduce(sum, 1 x f64) per attempt + 8-byte D2H
     NCCL_TRY(c, g_nccl.AllReduce(c->d_result, c->d_result, 1, ncclDouble, ncclSum, c->comm, c->stream));
     c->collectives++;
     CUDA_TRY(c, cudaMemcpyAsync(c->h_result, c->d_result, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -325,14 +387,15 @@ static int fetch_global_sum(b200rk_ctx* c, double* out) {
     *out = *(volatile double*)c->h_result;
     return B200RK_OK;
   }
+  // single GPU, or sharded with the all-reduce done inside the kernel over the peer mailboxes
+  const unsigned long long want = c->seq;
+  volatile unsigned long long* flag = c->h_seq;
   if (c->spin_readback) {
-    const unsigned long long want = c->seq;
-    volatile unsigned long long* flag = c->h_seq;
-    for (long spins = 0; *flag != want; ++spins) {
+    for (long spins = 0; (*flag & ~kPeerTimeoutFlag) != want; ++spins) {
       __builtin_ia32_pause();
       if (spins > 2000000L) {  // ~10 ms: far beyond any kernel of this path at sane sizes -> blocking wait
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-        if (*flag != want) return fail(c, B200RK_ECUDA, "reduction result never arrived");
+        if ((*flag & ~kPeerTimeoutFlag) != want) return fail(c, B200RK_ECUDA, "reduction result never arrived");
         break;
       }
     }
@@ -340,6 +403,7 @@ static int fetch_global_sum(b200rk_ctx* c, double* out) {
   } else {
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   }
+  if (*flag & kPeerTimeoutFlag) return fail(c, B200RK_ENCCL, "peer mailbox all-reduce timed out: a rank did not publish its partial sum");
   *out = *(volatile double*)c->h_result;
   return B200RK_OK;
 }
@@ -1024,6 +1088,7 @@ int b200rk_init_distributed(b200rk_ctx** out, int device, int rank, int world, c
       ncclResult_t e = g_nccl.CommInitRank(&c->comm, world, id, rank);
       if (e != ncclSuccess) rc = fail(c, B200RK_ENCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(e));
     }
+    if (rc == B200RK_OK) rc = setup_p2p(c);
   }
   if (rc != B200RK_OK) { g_thread_err = c->err; delete c; return rc; }
   *out = c;
@@ -1037,6 +1102,8 @@ void b200rk_destroy(b200rk_ctx* c) {
   for (auto* v : c->pool) { cudaFree(v->d); delete v; }
   for (auto& r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : c->ev_free) cudaEventDestroy(e);
+  for (int p = 0; p < kMaxPeers; ++p) if (c->peer_opened[p]) cudaIpcCloseMemHandle(c->peer_mail[p]);
+  if (c->d_mail) cudaFree(c->d_mail);
   if (c->comm) g_nccl.CommDestroy(c->comm);
   cudaFree(c->d_partials); cudaFree(c->d_ticket); cudaFree(c->d_result); cudaFree(c->d_halo); cudaFreeHost(c->h_result); cudaFreeHost(c->h_seq);
   cudaStreamDestroy(c->stream);
@@ -1077,6 +1144,7 @@ int b200rk_get(const b200rk_ctx* c, const char* key, int64_t* v) {
   else if (k == "finish_ctas_per_sm") *v = c->finish_ctas_per_sm;
   else if (k == "fuse_pointwise") *v = c->fuse_pointwise;
   else if (k == "spin_readback") *v = c->spin_readback;
+  else if (k == "p2p") *v = c->p2p;
   else if (k == "fused_ctas_per_sm") *v = c->fused_ctas_per_sm;
   else if (k == "profile") *v = c->profile;
   else if (k == "sm_count") *v = c->sm_count;

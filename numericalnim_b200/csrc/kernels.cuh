@@ -207,6 +207,22 @@ __global__ void __launch_bounds__(THREADS)
 // Deterministic sum reduction: warp shuffle -> shared -> one partial per block -> the last block to
 // finish (atomic ticket) adds the partials in index order. No floating-point atomics anywhere.
 // ---------------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 16;
+
+// Peer mailboxes for the sharded error norm: the collective is fused INTO the reducing kernel. Every rank
+// owns a small device buffer that all peers have mapped (CUDA IPC, NVLink/NVSwitch peer stores); the last
+// CTA of a rank's kernel stores its shard's partial sum and the launch sequence number into slot [rank] of
+// every peer's mailbox, then waits until the `world` slots of its own mailbox carry this sequence number
+// and adds them in rank order — the same order on every rank, so all ranks obtain the identical bits and
+// take the identical accept/reject decision. 8 bytes per peer per attempt: pure latency, no NCCL launch,
+// no separate kernel, no host round trip beyond the read-back the single-GPU path already has.
+struct PeerMail {
+  int world;   // <= 1: no exchange
+  int rank;
+  unsigned long long* box[kMaxPeers];  // box[p] = base of rank p's mailbox: [2 parities][kMaxPeers][2] words
+};
+constexpr unsigned long long kPeerTimeoutFlag = 1ull << 63;
+
 struct ReduceScratch {
   double* partials;        // gridDim.x doubles
   unsigned int* ticket;    // zero before launch; reset to zero by the last block
@@ -214,7 +230,44 @@ struct ReduceScratch {
   double* result_host;     // optional zero-copy mirror (mapped pinned host memory), may be null
   unsigned long long* seq_host;  // mapped pinned host word: set to `seq` after result_host is visible
   unsigned long long seq;        // launch sequence number the host spins on (no cudaStreamSynchronize)
+  PeerMail mail;
 };
+
+// Runs in the last CTA only (all threads): exchange `local` with the peers, return the global sum in thread 0.
+template <int THREADS>
+__device__ __forceinline__ double peer_allreduce(double local, const ReduceScratch& rs, bool* timed_out) {
+  __shared__ double peer_vals[kMaxPeers];
+  __shared__ int peer_bad;
+  const int q = threadIdx.x;
+  const int world = rs.mail.world, rank = rs.mail.rank;
+  const unsigned long long par = rs.seq & 1ull;
+  if (q == 0) peer_bad = 0;
+  __syncthreads();
+  if (q < world) {
+    // publish into peer q's mailbox (for q == rank this is a local store)
+    volatile unsigned long long* dst = rs.mail.box[q] + ((par * kMaxPeers + rank) << 1);
+    dst[1] = (unsigned long long)__double_as_longlong(local);
+    __threadfence_system();
+    dst[0] = rs.seq;
+    // gather slot q of my own mailbox
+    volatile unsigned long long* src = rs.mail.box[rank] + ((par * kMaxPeers + q) << 1);
+    const long long t0 = clock64();
+    bool ok = true;
+    while (src[0] != rs.seq) {
+      if (clock64() - t0 > (2ll << 30)) { ok = false; break; }  // ~1 s: a peer died; report instead of hanging
+    }
+    __threadfence_system();
+    peer_vals[q] = ok ? __longlong_as_double((long long)src[1]) : 0.0;
+    if (!ok) atomicExch(&peer_bad, 1);
+  }
+  __syncthreads();
+  double total = 0.0;
+  if (q == 0) {
+    for (int p = 0; p < world; ++p) total = __dadd_rn(total, peer_vals[p]);  // rank order: identical on every rank
+    *timed_out = peer_bad != 0;
+  }
+  return total;
+}
 
 template <int THREADS>
 __device__ __forceinline__ double block_sum(double v) {
@@ -249,14 +302,21 @@ __device__ __forceinline__ void grid_sum_finish(double thread_val, const ReduceS
     __threadfence();
     double acc = 0.0;
     for (unsigned int i = threadIdx.x; i < gridDim.x; i += THREADS) acc = __dadd_rn(acc, __ldcg(rs.partials + i));
-    const double total = block_sum<THREADS>(acc);
+    double total = block_sum<THREADS>(acc);
+    bool timed_out = false;
+    if (rs.mail.world > 1) {  // sharded: all-reduce the scalar over the peers' mailboxes, inside this kernel
+      __shared__ double local_total;
+      if (threadIdx.x == 0) local_total = total;
+      __syncthreads();
+      total = peer_allreduce<THREADS>(local_total, rs, &timed_out);
+    }
     if (threadIdx.x == 0) {
       *rs.result = total;
       *rs.ticket = 0u;
       if (rs.result_host) {
         *(volatile double*)rs.result_host = total;
         __threadfence_system();  // the value is visible to the host before the sequence word
-        *(volatile unsigned long long*)rs.seq_host = rs.seq;
+        *(volatile unsigned long long*)rs.seq_host = timed_out ? (rs.seq | kPeerTimeoutFlag) : rs.seq;
       }
       __threadfence_system();
     }

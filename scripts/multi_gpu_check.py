@@ -23,6 +23,8 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = D.init_context(local)
     assert (ctx.rank, ctx.world) == (rank, world)
+    if rank == 0:
+        print(f"[multi-gpu world={world}] error-norm all-reduce: {'in-kernel peer mailboxes (NVLink, CUDA IPC)' if ctx.get('p2p') else 'ncclAllReduce'}", flush=True)
     n = 100003
     lam = 0.1 + 9.9 * np.arange(n) / (n - 1)
     y0 = 1.0 + 0.5 * np.sin(2 * np.pi * np.arange(n) / n)

@@ -96,6 +96,21 @@ def main():
     for m in ("dopri54", "tsit54", "vern65", "rk4"):
         add(f"dense_diag8_{m}", m, {"kind": "diag", "lam": hexlist(lam8)}, R.rhs_diag(lam8), [1.0 + 0.1 * i for i in range(8)], tsd,
             dict(absTol=1e-6, relTol=1e-6, dtMax=0.5, dtMin=1e-8, dt=1e-2), True)
+    # edge cases of the driver's tspan handling (ode.nim:476-487, 499-502, 542, 585-586)
+    optE = dict(absTol=1e-6, relTol=1e-6, dtMax=0.25, dtMin=1e-8, dt=1e-2)
+    y0e = [1.0 + 0.1 * i for i in range(8)]
+    edge = {
+        "only_tstart": ([0.0], {}),                         # nothing to integrate: returns (tStart, y0)
+        "tstart_inside_not_listed": ([0.0, 0.5, 1.0], dict(tStart=0.25)),   # both directions, tZero empty, dense
+        "duplicates": ([0.0, 1.0, 1.0, 2.0], {}),           # dense loop emits the duplicate, final add(y) adds one more
+        "negative_only_len2": ([-1.0, -0.5], {}),           # len 2 => no dense: 2 times, 1 state
+        "straddle_len2": ([-0.5, 0.5], {}),                 # len 2, tStart between: one state per direction
+        "unsorted": ([1.0, -1.0, 0.0, 0.5], {}),            # sorted by solveODE (ode.nim:609)
+        "nonzero_tstart_listed": ([1.0, 1.5, 2.0], dict(tStart=1.0)),
+    }
+    for ename, (ts, extra) in edge.items():
+        for m in ("tsit54", "rk4"):
+            add(f"edge_{ename}_{m}", m, {"kind": "diag", "lam": hexlist(lam8)}, R.rhs_diag(lam8), y0e, ts, dict(optE, **extra), True)
     with open(os.path.join(HERE, "trajectories.json"), "w") as fh:
         json.dump(cases, fh, indent=0, sort_keys=True)
     print("wrote", len(tabs), "tableaux and", len(cases), "trajectories")

@@ -171,6 +171,7 @@ def run_ours(args):
         """W untimed + K timed accepted steps with the given fuse_pointwise setting; device time (CUDA events on
         the library stream), max over ranks; per-kernel-class event times from the library's profiler."""
         ctx.set("fuse_pointwise", fuse)
+        ctx.set("fuse_stencil", fuse)
         ctx.set("profile", 0)
         solver = nn.Solver(integrator, rhs, gy0, 1e12, opts)
         solver.advance(args.warmup)
@@ -210,10 +211,13 @@ def run_ours(args):
                     rejected=st1["rejected"] - st0["rejected"], launches=cs1["launches"] - cs0["launches"],
                     collectives=cs1["collectives"] - cs0["collectives"], t=t_now_, dt_next=dt_next_)
 
-    fusable = rhs_kind == "diag" and not args.no_fuse
+    # fused paths for built-in right-hand sides: diag-linear (element-local) -> whole attempt in one kernel;
+    # Lorenz-96 on one GPU -> stage accumulate + stencil in one kernel (shared-memory tile)
+    fusable = not args.no_fuse and (rhs_kind == "diag" or world == 1)
     pipe = timed_steps(0)                       # stage / RHS / finish pipeline (what any user closure gets)
     head = timed_steps(1) if fusable else pipe  # headline: the library's default path for this workload
     ctx.set("fuse_pointwise", 1 if fusable else 0)
+    ctx.set("fuse_stencil", 1 if fusable else 0)
     ms, ms_max, prof = head["ms"], head["ms_max"], head["prof"]
     attempts, launches, t_now, dt_next = head["attempts"], head["launches"], head["t"], head["dt_next"]
 
@@ -283,10 +287,23 @@ def run_ours(args):
                     "instrumented_ms_per_step": r["prof"]["instrumented_ms"] / args.steps,
                     "kernel_time_share_of_step": kms / r["prof"]["instrumented_ms"] if r["prof"]["instrumented_ms"] > 0 else None}
 
+        pipeline_obj = None
+        if head is not pipe:
+            pipeline_obj = {"note": "same K steps with the fused paths off: the stage / RHS / finish pipeline every user-supplied right-hand side runs through",
+                            "value": args.steps * world / (pipe["ms_max"] * 1e-3), "ms_per_step": pipe["ms_max"] / args.steps, "attempts": pipe["attempts"],
+                            "gpu_launches": pipe["launches"],
+                            "hbm_gbs_step": ALG_BYTES_PER_ELEM.get(integrator, 0) * n_shard * pipe["attempts"] / (pipe["ms"] * 1e-3) / 1e9,
+                            "roofline": stage_roofline(pipe)}
         if head is pipe:
             roofline = stage_roofline(pipe)
-            pipeline_obj = None
+            path = "stage/RHS/finish pipeline"
+        elif rhs_kind != "diag":
+            roofline = stage_roofline(head)
+            roofline["kernel"] = "stage_l96_kernel<M> (stage accumulate fused with the Lorenz-96 stencil through a shared-memory tile; all %d launches)" % head["prof"]["stage"]["launches"]
+            roofline["traffic"] = traffic_db.get("stage_l96_kernel_%s_2p%d" % (integrator, lg))
+            path = "stage+stencil fused (built-in Lorenz-96), finish kernel"
         else:
+            path = "fused_attempt (element-local built-in RHS)"
             fu = prof["fused"]
             a = gbs(fu)
             roofline = {"bound": "hbm", "kernel": "fused_attempt_kernel<S,RHS> (whole attempt of an element-local IVP in one kernel: all stages, RHS, yNew, error norm)",
@@ -295,18 +312,13 @@ def run_ours(args):
                         "avg_launch_us": 1e3 * fu["ms"] / max(1, fu["launches"]), "algorithmic_bytes_per_launch": fu["bytes"] / max(1, fu["launches"]),
                         "instrumented_ms_per_step": prof["instrumented_ms"] / args.steps,
                         "kernel_time_share_of_step": fu["ms"] / prof["instrumented_ms"] if prof["instrumented_ms"] > 0 else None}
-            pipeline_obj = {"note": "same K steps with fuse_pointwise=0: the stage / RHS / finish pipeline every user-supplied right-hand side runs through",
-                            "value": args.steps * world / (pipe["ms_max"] * 1e-3), "ms_per_step": pipe["ms_max"] / args.steps, "attempts": pipe["attempts"],
-                            "gpu_launches": pipe["launches"],
-                            "hbm_gbs_step": ALG_BYTES_PER_ELEM.get(integrator, 0) * n_shard * pipe["attempts"] / (pipe["ms"] * 1e-3) / 1e9,
-                            "roofline": stage_roofline(pipe)}
         line = {
             "metric": "rk_steps_per_sec", "value": args.steps * world / (ms_max * 1e-3), "unit": "RK steps/s (x 2^%d-element shard, summed over GPUs)" % lg,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "integrator": integrator, "rhs": rhs_kind, "elems_per_gpu": n_shard, "elems_global": n_global,
                        "options": OPTS, "l2": "working set (>= 10 vectors x %d MiB per GPU) exceeds the 126 MB L2; no flush" % (n_shard * 8 >> 20),
-                       "sharding": "contiguous, 1 ncclAllReduce(1 x f64) per attempt" if world > 1 else "single GPU, no collective",
+                       "sharding": "contiguous shards, 1 all-reduce(sum, 1 x f64) of the error norm per attempt" if world > 1 else "single GPU, no collective",
                        "vec_width": ctx.get("vec_width"), "ctas_per_sm": ctx.get("ctas_per_sm"), "finish_ctas_per_sm": ctx.get("finish_ctas_per_sm"),
                        "fuse_pointwise": ctx.get("fuse_pointwise"), "fused_ctas_per_sm": ctx.get("fused_ctas_per_sm"),
                        "spin_readback": ctx.get("spin_readback"),
@@ -314,7 +326,7 @@ def run_ours(args):
             "attempts": attempts, "attempts_per_sec": attempts * world / (ms_max * 1e-3), "rejected": head["rejected"],
             "t_reached": t_now, "dt_next": dt_next,
             "gpu_launches": launches, "collectives": head["collectives"],
-            "path": "fused_attempt (element-local built-in RHS)" if head is not pipe else "stage/RHS/finish pipeline",
+            "path": path,
             "roofline": roofline,
             "pipeline": pipeline_obj,
             "cpu_baseline": cpu,

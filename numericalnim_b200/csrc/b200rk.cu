@@ -66,6 +66,7 @@ struct b200rk_ctx {
   int finish_ctas_per_sm = 2;  // reducing kernels: persistent grid, one partial per CTA (measured best)
   int fused_ctas_per_sm = 4;   // fused pointwise attempt kernel (54 registers -> 4 CTAs/SM resident; measured best)
   bool fuse_pointwise = true;  // element-local built-in RHS: whole attempt in one kernel
+  bool fuse_stencil = true;    // built-in Lorenz-96 (single GPU): stage accumulate + stencil RHS in one kernel
   bool strict_zeros = false;
   bool profile = false;
   // counters
@@ -567,6 +568,43 @@ static int run_row(b200rk_ctx* c, const Row& row, double cfac, bool chain, doubl
   return launch_stage(c, m, y->d, kp, w, cc, chain, out->d, y->n_local);
 }
 
+// Stage row fused with the built-in Lorenz-96 right-hand side (kernels.cuh: stage_l96_kernel): writes
+// k_s = f(stage input) directly; the stage input itself is stored only when `in_out` is given.
+template <int M>
+static int launch_stage_l96_m(b200rk_ctx* c, const double* y, const double* const* kp, const double* w, double cc,
+                              double F, double sgn, double* in_out, double* kout, size_t n) {
+  StageArgs<M> a;
+  a.y = y; a.c = cc; a.out = in_out; a.n = n;
+  for (int j = 0; j < M; ++j) { a.k[j] = kp[j]; a.w[j] = w[j]; }
+  ProfScope ps(c, B200RK_K_STAGE, 8.0 * double(n) * (M + 2 + (in_out ? 1 : 0)));
+  const unsigned grid = (unsigned)((n + kThreads * 4 - 1) / (kThreads * 4));
+  stage_l96_kernel<M, kThreads><<<grid, kThreads, 0, c->stream>>>(a, F, sgn, kout);
+  CUDA_TRY(c, cudaGetLastError());
+  return B200RK_OK;
+}
+static int run_row_l96(b200rk_ctx* c, const Row& row, double cfac, double dt, const b200rk_vec* y, b200rk_vec* const* k,
+                       double F, bool negate, b200rk_vec* in_out, b200rk_vec* kout) {
+  const double* kp[kMaxTerms];
+  double w[kMaxTerms];
+  const int m = gather_row(c, row, k, kp, w);
+  const double cc = (cfac == 1.0) ? dt : cfac * dt;
+  const double sgn = negate ? -1.0 : 1.0;
+  double* io = in_out ? in_out->d : nullptr;
+  const size_t n = y->n_local;
+  switch (m) {
+    case 1: return launch_stage_l96_m<1>(c, y->d, kp, w, cc, F, sgn, io, kout->d, n);
+    case 2: return launch_stage_l96_m<2>(c, y->d, kp, w, cc, F, sgn, io, kout->d, n);
+    case 3: return launch_stage_l96_m<3>(c, y->d, kp, w, cc, F, sgn, io, kout->d, n);
+    case 4: return launch_stage_l96_m<4>(c, y->d, kp, w, cc, F, sgn, io, kout->d, n);
+    case 5: return launch_stage_l96_m<5>(c, y->d, kp, w, cc, F, sgn, io, kout->d, n);
+    case 6: return launch_stage_l96_m<6>(c, y->d, kp, w, cc, F, sgn, io, kout->d, n);
+    case 7: return launch_stage_l96_m<7>(c, y->d, kp, w, cc, F, sgn, io, kout->d, n);
+    case 8: return launch_stage_l96_m<8>(c, y->d, kp, w, cc, F, sgn, io, kout->d, n);
+    case 9: return launch_stage_l96_m<9>(c, y->d, kp, w, cc, F, sgn, io, kout->d, n);
+  }
+  return fail(c, B200RK_EINVAL, "stage_l96: m must be in 1..9");
+}
+
 static int plan_finish(const b200rk_ctx* c, const MethodDef& md, double dt, double absTol, double relTol,
                        const b200rk_vec* y, b200rk_vec* const* k, b200rk_vec* ynew, bool ynew_ready, double* err_out,
                        FinishPlan* p) {
@@ -749,6 +787,8 @@ static int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, doubl
   bool fused = c->fuse_pointwise && pointwise_kind(rhs, &pw_kind, &br) && method_fusable(md) &&
                (md.rk4_final || (fsal && fsal_new));
   if (fused && !md.rk4_final) { fused_pat = fused_pattern_of(c, md); fused = fused_pat >= 0; }
+  const bool stencil_fused = !fused && c->fuse_stencil && c->world == 1 && rhs.f == &builtin_rhs_fn &&
+                             static_cast<const BuiltinRhs*>(rhs.user)->kind == B200RK_RHS_LORENZ96 && y->n_global >= 4;
   if (fused && pw_kind == PW_DIAG) TRY(check_same(c, y, br->lambda));
   if (md.k1_from_fsal) {
     if (!fsal) return fail(c, B200RK_EINVAL, std::string(md.name) + ": FSAL vector required");
@@ -785,7 +825,15 @@ static int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, doubl
     } else {
     if (!md.k1_from_fsal) TRY(eval_rhs(c, rhs, t, y, k[1]));
     for (int s = 2; s <= S; ++s) {
-      b200rk_vec* in = (s == S && last_input_is_ynew) ? y_new : tmp;
+      const bool in_is_ynew = (s == S && last_input_is_ynew);
+      b200rk_vec* in = in_is_ynew ? y_new : tmp;
+      if (stencil_fused && !md.a_chain[s]) {
+        // built-in Lorenz-96: stage input staged in shared memory, k_s written directly (no tmp round trip)
+        if (rhs.evals) ++*rhs.evals;
+        TRY(run_row_l96(c, md.a[s], md.a_cfac[s], dt, y, k, static_cast<const BuiltinRhs*>(rhs.user)->scalar, rhs.negate_time,
+                        in_is_ynew ? y_new : nullptr, k[s]));
+        continue;
+      }
       TRY(run_row(c, md.a[s], md.a_cfac[s], md.a_chain[s], dt, y, k, in));
       TRY(eval_rhs(c, rhs, t + dt * md.c[s], in, k[s]));
     }
@@ -1052,6 +1100,7 @@ static int ctx_common_init(b200rk_ctx* c) {
   if (const char* e = getenv("B200RK_FINISH_CTAS_PER_SM")) c->finish_ctas_per_sm = std::max(0, atoi(e));
   if (const char* e = getenv("B200RK_STRICT_ZEROS")) c->strict_zeros = atoi(e) != 0;
   if (const char* e = getenv("B200RK_FUSE_POINTWISE")) c->fuse_pointwise = atoi(e) != 0;
+  if (const char* e = getenv("B200RK_FUSE_STENCIL")) c->fuse_stencil = atoi(e) != 0;
   CUDA_TRY(c, cudaDeviceSynchronize());
   return B200RK_OK;
 }
@@ -1124,6 +1173,7 @@ int b200rk_set(b200rk_ctx* c, const char* key, int64_t v) {
   else if (k == "profile") c->profile = v != 0;
   else if (k == "fuse_pointwise") c->fuse_pointwise = v != 0;
   else if (k == "spin_readback") c->spin_readback = v != 0;
+  else if (k == "fuse_stencil") c->fuse_stencil = v != 0;
   else if (k == "fused_ctas_per_sm") { if (v < 0) return fail(c, B200RK_EINVAL, "fused_ctas_per_sm must be >= 0"); c->fused_ctas_per_sm = (int)v; }
   else if (k == "pool_budget_mb") {
     c->pool_budget_bytes = (size_t)std::max<int64_t>(0, v) << 20;
@@ -1145,6 +1195,7 @@ int b200rk_get(const b200rk_ctx* c, const char* key, int64_t* v) {
   else if (k == "fuse_pointwise") *v = c->fuse_pointwise;
   else if (k == "spin_readback") *v = c->spin_readback;
   else if (k == "p2p") *v = c->p2p;
+  else if (k == "fuse_stencil") *v = c->fuse_stencil;
   else if (k == "fused_ctas_per_sm") *v = c->fused_ctas_per_sm;
   else if (k == "profile") *v = c->profile;
   else if (k == "sm_count") *v = c->sm_count;

@@ -777,4 +777,92 @@ __global__ void __launch_bounds__(THREADS)
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Stage accumulate FUSED with the Lorenz-96 stencil right-hand side (single GPU, cyclic):
+//   in[i] = y[i] + c*(w1 k1[i] + ... + wM kM[i])          (same arithmetic as stage_kernel)
+//   k[i]  = sgn * (((in[i+1] - in[i-2]) * in[i-1] - in[i]) + F)      (same as lorenz96_kernel [+ negate])
+// The stage input never travels to HBM: each CTA stages its tile of `in` plus a 2+1 element halo (recomputed
+// from y and the k's, wrapping cyclically) in shared memory and applies the stencil from there. Per stage
+// this removes the write and the re-read of the intermediate vector: (M+2)+2 passes become M+2. `in` is
+// stored only when the caller needs it (the last stage of DOPRI54/Tsit54, whose input is yNew).
+// ---------------------------------------------------------------------------------------------------
+template <int M, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+    stage_l96_kernel(const StageArgs<M> a, double F, double sgn, double* __restrict__ kout) {
+  constexpr int W = 4, TILE = THREADS * W;
+  __shared__ double s[TILE + 4];  // s[0..1] left halo | s[2 .. 2+TILE) tile | right halo directly after the last valid element
+  const size_t n = a.n;
+  const size_t tile0 = (size_t)blockIdx.x * TILE;
+  const size_t tile_len = (tile0 + TILE <= n) ? (size_t)TILE : n - tile0;
+  const size_t i0 = tile0 + (size_t)threadIdx.x * W;
+  double in[W];
+  if (i0 + W <= n) {
+    const Pk<W> yv = ld_stream<W>(a.y + i0);
+    Pk<W> kv[M];
+#pragma unroll
+    for (int j = 0; j < M; ++j) kv[j] = ld_stream<W>(a.k[j] + i0);
+#pragma unroll
+    for (int e = 0; e < W; ++e) {
+      double ke[M];
+#pragma unroll
+      for (int j = 0; j < M; ++j) ke[j] = kv[j].v[e];
+      in[e] = stage_elem<M, false>(yv.v[e], ke, a.w, a.c);
+    }
+    if (a.out) {
+      Pk<W> o;
+#pragma unroll
+      for (int e = 0; e < W; ++e) o.v[e] = in[e];
+      st_stream<W>(a.out + i0, o);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < W; ++e) {
+      const size_t i = i0 + e;
+      in[e] = 0.0;
+      if (i < n) {
+        double ke[M];
+#pragma unroll
+        for (int j = 0; j < M; ++j) ke[j] = a.k[j][i];
+        in[e] = stage_elem<M, false>(a.y[i], ke, a.w, a.c);
+        if (a.out) a.out[i] = in[e];
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < W; ++e) s[2 + threadIdx.x * W + e] = in[e];
+  if (threadIdx.x < 3) {  // halo: global indices tile0-2, tile0-1 (left) and tile0+tile_len (right), cyclic
+    const size_t g = (threadIdx.x < 2) ? (tile0 + n - 2 + threadIdx.x) % n : (tile0 + tile_len) % n;
+    double ke[M];
+#pragma unroll
+    for (int j = 0; j < M; ++j) ke[j] = a.k[j][g];
+    const double h = stage_elem<M, false>(a.y[g], ke, a.w, a.c);
+    // the right halo is written after the block-wide barrier below so it cannot race with a thread storing a
+    // padded element of a ragged last tile into the same slot
+    if (threadIdx.x < 2) s[threadIdx.x] = h;
+    else in[0] = h;  // thread 2 keeps it in a register until the barrier (its own in[0] is already in shared memory)
+  }
+  __syncthreads();
+  if (threadIdx.x == 2) s[2 + tile_len] = in[0];
+  __syncthreads();
+  if (i0 < n) {
+    const int b = 2 + threadIdx.x * W;
+    double k[W];
+#pragma unroll
+    for (int e = 0; e < W; ++e) {
+      const double v = __dadd_rn(__dadd_rn(__dmul_rn(__dadd_rn(s[b + e + 1], -s[b + e - 2]), s[b + e - 1]), -s[b + e]), F);
+      k[e] = __dmul_rn(v, sgn);  // sgn = +1, or -1 for the backward pass g = -f(-t, y): exact either way
+    }
+    if (i0 + W <= n) {
+      Pk<W> o;
+#pragma unroll
+      for (int e = 0; e < W; ++e) o.v[e] = k[e];
+      st_stream<W>(kout + i0, o);
+    } else {
+#pragma unroll
+      for (int e = 0; e < W; ++e)
+        if (i0 + e < n) kout[i0 + e] = k[e];
+    }
+  }
+}
+
 }  // namespace b200rk

@@ -58,8 +58,10 @@ def fuse_mode(nn, request):
     Solver-level tests run in both modes."""
     ctx = nn.default_context()
     ctx.set("fuse_pointwise", request.param)
+    ctx.set("fuse_stencil", request.param)  # built-in Lorenz-96: stage accumulate + stencil RHS in one kernel
     yield request.param
     ctx.set("fuse_pointwise", 1)
+    ctx.set("fuse_stencil", 1)
 
 
 def rng_vec(rng, n, scale=1.0):
@@ -571,3 +573,58 @@ def test_fused_backward_time_bitwise(nn):
         assert_bitwise_equal(res[1], ref.y, "rk4 fused vs oracle")
     finally:
         ctx.set("fuse_pointwise", 1)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Stage accumulate fused with the Lorenz-96 stencil (shared-memory tile + cyclic halo)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("method", ["dopri54", "tsit54", "vern65", "rk4", "bs32", "kutta3"])
+def test_stencil_fused_stage_bitwise_equals_pipeline(nn, method):
+    """One step with the Lorenz-96 right-hand side: the fused stage+stencil kernel gives the same bits as the
+    stage kernel followed by the RHS kernel, at sizes around the 1024-element tile and its cyclic seams, and both
+    equal the oracle."""
+    ctx = nn.default_context()
+    rng = np.random.default_rng(91)
+    rhs = nn.rhsLorenz96(8.0)
+    o = nn.newODEoptions(absTol=1e-2, relTol=1e-2, dtMax=1.0, dtMin=1e-8, dt=0.005)
+    try:
+        for n in [4, 5, 6, 7, 9, 1022, 1023, 1024, 1025, 1027, 2048, 4099, 65536 + 3]:
+            y = 8.0 + rng_vec(rng, n)
+            gy = nn.newVector(y)
+            fs = O.rhs_eval(O.rhs_lorenz96(8.0), 0.0, y)
+            gf = nn.newVector(fs)
+            out = {}
+            for fuse in (1, 0):
+                ctx.set("fuse_stencil", fuse)
+                l0 = ctx.stats()["launches"]
+                yn, fn, dt_used, err = nn.integratorStep(method, rhs, 0.0, gy, gf, 0.005, o)
+                out[fuse] = (yn.to_numpy(), fn.to_numpy(), dt_used, err, ctx.stats()["launches"] - l0)
+            assert_bitwise_equal(out[1][0], out[0][0], f"{method} yNew n={n}")
+            assert_bitwise_equal(out[1][1], out[0][1], f"{method} FSAL n={n}")
+            assert out[1][2] == out[0][2] and out[1][4] < out[0][4]
+            yn_ref, fn_ref, dt_ref, err_ref, st = O.step_vector(method, O.rhs_lorenz96(8.0), 0.0, y, fs, 0.005, O.new_options(absTol=1e-2, relTol=1e-2, dtMax=1.0, dtMin=1e-8, dt=0.005))
+            assert st.rejected == 0
+            assert_bitwise_equal(out[1][0], yn_ref, f"{method} yNew vs oracle n={n}")
+            assert_bitwise_equal(out[1][1], fn_ref, f"{method} FSAL vs oracle n={n}")
+    finally:
+        ctx.set("fuse_stencil", 1)
+
+
+def test_stencil_fused_backward_and_dense(nn):
+    """Lorenz-96 through solveODE with dense output and the backward pass (g = -f(-t, y)), fixed step: the
+    fused stage+stencil path is bit-identical to the pipeline and to the oracle."""
+    ctx = nn.default_context()
+    n = 1500
+    y0 = 8.0 + 0.01 * np.sin(2 * np.pi * 37 * np.arange(n) / n)
+    ts = nn.linspace(-0.05, 0.1, 7)
+    res = {}
+    try:
+        for fuse in (1, 0):
+            ctx.set("fuse_stencil", fuse)
+            t, ys = nn.solveODE(nn.rhsLorenz96(8.0), nn.newVector(y0), ts, nn.newODEoptions(dt=2e-3), integrator="rk4")
+            res[fuse] = np.array([v.to_numpy() for v in ys])
+        assert_bitwise_equal(res[1], res[0], "l96 rk4 fused-stencil vs pipeline")
+        ref = O.solve_vector("rk4", O.rhs_lorenz96(8.0), y0, ts, O.new_options(dt=2e-3))
+        assert_bitwise_equal(res[1], ref.y, "l96 rk4 vs oracle")
+    finally:
+        ctx.set("fuse_stencil", 1)

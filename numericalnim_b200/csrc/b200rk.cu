@@ -57,6 +57,7 @@ struct b200rk_ctx {
   bool peer_opened[kMaxPeers] = {false};
   bool p2p = false;
   std::string p2p_note;
+  long last_zero_slot = -1;  // index in y_out of the tStart state of the last b200rk_solve (-1: none)
   // workspace pool (free vectors by global length)
   std::vector<b200rk_vec*> pool;
   size_t pool_budget_bytes = (size_t)48 << 30;
@@ -1455,6 +1456,7 @@ int b200rk_solve(b200rk_ctx* c, int method, b200rk_rhs_fn f, void* user, const b
   if (has_zero) t_out[it++] = t0;
   for (double x : tPos) t_out[it++] = x;
   for (auto r = yNeg.rbegin(); r != yNeg.rend(); ++r) y_out[iy++] = *r;
+  c->last_zero_slot = yZero.empty() ? -1 : (long)iy;  // the state returned for tStart is y0 itself (ode.nim:485-487)
   for (auto* v : yZero) y_out[iy++] = v;
   for (auto* v : yPos) y_out[iy++] = v;
   *n_y_out = iy;

@@ -68,6 +68,7 @@ struct b200rk_ctx {
   int fused_ctas_per_sm = 4;   // fused pointwise attempt kernel (54 registers -> 4 CTAs/SM resident; measured best)
   bool fuse_pointwise = true;  // element-local built-in RHS: whole attempt in one kernel
   bool fuse_stencil = true;    // built-in Lorenz-96 (single GPU): stage accumulate + stencil RHS in one kernel
+  bool l2_hints = false;       // pipeline path: producer stores evict_last / streams evict_first (126 MB L2 hand-off)
   bool strict_zeros = false;
   bool profile = false;
   // counters
@@ -209,7 +210,8 @@ template <int M, int W, bool CHAIN>
 static int launch_stage_mw(b200rk_ctx* c, const StageArgs<M>& a) {
   constexpr int U = StageUnroll<M, W>::value;
   unsigned grid = grid_for(c, a.n / W, kThreads * U);
-  stage_kernel<M, W, U, CHAIN, kThreads><<<grid, kThreads, 0, c->stream>>>(a);
+  if (c->l2_hints && !CHAIN) stage_kernel<M, W, U, CHAIN, kThreads, 1><<<grid, kThreads, 0, c->stream>>>(a);
+  else stage_kernel<M, W, U, CHAIN, kThreads><<<grid, kThreads, 0, c->stream>>>(a);
   CUDA_TRY(c, cudaGetLastError());
   return B200RK_OK;
 }
@@ -417,7 +419,12 @@ static int launch_ewise(b200rk_ctx* c, const double* a, const double* b, double 
   const int streams = EwiseArity<OP>::binary ? 3 : 2;
   ProfScope ps(c, cls, 8.0 * double(n) * streams);
   unsigned grid = grid_for(c, n / W, kThreads * U);
-  ewise_kernel<OP, W, U, kThreads><<<grid, kThreads, 0, c->stream>>>(a, b, s, out, n);
+  if (c->l2_hints && cls == B200RK_K_RHS && out != a && out != b) {  // 256-bit accesses: the only width the L2 modifiers accept
+    grid = grid_for(c, n / 4, kThreads * 2);
+    ewise_kernel<OP, 4, 2, kThreads, 1><<<grid, kThreads, 0, c->stream>>>(a, b, s, out, n);
+  } else {
+    ewise_kernel<OP, W, U, kThreads><<<grid, kThreads, 0, c->stream>>>(a, b, s, out, n);
+  }
   CUDA_TRY(c, cudaGetLastError());
   return B200RK_OK;
 }
@@ -1102,6 +1109,7 @@ static int ctx_common_init(b200rk_ctx* c) {
   if (const char* e = getenv("B200RK_STRICT_ZEROS")) c->strict_zeros = atoi(e) != 0;
   if (const char* e = getenv("B200RK_FUSE_POINTWISE")) c->fuse_pointwise = atoi(e) != 0;
   if (const char* e = getenv("B200RK_FUSE_STENCIL")) c->fuse_stencil = atoi(e) != 0;
+  if (const char* e = getenv("B200RK_L2_HINTS")) c->l2_hints = atoi(e) != 0;
   CUDA_TRY(c, cudaDeviceSynchronize());
   return B200RK_OK;
 }
@@ -1175,6 +1183,7 @@ int b200rk_set(b200rk_ctx* c, const char* key, int64_t v) {
   else if (k == "fuse_pointwise") c->fuse_pointwise = v != 0;
   else if (k == "spin_readback") c->spin_readback = v != 0;
   else if (k == "fuse_stencil") c->fuse_stencil = v != 0;
+  else if (k == "l2_hints") c->l2_hints = v != 0;
   else if (k == "fused_ctas_per_sm") { if (v < 0) return fail(c, B200RK_EINVAL, "fused_ctas_per_sm must be >= 0"); c->fused_ctas_per_sm = (int)v; }
   else if (k == "pool_budget_mb") {
     c->pool_budget_bytes = (size_t)std::max<int64_t>(0, v) << 20;
@@ -1197,6 +1206,7 @@ int b200rk_get(const b200rk_ctx* c, const char* key, int64_t* v) {
   else if (k == "spin_readback") *v = c->spin_readback;
   else if (k == "p2p") *v = c->p2p;
   else if (k == "fuse_stencil") *v = c->fuse_stencil;
+  else if (k == "l2_hints") *v = c->l2_hints;
   else if (k == "fused_ctas_per_sm") *v = c->fused_ctas_per_sm;
   else if (k == "profile") *v = c->profile;
   else if (k == "sm_count") *v = c->sm_count;

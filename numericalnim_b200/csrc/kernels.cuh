@@ -87,6 +87,42 @@ __device__ __forceinline__ void st_stream<4>(double* p, const Pk<4>& x) {
                : "memory");
 }
 
+// L2 eviction-priority variants (SASS: LDG.E.NA.EFL2 / STG.E.NA.ELL2). The 126 MB L2 can hold one 64 MiB
+// vector: a producer stores its output with evict_last while streaming its inputs with evict_first, so the
+// consumer kernel launched next finds that vector in L2 instead of HBM (stage input -> RHS, k_s -> next stage).
+enum L2Policy : int { L2_NORMAL = 0, L2_EVICT_FIRST = 1, L2_EVICT_LAST = 2 };
+
+template <int W, int POL>
+__device__ __forceinline__ Pk<W> ld_pol(const double* p) {
+  Pk<W> r = {};
+  if (POL == L2_NORMAL) return ld_stream<W>(p);
+  if constexpr (W == 4) {
+    if (POL == L2_EVICT_FIRST)
+      asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];"
+                   : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[W > 2 ? 2 : 0]), "=d"(r.v[W > 3 ? 3 : 0]) : "l"(p));
+    else
+      asm volatile("ld.global.nc.L1::no_allocate.L2::evict_last.v4.f64 {%0,%1,%2,%3}, [%4];"
+                   : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[W > 2 ? 2 : 0]), "=d"(r.v[W > 3 ? 3 : 0]) : "l"(p));
+  } else {
+    return ld_stream<W>(p);  // ptxas accepts the .L2:: eviction modifiers on 256-bit accesses only
+  }
+  return r;
+}
+template <int W, int POL>
+__device__ __forceinline__ void st_pol(double* p, const Pk<W>& x) {
+  if (POL == L2_NORMAL) { st_stream<W>(p, x); return; }
+  if constexpr (W == 4) {
+    if (POL == L2_EVICT_FIRST)
+      asm volatile("st.global.L1::no_allocate.L2::evict_first.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(x.v[0]), "d"(x.v[1]),
+                   "d"(x.v[W > 2 ? 2 : 0]), "d"(x.v[W > 3 ? 3 : 0]) : "memory");
+    else
+      asm volatile("st.global.L1::no_allocate.L2::evict_last.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(x.v[0]), "d"(x.v[1]),
+                   "d"(x.v[W > 2 ? 2 : 0]), "d"(x.v[W > 3 ? 3 : 0]) : "memory");
+  } else {
+    st_stream<W>(p, x);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Stage accumulate:  out = y + c * (w0*k0 + w1*k1 + ... )      (left-associated, no FMA)
 //   CHAIN form (Kutta3's third stage, ode.nim:128):  out = ((y + w0*k0) + w1*k1) + ...   (c unused)
@@ -115,8 +151,9 @@ __device__ __forceinline__ double stage_elem(double y, const double (&k)[M], con
   return __dadd_rn(y, __dmul_rn(acc, c));
 }
 
-template <int M, int W, int U, bool CHAIN, int THREADS>
+template <int M, int W, int U, bool CHAIN, int THREADS, int L2 = 0>
 __global__ void __launch_bounds__(THREADS) stage_kernel(const StageArgs<M> a) {
+  constexpr int LDP = L2 ? L2_EVICT_FIRST : L2_NORMAL, STP = L2 ? L2_EVICT_LAST : L2_NORMAL;
   const size_t nvec = a.n / W;
   const size_t tile = (size_t)THREADS * U;
   for (size_t base = (size_t)blockIdx.x * tile; base < nvec; base += (size_t)gridDim.x * tile) {
@@ -125,9 +162,9 @@ __global__ void __launch_bounds__(THREADS) stage_kernel(const StageArgs<M> a) {
     for (int u = 0; u < U; ++u) {
       const size_t v = base + (size_t)u * THREADS + threadIdx.x;
       if (v < nvec) {
-        yv[u] = ld_stream<W>(a.y + v * W);
+        yv[u] = ld_pol<W, LDP>(a.y + v * W);
 #pragma unroll
-        for (int j = 0; j < M; ++j) kv[u][j] = ld_stream<W>(a.k[j] + v * W);
+        for (int j = 0; j < M; ++j) kv[u][j] = ld_pol<W, LDP>(a.k[j] + v * W);
       }
     }
 #pragma unroll
@@ -142,7 +179,7 @@ __global__ void __launch_bounds__(THREADS) stage_kernel(const StageArgs<M> a) {
           for (int j = 0; j < M; ++j) ke[j] = kv[u][j].v[e];
           o.v[e] = stage_elem<M, CHAIN>(yv[u].v[e], ke, a.w, a.c);
         }
-        st_stream<W>(a.out + v * W, o);
+        st_pol<W, STP>(a.out + v * W, o);
       }
     }
   }
@@ -697,7 +734,9 @@ __device__ __forceinline__ double ewise_elem(double a, double b, double s) {
 template <int OP>
 struct EwiseArity { static constexpr bool binary = (OP == EW_ADD || OP == EW_SUB || OP == EW_HMUL || OP == EW_HDIV || OP == EW_NEG_HMUL); };
 
-template <int OP, int W, int U, int THREADS>
+// L2 != 0 (right-hand-side use, out never aliases an input): inputs stream through with evict_first, the
+// result is stored evict_last for the stage kernel that consumes it next.
+template <int OP, int W, int U, int THREADS, int L2 = 0>
 __global__ void __launch_bounds__(THREADS)
     ewise_kernel(const double* a, const double* b, double s, double* out, size_t n) {
   constexpr bool BIN = EwiseArity<OP>::binary;
@@ -709,8 +748,8 @@ __global__ void __launch_bounds__(THREADS)
     for (int u = 0; u < U; ++u) {
       const size_t v = base + (size_t)u * THREADS + threadIdx.x;
       if (v < nvec) {
-        av[u] = ld_plain<W>(a + v * W);
-        if (BIN) bv[u] = ld_plain<W>(b + v * W);
+        av[u] = L2 ? ld_pol<W, L2_EVICT_FIRST>(a + v * W) : ld_plain<W>(a + v * W);
+        if (BIN) bv[u] = L2 ? ld_pol<W, L2_EVICT_FIRST>(b + v * W) : ld_plain<W>(b + v * W);
       }
     }
 #pragma unroll
@@ -720,7 +759,7 @@ __global__ void __launch_bounds__(THREADS)
         Pk<W> o;
 #pragma unroll
         for (int e = 0; e < W; ++e) o.v[e] = ewise_elem<OP>(av[u].v[e], BIN ? bv[u].v[e] : 0.0, s);
-        st_stream<W>(out + v * W, o);
+        st_pol<W, L2 ? L2_EVICT_LAST : L2_NORMAL>(out + v * W, o);
       }
     }
   }

@@ -321,7 +321,7 @@ def run_ours(args):
                        "sharding": "contiguous shards, 1 all-reduce(sum, 1 x f64) of the error norm per attempt" if world > 1 else "single GPU, no collective",
                        "vec_width": ctx.get("vec_width"), "ctas_per_sm": ctx.get("ctas_per_sm"), "finish_ctas_per_sm": ctx.get("finish_ctas_per_sm"),
                        "fuse_pointwise": ctx.get("fuse_pointwise"), "fused_ctas_per_sm": ctx.get("fused_ctas_per_sm"),
-                       "spin_readback": ctx.get("spin_readback"),
+                       "spin_readback": ctx.get("spin_readback"), "l2_hints": ctx.get("l2_hints"),
                        "error_norm_allreduce": ("in-kernel peer mailboxes over NVLink (CUDA IPC)" if ctx.get("p2p") else "ncclAllReduce") if world > 1 else None},
             "attempts": attempts, "attempts_per_sec": attempts * world / (ms_max * 1e-3), "rejected": head["rejected"],
             "t_reached": t_now, "dt_next": dt_next,

@@ -57,7 +57,6 @@ struct b200rk_ctx {
   bool peer_opened[kMaxPeers] = {false};
   bool p2p = false;
   std::string p2p_note;
-  long last_zero_slot = -1;  // index in y_out of the tStart state of the last b200rk_solve (-1: none)
   // workspace pool (free vectors by global length)
   std::vector<b200rk_vec*> pool;
   size_t pool_budget_bytes = (size_t)48 << 30;
@@ -68,7 +67,8 @@ struct b200rk_ctx {
   int fused_ctas_per_sm = 4;   // fused pointwise attempt kernel (54 registers -> 4 CTAs/SM resident; measured best)
   bool fuse_pointwise = true;  // element-local built-in RHS: whole attempt in one kernel
   bool fuse_stencil = true;    // built-in Lorenz-96 (single GPU): stage accumulate + stencil RHS in one kernel
-  bool l2_hints = false;       // pipeline path: producer stores evict_last / streams evict_first (126 MB L2 hand-off)
+  int l2_hints = -1;           // producer stores evict_last / streams evict_first: -1 auto (vector <= 0.65 L2), 0 off, 1 on
+  size_t l2_bytes = 126u << 20;
   bool strict_zeros = false;
   bool profile = false;
   // counters
@@ -198,6 +198,13 @@ struct StageUnroll {  // keep ~16 doubles of loads in flight per thread
   static constexpr int value = raw < 1 ? 1 : (raw > 4 ? 4 : raw);
 };
 
+// L2 hand-off between producer and consumer kernels (kernels.cuh: L2Policy): worthwhile while one vector
+// fits comfortably in the L2 (measured: +13 % at 2^22, +16 % at 2^23, -2 % at 2^24 = 128 MiB per vector).
+static inline bool l2_on(const b200rk_ctx* c, size_t n_local) {
+  if (c->l2_hints >= 0) return c->l2_hints != 0;
+  return n_local * sizeof(double) <= (size_t)(0.65 * (double)c->l2_bytes);
+}
+
 static inline unsigned grid_for(const b200rk_ctx* c, size_t nvec, int per_block, int ctas_per_sm = -1) {
   size_t tiles = (nvec + per_block - 1) / per_block;
   if (tiles == 0) tiles = 1;
@@ -210,7 +217,7 @@ template <int M, int W, bool CHAIN>
 static int launch_stage_mw(b200rk_ctx* c, const StageArgs<M>& a) {
   constexpr int U = StageUnroll<M, W>::value;
   unsigned grid = grid_for(c, a.n / W, kThreads * U);
-  if (c->l2_hints && !CHAIN) stage_kernel<M, W, U, CHAIN, kThreads, 1><<<grid, kThreads, 0, c->stream>>>(a);
+  if (l2_on(c, a.n) && !CHAIN) stage_kernel<M, W, U, CHAIN, kThreads, 1><<<grid, kThreads, 0, c->stream>>>(a);
   else stage_kernel<M, W, U, CHAIN, kThreads><<<grid, kThreads, 0, c->stream>>>(a);
   CUDA_TRY(c, cudaGetLastError());
   return B200RK_OK;
@@ -419,7 +426,7 @@ static int launch_ewise(b200rk_ctx* c, const double* a, const double* b, double 
   const int streams = EwiseArity<OP>::binary ? 3 : 2;
   ProfScope ps(c, cls, 8.0 * double(n) * streams);
   unsigned grid = grid_for(c, n / W, kThreads * U);
-  if (c->l2_hints && cls == B200RK_K_RHS && out != a && out != b) {  // 256-bit accesses: the only width the L2 modifiers accept
+  if (l2_on(c, n) && cls == B200RK_K_RHS && out != a && out != b) {  // 256-bit accesses: the only width the L2 modifiers accept
     grid = grid_for(c, n / 4, kThreads * 2);
     ewise_kernel<OP, 4, 2, kThreads, 1><<<grid, kThreads, 0, c->stream>>>(a, b, s, out, n);
   } else {
@@ -708,7 +715,8 @@ static int launch_fused_cfg(b200rk_ctx* c, const FusedArgs<Pattern<PAT>::S>& a) 
   if (c->vec_width == 4) {
     unsigned grid = grid_for(c, n / 4, kThreads, c->fused_ctas_per_sm);
     TRY(ensure_partials(c, grid));
-    fused_attempt_kernel<PAT, KIND, 4, kThreads><<<grid, kThreads, 0, c->stream>>>(a);
+    if (l2_on(c, n)) fused_attempt_kernel<PAT, KIND, 4, kThreads, 1><<<grid, kThreads, 0, c->stream>>>(a);
+    else fused_attempt_kernel<PAT, KIND, 4, kThreads><<<grid, kThreads, 0, c->stream>>>(a);
   } else {
     unsigned grid = grid_for(c, n / 2, kThreads, c->fused_ctas_per_sm);
     TRY(ensure_partials(c, grid));
@@ -1091,6 +1099,7 @@ static int ctx_common_init(b200rk_ctx* c) {
   cudaDeviceProp prop;
   CUDA_TRY(c, cudaGetDeviceProperties(&prop, c->device));
   c->sm_count = prop.multiProcessorCount;
+  if (prop.l2CacheSize > 0) c->l2_bytes = (size_t)prop.l2CacheSize;
   CUDA_TRY(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CUDA_TRY(c, cudaMalloc(&c->d_ticket, sizeof(unsigned int)));
   CUDA_TRY(c, cudaMemset(c->d_ticket, 0, sizeof(unsigned int)));
@@ -1109,7 +1118,7 @@ static int ctx_common_init(b200rk_ctx* c) {
   if (const char* e = getenv("B200RK_STRICT_ZEROS")) c->strict_zeros = atoi(e) != 0;
   if (const char* e = getenv("B200RK_FUSE_POINTWISE")) c->fuse_pointwise = atoi(e) != 0;
   if (const char* e = getenv("B200RK_FUSE_STENCIL")) c->fuse_stencil = atoi(e) != 0;
-  if (const char* e = getenv("B200RK_L2_HINTS")) c->l2_hints = atoi(e) != 0;
+  if (const char* e = getenv("B200RK_L2_HINTS")) c->l2_hints = atoi(e) < 0 ? -1 : (atoi(e) != 0);
   CUDA_TRY(c, cudaDeviceSynchronize());
   return B200RK_OK;
 }
@@ -1183,7 +1192,7 @@ int b200rk_set(b200rk_ctx* c, const char* key, int64_t v) {
   else if (k == "fuse_pointwise") c->fuse_pointwise = v != 0;
   else if (k == "spin_readback") c->spin_readback = v != 0;
   else if (k == "fuse_stencil") c->fuse_stencil = v != 0;
-  else if (k == "l2_hints") c->l2_hints = v != 0;
+  else if (k == "l2_hints") c->l2_hints = v < 0 ? -1 : (v != 0);
   else if (k == "fused_ctas_per_sm") { if (v < 0) return fail(c, B200RK_EINVAL, "fused_ctas_per_sm must be >= 0"); c->fused_ctas_per_sm = (int)v; }
   else if (k == "pool_budget_mb") {
     c->pool_budget_bytes = (size_t)std::max<int64_t>(0, v) << 20;
@@ -1466,7 +1475,6 @@ int b200rk_solve(b200rk_ctx* c, int method, b200rk_rhs_fn f, void* user, const b
   if (has_zero) t_out[it++] = t0;
   for (double x : tPos) t_out[it++] = x;
   for (auto r = yNeg.rbegin(); r != yNeg.rend(); ++r) y_out[iy++] = *r;
-  c->last_zero_slot = yZero.empty() ? -1 : (long)iy;  // the state returned for tStart is y0 itself (ode.nim:485-487)
   for (auto* v : yZero) y_out[iy++] = v;
   for (auto* v : yPos) y_out[iy++] = v;
   *n_y_out = iy;

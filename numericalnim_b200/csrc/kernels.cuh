@@ -595,8 +595,14 @@ __device__ __forceinline__ double fused_elem(double y, double k1, double lam, co
   return __dmul_rn(r, r);
 }
 
-template <int PAT, int KIND, int W, int THREADS>
+// L2 != 0: one of the five vectors of an attempt is kept in the 126 MB L2 across launches and everything else
+// streams through with evict_first. PW_DIAG keeps lambda (read by EVERY attempt, accepted or not, never
+// written); PW_SCALE keeps yNew (the next attempt's y after an accepted step).
+template <int PAT, int KIND, int W, int THREADS, int L2 = 0>
 __global__ void __launch_bounds__(THREADS) fused_attempt_kernel(const FusedArgs<Pattern<PAT>::S> a) {
+  constexpr int LDP = L2 ? L2_EVICT_FIRST : L2_NORMAL;
+  constexpr int LAMP = L2 ? L2_EVICT_LAST : L2_NORMAL;
+  constexpr int YSTP = (L2 && KIND != PW_DIAG) ? L2_EVICT_LAST : (L2 ? L2_EVICT_FIRST : L2_NORMAL);
   const size_t nvec = a.n / W;
   const size_t stride = (size_t)gridDim.x * THREADS;
   double acc = 0.0;
@@ -606,24 +612,24 @@ __global__ void __launch_bounds__(THREADS) fused_attempt_kernel(const FusedArgs<
   size_t v = (size_t)blockIdx.x * THREADS + threadIdx.x;
   Pk<W> yv, kv, lv;
   if (v < nvec) {
-    yv = ld_stream<W>(a.y + v * W);
-    kv = ld_stream<W>(a.k1 + v * W);
-    if (KIND == PW_DIAG) lv = ld_stream<W>(a.lam + v * W);
+    yv = ld_pol<W, LDP>(a.y + v * W);
+    kv = ld_pol<W, LDP>(a.k1 + v * W);
+    if (KIND == PW_DIAG) lv = ld_pol<W, LAMP>(a.lam + v * W);
   }
   while (v < nvec) {
     const size_t vn = v + stride;
     Pk<W> yn_, kn_, ln_;
     if (vn < nvec) {
-      yn_ = ld_stream<W>(a.y + vn * W);
-      kn_ = ld_stream<W>(a.k1 + vn * W);
-      if (KIND == PW_DIAG) ln_ = ld_stream<W>(a.lam + vn * W);
+      yn_ = ld_pol<W, LDP>(a.y + vn * W);
+      kn_ = ld_pol<W, LDP>(a.k1 + vn * W);
+      if (KIND == PW_DIAG) ln_ = ld_pol<W, LAMP>(a.lam + vn * W);
     }
     Pk<W> yo, ko;
 #pragma unroll
     for (int e = 0; e < W; ++e)
       acc = __dadd_rn(acc, fused_elem<PAT, KIND>(yv.v[e], kv.v[e], KIND == PW_DIAG ? lv.v[e] : 0.0, a, yo.v[e], ko.v[e]));
-    st_stream<W>(a.ynew + v * W, yo);
-    st_stream<W>(a.ks_out + v * W, ko);
+    st_pol<W, YSTP>(a.ynew + v * W, yo);
+    st_pol<W, L2 ? L2_EVICT_FIRST : L2_NORMAL>(a.ks_out + v * W, ko);
     yv = yn_; kv = kn_;
     if (KIND == PW_DIAG) lv = ln_;
     v = vn;

@@ -1,0 +1,374 @@
+// executor.cu — one IntegratorProc call (ode.nim:38) on device vectors: built-in right-hand sides, stage rows,
+// the fused paths (whole attempt for element-local RHS, stage + Lorenz-96 stencil) and the adaptive retry loop
+// of commonAdaptiveMethodCode (ode.nim:57-76).
+#include "internal.hpp"
+
+int builtin_rhs_fn(double /*t*/, const b200rk_vec* y, b200rk_vec* dydt, void* user) {
+  BuiltinRhs* r = static_cast<BuiltinRhs*>(user);
+  b200rk_ctx* c = r->ctx;
+  const size_t n = y->n_local;
+  switch (r->kind) {
+    case B200RK_RHS_SCALE:
+      return launch_ewise(c, EW_SCALE, y->d, nullptr, r->scalar, dydt->d, n, B200RK_K_RHS);
+    case B200RK_RHS_DIAG_LINEAR:
+      TRY(check_same(c, y, r->lambda));
+      return launch_ewise(c, EW_NEG_HMUL, r->lambda->d, y->d, 0.0, dydt->d, n, B200RK_K_RHS);
+    case B200RK_RHS_LORENZ96: {
+      if (y->n_global < 4) return fail(c, B200RK_EINVAL, "lorenz96 needs n >= 4");
+      const double *left2 = y->d + n - 2, *right1 = y->d;  // single GPU: the cyclic neighbours are in the vector itself
+      if (c->world > 1) {
+        // Sharded stencil: 3-element halo per evaluation over NVLink. Each rank sends its
+        // first element to the left neighbour and its last two to the right neighbour (ring), on the
+        // context stream, so the exchange is ordered with the producing and consuming kernels.
+        if (n < 2) return fail(c, B200RK_EINVAL, "lorenz96: every shard needs at least 2 elements");
+        const int left = (c->rank + c->world - 1) % c->world, right = (c->rank + 1) % c->world;
+        NCCL_TRY(c, g_nccl.GroupStart());
+        NCCL_TRY(c, g_nccl.Send(y->d, 1, ncclDouble, left, c->comm, c->stream));
+        NCCL_TRY(c, g_nccl.Send(y->d + n - 2, 2, ncclDouble, right, c->comm, c->stream));
+        NCCL_TRY(c, g_nccl.Recv(c->d_halo + 2, 1, ncclDouble, right, c->comm, c->stream));
+        NCCL_TRY(c, g_nccl.Recv(c->d_halo, 2, ncclDouble, left, c->comm, c->stream));
+        NCCL_TRY(c, g_nccl.GroupEnd());
+        c->collectives++;
+        left2 = c->d_halo;
+        right1 = c->d_halo + 2;
+      }
+      return launch_lorenz96(c, y->d, left2, right1, r->scalar, dydt->d, n);
+    }
+  }
+  return fail(c, B200RK_EINVAL, "unknown builtin rhs");
+}
+
+int eval_rhs(b200rk_ctx* c, const RhsCall& r, double t, const b200rk_vec* y, b200rk_vec* out) {
+  if (r.evals) ++*r.evals;
+  int rc = r.f(r.negate_time ? -t : t, y, out, r.user);
+  if (rc != 0) {
+    if (r.f == &builtin_rhs_fn) return rc;  // our own launcher already recorded the error
+    return fail(c, B200RK_ECALLBACK, "right-hand side callback returned " + std::to_string(rc));
+  }
+  if (r.negate_time) return launch_ewise(c, EW_NEG, out->d, nullptr, 0.0, out->d, out->n_local, B200RK_K_OTHER);
+  return B200RK_OK;
+}
+
+// Compact a reference row into launch arguments; zero weights dropped unless strict.
+static int gather_row(const b200rk_ctx* c, const Row& row, b200rk_vec* const* k /*1-based*/, const double** kp, double* w) {
+  int m = 0;
+  for (int j = 0; j < row.m; ++j) {
+    if (row.w[j] == 0.0 && !c->strict_zeros && row.m > 1) continue;
+    kp[m] = k[row.idx[j]]->d;
+    w[m] = row.w[j];
+    ++m;
+  }
+  if (m == 0) {  // all-zero row: keep the first term so the kernel still has one stream
+    kp[0] = k[row.idx[0]]->d; w[0] = row.w[0]; m = 1;
+  }
+  return m;
+}
+
+int run_row(b200rk_ctx* c, const Row& row, double cfac, bool chain, double dt, const b200rk_vec* y,
+                   b200rk_vec* const* k, b200rk_vec* out) {
+  const double* kp[kMaxTerms];
+  double w[kMaxTerms];
+  int m = gather_row(c, row, k, kp, w);
+  double cc = (cfac == 1.0) ? dt : cfac * dt;
+  if (chain) {
+    for (int j = 0; j < m; ++j) w[j] = w[j] * dt;  // (-1*dt), (2*dt): exact
+    cc = 0.0;
+  }
+  return launch_stage(c, m, y->d, kp, w, cc, chain, out->d, y->n_local);
+}
+
+// Stage row fused with the built-in Lorenz-96 right-hand side (kernels.cuh: stage_l96_kernel): writes
+// k_s = f(stage input) directly; the stage input itself is stored only when `in_out` is given.
+template <int M>
+static int launch_stage_l96_m(b200rk_ctx* c, const double* y, const double* const* kp, const double* w, double cc,
+                              double F, double sgn, double* in_out, double* kout, size_t n) {
+  StageArgs<M> a;
+  a.y = y; a.c = cc; a.out = in_out; a.n = n;
+  for (int j = 0; j < M; ++j) { a.k[j] = kp[j]; a.w[j] = w[j]; }
+  ProfScope ps(c, B200RK_K_STAGE, 8.0 * double(n) * (M + 2 + (in_out ? 1 : 0)));
+  const unsigned grid = (unsigned)((n + kThreads * 4 - 1) / (kThreads * 4));
+  stage_l96_kernel<M, kThreads><<<grid, kThreads, 0, c->stream>>>(a, F, sgn, kout);
+  CUDA_TRY(c, cudaGetLastError());
+  return B200RK_OK;
+}
+static int run_row_l96(b200rk_ctx* c, const Row& row, double cfac, double dt, const b200rk_vec* y, b200rk_vec* const* k,
+                       double F, bool negate, b200rk_vec* in_out, b200rk_vec* kout) {
+  const double* kp[kMaxTerms];
+  double w[kMaxTerms];
+  const int m = gather_row(c, row, k, kp, w);
+  const double cc = (cfac == 1.0) ? dt : cfac * dt;
+  const double sgn = negate ? -1.0 : 1.0;
+  double* io = in_out ? in_out->d : nullptr;
+  const size_t n = y->n_local;
+  switch (m) {
+    case 1: return launch_stage_l96_m<1>(c, y->d, kp, w, cc, F, sgn, io, kout->d, n);
+    case 2: return launch_stage_l96_m<2>(c, y->d, kp, w, cc, F, sgn, io, kout->d, n);
+    case 3: return launch_stage_l96_m<3>(c, y->d, kp, w, cc, F, sgn, io, kout->d, n);
+    case 4: return launch_stage_l96_m<4>(c, y->d, kp, w, cc, F, sgn, io, kout->d, n);
+    case 5: return launch_stage_l96_m<5>(c, y->d, kp, w, cc, F, sgn, io, kout->d, n);
+    case 6: return launch_stage_l96_m<6>(c, y->d, kp, w, cc, F, sgn, io, kout->d, n);
+    case 7: return launch_stage_l96_m<7>(c, y->d, kp, w, cc, F, sgn, io, kout->d, n);
+    case 8: return launch_stage_l96_m<8>(c, y->d, kp, w, cc, F, sgn, io, kout->d, n);
+    case 9: return launch_stage_l96_m<9>(c, y->d, kp, w, cc, F, sgn, io, kout->d, n);
+  }
+  return fail(c, B200RK_EINVAL, "stage_l96: m must be in 1..9");
+}
+
+int plan_finish(const b200rk_ctx* c, const MethodDef& md, double dt, double absTol, double relTol,
+                       const b200rk_vec* y, b200rk_vec* const* k, b200rk_vec* ynew, bool ynew_ready, double* err_out,
+                       FinishPlan* p) {
+  // Union of the derivative streams the two rows touch, slots ascending in stage index so that the
+  // kernel's left-to-right walk over slots reproduces the reference's association (both rows list their
+  // terms in ascending stage order in ode.nim).
+  p->direct = md.err_direct;
+  const bool use_b = !(md.err_direct && ynew_ready);
+  double wb_of[kMaxStages + 1] = {0}, wbh_of[kMaxStages + 1] = {0};
+  bool in_b[kMaxStages + 1] = {false}, in_bh[kMaxStages + 1] = {false};
+  int prev = 0;
+  if (use_b)
+    for (int j = 0; j < md.b.m; ++j) {
+      if (md.b.idx[j] <= prev) return fail(c, B200RK_EINVAL, "finish: b row not in ascending stage order");
+      prev = md.b.idx[j];
+      if (md.b.w[j] == 0.0 && !c->strict_zeros) continue;
+      in_b[md.b.idx[j]] = true; wb_of[md.b.idx[j]] = md.b.w[j];
+    }
+  prev = 0;
+  for (int j = 0; j < md.bhat.m; ++j) {
+    if (md.bhat.idx[j] <= prev) return fail(c, B200RK_EINVAL, "finish: bhat row not in ascending stage order");
+    prev = md.bhat.idx[j];
+    if (md.bhat.w[j] == 0.0 && !c->strict_zeros) continue;
+    in_bh[md.bhat.idx[j]] = true; wbh_of[md.bhat.idx[j]] = md.bhat.w[j];
+  }
+  for (int s = 1; s <= md.stages; ++s) {
+    if (!in_b[s] && !in_bh[s]) continue;
+    p->k[p->nk] = k[s]->d; p->wb[p->nk] = wb_of[s]; p->wbh[p->nk] = wbh_of[s];
+    if (in_b[s]) p->mask_b |= 1u << p->nk;
+    if (in_bh[s]) p->mask_bh |= 1u << p->nk;
+    ++p->nk;
+  }
+  if (p->nk == 0) return fail(c, B200RK_EINVAL, "finish: empty rows");
+  p->cb = (md.b_cfac == 1.0) ? dt : dt * md.b_cfac;
+  p->cbh = (md.bhat_cfac == 1.0) ? dt : dt * md.bhat_cfac;
+  p->absTol = absTol; p->relTol = relTol; p->n = y->n_local; p->err_out = err_out;
+  if (md.err_direct && ynew_ready) { p->ynew_mode = 2; p->y = ynew->d; }
+  else if (ynew_ready) { p->ynew_mode = 0; p->y = y->d; }
+  else { p->ynew_mode = 1; p->y = y->d; p->ynew_out = ynew->d; }
+  if (md.err_direct && !ynew_ready) return fail(c, B200RK_EINVAL, "finish: direct-error methods need yNew first");
+  return B200RK_OK;
+}
+
+// ---- fused attempt for element-local built-in right-hand sides (kernels.cuh: fused_attempt_kernel) ----
+static bool pointwise_kind(const RhsCall& rhs, int* pw_kind, const BuiltinRhs** br) {
+  if (rhs.f != &builtin_rhs_fn) return false;
+  const BuiltinRhs* r = static_cast<const BuiltinRhs*>(rhs.user);
+  if (r->kind == B200RK_RHS_SCALE) *pw_kind = PW_SCALE;
+  else if (r->kind == B200RK_RHS_DIAG_LINEAR) *pw_kind = PW_DIAG;
+  else return false;
+  *br = r;
+  return true;
+}
+static bool method_fusable(const MethodDef& md) {
+  if (md.rk4_final) return true;
+  if (!(md.adaptive && md.k1_from_fsal && md.fsal_out == md.stages && (md.stages == 7 || md.stages == 9))) return false;
+  for (int s = 2; s <= md.stages; ++s)
+    if (md.a_cfac[s] != 1.0 || md.a_chain[s] || md.a[s].m != s - 1) return false;
+  return md.b_cfac == 1.0 && md.bhat_cfac == 1.0;
+}
+
+static uint32_t row_mask(const b200rk_ctx* c, const Row& row, double* w_dense, int width) {
+  uint32_t mask = 0;
+  for (int j = 0; j < width; ++j) w_dense[j] = 0.0;
+  int kept = 0;
+  for (int j = 0; j < row.m; ++j) {
+    w_dense[row.idx[j] - 1] = row.w[j];
+    if (row.w[j] == 0.0 && !c->strict_zeros && row.m > 1) continue;
+    mask |= 1u << (row.idx[j] - 1);
+    ++kept;
+  }
+  if (!kept) mask |= 1u << (row.idx[0] - 1);  // same rule as gather_row: an all-zero row keeps its first term
+  return mask;
+}
+
+template <int PAT, int KIND>
+static int launch_fused_cfg(b200rk_ctx* c, const FusedArgs<Pattern<PAT>::S>& a) {
+  const size_t n = a.n;
+  if (c->vec_width == 4) {
+    unsigned grid = grid_for(c, n / 4, kThreads, c->fused_ctas_per_sm);
+    TRY(ensure_partials(c, grid));
+    // L2-resident lambda / yNew: measured neutral at 2^23 (64.8 vs 65.8 us; the kernel is co-limited by the fp64
+    // pipe) and +3 % at 2^22, so only on explicit request, not under the auto policy
+    if (c->l2_hints == 1) fused_attempt_kernel<PAT, KIND, 4, kThreads, 1><<<grid, kThreads, 0, c->stream>>>(a);
+    else fused_attempt_kernel<PAT, KIND, 4, kThreads><<<grid, kThreads, 0, c->stream>>>(a);
+  } else {
+    unsigned grid = grid_for(c, n / 2, kThreads, c->fused_ctas_per_sm);
+    TRY(ensure_partials(c, grid));
+    fused_attempt_kernel<PAT, KIND, 2, kThreads><<<grid, kThreads, 0, c->stream>>>(a);
+  }
+  CUDA_TRY(c, cudaGetLastError());
+  return B200RK_OK;
+}
+
+// Runtime masks of the method (same dropping rules as gather_row / plan_finish) must equal the kernel's
+// compile-time pattern; otherwise the caller falls back to the pipeline.
+template <int PAT>
+static bool pattern_matches(const b200rk_ctx* c, const MethodDef& md) {
+  constexpr int S = Pattern<PAT>::S;
+  if (md.stages != S || md.err_direct != Pattern<PAT>::direct || md.ynew_is_last_stage_input != Pattern<PAT>::last) return false;
+  double scratch[kMaxStages];
+  for (int s = 2; s <= S; ++s)
+    if (row_mask(c, md.a[s], scratch, S - 1) != Pattern<PAT>::a(s - 2)) return false;
+  uint32_t bm = 0, bhm = 0;
+  for (int j = 0; j < md.b.m; ++j) if (md.b.w[j] != 0.0 || c->strict_zeros) bm |= 1u << (md.b.idx[j] - 1);
+  for (int j = 0; j < md.bhat.m; ++j) if (md.bhat.w[j] != 0.0 || c->strict_zeros) bhm |= 1u << (md.bhat.idx[j] - 1);
+  if (!Pattern<PAT>::last && bm != Pattern<PAT>::b()) return false;
+  return bhm == Pattern<PAT>::bh();
+}
+
+static int fused_pattern_of(const b200rk_ctx* c, const MethodDef& md) {
+  if (pattern_matches<PAT_DOPRI54>(c, md) && !std::strcmp(md.name, "dopri54")) return PAT_DOPRI54;
+  if (pattern_matches<PAT_DOPRI54_STRICT>(c, md) && !std::strcmp(md.name, "dopri54")) return PAT_DOPRI54_STRICT;
+  if (pattern_matches<PAT_TSIT54>(c, md) && !std::strcmp(md.name, "tsit54")) return PAT_TSIT54;
+  if (pattern_matches<PAT_VERN65>(c, md)) return PAT_VERN65;
+  if (pattern_matches<PAT_VERN65_STRICT>(c, md)) return PAT_VERN65_STRICT;
+  return -1;
+}
+
+template <int PAT>
+static int launch_fused_pair(b200rk_ctx* c, const MethodDef& md, int pw_kind, const BuiltinRhs* br, bool negate, double dt,
+                             const b200rk_options& o, const b200rk_vec* y, const b200rk_vec* fsal, b200rk_vec* y_new,
+                             b200rk_vec* fsal_new) {
+  constexpr int S = Pattern<PAT>::S;
+  FusedArgs<S> a;
+  std::memset(&a, 0, sizeof(a));
+  a.y = y->d; a.k1 = fsal->d; a.lam = br->lambda ? br->lambda->d : nullptr;
+  a.rhs_scalar = negate ? -br->scalar : br->scalar;   // -(y*c) == y*(-c) exactly
+  a.rhs_sign = negate ? 1.0 : -1.0;                   // k = (lam*y)*sign
+  for (int s = 2; s <= S; ++s) row_mask(c, md.a[s], a.a[s - 2], S - 1);
+  row_mask(c, md.b, a.b, S);
+  row_mask(c, md.bhat, a.bh, S);
+  a.dt = dt; a.cb = dt; a.cbh = dt; a.absTol = o.absTol; a.relTol = o.relTol;
+  a.ynew = y_new->d; a.ks_out = fsal_new->d; a.n = y->n_local;
+  a.rs = reduce_scratch(c);
+  const int streams = 4 + (pw_kind == PW_DIAG ? 1 : 0);  // y, k1 (+ lambda) read; yNew, k_S written
+  ProfScope ps(c, B200RK_K_FUSED, 8.0 * double(y->n_local) * streams);
+  if (pw_kind == PW_SCALE) return launch_fused_cfg<PAT, PW_SCALE>(c, a);
+  return launch_fused_cfg<PAT, PW_DIAG>(c, a);
+}
+
+static int launch_fused_rk4(b200rk_ctx* c, int pw_kind, const BuiltinRhs* br, bool negate, double dt, const b200rk_vec* y,
+                            b200rk_vec* y_new) {
+  const size_t n = y->n_local;
+  if (!n) return B200RK_OK;
+  ProfScope ps(c, B200RK_K_FUSED, 8.0 * double(n) * (2 + (pw_kind == PW_DIAG ? 1 : 0)));
+  const double hdt = 0.5 * dt, c6 = dt / 6.0;
+  const double* lam = br->lambda ? br->lambda->d : nullptr;
+  unsigned grid = grid_for(c, n / 4, kThreads, c->ctas_per_sm);
+  const double cs = negate ? -br->scalar : br->scalar, sgn = negate ? 1.0 : -1.0;
+  if (pw_kind == PW_SCALE) fused_rk4_kernel<PW_SCALE, 4, kThreads><<<grid, kThreads, 0, c->stream>>>(y->d, lam, cs, sgn, hdt, dt, c6, y_new->d, n);
+  else fused_rk4_kernel<PW_DIAG, 4, kThreads><<<grid, kThreads, 0, c->stream>>>(y->d, lam, cs, sgn, hdt, dt, c6, y_new->d, n);
+  CUDA_TRY(c, cudaGetLastError());
+  return B200RK_OK;
+}
+
+// One IntegratorProc call. y, fsal read-only; y_new, fsal_new written.
+int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, double t, const b200rk_vec* y,
+                   const b200rk_vec* fsal, double dt_in, const b200rk_options& o, b200rk_vec* y_new,
+                   b200rk_vec* fsal_new, double* dt_used, double* error_out, StepCounters* cnt) {
+  const size_t N = y->n_global;
+  const int S = md.stages;
+  Workspace ws(c);
+  b200rk_vec* k[kMaxStages + 1] = {nullptr};
+  b200rk_vec* tmp = nullptr;
+  int pw_kind = 0;
+  const BuiltinRhs* br = nullptr;
+  int fused_pat = -1;
+  bool fused = c->fuse_pointwise && pointwise_kind(rhs, &pw_kind, &br) && method_fusable(md) &&
+               (md.rk4_final || (fsal && fsal_new));
+  if (fused && !md.rk4_final) { fused_pat = fused_pattern_of(c, md); fused = fused_pat >= 0; }
+  const bool stencil_fused = !fused && c->fuse_stencil && c->world == 1 && rhs.f == &builtin_rhs_fn &&
+                             static_cast<const BuiltinRhs*>(rhs.user)->kind == B200RK_RHS_LORENZ96 && y->n_global >= 4;
+  if (fused && pw_kind == PW_DIAG) TRY(check_same(c, y, br->lambda));
+  if (md.k1_from_fsal) {
+    if (!fsal) return fail(c, B200RK_EINVAL, std::string(md.name) + ": FSAL vector required");
+    TRY(check_same(c, y, fsal));
+    k[1] = const_cast<b200rk_vec*>(fsal);
+  } else if (!fused) {
+    TRY(ws.get(N, &k[1]));
+  }
+  const bool last_input_is_ynew = md.ynew_is_last_stage_input;
+  if (!fused) {
+    for (int s = 2; s <= S; ++s) {
+      if (s == md.fsal_out && fsal_new) k[s] = fsal_new;
+      else TRY(ws.get(N, &k[s]));
+    }
+    if (!(last_input_is_ynew && S == 2)) TRY(ws.get(N, &tmp));
+  }
+
+  double dt = dt_in, error = 0.0;
+  int limitCounter = 0;
+  while (true) {
+    if (cnt) cnt->attempts++;
+    if (fused) {
+      // element-local right-hand side: the whole attempt is one kernel (the callbacks it stands for are
+      // still counted so rhs_evals matches the unfused path)
+      if (rhs.evals) *rhs.evals += md.rk4_final ? 4 : (S - 1);
+      if (md.rk4_final) { TRY(launch_fused_rk4(c, pw_kind, br, rhs.negate_time, dt, y, y_new)); break; }
+      switch (fused_pat) {
+        case PAT_DOPRI54: TRY(launch_fused_pair<PAT_DOPRI54>(c, md, pw_kind, br, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new)); break;
+        case PAT_DOPRI54_STRICT: TRY(launch_fused_pair<PAT_DOPRI54_STRICT>(c, md, pw_kind, br, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new)); break;
+        case PAT_TSIT54: TRY(launch_fused_pair<PAT_TSIT54>(c, md, pw_kind, br, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new)); break;
+        case PAT_VERN65: TRY(launch_fused_pair<PAT_VERN65>(c, md, pw_kind, br, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new)); break;
+        default: TRY(launch_fused_pair<PAT_VERN65_STRICT>(c, md, pw_kind, br, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new)); break;
+      }
+    } else {
+    if (!md.k1_from_fsal) TRY(eval_rhs(c, rhs, t, y, k[1]));
+    for (int s = 2; s <= S; ++s) {
+      const bool in_is_ynew = (s == S && last_input_is_ynew);
+      b200rk_vec* in = in_is_ynew ? y_new : tmp;
+      if (stencil_fused && !md.a_chain[s]) {
+        // built-in Lorenz-96: stage input staged in shared memory, k_s written directly (no tmp round trip)
+        if (rhs.evals) ++*rhs.evals;
+        TRY(run_row_l96(c, md.a[s], md.a_cfac[s], dt, y, k, static_cast<const BuiltinRhs*>(rhs.user)->scalar, rhs.negate_time,
+                        in_is_ynew ? y_new : nullptr, k[s]));
+        continue;
+      }
+      TRY(run_row(c, md.a[s], md.a_cfac[s], md.a_chain[s], dt, y, k, in));
+      TRY(eval_rhs(c, rhs, t + dt * md.c[s], in, k[s]));
+    }
+    if (!md.adaptive) {
+      if (md.rk4_final) {
+        TRY(launch_rk4_final(c, y->d, k[1]->d, k[2]->d, k[3]->d, k[4]->d, dt / 6.0, y_new->d, y->n_local));
+      } else {
+        TRY(run_row(c, md.b, md.b_cfac, false, dt, y, k, y_new));
+      }
+      break;
+    }
+    FinishPlan p;
+    TRY(plan_finish(c, md, dt, o.absTol, o.relTol, y, k, y_new, last_input_is_ynew, nullptr, &p));
+    TRY(launch_finish(c, p));
+    }  // !fused
+    double S2 = 0.0;
+    TRY(fetch_global_sum(c, &S2));
+    error = std::sqrt(1.0 / double(N) * S2);                                     // ode.nim:64-65
+    if (error <= 1) break;                                                       // ode.nim:69-70
+    if (std::isnan(error)) {
+      *dt_used = dt; *error_out = error;
+      return fail(c, B200RK_ENONFINITE, "error norm is NaN (the reference would loop forever here)");
+    }
+    if (cnt) cnt->rejected++;
+    dt = dt * nim_min(4, nim_max(0.125, 0.9 * std::pow(1.0 / error, 1.0 / double(md.order_int))));  // ode.nim:71
+    if (std::fabs(dt) < o.dtMin) {                                               // ode.nim:72-74
+      dt = o.dtMin;
+      limitCounter += 1;
+      if (cnt) cnt->limiter_hits++;
+    } else if (o.dtMax < std::fabs(dt)) {                                        // ode.nim:75-76
+      dt = o.dtMax;
+    }
+    if (!(limitCounter < 2)) break;                                              // ode.nim:58
+  }
+  if (fsal_new && md.fsal_out == 0)  // non-FSAL steppers return (yNew, yNew, ...) (ode.nim:113,189,210)
+    CUDA_TRY(c, cudaMemcpyAsync(fsal_new->d, y_new->d, y_new->n_local * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  *dt_used = dt;
+  *error_out = error;
+  return B200RK_OK;
+}

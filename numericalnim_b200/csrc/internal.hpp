@@ -1,0 +1,261 @@
+// internal.hpp — declarations shared by the translation units of libb200rk.so (not installed).
+//   runtime.cu   context, NCCL binding, peer mailboxes, vector pool, knobs, profiler
+//   launch.cu    generic kernel launchers (stage / finish / element-wise / Hermite / sum / RK4) + read-back
+//   executor.cu  built-in right-hand sides, stage rows, fused paths, one IntegratorProc call (do_step)
+//   driver.cu    the resumable ODESolver loop and the step / solve entry points
+//   capi.cu      the remaining extern "C" surface (options, dispatch, Vector operators, raw kernels)
+#pragma once
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is bound at run time, see NcclApi below
+
+#include <algorithm>
+#include <cctype>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200rk.h"
+#include "kernels.cuh"
+#include "methods.h"
+
+using namespace b200rk;
+
+// =====================================================================================================
+// context / vector objects
+// =====================================================================================================
+struct ProfRec {
+  int cls;
+  double bytes;
+  cudaEvent_t a, b;
+};
+
+struct b200rk_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  int rank = 0, world = 1;
+  ncclComm_t comm = nullptr;
+  // reduction scratch
+  double* d_partials = nullptr;
+  size_t partials_cap = 0;
+  unsigned int* d_ticket = nullptr;
+  double* d_result = nullptr;   // device scalar (allreduce buffer)
+  double* h_result = nullptr;   // pinned + mapped host scalar
+  double* h_result_dev = nullptr;  // device alias of h_result
+  double* d_halo = nullptr;        // 3 doubles: stencil halo of the sharded Lorenz-96 right-hand side
+  unsigned long long* h_seq = nullptr;      // pinned + mapped: sequence word of the last finished reduction
+  unsigned long long* h_seq_dev = nullptr;  // device alias
+  unsigned long long seq = 0;               // last sequence number handed to a reducing launch
+  bool spin_readback = true;                // poll h_seq instead of cudaStreamSynchronize (single GPU)
+  // in-kernel all-reduce of the error norm over peer mailboxes (multi-GPU)
+  unsigned long long* d_mail = nullptr;     // this rank's mailbox
+  unsigned long long* peer_mail[kMaxPeers] = {nullptr};
+  bool peer_opened[kMaxPeers] = {false};
+  bool p2p = false;
+  std::string p2p_note;
+  // workspace pool (free vectors by global length)
+  std::vector<b200rk_vec*> pool;
+  size_t pool_budget_bytes = (size_t)48 << 30;
+  // knobs
+  int vec_width = 4;
+  int ctas_per_sm = 0;         // stage/element-wise kernels: 0 = one tile per CTA (measured best, profiles/)
+  int finish_ctas_per_sm = 2;  // reducing kernels: persistent grid, one partial per CTA (measured best)
+  int fused_ctas_per_sm = 4;   // fused pointwise attempt kernel (54 registers -> 4 CTAs/SM resident; measured best)
+  bool fuse_pointwise = true;  // element-local built-in RHS: whole attempt in one kernel
+  bool fuse_stencil = true;    // built-in Lorenz-96 (single GPU): stage accumulate + stencil RHS in one kernel
+  int l2_hints = -1;           // producer stores evict_last / streams evict_first: -1 auto (vector <= 0.65 L2), 0 off, 1 on
+  size_t l2_bytes = 126u << 20;
+  bool strict_zeros = false;
+  bool profile = false;
+  // counters
+  int64_t launches = 0, collectives = 0;
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_free;
+  mutable std::string err;
+};
+
+struct b200rk_vec {
+  b200rk_ctx* ctx;
+  size_t n_global, offset, n_local;
+  double* d;
+};
+
+int fail(const b200rk_ctx* ctx, int code, const std::string& msg);   // records the message, returns `code`
+std::string& thread_error();                                          // last error of this thread (ctx == NULL)
+
+#define CUDA_TRY(ctx, expr)                                                                         \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      return fail(ctx, B200RK_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));           \
+  } while (0)
+#define NCCL_TRY(ctx, expr)                                                                         \
+  do {                                                                                              \
+    ncclResult_t _e = (expr);                                                                       \
+    if (_e != ncclSuccess)                                                                          \
+      return fail(ctx, B200RK_ENCCL, std::string(#expr) + ": " + g_nccl.GetErrorString(_e));        \
+  } while (0)
+#define TRY(expr)                      \
+  do {                                 \
+    int _rc = (expr);                  \
+    if (_rc != B200RK_OK) return _rc;  \
+  } while (0)
+
+inline double nim_min(double x, double y) { return (x <= y) ? x : y; }  // Nim system.min
+inline double nim_max(double x, double y) { return (y <= x) ? x : y; }  // Nim system.max
+
+// ---- NCCL, bound lazily ------------------------------------------------------------------------------
+// libb200rk.so does not link libnccl: a process may already hold a libnccl.so.2 (PyTorch bundles its own,
+// newer than the system one, and resolves symbols against whichever copy was loaded first). The first
+// distributed call binds, in order: a copy already in the process, $B200RK_NCCL_LIB, then the default
+// search path. Single-GPU use never touches NCCL.
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*GetVersion)(int*) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  std::string where;
+};extern NcclApi g_nccl;
+int nccl_bind(const b200rk_ctx* ctx);
+
+// ---- profiling: one CUDA-event pair per launch on the context stream --------------------------------
+struct ProfScope {
+  b200rk_ctx* c;
+  cudaEvent_t a = nullptr, b = nullptr;
+  int cls;
+  double bytes;
+  ProfScope(b200rk_ctx* ctx, int cls_, double bytes_) : c(ctx), cls(cls_), bytes(bytes_) {
+    c->launches++;
+    if (!c->profile) return;
+    a = take();
+    b = take();
+    cudaEventRecord(a, c->stream);
+  }
+  cudaEvent_t take() {
+    if (!c->ev_free.empty()) { cudaEvent_t e = c->ev_free.back(); c->ev_free.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+  ~ProfScope() {
+    if (!a) return;
+    cudaEventRecord(b, c->stream);
+    c->prof.push_back(ProfRec{cls, bytes, a, b});
+  }
+};
+
+// =====================================================================================================
+// launch geometry (shared by every translation unit that launches kernels)
+// =====================================================================================================
+static constexpr int kThreads = 256;
+
+template <int M, int W>
+struct StageUnroll {  // keep ~16 doubles of loads in flight per thread
+  static constexpr int raw = 16 / ((M + 1) * W);
+  static constexpr int value = raw < 1 ? 1 : (raw > 4 ? 4 : raw);
+};
+
+// L2 hand-off between producer and consumer kernels (kernels.cuh: L2Policy): worthwhile while one vector
+// fits comfortably in the L2 (measured: +13 % at 2^22, +16 % at 2^23, -2 % at 2^24 = 128 MiB per vector).
+inline bool l2_on(const b200rk_ctx* c, size_t n_local) {
+  if (c->l2_hints >= 0) return c->l2_hints != 0;
+  return n_local * sizeof(double) <= (size_t)(0.65 * (double)c->l2_bytes);
+}
+
+inline unsigned grid_for(const b200rk_ctx* c, size_t nvec, int per_block, int ctas_per_sm = -1) {
+  size_t tiles = (nvec + per_block - 1) / per_block;
+  if (tiles == 0) tiles = 1;
+  if (ctas_per_sm < 0) ctas_per_sm = c->ctas_per_sm;
+  if (ctas_per_sm > 0) tiles = std::min(tiles, (size_t)ctas_per_sm * c->sm_count);
+  return (unsigned)std::min(tiles, (size_t)0x7fffffff);
+}
+
+struct FinishPlan {
+  int nk = 0;
+  const double* k[kMaxTerms];
+  double wb[kMaxTerms], wbh[kMaxTerms];
+  uint32_t mask_b = 0, mask_bh = 0;
+  double cb = 0, cbh = 0, absTol = 0, relTol = 0;
+  const double* y = nullptr;
+  double* ynew_out = nullptr;
+  double* err_out = nullptr;
+  bool direct = false;
+  int ynew_mode = 0;
+  size_t n = 0;
+};
+
+struct BuiltinRhs {
+  b200rk_ctx* ctx;
+  int kind;
+  double scalar;
+  const b200rk_vec* lambda;
+};
+
+struct RhsCall {
+  b200rk_rhs_fn f;
+  void* user;
+  bool negate_time;  // backward pass: g(t, y) = -f(-t, y)   (ode.nim:545)
+  int64_t* evals;
+};
+
+// ---- runtime.cu -------------------------------------------------------------------------------------
+int ensure_partials(b200rk_ctx* c, size_t blocks);
+ReduceScratch reduce_scratch(b200rk_ctx* c);                 // hands out the next reduction sequence number
+int setup_p2p(b200rk_ctx* c);
+void shard_range(size_t n, int rank, int world, size_t* off, size_t* len);
+int vec_alloc(b200rk_ctx* c, size_t n_global, b200rk_vec** out);
+void vec_release(b200rk_vec* v);
+int check_same(const b200rk_ctx* c, const b200rk_vec* a, const b200rk_vec* b);
+int vec_copy_raw(b200rk_ctx* c, b200rk_vec* dst, const b200rk_vec* src);
+
+struct Workspace {
+  b200rk_ctx* c;
+  std::vector<b200rk_vec*> held;
+  explicit Workspace(b200rk_ctx* ctx) : c(ctx) {}
+  int get(size_t n, b200rk_vec** out) {
+    TRY(vec_alloc(c, n, out));
+    held.push_back(*out);
+    return B200RK_OK;
+  }
+  ~Workspace() { for (auto* v : held) vec_release(v); }
+};
+
+struct StepCounters { int64_t attempts = 0, rejected = 0, limiter_hits = 0; };
+
+// ---- launch.cu --------------------------------------------------------------------------------------
+int launch_stage(b200rk_ctx* c, int m, const double* y, const double* const* k, const double* w, double cc, bool chain,
+                 double* out, size_t n);
+int launch_finish(b200rk_ctx* c, const FinishPlan& p);
+int fetch_global_sum(b200rk_ctx* c, double* out);
+int launch_ewise(b200rk_ctx* c, int op, const double* a, const double* b, double s, double* out, size_t n, int cls);
+int launch_hermite(b200rk_ctx* c, const double* y1, const double* dy1, const double* y2, const double* dy2, double h00,
+                   double hA, double h01, double hB, double* out, size_t n);
+int launch_rk4_final(b200rk_ctx* c, const double* y, const double* k1, const double* k2, const double* k3, const double* k4,
+                     double c6, double* out, size_t n);
+int launch_lorenz96(b200rk_ctx* c, const double* y, const double* left2, const double* right1, double F, double* out, size_t n);
+int launch_sum(b200rk_ctx* c, const double* a, size_t n);
+
+// ---- executor.cu ------------------------------------------------------------------------------------
+int builtin_rhs_fn(double t, const b200rk_vec* y, b200rk_vec* dydt, void* user);
+int eval_rhs(b200rk_ctx* c, const RhsCall& r, double t, const b200rk_vec* y, b200rk_vec* out);
+int run_row(b200rk_ctx* c, const Row& row, double cfac, bool chain, double dt, const b200rk_vec* y, b200rk_vec* const* k,
+            b200rk_vec* out);
+int plan_finish(const b200rk_ctx* c, const MethodDef& md, double dt, double absTol, double relTol, const b200rk_vec* y,
+                b200rk_vec* const* k, b200rk_vec* ynew, bool ynew_ready, double* err_out, FinishPlan* p);
+int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, double t, const b200rk_vec* y, const b200rk_vec* fsal,
+            double dt_in, const b200rk_options& o, b200rk_vec* y_new, b200rk_vec* fsal_new, double* dt_used,
+            double* error_out, StepCounters* cnt);
+int hermite_into(b200rk_ctx* c, b200rk_vec* out, double x, double x1, double x2, const b200rk_vec* y1, const b200rk_vec* y2,
+                 const b200rk_vec* dy1, const b200rk_vec* dy2);

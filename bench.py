@@ -480,8 +480,12 @@ def run_sweep(args):
         glam = nn.GpuVector.from_local(n, 0.1 + 9.9 * i / float(max(n - 1, 1)), ctx)
         gy0 = nn.GpuVector.from_local(n, 1.0 + 0.5 * np.sin(2.0 * np.pi * i / float(n)), ctx)
         rhs = nn.rhsDiagLinear(glam)
-        for fuse in (0, 1):
+        # general pipeline / fused attempt driven by the host / fused attempt inside the persistent device loop
+        for name, fuse, devloop in (("pipeline", 0, 0), ("fused", 1, 0), ("fused_device_loop", 1, 1)):
+            if devloop and world > 1:
+                continue
             ctx.set("fuse_pointwise", fuse)
+            ctx.set("device_loop", devloop)
             sv = nn.Solver("dopri54", rhs, gy0, 1e12, nn.newODEoptions(**OPTS))
             sv.advance(8)
             torch.cuda.synchronize()
@@ -490,11 +494,12 @@ def run_sweep(args):
             torch.cuda.synchronize()
             dt_s = allmax(time.perf_counter() - t0)
             sv.close()
-            row = {"log2n": lg, "n_gpus": world, "kernel": "solver_dopri54_" + ("fused" if fuse else "pipeline"),
+            row = {"log2n": lg, "n_gpus": world, "kernel": "solver_dopri54_" + name,
                    "steps_per_sec": args.sweep_solver_steps / dt_s, "us_per_step": 1e6 * dt_s / args.sweep_solver_steps}
             rows.append(row)
             if rank == 0:
                 print(json.dumps(row), flush=True)
+        ctx.set("device_loop", -1)
         ctx.set("fuse_pointwise", 1)
         for v in vecs + [out, glam, gy0]:
             v.free()

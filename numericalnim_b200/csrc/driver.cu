@@ -108,6 +108,20 @@ static int solver_advance(b200rk_solver* s, int64_t max_steps, int64_t* steps_do
   const MethodDef& md = *s->md;
   int64_t done = 0;
   const long high = (long)s->targets.size() - 1;
+  // Small N, element-local built-in RHS, no dense output: the whole loop below runs inside ONE persistent
+  // cooperative kernel (grid barrier per attempt, controller on the device) — kernels.cuh: fused_run_kernel.
+  if (!s->finished && !s->dense && md.use_fsal && s->cur == s->fcur && s->t < s->tEnd &&
+      device_loop_eligible(c, md, s->rhs, s->Y[0]->n_local)) {
+    DeviceLoopIO io{{s->Y[0], s->Y[1]}, {s->F[0], s->F[1]}, s->cur, s->t, s->dt, s->tEnd, s->error, 0, 0, 0, 0};
+    TRY(run_device_loop(c, md, s->rhs, s->o, &io, max_steps));
+    s->cur = s->fcur = io.cur;
+    s->t = io.t; s->dt = io.dt; s->error = io.error;
+    s->stats.steps += io.steps;
+    s->stats.rhs_evals += io.attempts * (md.stages - 1);
+    s->cnt.attempts += io.attempts; s->cnt.rejected += io.rejected; s->cnt.limiter_hits += io.limiter_hits;
+    done = io.steps;
+    if (s->t < s->tEnd) { if (steps_done) *steps_done = done; return B200RK_OK; }  // stopped at max_steps
+  }
   while (!s->finished && s->t < s->tEnd) {
     if (s->dense) {
       if (high < s->denseIndex) break;

@@ -372,3 +372,95 @@ int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, double t, co
   *error_out = error;
   return B200RK_OK;
 }
+
+// =====================================================================================================
+// device-resident driver loop (small N): one cooperative kernel for many accepted steps
+// =====================================================================================================
+bool device_loop_eligible(const b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, size_t n_local) {
+  if (c->device_loop == 0 || c->world != 1 || !c->fuse_pointwise || n_local == 0) return false;
+  if (c->device_loop < 0 && n_local > ((size_t)1 << 21)) return false;  // beyond ~2^21 the launch + read-back is < 10 % of a step
+  int kind = 0;
+  const BuiltinRhs* br = nullptr;
+  if (!pointwise_kind(rhs, &kind, &br) || md.rk4_final || !method_fusable(md)) return false;
+  return fused_pattern_of(c, md) >= 0;
+}
+
+template <int PAT, int KIND, int W>
+static int launch_run_cfg(b200rk_ctx* c, RunArgs<Pattern<PAT>::S>& a) {
+  auto kernel = fused_run_kernel<PAT, KIND, W, kThreads>;
+  int per_sm = 0;
+  CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0));
+  if (per_sm < 1) return fail(c, B200RK_ECUDA, "device loop: kernel does not fit on an SM");
+  const size_t tiles = std::max<size_t>(1, (a.f.n / W + kThreads - 1) / kThreads);
+  const unsigned grid = (unsigned)std::min<size_t>(tiles, (size_t)per_sm * c->sm_count);  // all CTAs co-resident (grid barrier)
+  TRY(ensure_partials(c, 2 * (size_t)grid));
+  a.partials = c->d_partials;
+  void* args[] = {&a};
+  CUDA_TRY(c, cudaLaunchCooperativeKernel((void*)kernel, dim3(grid), dim3(kThreads), args, 0, c->stream));
+  return B200RK_OK;
+}
+template <int PAT>
+static int launch_run_pat(b200rk_ctx* c, int kind, RunArgs<Pattern<PAT>::S>& a) {
+  const bool w4 = a.f.n >= ((size_t)1 << 20);
+  if (kind == PW_SCALE) return w4 ? launch_run_cfg<PAT, PW_SCALE, 4>(c, a) : launch_run_cfg<PAT, PW_SCALE, 2>(c, a);
+  return w4 ? launch_run_cfg<PAT, PW_DIAG, 4>(c, a) : launch_run_cfg<PAT, PW_DIAG, 2>(c, a);
+}
+
+template <int PAT>
+static int run_device_loop_pat(b200rk_ctx* c, const MethodDef& md, int kind, const BuiltinRhs* br, bool negate,
+                               const b200rk_options& o, DeviceLoopIO* io, int64_t max_steps) {
+  constexpr int S = Pattern<PAT>::S;
+  RunArgs<S> a;
+  std::memset(&a, 0, sizeof(a));
+  a.f.lam = br->lambda ? br->lambda->d : nullptr;
+  a.f.rhs_scalar = negate ? -br->scalar : br->scalar;
+  a.f.rhs_sign = negate ? 1.0 : -1.0;
+  for (int s = 2; s <= S; ++s) row_mask(c, md.a[s], a.f.a[s - 2], S - 1);
+  row_mask(c, md.b, a.f.b, S);
+  row_mask(c, md.bhat, a.f.bh, S);
+  a.f.absTol = o.absTol; a.f.relTol = o.relTol; a.f.n = io->Y[0]->n_local;
+  for (int i = 0; i < 2; ++i) { a.Y[i] = io->Y[i]->d; a.F[i] = io->F[i]->d; }
+  a.dtMin = o.dtMin; a.dtMax = o.dtMax;
+  a.inv_order_inner = 1.0 / double(md.order_int);   // ode.nim:71 (int order)
+  a.inv_order_outer = 1.0 / md.order;               // ode.nim:537 (float order)
+  a.n_global = double(io->Y[0]->n_global);
+  a.max_steps = max_steps < 0 ? (long long)1 << 62 : (long long)max_steps;
+  if (!c->d_run_state) {
+    CUDA_TRY(c, cudaMalloc(&c->d_run_state, sizeof(RunState)));
+    CUDA_TRY(c, cudaHostAlloc(&c->h_run_state, sizeof(RunState), cudaHostAllocMapped));
+    CUDA_TRY(c, cudaHostGetDevicePointer(&c->h_run_state_dev, c->h_run_state, 0));
+  }
+  RunState st{};
+  st.t = io->t; st.dt = io->dt; st.t_end = io->t_end; st.error = io->error; st.cur = io->cur;
+  CUDA_TRY(c, cudaMemcpyAsync(c->d_run_state, &st, sizeof(st), cudaMemcpyHostToDevice, c->stream));
+  a.state = c->d_run_state;
+  a.state_host = c->h_run_state_dev;
+  a.seq_host = c->h_seq_dev;
+  a.seq = ++c->seq;
+  {
+    ProfScope ps(c, B200RK_K_FUSED, 0.0);  // bytes unknown up front (data-dependent number of attempts)
+    TRY(launch_run_pat<PAT>(c, kind, a));
+  }
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // one wait per launch (many steps), not per attempt
+  const RunState out = *c->h_run_state;
+  io->t = out.t; io->dt = out.dt; io->error = out.error; io->cur = out.cur;
+  io->steps = out.steps; io->attempts = out.attempts; io->rejected = out.rejected; io->limiter_hits = out.limiter_hits;
+  if (out.status != 0) return fail(c, B200RK_ENONFINITE, "error norm is NaN (the reference would loop forever here)");
+  return B200RK_OK;
+}
+
+int run_device_loop(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, const b200rk_options& o, DeviceLoopIO* io,
+                    int64_t max_steps) {
+  int kind = 0;
+  const BuiltinRhs* br = nullptr;
+  if (!pointwise_kind(rhs, &kind, &br)) return fail(c, B200RK_EINVAL, "device loop: right-hand side is not element-local");
+  if (kind == PW_DIAG) TRY(check_same(c, io->Y[0], br->lambda));
+  switch (fused_pattern_of(c, md)) {
+    case PAT_DOPRI54: return run_device_loop_pat<PAT_DOPRI54>(c, md, kind, br, rhs.negate_time, o, io, max_steps);
+    case PAT_DOPRI54_STRICT: return run_device_loop_pat<PAT_DOPRI54_STRICT>(c, md, kind, br, rhs.negate_time, o, io, max_steps);
+    case PAT_TSIT54: return run_device_loop_pat<PAT_TSIT54>(c, md, kind, br, rhs.negate_time, o, io, max_steps);
+    case PAT_VERN65: return run_device_loop_pat<PAT_VERN65>(c, md, kind, br, rhs.negate_time, o, io, max_steps);
+    case PAT_VERN65_STRICT: return run_device_loop_pat<PAT_VERN65_STRICT>(c, md, kind, br, rhs.negate_time, o, io, max_steps);
+  }
+  return fail(c, B200RK_EINVAL, "device loop: unsupported method");
+}

@@ -51,6 +51,10 @@ struct b200rk_ctx {
   unsigned long long* h_seq_dev = nullptr;  // device alias
   unsigned long long seq = 0;               // last sequence number handed to a reducing launch
   bool spin_readback = true;                // poll h_seq instead of cudaStreamSynchronize (single GPU)
+  int device_loop = -1;                     // persistent cooperative driver loop: -1 auto (n_local <= 2^21), 0 off, 1 on
+  RunState* d_run_state = nullptr;          // device copy of the loop state
+  RunState* h_run_state = nullptr;          // pinned + mapped mirror
+  RunState* h_run_state_dev = nullptr;
   // in-kernel all-reduce of the error norm over peer mailboxes (multi-GPU)
   unsigned long long* d_mail = nullptr;     // this rank's mailbox
   unsigned long long* peer_mail[kMaxPeers] = {nullptr};
@@ -257,5 +261,16 @@ int plan_finish(const b200rk_ctx* c, const MethodDef& md, double dt, double absT
 int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, double t, const b200rk_vec* y, const b200rk_vec* fsal,
             double dt_in, const b200rk_options& o, b200rk_vec* y_new, b200rk_vec* fsal_new, double* dt_used,
             double* error_out, StepCounters* cnt);
+// Device-resident driver loop (kernels.cuh: fused_run_kernel): element-local built-in RHS, FSAL pair, one GPU.
+struct DeviceLoopIO {
+  b200rk_vec* Y[2];
+  b200rk_vec* F[2];
+  int cur;
+  double t, dt, t_end, error;
+  int64_t steps, attempts, rejected, limiter_hits;
+};
+bool device_loop_eligible(const b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, size_t n_local);
+int run_device_loop(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, const b200rk_options& o, DeviceLoopIO* io,
+                    int64_t max_steps);
 int hermite_into(b200rk_ctx* c, b200rk_vec* out, double x, double x1, double x2, const b200rk_vec* y1, const b200rk_vec* y2,
                  const b200rk_vec* dy1, const b200rk_vec* dy2);

@@ -20,6 +20,7 @@
 // touched exactly once per launch). The Butcher row travels as kernel parameters, i.e. in the constant
 // bank: one uniform broadcast read per weight, no shared-memory staging or barrier needed.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -644,6 +645,127 @@ __global__ void __launch_bounds__(THREADS) fused_attempt_kernel(const FusedArgs<
     }
   }
   grid_sum_finish<THREADS>(acc, a.rs);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Device-resident driver loop for element-local right-hand sides (small N):
+// ONE persistent cooperative kernel runs up to `max_steps` accepted steps of the `while t < tEnd` loop
+// (ode.nim:511-541) including the retry loop (ode.nim:57-76) and both controllers, with a grid-wide barrier
+// per attempt instead of a kernel launch + host read-back per attempt. Every CTA adds the per-CTA partials in
+// index order after the barrier, so all CTAs compute the same error and take the same branch. The state
+// vectors ping-pong between Y[0]/Y[1] and F[0]/F[1] exactly like the host-driven path. Element-wise
+// arithmetic is the same fused_elem as fused_attempt_kernel (bit-identical per attempt for a given dt); the
+// controller uses the device pow(), which may differ from glibc's in the last ulp, so step sequences agree
+// with the host-driven path within the tolerances stated in DESIGN.md §5, not bit for bit.
+// ---------------------------------------------------------------------------------------------------
+struct RunState {
+  double t, dt, t_end, error;
+  long long steps, attempts, rejected, limiter_hits;
+  int cur;     // Y[cur], F[cur] hold the current state / FSAL
+  int status;  // 0 ok, 1 error norm is NaN
+};
+
+template <int S>
+struct RunArgs {
+  FusedArgs<S> f;  // weights, tolerances, RHS parameters (pointers and dt are overridden per attempt)
+  double* Y[2];
+  double* F[2];
+  double dtMin, dtMax, inv_order_inner, inv_order_outer, n_global;
+  long long max_steps;
+  double* partials;  // [2][gridDim.x]
+  RunState* state;        // device
+  RunState* state_host;   // mapped pinned mirror, written once at exit
+  unsigned long long* seq_host;
+  unsigned long long seq;
+};
+
+__device__ __forceinline__ double dev_nim_min(double x, double y) { return (x <= y) ? x : y; }
+__device__ __forceinline__ double dev_nim_max(double x, double y) { return (y <= x) ? x : y; }
+
+template <int PAT, int KIND, int W, int THREADS>
+__global__ void __launch_bounds__(THREADS) fused_run_kernel(const RunArgs<Pattern<PAT>::S> a) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  __shared__ double bcast;
+  RunState st = *a.state;
+  FusedArgs<Pattern<PAT>::S> f = a.f;
+  const size_t nvec = f.n / W;
+  const size_t stride = (size_t)gridDim.x * THREADS;
+  int parity = 0;
+  long long done = 0;
+  while (st.t < st.t_end && done < a.max_steps && st.status == 0) {
+    double dt = dev_nim_min(st.dt, st.t_end - st.t);                      // ode.nim:525
+    int limit = 0;
+    double error = 0.0;
+    while (true) {                                                        // ode.nim:58
+      f.dt = dt; f.cb = dt; f.cbh = dt;
+      const double* y = a.Y[st.cur];
+      const double* k1 = a.F[st.cur];
+      double* yn = a.Y[1 - st.cur];
+      double* ks = a.F[1 - st.cur];
+      double acc = 0.0;
+      for (size_t v = (size_t)blockIdx.x * THREADS + threadIdx.x; v < nvec; v += stride) {
+        const Pk<W> yv = ld_plain<W>(y + v * W), kv = ld_plain<W>(k1 + v * W);  // coherent: buffers are rewritten inside this kernel
+        Pk<W> lv;
+        if (KIND == PW_DIAG) lv = ld_stream<W>(f.lam + v * W);
+        Pk<W> yo, ko;
+#pragma unroll
+        for (int e = 0; e < W; ++e)
+          acc = __dadd_rn(acc, fused_elem<PAT, KIND>(yv.v[e], kv.v[e], KIND == PW_DIAG ? lv.v[e] : 0.0, f, yo.v[e], ko.v[e]));
+        st_stream<W>(yn + v * W, yo);
+        st_stream<W>(ks + v * W, ko);
+      }
+      if (blockIdx.x == 0) {
+        const size_t i = nvec * W + threadIdx.x;
+        if (i < f.n) {
+          double y1, k1o;
+          acc = __dadd_rn(acc, fused_elem<PAT, KIND>(y[i], k1[i], KIND == PW_DIAG ? f.lam[i] : 0.0, f, y1, k1o));
+          yn[i] = y1;
+          ks[i] = k1o;
+        }
+      }
+      const double bsum = block_sum<THREADS>(acc);
+      double* part = a.partials + (size_t)parity * gridDim.x;
+      if (threadIdx.x == 0) part[blockIdx.x] = bsum;
+      __threadfence();
+      grid.sync();
+      double p = 0.0;
+      for (unsigned int i = threadIdx.x; i < gridDim.x; i += THREADS) p = __dadd_rn(p, __ldcg(part + i));
+      const double total = block_sum<THREADS>(p);
+      if (threadIdx.x == 0) bcast = total;
+      __syncthreads();
+      const double S2 = bcast;
+      __syncthreads();
+      parity ^= 1;
+      st.attempts++;
+      error = sqrt(1.0 / a.n_global * S2);                                // ode.nim:64-65
+      if (error <= 1) break;                                              // ode.nim:69-70
+      if (error != error) { st.status = 1; break; }
+      st.rejected++;
+      dt = dt * dev_nim_min(4, dev_nim_max(0.125, 0.9 * pow(1.0 / error, a.inv_order_inner)));  // ode.nim:71
+      if (fabs(dt) < a.dtMin) { dt = a.dtMin; limit += 1; st.limiter_hits++; }                  // ode.nim:72-74
+      else if (a.dtMax < fabs(dt)) dt = a.dtMax;                                                // ode.nim:75-76
+      if (!(limit < 2)) break;
+    }
+    st.error = error;
+    if (st.status != 0) break;
+    st.cur = 1 - st.cur;
+    st.t += dt;                                                           // ode.nim:532
+    st.steps++;
+    ++done;
+    if (error == 0.0) dt *= 5;                                            // ode.nim:533-541
+    else dt = dt * dev_nim_min(4, dev_nim_max(0.125, 0.9 * pow(1.0 / error, a.inv_order_outer)));
+    if (dt < a.dtMin) dt = a.dtMin;
+    else if (a.dtMax < dt) dt = a.dtMax;
+    st.dt = dt;
+  }
+  grid.sync();  // every store of the last attempt is done before the host is told
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *a.state = st;
+    *a.state_host = st;
+    __threadfence_system();
+    *(volatile unsigned long long*)a.seq_host = a.seq;
+    __threadfence_system();
+  }
 }
 
 // Fused RK4 step for element-local right-hand sides (ode.nim:180-189): reads y (+ lambda), writes yNew.

@@ -180,6 +180,7 @@ static int ctx_common_init(b200rk_ctx* c) {
   *c->h_seq = 0;
   CUDA_TRY(c, cudaHostGetDevicePointer(&c->h_seq_dev, c->h_seq, 0));
   if (const char* e = getenv("B200RK_SPIN_READBACK")) c->spin_readback = atoi(e) != 0;
+  if (const char* e = getenv("B200RK_DEVICE_LOOP")) c->device_loop = atoi(e) < 0 ? -1 : (atoi(e) != 0);
   TRY(ensure_partials(c, 1));
   if (const char* e = getenv("B200RK_VEC_WIDTH")) c->vec_width = (atoi(e) == 2) ? 2 : 4;
   if (const char* e = getenv("B200RK_CTAS_PER_SM")) c->ctas_per_sm = std::max(0, atoi(e));
@@ -242,6 +243,10 @@ void b200rk_destroy(b200rk_ctx* c) {
   if (c->d_mail) cudaFree(c->d_mail);
   if (c->comm) g_nccl.CommDestroy(c->comm);
   cudaFree(c->d_partials); cudaFree(c->d_ticket); cudaFree(c->d_result); cudaFree(c->d_halo); cudaFreeHost(c->h_result); cudaFreeHost(c->h_seq);
+  if (c->d_run_state) cudaFree(c->d_run_state);
+  if (c->h_run_state) cudaFreeHost(c->h_run_state);
+  if (c->d_run_state) cudaFree(c->d_run_state);
+  if (c->h_run_state) cudaFreeHost(c->h_run_state);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -260,6 +265,7 @@ int b200rk_set(b200rk_ctx* c, const char* key, int64_t v) {
   else if (k == "profile") c->profile = v != 0;
   else if (k == "fuse_pointwise") c->fuse_pointwise = v != 0;
   else if (k == "spin_readback") c->spin_readback = v != 0;
+  else if (k == "device_loop") c->device_loop = v < 0 ? -1 : (v != 0);
   else if (k == "fuse_stencil") c->fuse_stencil = v != 0;
   else if (k == "l2_hints") c->l2_hints = v < 0 ? -1 : (v != 0);
   else if (k == "fused_ctas_per_sm") { if (v < 0) return fail(c, B200RK_EINVAL, "fused_ctas_per_sm must be >= 0"); c->fused_ctas_per_sm = (int)v; }
@@ -282,6 +288,7 @@ int b200rk_get(const b200rk_ctx* c, const char* key, int64_t* v) {
   else if (k == "finish_ctas_per_sm") *v = c->finish_ctas_per_sm;
   else if (k == "fuse_pointwise") *v = c->fuse_pointwise;
   else if (k == "spin_readback") *v = c->spin_readback;
+  else if (k == "device_loop") *v = c->device_loop;
   else if (k == "p2p") *v = c->p2p;
   else if (k == "fuse_stencil") *v = c->fuse_stencil;
   else if (k == "l2_hints") *v = c->l2_hints;

@@ -303,12 +303,22 @@ def run_ours(args):
             roofline["traffic"] = traffic_db.get("stage_l96_kernel_%s_2p%d" % (integrator, lg))
             path = "stage+stencil fused (built-in Lorenz-96), finish kernel"
         else:
-            path = "fused_attempt (element-local built-in RHS)"
+            devloop = world == 1 and ctx.get("device_loop") != 0
             fu = prof["fused"]
             a = gbs(fu)
-            roofline = {"bound": "hbm", "kernel": "fused_attempt_kernel<S,RHS> (whole attempt of an element-local IVP in one kernel: all stages, RHS, yNew, error norm)",
+            attempts_instr = fu["bytes"] / (8.0 * n_shard * 5) if n_shard else 0.0  # 5 vector passes per attempt
+            if devloop:
+                path = "fused_run (element-local built-in RHS: all K steps in one persistent cooperative kernel, controller on the device)"
+                kname = ("fused_run_kernel<PAT,RHS> (persistent cooperative kernel: every attempt = all stages, RHS, yNew, error norm, "
+                         "grid barrier, device-side controller; one launch runs the K steps)")
+            else:
+                path = "fused_attempt (element-local built-in RHS)"
+                kname = "fused_attempt_kernel<PAT,RHS> (whole attempt of an element-local IVP in one kernel: all stages, RHS, yNew, error norm)"
+            roofline = {"bound": "hbm", "kernel": kname,
                         "achieved": a, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": a / peak, "frac_of_nominal_8000": a / 8000.0,
-                        "traffic": traffic_db.get("fused_attempt_kernel_%s_2p%d" % (integrator, lg)), "launches": fu["launches"],
+                        "traffic": (traffic_db.get("fused_run_kernel_per_attempt_%s_2p%d" % (integrator, lg), 0.0) * attempts_instr / max(1, fu["launches"]) or None)
+                        if devloop else traffic_db.get("fused_attempt_kernel_%s_2p%d" % (integrator, lg)),
+                        "launches": fu["launches"], "attempts_in_launches": attempts_instr, "us_per_attempt": 1e3 * fu["ms"] / max(1.0, attempts_instr),
                         "avg_launch_us": 1e3 * fu["ms"] / max(1, fu["launches"]), "algorithmic_bytes_per_launch": fu["bytes"] / max(1, fu["launches"]),
                         "instrumented_ms_per_step": prof["instrumented_ms"] / args.steps,
                         "kernel_time_share_of_step": fu["ms"] / prof["instrumented_ms"] if prof["instrumented_ms"] > 0 else None}
@@ -321,7 +331,7 @@ def run_ours(args):
                        "sharding": "contiguous shards, 1 all-reduce(sum, 1 x f64) of the error norm per attempt" if world > 1 else "single GPU, no collective",
                        "vec_width": ctx.get("vec_width"), "ctas_per_sm": ctx.get("ctas_per_sm"), "finish_ctas_per_sm": ctx.get("finish_ctas_per_sm"),
                        "fuse_pointwise": ctx.get("fuse_pointwise"), "fused_ctas_per_sm": ctx.get("fused_ctas_per_sm"),
-                       "spin_readback": ctx.get("spin_readback"), "l2_hints": ctx.get("l2_hints"),
+                       "spin_readback": ctx.get("spin_readback"), "l2_hints": ctx.get("l2_hints"), "device_loop": ctx.get("device_loop"),
                        "error_norm_allreduce": ("in-kernel peer mailboxes over NVLink (CUDA IPC)" if ctx.get("p2p") else "ncclAllReduce") if world > 1 else None},
             "attempts": attempts, "attempts_per_sec": attempts * world / (ms_max * 1e-3), "rejected": head["rejected"],
             "t_reached": t_now, "dt_next": dt_next,

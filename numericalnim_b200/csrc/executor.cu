@@ -378,7 +378,8 @@ int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, double t, co
 // =====================================================================================================
 bool device_loop_eligible(const b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, size_t n_local) {
   if (c->device_loop == 0 || c->world != 1 || !c->fuse_pointwise || n_local == 0) return false;
-  if (c->device_loop < 0 && n_local > ((size_t)1 << 21)) return false;  // beyond ~2^21 the launch + read-back is < 10 % of a step
+  // measured (profiles/r01_sweep_small_device_loop.json): 2.4x at 2^16 (5.8 vs 14.1 us/step), still +5 % at 2^23, so
+  // the auto policy (-1) takes the device loop at every size
   int kind = 0;
   const BuiltinRhs* br = nullptr;
   if (!pointwise_kind(rhs, &kind, &br) || md.rk4_final || !method_fusable(md)) return false;
@@ -437,12 +438,15 @@ static int run_device_loop_pat(b200rk_ctx* c, const MethodDef& md, int kind, con
   a.state_host = c->h_run_state_dev;
   a.seq_host = c->h_seq_dev;
   a.seq = ++c->seq;
+  const size_t prof_slot = c->prof.size();
   {
-    ProfScope ps(c, B200RK_K_FUSED, 0.0);  // bytes unknown up front (data-dependent number of attempts)
+    ProfScope ps(c, B200RK_K_FUSED, 0.0);  // bytes patched below: the number of attempts is data-dependent
     TRY(launch_run_pat<PAT>(c, kind, a));
   }
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // one wait per launch (many steps), not per attempt
   const RunState out = *c->h_run_state;
+  if (c->profile && c->prof.size() > prof_slot)  // y, k1 (+ lambda) read, yNew and k_S written, per attempt
+    c->prof[prof_slot].bytes = 8.0 * double(a.f.n) * (4 + (kind == PW_DIAG ? 1 : 0)) * double(out.attempts);
   io->t = out.t; io->dt = out.dt; io->error = out.error; io->cur = out.cur;
   io->steps = out.steps; io->attempts = out.attempts; io->rejected = out.rejected; io->limiter_hits = out.limiter_hits;
   if (out.status != 0) return fail(c, B200RK_ENONFINITE, "error norm is NaN (the reference would loop forever here)");

@@ -51,7 +51,7 @@ struct b200rk_ctx {
   unsigned long long* h_seq_dev = nullptr;  // device alias
   unsigned long long seq = 0;               // last sequence number handed to a reducing launch
   bool spin_readback = true;                // poll h_seq instead of cudaStreamSynchronize (single GPU)
-  int device_loop = -1;                     // persistent cooperative driver loop: -1 auto (n_local <= 2^21), 0 off, 1 on
+  int device_loop = -1;                     // persistent cooperative driver loop: -1 auto (= on, single GPU), 0 off, 1 on
   RunState* d_run_state = nullptr;          // device copy of the loop state
   RunState* h_run_state = nullptr;          // pinned + mapped mirror
   RunState* h_run_state_dev = nullptr;

@@ -303,7 +303,7 @@ def run_ours(args):
             roofline["traffic"] = traffic_db.get("stage_l96_kernel_%s_2p%d" % (integrator, lg))
             path = "stage+stencil fused (built-in Lorenz-96), finish kernel"
         else:
-            devloop = world == 1 and ctx.get("device_loop") != 0
+            devloop = ctx.get("device_loop") != 0 and (world == 1 or bool(ctx.get("p2p")))
             fu = prof["fused"]
             a = gbs(fu)
             attempts_instr = fu["bytes"] / (8.0 * n_shard * 5) if n_shard else 0.0  # 5 vector passes per attempt
@@ -492,7 +492,7 @@ def run_sweep(args):
         rhs = nn.rhsDiagLinear(glam)
         # general pipeline / fused attempt driven by the host / fused attempt inside the persistent device loop
         for name, fuse, devloop in (("pipeline", 0, 0), ("fused", 1, 0), ("fused_device_loop", 1, 1)):
-            if devloop and world > 1:
+            if devloop and world > 1 and not ctx.get("p2p"):
                 continue
             ctx.set("fuse_pointwise", fuse)
             ctx.set("device_loop", devloop)

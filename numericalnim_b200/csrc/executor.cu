@@ -377,7 +377,8 @@ int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, double t, co
 // device-resident driver loop (small N): one cooperative kernel for many accepted steps
 // =====================================================================================================
 bool device_loop_eligible(const b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, size_t n_local) {
-  if (c->device_loop == 0 || c->world != 1 || !c->fuse_pointwise || n_local == 0) return false;
+  if (c->device_loop == 0 || !c->fuse_pointwise || n_local == 0) return false;
+  if (c->world > 1 && !c->p2p) return false;  // sharded: needs the peer mailboxes for the in-kernel all-reduce
   // measured (profiles/r01_sweep_small_device_loop.json): 2.4x at 2^16 (5.8 vs 14.1 us/step), still +5 % at 2^23, so
   // the auto policy (-1) takes the device loop at every size
   int kind = 0;
@@ -437,7 +438,10 @@ static int run_device_loop_pat(b200rk_ctx* c, const MethodDef& md, int kind, con
   a.state = c->d_run_state;
   a.state_host = c->h_run_state_dev;
   a.seq_host = c->h_seq_dev;
-  a.seq = ++c->seq;
+  a.seq = c->seq + 1;  // attempt i of this launch uses sequence number seq + i (same on every rank: lockstep)
+  a.mail.world = (c->world > 1 && c->p2p) ? c->world : 1;
+  a.mail.rank = c->rank;
+  for (int p = 0; p < kMaxPeers; ++p) a.mail.box[p] = (a.mail.world > 1 && p < c->world) ? c->peer_mail[p] : nullptr;
   const size_t prof_slot = c->prof.size();
   {
     ProfScope ps(c, B200RK_K_FUSED, 0.0);  // bytes patched below: the number of attempts is data-dependent
@@ -445,10 +449,13 @@ static int run_device_loop_pat(b200rk_ctx* c, const MethodDef& md, int kind, con
   }
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // one wait per launch (many steps), not per attempt
   const RunState out = *c->h_run_state;
+  c->seq += (unsigned long long)std::max<long long>(1, out.attempts);
+  if (a.mail.world > 1) c->collectives += out.attempts;
   if (c->profile && c->prof.size() > prof_slot)  // y, k1 (+ lambda) read, yNew and k_S written, per attempt
     c->prof[prof_slot].bytes = 8.0 * double(a.f.n) * (4 + (kind == PW_DIAG ? 1 : 0)) * double(out.attempts);
   io->t = out.t; io->dt = out.dt; io->error = out.error; io->cur = out.cur;
   io->steps = out.steps; io->attempts = out.attempts; io->rejected = out.rejected; io->limiter_hits = out.limiter_hits;
+  if (out.status == 2) return fail(c, B200RK_ENCCL, "peer mailbox all-reduce timed out inside the device loop");
   if (out.status != 0) return fail(c, B200RK_ENONFINITE, "error norm is NaN (the reference would loop forever here)");
   return B200RK_OK;
 }

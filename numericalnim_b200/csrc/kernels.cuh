@@ -58,16 +58,17 @@ __device__ __forceinline__ Pk<4> ld_stream<4>(const double* p) {
                : "l"(p));
   return r;
 }
-// coherent variant for kernels whose output may alias an input (in-place Vector ops)
+// coherent variant for kernels whose output may alias an input (in-place Vector ops) or that re-read buffers
+// they rewrite themselves (the device-resident loop): plain ld.global (no .nc), still one 128/256-bit access
 template <int W>
 __device__ __forceinline__ Pk<W> ld_plain(const double* p) {
-  Pk<W> r;
-  if (W == 2) {
-    const double2 t = *reinterpret_cast<const double2*>(p);
-    r.v[0] = t.x; r.v[W > 1 ? 1 : 0] = t.y;
+  Pk<W> r = {};
+  if constexpr (W == 4) {
+    asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p) : "memory");
+  } else if constexpr (W == 2) {
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.v[0]), "=d"(r.v[1]) : "l"(p) : "memory");
   } else {
-#pragma unroll
-    for (int e = 0; e < W; ++e) r.v[e] = p[e];
+    r.v[0] = *p;
   }
   return r;
 }
@@ -676,14 +677,15 @@ struct RunArgs {
   RunState* state;        // device
   RunState* state_host;   // mapped pinned mirror, written once at exit
   unsigned long long* seq_host;
-  unsigned long long seq;
+  unsigned long long seq;        // sequence number of attempt 0 of this launch (attempt i uses seq + i)
+  PeerMail mail;                 // world > 1: the error norm is all-reduced over the peer mailboxes every attempt
 };
 
 __device__ __forceinline__ double dev_nim_min(double x, double y) { return (x <= y) ? x : y; }
 __device__ __forceinline__ double dev_nim_max(double x, double y) { return (y <= x) ? x : y; }
 
 template <int PAT, int KIND, int W, int THREADS>
-__global__ void __launch_bounds__(THREADS) fused_run_kernel(const RunArgs<Pattern<PAT>::S> a) {
+__global__ void __launch_bounds__(THREADS, 2) fused_run_kernel(const RunArgs<Pattern<PAT>::S> a) {
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
   __shared__ double bcast;
   RunState st = *a.state;
@@ -703,16 +705,32 @@ __global__ void __launch_bounds__(THREADS) fused_run_kernel(const RunArgs<Patter
       double* yn = a.Y[1 - st.cur];
       double* ks = a.F[1 - st.cur];
       double acc = 0.0;
-      for (size_t v = (size_t)blockIdx.x * THREADS + threadIdx.x; v < nvec; v += stride) {
-        const Pk<W> yv = ld_plain<W>(y + v * W), kv = ld_plain<W>(k1 + v * W);  // coherent: buffers are rewritten inside this kernel
-        Pk<W> lv;
-        if (KIND == PW_DIAG) lv = ld_stream<W>(f.lam + v * W);
-        Pk<W> yo, ko;
+      {  // software-pipelined grid-stride loop (see fused_attempt_kernel); coherent loads: Y/F are rewritten inside this kernel
+        size_t v = (size_t)blockIdx.x * THREADS + threadIdx.x;
+        Pk<W> yv, kv, lv;
+        if (v < nvec) {
+          yv = ld_plain<W>(y + v * W);
+          kv = ld_plain<W>(k1 + v * W);
+          if (KIND == PW_DIAG) lv = ld_stream<W>(f.lam + v * W);
+        }
+        while (v < nvec) {
+          const size_t vn = v + stride;
+          Pk<W> yn_, kn_, ln_;
+          if (vn < nvec) {
+            yn_ = ld_plain<W>(y + vn * W);
+            kn_ = ld_plain<W>(k1 + vn * W);
+            if (KIND == PW_DIAG) ln_ = ld_stream<W>(f.lam + vn * W);
+          }
+          Pk<W> yo, ko;
 #pragma unroll
-        for (int e = 0; e < W; ++e)
-          acc = __dadd_rn(acc, fused_elem<PAT, KIND>(yv.v[e], kv.v[e], KIND == PW_DIAG ? lv.v[e] : 0.0, f, yo.v[e], ko.v[e]));
-        st_stream<W>(yn + v * W, yo);
-        st_stream<W>(ks + v * W, ko);
+          for (int e = 0; e < W; ++e)
+            acc = __dadd_rn(acc, fused_elem<PAT, KIND>(yv.v[e], kv.v[e], KIND == PW_DIAG ? lv.v[e] : 0.0, f, yo.v[e], ko.v[e]));
+          st_stream<W>(yn + v * W, yo);
+          st_stream<W>(ks + v * W, ko);
+          yv = yn_; kv = kn_;
+          if (KIND == PW_DIAG) lv = ln_;
+          v = vn;
+        }
       }
       if (blockIdx.x == 0) {
         const size_t i = nvec * W + threadIdx.x;
@@ -733,8 +751,44 @@ __global__ void __launch_bounds__(THREADS) fused_run_kernel(const RunArgs<Patter
       const double total = block_sum<THREADS>(p);
       if (threadIdx.x == 0) bcast = total;
       __syncthreads();
-      const double S2 = bcast;
+      double S2 = bcast;
       __syncthreads();
+      if (a.mail.world > 1) {
+        // Sharded: block 0 publishes this shard's partial to every peer's mailbox; EVERY CTA then reads the
+        // `world` slots of the local mailbox and adds them in rank order, so no second grid barrier is needed
+        // and all CTAs of all ranks obtain the same bits.
+        __shared__ double peer_vals[kMaxPeers];
+        __shared__ int peer_bad;
+        const unsigned long long seq = a.seq + (unsigned long long)st.attempts;
+        const unsigned long long par = seq & 1ull;
+        const int q = threadIdx.x;
+        if (q == 0) peer_bad = 0;
+        __syncthreads();
+        if (q < a.mail.world) {
+          if (blockIdx.x == 0) {
+            volatile unsigned long long* dst = a.mail.box[q] + ((par * kMaxPeers + a.mail.rank) << 1);
+            dst[1] = (unsigned long long)__double_as_longlong(S2);
+            __threadfence_system();
+            dst[0] = seq;
+          }
+          volatile unsigned long long* src = a.mail.box[a.mail.rank] + ((par * kMaxPeers + q) << 1);
+          const long long t0 = clock64();
+          bool ok = true;
+          while (src[0] != seq) {
+            if (clock64() - t0 > (2ll << 30)) { ok = false; break; }
+          }
+          __threadfence_system();
+          peer_vals[q] = ok ? __longlong_as_double((long long)src[1]) : 0.0;
+          if (!ok) atomicExch(&peer_bad, 1);
+        }
+        __syncthreads();
+        double g = 0.0;
+        for (int p2 = 0; p2 < a.mail.world; ++p2) g = __dadd_rn(g, peer_vals[p2]);
+        S2 = g;
+        const int bad = peer_bad;
+        __syncthreads();
+        if (bad) { st.status = 2; st.attempts++; break; }
+      }
       parity ^= 1;
       st.attempts++;
       error = sqrt(1.0 / a.n_global * S2);                                // ode.nim:64-65
@@ -763,7 +817,7 @@ __global__ void __launch_bounds__(THREADS) fused_run_kernel(const RunArgs<Patter
     *a.state = st;
     *a.state_host = st;
     __threadfence_system();
-    *(volatile unsigned long long*)a.seq_host = a.seq;
+    *(volatile unsigned long long*)a.seq_host = a.seq + (unsigned long long)st.attempts;
     __threadfence_system();
   }
 }

@@ -428,7 +428,8 @@ static int run_device_loop_pat(b200rk_ctx* c, const MethodDef& md, int kind, con
   a.n_global = double(io->Y[0]->n_global);
   a.max_steps = max_steps < 0 ? (long long)1 << 62 : (long long)max_steps;
   if (!c->d_run_state) {
-    CUDA_TRY(c, cudaMalloc(&c->d_run_state, sizeof(RunState)));
+    CUDA_TRY(c, cudaMalloc(&c->d_run_state, sizeof(RunState) + 64));   // + [2][2] words: global-sum hand-off between CTAs
+    CUDA_TRY(c, cudaMemset(c->d_run_state, 0, sizeof(RunState) + 64));
     CUDA_TRY(c, cudaHostAlloc(&c->h_run_state, sizeof(RunState), cudaHostAllocMapped));
     CUDA_TRY(c, cudaHostGetDevicePointer(&c->h_run_state_dev, c->h_run_state, 0));
   }
@@ -442,6 +443,7 @@ static int run_device_loop_pat(b200rk_ctx* c, const MethodDef& md, int kind, con
   a.mail.world = (c->world > 1 && c->p2p) ? c->world : 1;
   a.mail.rank = c->rank;
   for (int p = 0; p < kMaxPeers; ++p) a.mail.box[p] = (a.mail.world > 1 && p < c->world) ? c->peer_mail[p] : nullptr;
+  a.bcast = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(c->d_run_state) + ((sizeof(RunState) + 31) / 32) * 32);
   const size_t prof_slot = c->prof.size();
   {
     ProfScope ps(c, B200RK_K_FUSED, 0.0);  // bytes patched below: the number of attempts is data-dependent
@@ -449,7 +451,7 @@ static int run_device_loop_pat(b200rk_ctx* c, const MethodDef& md, int kind, con
   }
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // one wait per launch (many steps), not per attempt
   const RunState out = *c->h_run_state;
-  c->seq += (unsigned long long)std::max<long long>(1, out.attempts);
+  c->seq += (unsigned long long)out.attempts;  // attempts used sequence numbers seq+1 .. seq+attempts
   if (a.mail.world > 1) c->collectives += out.attempts;
   if (c->profile && c->prof.size() > prof_slot)  // y, k1 (+ lambda) read, yNew and k_S written, per attempt
     c->prof[prof_slot].bytes = 8.0 * double(a.f.n) * (4 + (kind == PW_DIAG ? 1 : 0)) * double(out.attempts);

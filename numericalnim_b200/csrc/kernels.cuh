@@ -679,6 +679,7 @@ struct RunArgs {
   unsigned long long* seq_host;
   unsigned long long seq;        // sequence number of attempt 0 of this launch (attempt i uses seq + i)
   PeerMail mail;                 // world > 1: the error norm is all-reduced over the peer mailboxes every attempt
+  unsigned long long* bcast;     // world > 1: [2][2] device words, CTA 0 -> all CTAs hand-off of the global sum
 };
 
 __device__ __forceinline__ double dev_nim_min(double x, double y) { return (x <= y) ? x : y; }
@@ -754,37 +755,56 @@ __global__ void __launch_bounds__(THREADS, 2) fused_run_kernel(const RunArgs<Pat
       double S2 = bcast;
       __syncthreads();
       if (a.mail.world > 1) {
-        // Sharded: block 0 publishes this shard's partial to every peer's mailbox; EVERY CTA then reads the
-        // `world` slots of the local mailbox and adds them in rank order, so no second grid barrier is needed
-        // and all CTAs of all ranks obtain the same bits.
+        // Sharded: only CTA 0 talks to the peers — it stores this shard's partial into every peer's mailbox,
+        // waits for the `world` slots of the local mailbox, adds them in rank order and hands the global sum to the
+        // other CTAs through a local (value, sequence) pair they poll in L2. Peer-written memory is thus polled by
+        // `world` threads instead of by every CTA, and there is still no second grid barrier.
         __shared__ double peer_vals[kMaxPeers];
         __shared__ int peer_bad;
         const unsigned long long seq = a.seq + (unsigned long long)st.attempts;
         const unsigned long long par = seq & 1ull;
-        const int q = threadIdx.x;
-        if (q == 0) peer_bad = 0;
-        __syncthreads();
-        if (q < a.mail.world) {
-          if (blockIdx.x == 0) {
+        volatile unsigned long long* gflag = a.bcast + (par << 1);      // [par][0] = sequence, [par][1] = value bits
+        if (blockIdx.x == 0) {
+          const int q = threadIdx.x;
+          if (q == 0) peer_bad = 0;
+          __syncthreads();
+          if (q < a.mail.world) {
             volatile unsigned long long* dst = a.mail.box[q] + ((par * kMaxPeers + a.mail.rank) << 1);
             dst[1] = (unsigned long long)__double_as_longlong(S2);
             __threadfence_system();
             dst[0] = seq;
+            volatile unsigned long long* src = a.mail.box[a.mail.rank] + ((par * kMaxPeers + q) << 1);
+            const long long t0 = clock64();
+            bool ok = true;
+            while (src[0] != seq) {
+              if (clock64() - t0 > (2ll << 30)) { ok = false; break; }
+            }
+            __threadfence_system();
+            peer_vals[q] = ok ? __longlong_as_double((long long)src[1]) : 0.0;
+            if (!ok) atomicExch(&peer_bad, 1);
           }
-          volatile unsigned long long* src = a.mail.box[a.mail.rank] + ((par * kMaxPeers + q) << 1);
+          __syncthreads();
+          if (q == 0) {
+            double g = 0.0;
+            for (int p2 = 0; p2 < a.mail.world; ++p2) g = __dadd_rn(g, peer_vals[p2]);
+            gflag[1] = (unsigned long long)__double_as_longlong(g);
+            __threadfence();
+            gflag[0] = peer_bad ? (seq | kPeerTimeoutFlag) : seq;
+          }
+        }
+        if (threadIdx.x == 0) {
           const long long t0 = clock64();
-          bool ok = true;
-          while (src[0] != seq) {
-            if (clock64() - t0 > (2ll << 30)) { ok = false; break; }
+          unsigned long long f = gflag[0];
+          while ((f & ~kPeerTimeoutFlag) != seq) {
+            if (clock64() - t0 > (4ll << 30)) { f = seq | kPeerTimeoutFlag; break; }
+            f = gflag[0];
           }
-          __threadfence_system();
-          peer_vals[q] = ok ? __longlong_as_double((long long)src[1]) : 0.0;
-          if (!ok) atomicExch(&peer_bad, 1);
+          __threadfence();
+          bcast = __longlong_as_double((long long)gflag[1]);
+          peer_bad = (f & kPeerTimeoutFlag) ? 1 : 0;
         }
         __syncthreads();
-        double g = 0.0;
-        for (int p2 = 0; p2 < a.mail.world; ++p2) g = __dadd_rn(g, peer_vals[p2]);
-        S2 = g;
+        S2 = bcast;
         const int bad = peer_bad;
         __syncthreads();
         if (bad) { st.status = 2; st.attempts++; break; }
@@ -815,9 +835,7 @@ __global__ void __launch_bounds__(THREADS, 2) fused_run_kernel(const RunArgs<Pat
   grid.sync();  // every store of the last attempt is done before the host is told
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     *a.state = st;
-    *a.state_host = st;
-    __threadfence_system();
-    *(volatile unsigned long long*)a.seq_host = a.seq + (unsigned long long)st.attempts;
+    *a.state_host = st;  // the host waits for the launch with a stream synchronisation (once per many steps)
     __threadfence_system();
   }
 }

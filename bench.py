@@ -5,9 +5,12 @@
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
     python bench.py --sweep [--out FILE]                     # BASELINE.json config 5: kernel bandwidth sweep
 
-A "step" is one accepted Runge–Kutta step of the adaptive driver loop (ode.nim:511-541): S-1 right-hand
-side launches, S-1 fused stage-accumulate launches, one fused combine+error-norm launch and an 8-byte
-read-back per attempt (plus one ncclAllReduce of a scalar when sharded).
+A "step" is one accepted Runge–Kutta step of the adaptive driver loop (ode.nim:511-541). On the general
+pipeline (any user right-hand side) an attempt is S-1 right-hand-side launches, S-1 fused stage-accumulate
+launches, one fused combine+error-norm launch and an 8-byte read-back; for the library's element-local built-in
+right-hand sides the whole loop runs inside one persistent kernel. When sharded, the scalar
+error norm is all-reduced once per attempt inside the reducing kernel (NVLink peer mailboxes).
+The JSON line reports the library's default path as `value` and the general pipeline under `pipeline`.
 
 Workload at every N: BASELINE.json configs[1] per GPU — DOPRI54, diag-linear IVP y' = -lambda .* y,
 2^23 fp64 state elements PER GPU (weak scaling: N_global = n_gpus * 2^23, contiguous shards), absTol =

@@ -169,9 +169,12 @@ B200RK_API int b200rk_step(b200rk_ctx* ctx, int method, b200rk_rhs_fn f, void* u
                            const b200rk_vec* y, const b200rk_vec* fsal, double dt, const b200rk_options* options,
                            b200rk_vec* y_new, b200rk_vec* fsal_new, double* dt_used, double* error);
 
-/* solveODE (ode.nim:589-651) on device vectors. t_out receives the n_tspan sorted times; y_out receives
- * *n_y_out newly allocated vectors (caller frees each), in the order of t_out. As in the reference,
- * n_y_out can be smaller than n_tspan. stats may be NULL. */
+/* solveODE (ode.nim:589-651) on device vectors. t_out (room for n_tspan) receives the sorted times; y_out
+ * receives *n_y_out newly allocated vectors (caller frees each), in the order of t_out. As in the reference,
+ * n_y_out can be smaller than n_tspan. The reference reports tStart once however
+ * often tspan holds it (ode.nim:485-487) and a NaN in tspan passes neither of its filters (ode.nim:479-480):
+ * the returned time list is then shorter than n_tspan and the unused tail of t_out is set to NaN.
+ * stats may be NULL. */
 B200RK_API int b200rk_solve(b200rk_ctx* ctx, int method, b200rk_rhs_fn f, void* user, const b200rk_vec* y0,
                             const double* tspan, size_t n_tspan, const b200rk_options* options, double* t_out,
                             b200rk_vec** y_out, size_t* n_y_out, b200rk_stats* stats);

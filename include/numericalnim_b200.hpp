@@ -104,6 +104,10 @@ inline GpuVector newVector(const std::vector<double>& components, std::shared_pt
 }
 
 namespace detail {
+// b200rk_solve marks the unused tail of t_out with NaN when tStart is repeated in tspan (ode.nim:485-487).
+inline void trim_times(std::vector<double>& t) {
+  while (!t.empty() && t.back() != t.back()) t.pop_back();
+}
 template <class F>
 inline GpuVector binary(const GpuVector& a, const GpuVector& b, F fn) {
   GpuVector out(a.device(), a.size());
@@ -229,6 +233,7 @@ inline Solution solveODE(const ODEProc& f, const GpuVector& y0, const std::vecto
   if (env.err) std::rethrow_exception(env.err);
   check(rc, y0.device()->handle());
   for (size_t i = 0; i < n_out; ++i) sol.y.push_back(GpuVector::adopt(y0.device(), slots[i]));
+  detail::trim_times(sol.t);
   return sol;
 }
 
@@ -261,6 +266,7 @@ inline Solution solveODE(const BuiltinRhs& f, const GpuVector& y0, const std::ve
   check(b200rk_solve(y0.device()->handle(), method, f.fn(), f.user(), y0.handle(), tspan.data(), tspan.size(), &options, sol.t.data(),
                      slots.data(), &n_out, &sol.stats), y0.device()->handle());
   for (size_t i = 0; i < n_out; ++i) sol.y.push_back(GpuVector::adopt(y0.device(), slots[i]));
+  detail::trim_times(sol.t);
   return sol;
 }
 

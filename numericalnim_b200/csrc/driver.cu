@@ -1,6 +1,8 @@
 // driver.cu — the ODESolver loop (ode.nim:471-586) as a resumable object, and the step / solve entry points.
 #include "internal.hpp"
 
+#include <limits>
+
 struct b200rk_solver {
   b200rk_ctx* c = nullptr;
   const MethodDef* md = nullptr;
@@ -225,7 +227,8 @@ int b200rk_solve(b200rk_ctx* c, int method, b200rk_rhs_fn f, void* user, const b
   const int64_t l0 = c->launches, c0 = c->collectives;
   b200rk_solver* s = nullptr;
   TRY(solver_create(c, method, f, user, options, y0->n_global, &s));
-  std::vector<double> ts(tspan, tspan + n_tspan);
+  std::vector<double> ts;
+  for (size_t i = 0; i < n_tspan; ++i) if (tspan[i] == tspan[i]) ts.push_back(tspan[i]);   // a NaN passes neither filter below
   std::sort(ts.begin(), ts.end());                                                // ode.nim:609
   const double t0 = s->o.tStart;
   std::vector<double> tPos, tNeg;
@@ -260,6 +263,8 @@ int b200rk_solve(b200rk_ctx* c, int method, b200rk_rhs_fn f, void* user, const b
   for (auto r = tNeg.rbegin(); r != tNeg.rend(); ++r) t_out[it++] = *r;
   if (has_zero) t_out[it++] = t0;
   for (double x : tPos) t_out[it++] = x;
+  // tStart is reported once however often it occurs in tspan (ode.nim:485-487): mark the unused slots
+  while (it < n_tspan) t_out[it++] = std::numeric_limits<double>::quiet_NaN();
   for (auto r = yNeg.rbegin(); r != yNeg.rend(); ++r) y_out[iy++] = *r;
   for (auto* v : yZero) y_out[iy++] = v;
   for (auto* v : yPos) y_out[iy++] = v;

@@ -188,4 +188,5 @@ proc solveODE*(f: ODEProc[GpuVector], y0: GpuVector, tspan: openArray[float],
   check(rc, y0.ctx)
   var ys = newSeq[GpuVector](nOut.int)
   for i in 0 ..< nOut.int: ys[i] = GpuVector(h: slots[i], ctx: y0.ctx, borrowed: false)
+  while tOut.len > 0 and tOut[^1] != tOut[^1]: tOut.setLen(tOut.len - 1)   # tStart repeated in tspan: NaN-marked tail
   result = (@tOut, ys)

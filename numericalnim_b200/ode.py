@@ -413,6 +413,12 @@ def _resolve_rhs(f, ctx: Context, numctx: NumContext):
 last_stats: dict = {}
 
 
+def _times(t_out) -> list:
+    """The library marks the unused tail of t_out with NaN when the reference's time list is shorter than tspan
+    (tStart repeated in tspan, ode.nim:485-487)."""
+    return t_out[~np.isnan(t_out)].tolist()
+
+
 def solveODE(f, y0, tspan: Sequence[float], options: ODEoptions | None = None, ctx: NumContext | None = None,
              integrator: str = "dopri54", device_ctx: Context | None = None):
     """ode.nim:589-651. Returns ``(t, y)``: t is the sorted tspan; y holds one state per returned time.
@@ -440,7 +446,7 @@ def solveODE(f, y0, tspan: Sequence[float], options: ODEoptions | None = None, c
         _reraise(rhs)
         capi.check(rc, dctx.handle)
         last_stats = st.as_dict()
-        return t_out.tolist(), [GpuVector(dctx, C.c_void_p(slots[i])) for i in range(n_out.value)]
+        return _times(t_out), [GpuVector(dctx, C.c_void_p(slots[i])) for i in range(n_out.value)]
 
     scalar = np.isscalar(y0)
     dctx = device_ctx or default_context()
@@ -456,8 +462,8 @@ def solveODE(f, y0, tspan: Sequence[float], options: ODEoptions | None = None, c
     last_stats = st.as_dict()
     ys = y_out[: n_out.value]
     if scalar:
-        return t_out.tolist(), [float(v[0]) for v in ys]
-    return t_out.tolist(), [v.copy() for v in ys]
+        return _times(t_out), [float(v[0]) for v in ys]
+    return _times(t_out), [v.copy() for v in ys]
 
 
 def _reraise(rhs):

@@ -151,7 +151,7 @@ def solve_vector(integrator: str, rhs: Rhs, y0, tspan, options: OracleOptions | 
     tspan = _f64(tspan)
     n = y0.size
     options = options or new_options()
-    t_out = np.empty(tspan.size, dtype=np.float64)
+    t_out = np.full(tspan.size, np.nan)  # the time list can be shorter than tspan (tStart repeated)
     y_out = np.empty((tspan.size, n), dtype=np.float64)
     n_y = C.c_size_t(0)
     st = OracleStats()
@@ -165,13 +165,13 @@ def solve_vector(integrator: str, rhs: Rhs, y0, tspan, options: OracleOptions | 
     del keep
     _check(rc)
     recs = [(tr[i].t, tr[i].dt_used, tr[i].error, tr[i].attempts) for i in range(min(n_tr.value, trace_cap))] if trace else []
-    return Solve(t_out, y_out[: n_y.value].copy(), st, recs)
+    return Solve(t_out[~np.isnan(t_out)], y_out[: n_y.value].copy(), st, recs)
 
 
 def solve_scalar(integrator: str, y0: float, tspan, options: OracleOptions | None = None, rhs_scale_c: float = -0.1, callback=None):
     tspan = _f64(tspan)
     options = options or new_options()
-    t_out = np.empty(tspan.size)
+    t_out = np.full(tspan.size, np.nan)
     y_out = np.empty(tspan.size)
     n_y = C.c_size_t(0)
     st = OracleStats()
@@ -184,7 +184,7 @@ def solve_scalar(integrator: str, y0: float, tspan, options: OracleOptions | Non
                                    C.c_size_t(tspan.size), C.byref(options), _p(t_out), _p(y_out), C.byref(n_y), C.byref(st))
     del keep
     _check(rc)
-    return t_out, y_out[: n_y.value].copy(), st
+    return t_out[~np.isnan(t_out)], y_out[: n_y.value].copy(), st
 
 
 def step_vector(integrator: str, rhs: Rhs, t: float, y, fsal, dt: float, options: OracleOptions | None = None):

@@ -32,6 +32,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("B200RK_JIT_CACHE", os.path.join(ROOT, ".jitcache"))  # compiled user right-hand sides (csrc/jit.cu)
 
 SHARD_LOG2 = 23
 OPTS = dict(absTol=1e-6, relTol=1e-6, dtMax=1.0, dtMin=1e-8)
@@ -170,7 +171,7 @@ def run_ours(args):
     clocks = ClockSampler(local_rank)
     clocks.__enter__()  # sampled from the warm-up through the timed regions and the end-to-end solves
 
-    def timed_steps(fuse: int) -> dict:
+    def timed_steps(fuse: int, rhs=rhs) -> dict:
         """W untimed + K timed accepted steps with the given fuse_pointwise setting; device time (CUDA events on
         the library stream), max over ranks; per-kernel-class event times from the library's profiler."""
         ctx.set("fuse_pointwise", fuse)
@@ -260,6 +261,27 @@ def run_ours(args):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_ms_max = float(e2e_t.item())
 
+    # ---- the same IVP with the right-hand side handed over as SOURCE ("-(p0*y)"): NVRTC compiles it into the fused
+    # kernels at run time (csrc/jit.cu) — what a user-defined element-local closure gets instead of the built-in.
+    # Runs after every other GPU measurement so that nothing it does can disturb them.
+    jit_obj = None
+    if rhs_kind == "diag" and fusable and world == 1 and not args.no_jit:  # N = 1 only: a rank-local failure must not desynchronise a sharded run
+        try:
+            t0 = time.time()
+            jrhs = nn.rhsJit("-(p0*y)", [glam])
+            jr = timed_steps(1, jrhs)
+            fu = jr["prof"]["fused"]
+            jit_obj = {"note": "right-hand side given as the source expression -(p0*y), compiled at run time (NVRTC) into the same fused kernels",
+                       "value": args.steps * world / (jr["ms_max"] * 1e-3), "ms_per_step": jr["ms_max"] / args.steps, "attempts": jr["attempts"],
+                       "gpu_launches": jr["launches"], "t_reached": jr["t"],
+                       "hbm_gbs": fu["bytes"] / (fu["ms"] * 1e-3) / 1e9 if fu["ms"] > 0 else None,
+                       "wall_s_including_compile": time.time() - t0}
+        except Exception as e:  # noqa: BLE001 — the headline must survive a missing NVRTC
+            jit_obj = {"error": str(e)[:400]}
+            try:
+                ctx.set("profile", 0)
+            except Exception:  # noqa: BLE001
+                pass
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on a bounded sample -----------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and rhs_kind == "diag":
@@ -342,6 +364,7 @@ def run_ours(args):
             "path": path,
             "roofline": roofline,
             "pipeline": pipeline_obj,
+            "jit_rhs": jit_obj,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_steps * world / (e2e_ms_max * 1e-3), "unit": "RK steps/s (solveODE on host buffers: H2D y0+lambda, solve, D2H states)",
                     "h2d_bytes_per_step": h2d / max(1, e2e_steps), "d2h_bytes_per_step": d2h / max(1, e2e_steps), "steps_per_solve": e2e_steps / reps,
@@ -598,6 +621,7 @@ def main():
     ap.add_argument("--log2n", type=int, default=0, help="override log2 of elements per GPU")
     ap.add_argument("--e2e-reps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-jit", action="store_true", help="skip the run-time compiled right-hand-side leg")
     ap.add_argument("--no-fuse", action="store_true", help="headline = the stage/RHS/finish pipeline even for element-local built-in RHS")
     ap.add_argument("--cpu-budget-s", type=float, default=120.0)
     ap.add_argument("--sweep", action="store_true")

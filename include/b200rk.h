@@ -160,6 +160,27 @@ B200RK_API int b200rk_builtin_rhs_new(b200rk_ctx* ctx, int kind, double scalar, 
                                       b200rk_rhs_fn* fn, void** user);
 B200RK_API int b200rk_builtin_rhs_free(void* user);
 
+/* ---- right-hand sides from source: element-local ODEProc closures compiled INTO the fused kernels ---- */
+/* The reference's extension point is the user's closure f(t, y, ctx) (ode.nim:36). An element-local closure,
+ *     dydt[i] = expr(t, y[i], p0[i], .., p3[i], c0, .., c7),
+ * can be handed over as a CUDA C++ expression in the variables t, y, p0..p<n_vec-1> (per-element parameter
+ * vectors, same length as y) and c0..c<n_scalar-1> (scalars): e.g. "-(p0*y)", "c0*y*(1.0 - y/p0)". It is
+ * compiled at run time (NVRTC, sm_100a, --fmad=false: a*b+c stays a multiply and an add like the reference's CPU
+ * arithmetic) into the same kernels the built-in right-hand sides use: the whole-attempt kernel of
+ * DOPRI54 / Tsit54 / Vern65, the device-resident driver loop, the one-kernel RK4 step, and a plain dydt kernel for
+ * every other method. The returned (fn, user) pair is an ordinary b200rk_rhs_fn for b200rk_step / b200rk_solve /
+ * b200rk_solver_new. A wrong expression -> B200RK_EINVAL with the compiler log in b200rk_last_error().
+ * The parameter vectors must outlive `user`. */
+B200RK_API int b200rk_jit_rhs_new(b200rk_ctx* ctx, const char* expr, int n_vec, const b200rk_vec* const* vecs,
+                                  int n_scalar, const double* scalars, b200rk_rhs_fn* fn, void** user);
+B200RK_API int b200rk_jit_rhs_set_scalars(void* user, int n_scalar, const double* scalars); /* no recompilation */
+B200RK_API int b200rk_jit_rhs_free(void* user);
+/* Host only (no device needed): compile one translation unit and return the sm_100a cubin (cubin_out may be NULL;
+ * *cubin_bytes receives the size) and the compiler log + kernel names. pattern: -1 = dydt / RK4 kernels,
+ * 0..4 = fused attempt + device-loop kernels (dopri54, dopri54 strict, tsit54, vern65, vern65 strict). */
+B200RK_API int b200rk_jit_compile_only(const char* expr, int n_vec, int n_scalar, int pattern, void* cubin_out,
+                                       size_t cubin_cap, size_t* cubin_bytes, char* log, size_t log_cap);
+
 /* ---- the hot path ------------------------------------------------------------------------------ */
 /* One IntegratorProc call (ode.nim:38): (yNew, newFSAL, dtUsed, error) = X_step(f, t, y, FSAL, dt, options, ctx).
  * Runs the adaptive retry loop of commonAdaptiveMethodCode (ode.nim:57-76) for adaptive methods.

@@ -255,7 +255,34 @@ class BuiltinRhs {
   b200rk_rhs_fn fn_ = nullptr;
   void* user_ = nullptr;
 };
-inline Solution solveODE(const BuiltinRhs& f, const GpuVector& y0, const std::vector<double>& tspan, const ODEoptions& options = newODEoptions(),
+// Element-local right-hand side given as source (b200rk_jit_rhs_new): dydt[i] = expr(t, y[i], p0[i].., c0..),
+// compiled at run time into the fused kernels. E.g. JitRhs(dev, "c0*y*(1.0 - y/p0)", {&K}, {r}).
+class JitRhs {
+ public:
+  JitRhs(std::shared_ptr<Device> dev, const std::string& expr, const std::vector<const GpuVector*>& vecs = {},
+         const std::vector<double>& scalars = {}) : dev_(std::move(dev)) {
+    std::vector<const b200rk_vec*> hs;
+    for (const GpuVector* v : vecs) { keep_.push_back(std::make_unique<GpuVector>(*v)); hs.push_back(keep_.back()->handle()); }
+    check(b200rk_jit_rhs_new(dev_->handle(), expr.c_str(), (int)hs.size(), hs.empty() ? nullptr : hs.data(), (int)scalars.size(),
+                             scalars.empty() ? nullptr : scalars.data(), &fn_, &user_), dev_->handle());
+  }
+  ~JitRhs() { b200rk_jit_rhs_free(user_); }
+  JitRhs(const JitRhs&) = delete;
+  void setScalars(const std::vector<double>& scalars) {
+    check(b200rk_jit_rhs_set_scalars(user_, (int)scalars.size(), scalars.empty() ? nullptr : scalars.data()), dev_->handle());
+  }
+  b200rk_rhs_fn fn() const { return fn_; }
+  void* user() const { return user_; }
+
+ private:
+  std::shared_ptr<Device> dev_;
+  std::vector<std::unique_ptr<GpuVector>> keep_;
+  b200rk_rhs_fn fn_ = nullptr;
+  void* user_ = nullptr;
+};
+
+template <class DeviceRhs, class = decltype(std::declval<const DeviceRhs&>().fn()), class = decltype(std::declval<const DeviceRhs&>().user())>
+inline Solution solveODE(const DeviceRhs& f, const GpuVector& y0, const std::vector<double>& tspan, const ODEoptions& options = newODEoptions(),
                          const std::string& integrator = "dopri54") {
   int method = 0;
   check(b200rk_method_from_name(integrator.c_str(), &method));

@@ -277,24 +277,51 @@ int b200rk_solve(b200rk_ctx* c, int method, b200rk_rhs_fn f, void* user, const b
 int b200rk_solve_host(b200rk_ctx* c, int method, b200rk_rhs_fn f, void* user, size_t n_global, const double* y0_local,
                       const double* tspan, size_t n_tspan, const b200rk_options* options, double* t_out,
                       double* y_out_local, size_t* n_y_out, b200rk_stats* stats) {
-  if (!c || !y0_local || !y_out_local) return fail(c, B200RK_EINVAL, "null argument");
+  if (!c || !y0_local || !y_out_local || !tspan) return fail(c, B200RK_EINVAL, "null argument");
   b200rk_vec* y0 = nullptr;
   TRY(vec_alloc(c, n_global, &y0));
   int rc = B200RK_OK;
-  cudaError_t e = cudaMemcpyAsync(y0->d, y0_local, y0->n_local * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+  const size_t bytes = y0->n_local * sizeof(double);
+  cudaError_t e = cudaMemcpyAsync(y0->d, y0_local, bytes, cudaMemcpyHostToDevice, c->stream);
   if (e != cudaSuccess) rc = fail(c, B200RK_ECUDA, cudaGetErrorString(e));
+  // The state reported at tStart is y0 itself (ode.nim:485-487). When no requested time lies before tStart it
+  // is output 0, known before the solve starts: send it back on a second stream now, so the copy rides the
+  // device-to-host engine while the solve runs instead of queueing behind it.
+  const double t0 = options ? options->tStart : 0.0;
+  bool has_zero = false, has_neg = false;
+  for (size_t i = 0; i < n_tspan; ++i) { has_zero |= (tspan[i] == t0); has_neg |= (tspan[i] < t0); }
+  bool early = false;
+  if (rc == B200RK_OK && has_zero && !has_neg && bytes) {
+    if (!c->copy_stream) {
+      if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&c->copy_event, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        if (c->copy_stream) { cudaStreamDestroy(c->copy_stream); c->copy_stream = nullptr; }
+      }
+    }
+    if (c->copy_stream && cudaEventRecord(c->copy_event, c->stream) == cudaSuccess &&
+        cudaStreamWaitEvent(c->copy_stream, c->copy_event, 0) == cudaSuccess &&
+        cudaMemcpyAsync(y_out_local, y0->d, bytes, cudaMemcpyDeviceToHost, c->copy_stream) == cudaSuccess)
+      early = true;
+    else
+      cudaGetLastError();
+  }
   std::vector<b200rk_vec*> ys(n_tspan, nullptr);
   size_t ny = 0;
   if (rc == B200RK_OK) rc = b200rk_solve(c, method, f, user, y0, tspan, n_tspan, options, t_out, ys.data(), &ny, stats);
   if (rc == B200RK_OK) {
-    for (size_t i = 0; i < ny; ++i) {
-      e = cudaMemcpyAsync(y_out_local + i * y0->n_local, ys[i]->d, y0->n_local * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    for (size_t i = early ? 1 : 0; i < ny; ++i) {
+      e = cudaMemcpyAsync(y_out_local + i * y0->n_local, ys[i]->d, bytes, cudaMemcpyDeviceToHost, c->stream);
       if (e != cudaSuccess) { rc = fail(c, B200RK_ECUDA, cudaGetErrorString(e)); break; }
     }
     e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess && rc == B200RK_OK) rc = fail(c, B200RK_ECUDA, cudaGetErrorString(e));
     for (size_t i = 0; i < ny; ++i) vec_release(ys[i]);
     if (n_y_out) *n_y_out = ny;
+  }
+  if (early) {  // y0 must stay untouched until its copy has left the device
+    e = cudaStreamSynchronize(c->copy_stream);
+    if (e != cudaSuccess && rc == B200RK_OK) rc = fail(c, B200RK_ECUDA, cudaGetErrorString(e));
   }
   vec_release(y0);
   return rc;

@@ -42,7 +42,7 @@ int eval_rhs(b200rk_ctx* c, const RhsCall& r, double t, const b200rk_vec* y, b20
   if (r.evals) ++*r.evals;
   int rc = r.f(r.negate_time ? -t : t, y, out, r.user);
   if (rc != 0) {
-    if (r.f == &builtin_rhs_fn) return rc;  // our own launcher already recorded the error
+    if (r.f == &builtin_rhs_fn || r.f == &jit_rhs_fn) return rc;  // our own launcher already recorded the error
     return fail(c, B200RK_ECALLBACK, "right-hand side callback returned " + std::to_string(rc));
   }
   if (r.negate_time) return launch_ewise(c, EW_NEG, out->d, nullptr, 0.0, out->d, out->n_local, B200RK_K_OTHER);
@@ -157,15 +157,50 @@ int plan_finish(const b200rk_ctx* c, const MethodDef& md, double dt, double absT
   return B200RK_OK;
 }
 
-// ---- fused attempt for element-local built-in right-hand sides (kernels.cuh: fused_attempt_kernel) ----
-static bool pointwise_kind(const RhsCall& rhs, int* pw_kind, const BuiltinRhs** br) {
+// ---- fused attempt for element-local right-hand sides (kernels.cuh: fused_attempt_kernel) -------------
+// Element-local = the built-in c*y and -(lambda .* y), and every right-hand side given as source (jit.cu).
+struct PwSpec {
+  int kind = -1;                                      // PW_SCALE / PW_DIAG / PW_USER
+  int np = 0;                                         // per-element parameter streams read next to y
+  const b200rk_vec* pv[kMaxUserVecs] = {nullptr};
+  double scalar = 0.0;                                // PW_SCALE
+  const double* cs = nullptr;                         // PW_USER: c0..c7
+  JitRhs* jit = nullptr;                              // PW_USER
+};
+static bool pointwise_spec(const RhsCall& rhs, PwSpec* pw) {
+  if (rhs.f == &jit_rhs_fn) {
+    pw->kind = PW_USER;
+    pw->jit = static_cast<JitRhs*>(rhs.user);
+    const b200rk_vec* const* vecs = nullptr;
+    jit_describe(pw->jit, &pw->np, &vecs, &pw->cs);
+    for (int j = 0; j < pw->np; ++j) pw->pv[j] = vecs[j];
+    return true;
+  }
   if (rhs.f != &builtin_rhs_fn) return false;
   const BuiltinRhs* r = static_cast<const BuiltinRhs*>(rhs.user);
-  if (r->kind == B200RK_RHS_SCALE) *pw_kind = PW_SCALE;
-  else if (r->kind == B200RK_RHS_DIAG_LINEAR) *pw_kind = PW_DIAG;
+  if (r->kind == B200RK_RHS_SCALE) { pw->kind = PW_SCALE; pw->scalar = r->scalar; }
+  else if (r->kind == B200RK_RHS_DIAG_LINEAR) { pw->kind = PW_DIAG; pw->np = 1; pw->pv[0] = r->lambda; }
   else return false;
-  *br = r;
   return true;
+}
+static int check_pw_sizes(const b200rk_ctx* c, const PwSpec& pw, const b200rk_vec* y) {
+  for (int j = 0; j < pw.np; ++j) TRY(check_same(c, y, pw.pv[j]));
+  return B200RK_OK;
+}
+// Right-hand-side part of the fused kernels' argument block. `negate`: backward pass g(t, y) = -f(-t, y) (ode.nim:545).
+template <int S>
+static void fill_pw_args(FusedArgs<S>& a, const PwSpec& pw, const MethodDef& md, bool negate, double t) {
+  for (int j = 0; j < pw.np; ++j) a.p[j] = pw.pv[j]->d;
+  if (pw.kind == PW_USER) {
+    a.rhs_sign = negate ? -1.0 : 1.0;                 // multiply by +-1: exact
+    a.tsign = negate ? -1.0 : 1.0;
+    a.t = t;
+    for (int j = 0; j < kMaxUserScalars; ++j) a.cs[j] = pw.cs[j];
+    for (int s = 2; s <= S; ++s) a.cnode[s - 1] = md.c[s];
+  } else {
+    a.rhs_scalar = negate ? -pw.scalar : pw.scalar;   // -(y*c) == y*(-c) exactly
+    a.rhs_sign = negate ? 1.0 : -1.0;                 // k = (lam*y)*sign
+  }
 }
 static bool method_fusable(const MethodDef& md) {
   if (md.rk4_final) return true;
@@ -234,37 +269,43 @@ static int fused_pattern_of(const b200rk_ctx* c, const MethodDef& md) {
 }
 
 template <int PAT>
-static int launch_fused_pair(b200rk_ctx* c, const MethodDef& md, int pw_kind, const BuiltinRhs* br, bool negate, double dt,
+static int launch_fused_pair(b200rk_ctx* c, const MethodDef& md, const PwSpec& pw, bool negate, double t, double dt,
                              const b200rk_options& o, const b200rk_vec* y, const b200rk_vec* fsal, b200rk_vec* y_new,
                              b200rk_vec* fsal_new) {
   constexpr int S = Pattern<PAT>::S;
   FusedArgs<S> a;
   std::memset(&a, 0, sizeof(a));
-  a.y = y->d; a.k1 = fsal->d; a.lam = br->lambda ? br->lambda->d : nullptr;
-  a.rhs_scalar = negate ? -br->scalar : br->scalar;   // -(y*c) == y*(-c) exactly
-  a.rhs_sign = negate ? 1.0 : -1.0;                   // k = (lam*y)*sign
+  a.y = y->d; a.k1 = fsal->d;
+  fill_pw_args(a, pw, md, negate, t);
   for (int s = 2; s <= S; ++s) row_mask(c, md.a[s], a.a[s - 2], S - 1);
   row_mask(c, md.b, a.b, S);
   row_mask(c, md.bhat, a.bh, S);
   a.dt = dt; a.cb = dt; a.cbh = dt; a.absTol = o.absTol; a.relTol = o.relTol;
   a.ynew = y_new->d; a.ks_out = fsal_new->d; a.n = y->n_local;
   a.rs = reduce_scratch(c);
-  const int streams = 4 + (pw_kind == PW_DIAG ? 1 : 0);  // y, k1 (+ lambda) read; yNew, k_S written
+  const int streams = 4 + pw.np;  // y, k1 (+ parameters) read; yNew, k_S written
   ProfScope ps(c, B200RK_K_FUSED, 8.0 * double(y->n_local) * streams);
-  if (pw_kind == PW_SCALE) return launch_fused_cfg<PAT, PW_SCALE>(c, a);
+  if (pw.kind == PW_USER) {  // the same kernel, compiled at run time around the caller's expression (jit.cu)
+    const int W = (c->vec_width == 4) ? 4 : 2;
+    const unsigned grid = grid_for(c, a.n / W, kThreads, c->fused_ctas_per_sm);
+    TRY(ensure_partials(c, grid));
+    return jit_launch(c, pw.jit, PAT, jit_slot_attempt(W), grid, &a, false);
+  }
+  if (pw.kind == PW_SCALE) return launch_fused_cfg<PAT, PW_SCALE>(c, a);
   return launch_fused_cfg<PAT, PW_DIAG>(c, a);
 }
 
-static int launch_fused_rk4(b200rk_ctx* c, int pw_kind, const BuiltinRhs* br, bool negate, double dt, const b200rk_vec* y,
+static int launch_fused_rk4(b200rk_ctx* c, const PwSpec& pw, bool negate, double t, double dt, const b200rk_vec* y,
                             b200rk_vec* y_new) {
   const size_t n = y->n_local;
   if (!n) return B200RK_OK;
-  ProfScope ps(c, B200RK_K_FUSED, 8.0 * double(n) * (2 + (pw_kind == PW_DIAG ? 1 : 0)));
+  if (pw.kind == PW_USER) return jit_launch_rk4(c, pw.jit, negate, t, dt, y, y_new);
+  ProfScope ps(c, B200RK_K_FUSED, 8.0 * double(n) * (2 + pw.np));
   const double hdt = 0.5 * dt, c6 = dt / 6.0;
-  const double* lam = br->lambda ? br->lambda->d : nullptr;
+  const double* lam = pw.np ? pw.pv[0]->d : nullptr;
   unsigned grid = grid_for(c, n / 4, kThreads, c->ctas_per_sm);
-  const double cs = negate ? -br->scalar : br->scalar, sgn = negate ? 1.0 : -1.0;
-  if (pw_kind == PW_SCALE) fused_rk4_kernel<PW_SCALE, 4, kThreads><<<grid, kThreads, 0, c->stream>>>(y->d, lam, cs, sgn, hdt, dt, c6, y_new->d, n);
+  const double cs = negate ? -pw.scalar : pw.scalar, sgn = negate ? 1.0 : -1.0;
+  if (pw.kind == PW_SCALE) fused_rk4_kernel<PW_SCALE, 4, kThreads><<<grid, kThreads, 0, c->stream>>>(y->d, lam, cs, sgn, hdt, dt, c6, y_new->d, n);
   else fused_rk4_kernel<PW_DIAG, 4, kThreads><<<grid, kThreads, 0, c->stream>>>(y->d, lam, cs, sgn, hdt, dt, c6, y_new->d, n);
   CUDA_TRY(c, cudaGetLastError());
   return B200RK_OK;
@@ -279,15 +320,14 @@ int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, double t, co
   Workspace ws(c);
   b200rk_vec* k[kMaxStages + 1] = {nullptr};
   b200rk_vec* tmp = nullptr;
-  int pw_kind = 0;
-  const BuiltinRhs* br = nullptr;
+  PwSpec pw;
   int fused_pat = -1;
-  bool fused = c->fuse_pointwise && pointwise_kind(rhs, &pw_kind, &br) && method_fusable(md) &&
+  bool fused = c->fuse_pointwise && pointwise_spec(rhs, &pw) && method_fusable(md) &&
                (md.rk4_final || (fsal && fsal_new));
   if (fused && !md.rk4_final) { fused_pat = fused_pattern_of(c, md); fused = fused_pat >= 0; }
   const bool stencil_fused = !fused && c->fuse_stencil && c->world == 1 && rhs.f == &builtin_rhs_fn &&
                              static_cast<const BuiltinRhs*>(rhs.user)->kind == B200RK_RHS_LORENZ96 && y->n_global >= 4;
-  if (fused && pw_kind == PW_DIAG) TRY(check_same(c, y, br->lambda));
+  if (fused) TRY(check_pw_sizes(c, pw, y));
   if (md.k1_from_fsal) {
     if (!fsal) return fail(c, B200RK_EINVAL, std::string(md.name) + ": FSAL vector required");
     TRY(check_same(c, y, fsal));
@@ -312,13 +352,13 @@ int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, double t, co
       // element-local right-hand side: the whole attempt is one kernel (the callbacks it stands for are
       // still counted so rhs_evals matches the unfused path)
       if (rhs.evals) *rhs.evals += md.rk4_final ? 4 : (S - 1);
-      if (md.rk4_final) { TRY(launch_fused_rk4(c, pw_kind, br, rhs.negate_time, dt, y, y_new)); break; }
+      if (md.rk4_final) { TRY(launch_fused_rk4(c, pw, rhs.negate_time, t, dt, y, y_new)); break; }
       switch (fused_pat) {
-        case PAT_DOPRI54: TRY(launch_fused_pair<PAT_DOPRI54>(c, md, pw_kind, br, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new)); break;
-        case PAT_DOPRI54_STRICT: TRY(launch_fused_pair<PAT_DOPRI54_STRICT>(c, md, pw_kind, br, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new)); break;
-        case PAT_TSIT54: TRY(launch_fused_pair<PAT_TSIT54>(c, md, pw_kind, br, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new)); break;
-        case PAT_VERN65: TRY(launch_fused_pair<PAT_VERN65>(c, md, pw_kind, br, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new)); break;
-        default: TRY(launch_fused_pair<PAT_VERN65_STRICT>(c, md, pw_kind, br, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new)); break;
+        case PAT_DOPRI54: TRY(launch_fused_pair<PAT_DOPRI54>(c, md, pw, rhs.negate_time, t, dt, o, y, fsal, y_new, fsal_new)); break;
+        case PAT_DOPRI54_STRICT: TRY(launch_fused_pair<PAT_DOPRI54_STRICT>(c, md, pw, rhs.negate_time, t, dt, o, y, fsal, y_new, fsal_new)); break;
+        case PAT_TSIT54: TRY(launch_fused_pair<PAT_TSIT54>(c, md, pw, rhs.negate_time, t, dt, o, y, fsal, y_new, fsal_new)); break;
+        case PAT_VERN65: TRY(launch_fused_pair<PAT_VERN65>(c, md, pw, rhs.negate_time, t, dt, o, y, fsal, y_new, fsal_new)); break;
+        default: TRY(launch_fused_pair<PAT_VERN65_STRICT>(c, md, pw, rhs.negate_time, t, dt, o, y, fsal, y_new, fsal_new)); break;
       }
     } else {
     if (!md.k1_from_fsal) TRY(eval_rhs(c, rhs, t, y, k[1]));
@@ -381,20 +421,23 @@ bool device_loop_eligible(const b200rk_ctx* c, const MethodDef& md, const RhsCal
   if (c->world > 1 && !c->p2p) return false;  // sharded: needs the peer mailboxes for the in-kernel all-reduce
   // measured (profiles/r01_sweep_small_device_loop.json): 2.4x at 2^16 (5.8 vs 14.1 us/step), still +5 % at 2^23, so
   // the auto policy (-1) takes the device loop at every size
-  int kind = 0;
-  const BuiltinRhs* br = nullptr;
-  if (!pointwise_kind(rhs, &kind, &br) || md.rk4_final || !method_fusable(md)) return false;
+  PwSpec pw;
+  if (!pointwise_spec(rhs, &pw) || md.rk4_final || !method_fusable(md)) return false;
   return fused_pattern_of(c, md) >= 0;
 }
 
+// all CTAs must be co-resident (grid barrier): at most per_sm * SMs, at most one tile each
+static unsigned run_grid(const b200rk_ctx* c, size_t n, int W, int per_sm) {
+  const size_t tiles = std::max<size_t>(1, (n / W + kThreads - 1) / kThreads);
+  return (unsigned)std::min<size_t>(tiles, (size_t)per_sm * c->sm_count);
+}
 template <int PAT, int KIND, int W>
 static int launch_run_cfg(b200rk_ctx* c, RunArgs<Pattern<PAT>::S>& a) {
   auto kernel = fused_run_kernel<PAT, KIND, W, kThreads>;
   int per_sm = 0;
   CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0));
   if (per_sm < 1) return fail(c, B200RK_ECUDA, "device loop: kernel does not fit on an SM");
-  const size_t tiles = std::max<size_t>(1, (a.f.n / W + kThreads - 1) / kThreads);
-  const unsigned grid = (unsigned)std::min<size_t>(tiles, (size_t)per_sm * c->sm_count);  // all CTAs co-resident (grid barrier)
+  const unsigned grid = run_grid(c, a.f.n, W, per_sm);
   TRY(ensure_partials(c, 2 * (size_t)grid));
   a.partials = c->d_partials;
   void* args[] = {&a};
@@ -402,21 +445,29 @@ static int launch_run_cfg(b200rk_ctx* c, RunArgs<Pattern<PAT>::S>& a) {
   return B200RK_OK;
 }
 template <int PAT>
-static int launch_run_pat(b200rk_ctx* c, int kind, RunArgs<Pattern<PAT>::S>& a) {
+static int launch_run_pat(b200rk_ctx* c, const PwSpec& pw, RunArgs<Pattern<PAT>::S>& a) {
   const bool w4 = a.f.n >= ((size_t)1 << 20);
-  if (kind == PW_SCALE) return w4 ? launch_run_cfg<PAT, PW_SCALE, 4>(c, a) : launch_run_cfg<PAT, PW_SCALE, 2>(c, a);
+  if (pw.kind == PW_USER) {  // run-time compiled instance of the same kernel (jit.cu)
+    const int W = w4 ? 4 : 2, slot = jit_slot_run(W);
+    int per_sm = 0;
+    TRY(jit_max_blocks_per_sm(c, pw.jit, PAT, slot, &per_sm));
+    if (per_sm < 1) return fail(c, B200RK_ECUDA, "device loop: kernel does not fit on an SM");
+    const unsigned grid = run_grid(c, a.f.n, W, per_sm);
+    TRY(ensure_partials(c, 2 * (size_t)grid));
+    a.partials = c->d_partials;
+    return jit_launch(c, pw.jit, PAT, slot, grid, &a, true);
+  }
+  if (pw.kind == PW_SCALE) return w4 ? launch_run_cfg<PAT, PW_SCALE, 4>(c, a) : launch_run_cfg<PAT, PW_SCALE, 2>(c, a);
   return w4 ? launch_run_cfg<PAT, PW_DIAG, 4>(c, a) : launch_run_cfg<PAT, PW_DIAG, 2>(c, a);
 }
 
 template <int PAT>
-static int run_device_loop_pat(b200rk_ctx* c, const MethodDef& md, int kind, const BuiltinRhs* br, bool negate,
+static int run_device_loop_pat(b200rk_ctx* c, const MethodDef& md, const PwSpec& pw, bool negate,
                                const b200rk_options& o, DeviceLoopIO* io, int64_t max_steps) {
   constexpr int S = Pattern<PAT>::S;
   RunArgs<S> a;
   std::memset(&a, 0, sizeof(a));
-  a.f.lam = br->lambda ? br->lambda->d : nullptr;
-  a.f.rhs_scalar = negate ? -br->scalar : br->scalar;
-  a.f.rhs_sign = negate ? 1.0 : -1.0;
+  fill_pw_args(a.f, pw, md, negate, io->t);  // the kernel refreshes f.t at every step
   for (int s = 2; s <= S; ++s) row_mask(c, md.a[s], a.f.a[s - 2], S - 1);
   row_mask(c, md.b, a.f.b, S);
   row_mask(c, md.bhat, a.f.bh, S);
@@ -447,14 +498,14 @@ static int run_device_loop_pat(b200rk_ctx* c, const MethodDef& md, int kind, con
   const size_t prof_slot = c->prof.size();
   {
     ProfScope ps(c, B200RK_K_FUSED, 0.0);  // bytes patched below: the number of attempts is data-dependent
-    TRY(launch_run_pat<PAT>(c, kind, a));
+    TRY(launch_run_pat<PAT>(c, pw, a));
   }
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // one wait per launch (many steps), not per attempt
   const RunState out = *c->h_run_state;
   c->seq += (unsigned long long)out.attempts;  // attempts used sequence numbers seq+1 .. seq+attempts
   if (a.mail.world > 1) c->collectives += out.attempts;
   if (c->profile && c->prof.size() > prof_slot)  // y, k1 (+ lambda) read, yNew and k_S written, per attempt
-    c->prof[prof_slot].bytes = 8.0 * double(a.f.n) * (4 + (kind == PW_DIAG ? 1 : 0)) * double(out.attempts);
+    c->prof[prof_slot].bytes = 8.0 * double(a.f.n) * (4 + pw.np) * double(out.attempts);
   io->t = out.t; io->dt = out.dt; io->error = out.error; io->cur = out.cur;
   io->steps = out.steps; io->attempts = out.attempts; io->rejected = out.rejected; io->limiter_hits = out.limiter_hits;
   if (out.status == 2) return fail(c, B200RK_ENCCL, "peer mailbox all-reduce timed out inside the device loop");
@@ -464,16 +515,15 @@ static int run_device_loop_pat(b200rk_ctx* c, const MethodDef& md, int kind, con
 
 int run_device_loop(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, const b200rk_options& o, DeviceLoopIO* io,
                     int64_t max_steps) {
-  int kind = 0;
-  const BuiltinRhs* br = nullptr;
-  if (!pointwise_kind(rhs, &kind, &br)) return fail(c, B200RK_EINVAL, "device loop: right-hand side is not element-local");
-  if (kind == PW_DIAG) TRY(check_same(c, io->Y[0], br->lambda));
+  PwSpec pw;
+  if (!pointwise_spec(rhs, &pw)) return fail(c, B200RK_EINVAL, "device loop: right-hand side is not element-local");
+  TRY(check_pw_sizes(c, pw, io->Y[0]));
   switch (fused_pattern_of(c, md)) {
-    case PAT_DOPRI54: return run_device_loop_pat<PAT_DOPRI54>(c, md, kind, br, rhs.negate_time, o, io, max_steps);
-    case PAT_DOPRI54_STRICT: return run_device_loop_pat<PAT_DOPRI54_STRICT>(c, md, kind, br, rhs.negate_time, o, io, max_steps);
-    case PAT_TSIT54: return run_device_loop_pat<PAT_TSIT54>(c, md, kind, br, rhs.negate_time, o, io, max_steps);
-    case PAT_VERN65: return run_device_loop_pat<PAT_VERN65>(c, md, kind, br, rhs.negate_time, o, io, max_steps);
-    case PAT_VERN65_STRICT: return run_device_loop_pat<PAT_VERN65_STRICT>(c, md, kind, br, rhs.negate_time, o, io, max_steps);
+    case PAT_DOPRI54: return run_device_loop_pat<PAT_DOPRI54>(c, md, pw, rhs.negate_time, o, io, max_steps);
+    case PAT_DOPRI54_STRICT: return run_device_loop_pat<PAT_DOPRI54_STRICT>(c, md, pw, rhs.negate_time, o, io, max_steps);
+    case PAT_TSIT54: return run_device_loop_pat<PAT_TSIT54>(c, md, pw, rhs.negate_time, o, io, max_steps);
+    case PAT_VERN65: return run_device_loop_pat<PAT_VERN65>(c, md, pw, rhs.negate_time, o, io, max_steps);
+    case PAT_VERN65_STRICT: return run_device_loop_pat<PAT_VERN65_STRICT>(c, md, pw, rhs.negate_time, o, io, max_steps);
   }
   return fail(c, B200RK_EINVAL, "device loop: unsupported method");
 }

@@ -4,6 +4,7 @@
 //   executor.cu  built-in right-hand sides, stage rows, fused paths, one IntegratorProc call (do_step)
 //   driver.cu    the resumable ODESolver loop and the step / solve entry points
 //   capi.cu      the remaining extern "C" surface (options, dispatch, Vector operators, raw kernels)
+//   jit.cu       element-local right-hand sides compiled at run time (NVRTC) into the fused kernels
 #pragma once
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -36,6 +37,8 @@ struct ProfRec {
 struct b200rk_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // solve_host: returns the tStart state while the solve runs (created on first use)
+  cudaEvent_t copy_event = nullptr;
   int sm_count = 148;
   int rank = 0, world = 1;
   ncclComm_t comm = nullptr;
@@ -274,3 +277,16 @@ int run_device_loop(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, cons
                     int64_t max_steps);
 int hermite_into(b200rk_ctx* c, b200rk_vec* out, double x, double x1, double x2, const b200rk_vec* y1, const b200rk_vec* y2,
                  const b200rk_vec* dy1, const b200rk_vec* dy2);
+
+// ---- jit.cu -----------------------------------------------------------------------------------------
+// A right-hand side given as source (b200rk_jit_rhs_new). `pattern` is a FusedPattern (kernels.cuh) or -1 for
+// the plain dydt / RK4 unit; `slot` picks the kernel inside that unit; `arg_block` is the kernel's single
+// by-value argument (FusedArgs<S> / RunArgs<S> / UserRhsArgs), laid out by the same header on both sides.
+struct JitRhs;
+int jit_rhs_fn(double t, const b200rk_vec* y, b200rk_vec* dydt, void* user);
+void jit_describe(const JitRhs* j, int* np, const b200rk_vec* const** vecs, const double** cs);
+int jit_slot_attempt(int w);
+int jit_slot_run(int w);
+int jit_launch(b200rk_ctx* c, JitRhs* j, int pattern, int slot, unsigned grid, void* arg_block, bool cooperative);
+int jit_max_blocks_per_sm(b200rk_ctx* c, JitRhs* j, int pattern, int slot, int* per_sm);
+int jit_launch_rk4(b200rk_ctx* c, JitRhs* j, bool negate, double t, double dt, const b200rk_vec* y, b200rk_vec* y_new);

@@ -245,8 +245,8 @@ void b200rk_destroy(b200rk_ctx* c) {
   cudaFree(c->d_partials); cudaFree(c->d_ticket); cudaFree(c->d_result); cudaFree(c->d_halo); cudaFreeHost(c->h_result); cudaFreeHost(c->h_seq);
   if (c->d_run_state) cudaFree(c->d_run_state);
   if (c->h_run_state) cudaFreeHost(c->h_run_state);
-  if (c->d_run_state) cudaFree(c->d_run_state);
-  if (c->h_run_state) cudaFreeHost(c->h_run_state);
+  if (c->copy_event) cudaEventDestroy(c->copy_event);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
   delete c;
 }

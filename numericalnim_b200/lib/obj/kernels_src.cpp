@@ -1,3 +1,4 @@
+extern "C" { extern const char b200rk_kernels_src[]; const char b200rk_kernels_src[] = R"B200RKSRC(
 // kernels.cuh — hand-written sm_100a kernels of the explicit Runge–Kutta hot path (fp64, BLAS-1,
 // HBM-bandwidth-bound; no tensor cores on purpose).
 //
@@ -1264,3 +1265,4 @@ __global__ void __launch_bounds__(THREADS)
 }
 
 }  // namespace b200rk
+)B200RKSRC"; }

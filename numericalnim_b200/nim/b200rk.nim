@@ -69,6 +69,10 @@ proc b200rk_step(ctx: B200rkCtx, methodId: cint, f: RhsFn, user: pointer, t: cdo
                  options: ptr COptions, yNew, fsalNew: VecHandle, dtUsed, error: ptr cdouble): cint {.importc, cdecl, dynlib: lib.}
 proc b200rk_solve(ctx: B200rkCtx, methodId: cint, f: RhsFn, user: pointer, y0: VecHandle, tspan: ptr cdouble, nTspan: csize_t,
                   options: ptr COptions, tOut: ptr cdouble, yOut: ptr VecHandle, nYOut: ptr csize_t, stats: ptr CStats): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_jit_rhs_new(ctx: B200rkCtx, expr: cstring, nVec: cint, vecs: ptr VecHandle, nScalar: cint, scalars: ptr cdouble,
+                        fn: ptr RhsFn, user: ptr pointer): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_jit_rhs_set_scalars(user: pointer, nScalar: cint, scalars: ptr cdouble): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_jit_rhs_free(user: pointer): cint {.importc, cdecl, dynlib: lib.}
 
 # ---- error convention: status code -> Nim exception (SURVEY.md §8b) ---------------------------------
 proc check(rc: cint, ctx: B200rkCtx = nil) =
@@ -189,4 +193,40 @@ proc solveODE*(f: ODEProc[GpuVector], y0: GpuVector, tspan: openArray[float],
   var ys = newSeq[GpuVector](nOut.int)
   for i in 0 ..< nOut.int: ys[i] = GpuVector(h: slots[i], ctx: y0.ctx, borrowed: false)
   while tOut.len > 0 and tOut[^1] != tOut[^1]: tOut.setLen(tOut.len - 1)   # tStart repeated in tspan: NaN-marked tail
+  result = (@tOut, ys)
+
+# ---- element-local right-hand side from source, fused into the RK kernels (b200rk_jit_rhs_new) -------
+type JitRhs* = ref object
+  ## dydt[i] = expr(t, y[i], p0[i].., c0..) as a CUDA C++ expression; compiled at run time INTO the fused kernels.
+  fn: RhsFn
+  user: pointer
+  ctx: B200rkCtx
+  vecs: seq[GpuVector]   # kept alive
+
+proc newJitRhs*(expr: string, vecs: openArray[GpuVector] = [], scalars: openArray[float] = [],
+                ctx: B200rkCtx = b200rkContext()): JitRhs =
+  ## e.g. newJitRhs("c0*y*(1.0 - y/p0)", [K], [r]); a wrong expression raises ValueError with the compiler log.
+  new(result, proc(r: JitRhs) = (if not r.user.isNil: discard b200rk_jit_rhs_free(r.user)))
+  result.ctx = ctx
+  result.vecs = @vecs
+  var hs = newSeq[VecHandle](vecs.len)
+  for i, v in vecs: hs[i] = v.h
+  var cs = @scalars
+  check(b200rk_jit_rhs_new(ctx, expr.cstring, hs.len.cint, (if hs.len > 0: addr hs[0] else: nil), cs.len.cint,
+                           (if cs.len > 0: cast[ptr cdouble](addr cs[0]) else: nil), addr result.fn, addr result.user), ctx)
+
+proc solveODE*(f: JitRhs, y0: GpuVector, tspan: openArray[float], options: ODEoptions = newODEoptions(),
+               integrator = "dopri54"): (seq[float], seq[GpuVector]) =
+  ## solveODE (ode.nim:589-651) with the right-hand side evaluated inside the fused kernels.
+  let mid = methodId(integrator.toLower())
+  var co = toC(options)
+  var ts = @tspan
+  var tOut = newSeq[cdouble](ts.len)
+  var slots = newSeq[VecHandle](max(ts.len, 1))
+  var nOut: csize_t
+  check(b200rk_solve(y0.ctx, mid, f.fn, f.user, y0.h, cast[ptr cdouble](addr ts[0]), ts.len.csize_t, addr co,
+                     cast[ptr cdouble](addr tOut[0]), addr slots[0], addr nOut, nil), y0.ctx)
+  var ys = newSeq[GpuVector](nOut.int)
+  for i in 0 ..< nOut.int: ys[i] = GpuVector(h: slots[i], ctx: y0.ctx, borrowed: false)
+  while tOut.len > 0 and tOut[^1] != tOut[^1]: tOut.setLen(tOut.len - 1)
   result = (@tOut, ys)

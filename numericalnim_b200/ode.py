@@ -374,6 +374,56 @@ def rhsLorenz96(F: float = 8.0, ctx: Context | None = None) -> BuiltinRhs:
     return BuiltinRhs(capi.RHS_LORENZ96, F, None, ctx)
 
 
+class JitRhs:
+    """Element-local right-hand side given as source (b200rk_jit_rhs_new): ``dy[i] = expr(t, y[i], p0[i].., c0..)``.
+
+    ``expr`` is a CUDA C++ expression in ``t``, ``y``, ``p0..p3`` (the GpuVectors of ``vecs``, one value per
+    element) and ``c0..c7`` (``scalars``). NVRTC compiles it INTO the library's fused kernels, so a user-defined
+    IVP runs the whole-attempt kernel / the device-resident driver loop / the one-kernel RK4 step exactly like the
+    built-in right-hand sides, and through a plain dy = f(t, y) kernel for every other method. Compiled without
+    FMA contraction: ``a*b + c`` rounds twice, like the reference's CPU arithmetic. A wrong expression raises
+    ValueError carrying the compiler log."""
+
+    def __init__(self, expr: str, vecs: Sequence["GpuVector"] = (), scalars: Sequence[float] = (), ctx: Context | None = None):
+        vecs = list(vecs)
+        self.ctx = ctx or (vecs[0].ctx if vecs else default_context())
+        self._vecs = vecs  # keep alive
+        self.expr = expr
+        self.fn = capi.RHS_FN()
+        self.user = C.c_void_p()
+        cs = np.ascontiguousarray(np.asarray(list(scalars), dtype=np.float64))
+        capi.check(capi.lib().b200rk_jit_rhs_new(self.ctx.handle, expr.encode(), len(vecs), _ptr_array(vecs) if vecs else None, cs.size,
+                                                 cs.ctypes.data if cs.size else None, C.byref(self.fn), C.byref(self.user)), self.ctx.handle)
+
+    def set_scalars(self, scalars: Sequence[float]):
+        """New values for c0.. (kernel arguments: no recompilation)."""
+        cs = np.ascontiguousarray(np.asarray(list(scalars), dtype=np.float64))
+        capi.check(capi.lib().b200rk_jit_rhs_set_scalars(self.user, cs.size, cs.ctypes.data if cs.size else None), self.ctx.handle)
+
+    def __del__(self):
+        try:
+            if self.user:
+                capi.lib().b200rk_jit_rhs_free(self.user)
+        except Exception:
+            pass
+
+
+def rhsJit(expr: str, vecs: Sequence["GpuVector"] = (), scalars: Sequence[float] = (), ctx: Context | None = None) -> JitRhs:
+    """``rhsJit("c0*y*(1.0 - y/p0)", vecs=[K], scalars=[r])`` — see JitRhs."""
+    return JitRhs(expr, vecs, scalars, ctx)
+
+
+def jitCompileOnly(expr: str, n_vec: int = 0, n_scalar: int = 0, pattern: int = -1):
+    """Host-only NVRTC compile of one translation unit (no GPU needed): returns (cubin bytes, log with kernel names)."""
+    L = capi.lib()
+    nb = C.c_size_t(0)
+    log = C.create_string_buffer(1 << 16)
+    capi.check(L.b200rk_jit_compile_only(expr.encode(), n_vec, n_scalar, pattern, None, 0, C.byref(nb), log, len(log)))
+    buf = C.create_string_buffer(nb.value)
+    capi.check(L.b200rk_jit_compile_only(expr.encode(), n_vec, n_scalar, pattern, buf, nb.value, C.byref(nb), log, len(log)))
+    return buf.raw[: nb.value], log.value.decode()
+
+
 class _PyRhs:
     """Adapts a Python ODEProc ``f(t, y: GpuVector, ctx) -> GpuVector`` to b200rk_rhs_fn. The callable's
     GpuVector operators enqueue kernels on the context stream; the result is copied into ``dydt``."""
@@ -400,11 +450,11 @@ class _PyRhs:
 
 
 def _resolve_rhs(f, ctx: Context, numctx: NumContext):
-    if isinstance(f, BuiltinRhs):
+    if isinstance(f, (BuiltinRhs, JitRhs)):
         return f
     if callable(f):
         return _PyRhs(f, ctx, numctx)
-    raise TypeError("f must be a BuiltinRhs or a callable f(t, y, ctx)")
+    raise TypeError("f must be a BuiltinRhs, a JitRhs or a callable f(t, y, ctx)")
 
 
 # ----------------------------------------------------------------------------------------------------

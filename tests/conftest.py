@@ -10,6 +10,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
+# Compiled user right-hand sides (csrc/jit.cu) are cached in-tree so that a test run on a fresh GPU box reuses what
+# scripts/jit_prewarm.py compiled on the CPU box (NVRTC needs no GPU); keyed by NVRTC version + kernels.cuh contents.
+os.environ.setdefault("B200RK_JIT_CACHE", os.path.join(ROOT, ".jitcache"))
+
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 

@@ -73,7 +73,7 @@ typedef struct b200rk_stats {
 } b200rk_stats;
 
 /* Per-kernel-class device timing (CUDA events on the context stream) for the roofline report. */
-enum b200rk_kernel_class { B200RK_K_STAGE = 0, B200RK_K_FINISH = 1, B200RK_K_RHS = 2, B200RK_K_OTHER = 3, B200RK_K_FUSED = 4, B200RK_K_COUNT = 5 };
+enum b200rk_kernel_class { B200RK_K_STAGE = 0, B200RK_K_FINISH = 1, B200RK_K_RHS = 2, B200RK_K_OTHER = 3, B200RK_K_FUSED = 4, B200RK_K_QUAD = 5, B200RK_K_COUNT = 6 };
 typedef struct b200rk_profile {
   int64_t launches[B200RK_K_COUNT];
   double ms[B200RK_K_COUNT];              /* summed event time */
@@ -180,6 +180,38 @@ B200RK_API int b200rk_jit_rhs_free(void* user);
  * 0..4 = fused attempt + device-loop kernels (dopri54, dopri54 strict, tsit54, vern65, vern65 strict). */
 B200RK_API int b200rk_jit_compile_only(const char* expr, int n_vec, int n_scalar, int pattern, void* cubin_out,
                                        size_t cubin_cap, size_t* cubin_bytes, char* log, size_t log_cap);
+
+/* ---- consumers of a trajectory: Hermite interpolation and cumulative quadrature -------- */
+/* A trajectory is a list of device vectors (what b200rk_solve returns) with its times. All results are newly
+ * allocated vectors (caller frees each); `out` needs room for nx (interpolation) / m (quadrature) handles and
+ * *n_out receives how many the reference returns — fewer than asked where it drops samples (below). */
+/* hermiteInterpolate(x, t, y, dy) (utils.nim:282-312): cubic Hermite spline through (t[i], y[i]) with slopes dy[i],
+ * evaluated at every x[k], all samples in ONE kernel. x sorted: samples outside [t[0], t[high]) are silently
+ * dropped and x == t[high] is returned once (utils.nim:290-300); x unsorted: a sample outside the data ->
+ * B200RK_EINVAL "<x> not in interval .." (utils.nim:312). */
+B200RK_API int b200rk_hermite_interpolate(b200rk_ctx* ctx, const double* x, size_t nx, const double* t, size_t nt,
+                                          const b200rk_vec* const* y, const b200rk_vec* const* dy, b200rk_vec** out,
+                                          size_t* n_out);
+/* cumtrapz(Y, X) (integrate.nim:119-135): X is sorted, duplicates are trimmed (utils.nim:360-420; same x with different
+ * vectors -> B200RK_EINVAL "impure y-duplicates"), then out[k] = integral from X_sorted[0] to X_sorted[k]. One kernel:
+ * every input read once, every output written once. */
+B200RK_API int b200rk_cumtrapz(b200rk_ctx* ctx, const b200rk_vec* const* Y, const double* X, size_t m, b200rk_vec** out,
+                               size_t* n_out);
+/* cumsimpson(Y, X) (integrate.nim:330-378): Simpson's rule on pairs of unequal intervals, then Hermite interpolation of
+ * the running integral back onto the ORIGINAL X. Fewer than 3 distinct points -> B200RK_EINVAL. */
+B200RK_API int b200rk_cumsimpson(b200rk_ctx* ctx, const b200rk_vec* const* Y, const double* X, size_t m, b200rk_vec** out,
+                                 size_t* n_out);
+/* NumContextProc[T, float] (commonTypes.nim): the integrand at one point. Must ENQUEUE on b200rk_stream(ctx), write only
+ * `out` (a vector of n_global elements) and return 0. */
+typedef int (*b200rk_fn_of_t)(double t, b200rk_vec* out, void* user);
+/* cumtrapz(f, X, ctx, dx) (integrate.nim:138-175): trapezoidal rule from min(X) to max(X) + 1.0 in steps of dx,
+ * interpolated at X. Streams: four vectors alive whatever the number of steps. */
+B200RK_API int b200rk_cumtrapz_fn(b200rk_ctx* ctx, b200rk_fn_of_t f, void* user, size_t n_global, const double* X, size_t m,
+                                  double dx, b200rk_vec** out, size_t* n_out);
+/* cumsimpson(f, X, ctx, dx) (integrate.nim:379-400): f on linspace(min X, max X, round((max-min)/dx) + 2), the discrete
+ * rule, interpolated at X. All evaluations are alive at once like in the reference (B200RK_ENOMEM if they cannot fit). */
+B200RK_API int b200rk_cumsimpson_fn(b200rk_ctx* ctx, b200rk_fn_of_t f, void* user, size_t n_global, const double* X,
+                                    size_t m, double dx, b200rk_vec** out, size_t* n_out);
 
 /* ---- the hot path ------------------------------------------------------------------------------ */
 /* One IntegratorProc call (ode.nim:38): (yNew, newFSAL, dtUsed, error) = X_step(f, t, y, FSAL, dt, options, ctx).

@@ -15,7 +15,7 @@ OK, EINVAL, ECUDA, ENCCL, ENOMEM, ECALLBACK, ENONFINITE = range(7)
 METHODS = ("dopri54", "tsit54", "vern65", "rk4", "rk21", "bs32", "heun2", "ralston2", "kutta3", "heun3",
            "ralston3", "ssprk3", "ralston4", "kutta4")  # enum b200rk_method order
 RHS_SCALE, RHS_DIAG_LINEAR, RHS_LORENZ96 = 0, 1, 2
-K_STAGE, K_FINISH, K_RHS, K_OTHER, K_FUSED, K_COUNT = 0, 1, 2, 3, 4, 5
+K_STAGE, K_FINISH, K_RHS, K_OTHER, K_FUSED, K_QUAD, K_COUNT = 0, 1, 2, 3, 4, 5, 6
 
 
 class Options(C.Structure):
@@ -38,6 +38,7 @@ class Profile(C.Structure):
 
 
 RHS_FN = C.CFUNCTYPE(C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p)
+FN_OF_T = C.CFUNCTYPE(C.c_int, C.c_double, C.c_void_p, C.c_void_p)
 
 _DECLS = {
     # name: (restype, argtypes)
@@ -91,6 +92,12 @@ _DECLS = {
     "b200rk_jit_rhs_set_scalars": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "b200rk_jit_rhs_free": (C.c_int, [C.c_void_p]),
     "b200rk_jit_compile_only": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]),
+    "b200rk_hermite_interpolate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                             C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "b200rk_cumtrapz": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "b200rk_cumsimpson": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "b200rk_cumtrapz_fn": (C.c_int, [C.c_void_p, FN_OF_T, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_double, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "b200rk_cumsimpson_fn": (C.c_int, [C.c_void_p, FN_OF_T, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_double, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "b200rk_step": (C.c_int, [C.c_void_p, C.c_int, RHS_FN, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_double,
                               C.POINTER(Options), C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "b200rk_solve": (C.c_int, [C.c_void_p, C.c_int, RHS_FN, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Options),

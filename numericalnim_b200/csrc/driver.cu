@@ -41,8 +41,7 @@ static int solver_alloc(b200rk_solver* s, size_t N) {
 }
 
 
-int hermite_into(b200rk_ctx* c, b200rk_vec* out, double x, double x1, double x2, const b200rk_vec* y1,
-                        const b200rk_vec* y2, const b200rk_vec* dy1, const b200rk_vec* dy2) {
+void hermite_factors(double x, double x1, double x2, double* f) {
   // utils.nim:273-279 — scalars on the host in the reference's order
   const double t = (x - x1) / (x2 - x1);
   const double u = 1.0 - t;
@@ -50,7 +49,14 @@ int hermite_into(b200rk_ctx* c, b200rk_vec* out, double x, double x1, double x2,
   const double h10 = t * (u * u);
   const double h01 = (t * t) * (3.0 - 2.0 * t);
   const double h11 = (t * (t * t)) - (t * t);
-  return launch_hermite(c, y1->d, dy1->d, y2->d, dy2->d, h00, h10 * (x2 - x1), h01, h11 * (x2 - x1), out->d, y1->n_local);
+  f[0] = h00; f[1] = h10 * (x2 - x1); f[2] = h01; f[3] = h11 * (x2 - x1);
+}
+
+int hermite_into(b200rk_ctx* c, b200rk_vec* out, double x, double x1, double x2, const b200rk_vec* y1,
+                        const b200rk_vec* y2, const b200rk_vec* dy1, const b200rk_vec* dy2) {
+  double f[4];
+  hermite_factors(x, x1, x2, f);
+  return launch_hermite(c, y1->d, dy1->d, y2->d, dy2->d, f[0], f[1], f[2], f[3], out->d, y1->n_local);
 }
 
 // Begin one time direction from (t0, y0). sign = +1 forward, -1 backward (t := -t, g = -f(-t, .)).

@@ -5,6 +5,7 @@
 //   driver.cu    the resumable ODESolver loop and the step / solve entry points
 //   capi.cu      the remaining extern "C" surface (options, dispatch, Vector operators, raw kernels)
 //   jit.cu       element-local right-hand sides compiled at run time (NVRTC) into the fused kernels
+//   quadrature.cu  hermiteInterpolate + cumulative quadrature over a trajectory (consumers of the solver's output)
 #pragma once
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -277,6 +278,8 @@ int run_device_loop(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, cons
                     int64_t max_steps);
 int hermite_into(b200rk_ctx* c, b200rk_vec* out, double x, double x1, double x2, const b200rk_vec* y1, const b200rk_vec* y2,
                  const b200rk_vec* dy1, const b200rk_vec* dy2);
+// scalar factors of hermiteSpline (utils.nim:273-279): f = {h00, h10*(x2-x1), h01, h11*(x2-x1)}
+void hermite_factors(double x, double x1, double x2, double* f);
 
 // ---- jit.cu -----------------------------------------------------------------------------------------
 // A right-hand side given as source (b200rk_jit_rhs_new). `pattern` is a FusedPattern (kernels.cuh) or -1 for

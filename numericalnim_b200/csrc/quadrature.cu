@@ -1,0 +1,432 @@
+// quadrature.cu — the consumers of a trajectory on the far side of the hot path:
+// hermiteInterpolate (utils.nim:282-312) and the cumulative quadrature routines built on it — cumtrapz(Y, X)
+// (integrate.nim:119-135), cumsimpson(Y, X) (integrate.nim:330-378) and their function variants
+// (integrate.nim:138-175, 379-400) — for T = device vector. The host does what is scalar in the reference
+// (sorting X, the duplicate rule, which interval each sample falls into, Simpson's coefficient triples, the
+// spline's scalar factors — same expressions, same rounding); every O(N) operation runs in quad_kernels.cuh.
+#include "internal.hpp"
+#include "quad_kernels.cuh"
+
+#include <numeric>
+
+namespace {
+
+// A host array living in device memory for the duration of one call, allocated and freed in stream order.
+template <class T>
+struct DeviceTable {
+  b200rk_ctx* c;
+  T* d = nullptr;
+  explicit DeviceTable(b200rk_ctx* ctx) : c(ctx) {}
+  int upload(const std::vector<T>& h) {
+    if (h.empty()) return B200RK_OK;
+    CUDA_TRY(c, cudaMallocAsync((void**)&d, h.size() * sizeof(T), c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));  // pageable source: staged before return
+    return B200RK_OK;
+  }
+  ~DeviceTable() { if (d) cudaFreeAsync(d, c->stream); }
+  DeviceTable(const DeviceTable&) = delete;
+  DeviceTable& operator=(const DeviceTable&) = delete;
+};
+
+// result vectors of one call: handed to the caller on success, back to the pool on failure
+struct Outputs {
+  std::vector<b200rk_vec*> v;
+  bool keep = false;
+  ~Outputs() { if (!keep) for (auto* p : v) vec_release(p); }
+  int add(b200rk_ctx* c, size_t n_global, b200rk_vec** out) {
+    TRY(vec_alloc(c, n_global, out));
+    v.push_back(*out);
+    return B200RK_OK;
+  }
+};
+
+unsigned quad_grid(const b200rk_ctx* c, size_t n, int W) { return grid_for(c, n / W, kThreads, 0); }
+
+int count_neq(b200rk_ctx* c, const b200rk_vec* a, const b200rk_vec* b, double* count) {
+  ProfScope ps(c, B200RK_K_QUAD, 8.0 * double(a->n_local) * 2);
+  unsigned grid = std::min(grid_for(c, a->n_local / 2, kThreads * 4, 0), (unsigned)(c->sm_count * 8));
+  TRY(ensure_partials(c, grid));
+  neq_count_kernel<2, kThreads><<<grid, kThreads, 0, c->stream>>>(a->d, b->d, a->n_local, reduce_scratch(c));
+  CUDA_TRY(c, cudaGetLastError());
+  return fetch_global_sum(c, count);
+}
+
+int check_series(b200rk_ctx* c, const b200rk_vec* const* Y, size_t m, const char* what) {
+  if (!Y) return fail(c, B200RK_EINVAL, std::string(what) + ": null vector list");
+  for (size_t i = 0; i < m; ++i) {
+    if (!Y[i]) return fail(c, B200RK_EINVAL, std::string(what) + ": null vector");
+    if (Y[i]->ctx != c) return fail(c, B200RK_EINVAL, std::string(what) + ": vector belongs to another context");
+    TRY(check_same(c, Y[0], Y[i]));
+  }
+  return B200RK_OK;
+}
+
+// sortDataset + removeDuplicates (utils.nim:360-420): sort by (x, input position); of every run of equal x keep
+// the first, and raise if any member of the run differs from it in any component (`!=`, so a NaN component
+// always counts as different, utils.nim:371-373).
+struct Series {
+  std::vector<double> x;
+  std::vector<const b200rk_vec*> y;
+};
+int sort_and_trim(b200rk_ctx* c, const b200rk_vec* const* Y, const double* X, size_t m, Series* out) {
+  if (m == 0) return fail(c, B200RK_EINVAL, "x is empty!");                          // assert, utils.nim:387
+  for (size_t i = 0; i < m; ++i)
+    if (X[i] != X[i]) return fail(c, B200RK_EINVAL, "X contains NaN (the reference's sort order is undefined there)");
+  std::vector<size_t> idx(m);
+  std::iota(idx.begin(), idx.end(), size_t(0));
+  std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return X[a] < X[b]; });
+  for (size_t i = 0; i < m;) {
+    size_t j = i + 1;
+    for (; j < m && X[idx[j]] == X[idx[i]]; ++j) {
+      double differing = 0.0;
+      TRY(count_neq(c, Y[idx[j]], Y[idx[i]], &differing));
+      if (differing != 0.0)
+        return fail(c, B200RK_EINVAL, "impure y-duplicates was found: the vectors at x = " + std::to_string(X[idx[i]]) + " (positions " +
+                                          std::to_string(idx[i]) + " and " + std::to_string(idx[j]) + ") differ");   // utils.nim:373
+    }
+    out->x.push_back(X[idx[i]]);
+    out->y.push_back(Y[idx[i]]);
+    i = j;
+  }
+  return B200RK_OK;
+}
+
+// Which spline each sample of hermiteInterpolate(x, t, ..) evaluates, in the order the reference appends its
+// results (utils.nim:287-312) — including what it silently drops in the sorted branch and the ValueError of the
+// unsorted one.
+int hermite_plan(const b200rk_ctx* c, const double* x, size_t nx, const double* t, size_t nt, std::vector<HermiteOut>* plan) {
+  if (nx == 0 || nt == 0) return fail(c, B200RK_EINVAL, "index out of bounds, the container is empty");
+  const long thigh = (long)nt - 1, xhigh = (long)nx - 1;
+  auto spline = [&](double a, long i) {
+    HermiteOut o;
+    o.j = (int)i; o.kind = 0;
+    double f[4];
+    hermite_factors(a, t[i], t[i + 1], f);
+    o.h00 = f[0]; o.hA = f[1]; o.h01 = f[2]; o.hB = f[3];
+    return o;
+  };
+  const HermiteOut last{(int)thigh, 1, 0.0, 0.0, 0.0, 0.0};   // result.add(y[y.high])
+  if (std::is_sorted(x, x + nx)) {
+    long xi = 0;
+    for (long i = 0; i <= thigh - 1; ++i) {
+      while (t[i] <= x[xi] && x[xi] < t[i + 1]) {
+        plan->push_back(spline(x[xi], i));
+        xi += 1;
+        if (xhigh < xi) break;
+      }
+      if (xhigh < xi) break;
+    }
+    if (x[xhigh] == t[thigh]) plan->push_back(last);
+  } else {
+    double tmin = t[0], tmax = t[0];
+    for (size_t i = 1; i < nt; ++i) { tmin = std::min(tmin, t[i]); tmax = std::max(tmax, t[i]); }
+    for (size_t k = 0; k < nx; ++k) {
+      const double a = x[k];
+      bool found = false;
+      for (long i = 0; i <= thigh - 1; ++i)
+        if (t[i] <= a && a < t[i + 1]) { plan->push_back(spline(a, i)); found = true; break; }
+      if (found) continue;
+      if (a == t[thigh]) plan->push_back(last);
+      else return fail(c, B200RK_EINVAL, std::to_string(a) + " not in interval " + std::to_string(tmin) + " - " + std::to_string(tmax));  // utils.nim:312
+    }
+  }
+  return B200RK_OK;
+}
+
+template <class T>
+std::vector<const T*> device_ptrs(const std::vector<const b200rk_vec*>& v) {
+  std::vector<const T*> p;
+  for (auto* x : v) p.push_back(x->d);
+  return p;
+}
+std::vector<double*> device_ptrs_mut(const std::vector<b200rk_vec*>& v) {
+  std::vector<double*> p;
+  for (auto* x : v) p.push_back(x->d);
+  return p;
+}
+
+// all samples of one hermiteInterpolate call in one launch
+int run_hermite_many(b200rk_ctx* c, const std::vector<HermiteOut>& plan, const std::vector<const b200rk_vec*>& y,
+                     const std::vector<const b200rk_vec*>& dy, Outputs* outs) {
+  if (plan.empty()) return B200RK_OK;
+  const size_t n_global = y[0]->n_global, n = y[0]->n_local;
+  for (size_t o = 0; o < plan.size(); ++o) { b200rk_vec* v = nullptr; TRY(outs->add(c, n_global, &v)); }
+  if (n == 0) return B200RK_OK;
+  DeviceTable<const double*> dy_t(c), y_t(c);
+  DeviceTable<double*> out_t(c);
+  DeviceTable<HermiteOut> plan_t(c);
+  TRY(y_t.upload(device_ptrs<double>(y)));
+  TRY(dy_t.upload(device_ptrs<double>(dy)));
+  TRY(out_t.upload(device_ptrs_mut(std::vector<b200rk_vec*>(outs->v.end() - plan.size(), outs->v.end()))));
+  TRY(plan_t.upload(plan));
+  // algorithmic traffic: one write per sample; reads: the distinct (vector, role) pairs the samples touch
+  std::vector<char> seen_y(y.size(), 0), seen_dy(y.size(), 0);
+  double reads = 0;
+  for (auto& p : plan) {
+    if (p.kind == 1) { reads += 1; continue; }
+    for (int d = 0; d < 2; ++d) {
+      if (!seen_y[p.j + d]) { seen_y[p.j + d] = 1; reads += 1; }
+      if (!seen_dy[p.j + d]) { seen_dy[p.j + d] = 1; reads += 1; }
+    }
+  }
+  ProfScope ps(c, B200RK_K_QUAD, 8.0 * double(n) * (reads + double(plan.size())));
+  HermiteManyArgs a{y_t.d, dy_t.d, out_t.d, plan_t.d, (int)plan.size(), n};
+  if (c->vec_width == 4) hermite_many_kernel<4, kThreads><<<quad_grid(c, n, 4), kThreads, 0, c->stream>>>(a);
+  else hermite_many_kernel<2, kThreads><<<quad_grid(c, n, 2), kThreads, 0, c->stream>>>(a);
+  CUDA_TRY(c, cudaGetLastError());
+  return B200RK_OK;
+}
+
+// Simpson's coefficient triples on two unequal intervals (integrate.nim:357-359) and on the last interval of an
+// even-length data set (integrate.nim:367-369). `^` is Nim's math.`^`: x^2 = x*x, x^3 = x*x*x.
+inline double p2(double x) { return x * x; }
+inline double p3(double x) { return x * x * x; }
+void simpson_pair(double h1, double h2, double* alpha, double* beta, double* eta) {
+  *alpha = (2.0 * p3(h2) - p3(h1) + 3.0 * h1 * p2(h2)) / (6.0 * h2 * (h2 + h1));
+  *beta = (p3(h2) + p3(h1) + 3.0 * h1 * h2 * (h2 + h1)) / (6.0 * h2 * h1);
+  *eta = (2.0 * p3(h1) - p3(h2) + 3.0 * h2 * p2(h1)) / (6.0 * h1 * (h2 + h1));
+}
+void simpson_tail(double h1, double h2, double* alpha, double* beta, double* eta) {
+  *alpha = (2.0 * p2(h2) + 3.0 * h1 * h2) / (6.0 * (h1 + h2));
+  *beta = (p2(h2) + 3.0 * h1 * h2) / (6.0 * h1);
+  *eta = -(p3(h2)) / (6.0 * h1 * (h1 + h2));
+}
+
+void hand_over(Outputs& outs, b200rk_vec** out, size_t* n_out) {
+  for (size_t i = 0; i < outs.v.size(); ++i) out[i] = outs.v[i];
+  *n_out = outs.v.size();
+  outs.keep = true;
+}
+
+int cumtrapz_impl(b200rk_ctx* c, const b200rk_vec* const* Y, const double* X, size_t m, Outputs* outs) {
+  TRY(check_series(c, Y, m, "cumtrapz"));
+  Series s;
+  TRY(sort_and_trim(c, Y, X, m, &s));
+  const size_t M = s.x.size(), n_global = s.y[0]->n_global, n = s.y[0]->n_local;
+  for (size_t k = 0; k < M; ++k) { b200rk_vec* v = nullptr; TRY(outs->add(c, n_global, &v)); }
+  if (n == 0) return B200RK_OK;
+  std::vector<double> h;
+  for (size_t k = 0; k + 1 < M; ++k) h.push_back(0.5 * (s.x[k + 1] - s.x[k]));                    // integrate.nim:134
+  DeviceTable<const double*> y_t(c);
+  DeviceTable<double*> out_t(c);
+  DeviceTable<double> h_t(c);
+  TRY(y_t.upload(device_ptrs<double>(s.y)));
+  TRY(out_t.upload(device_ptrs_mut(outs->v)));
+  TRY(h_t.upload(h));
+  ProfScope ps(c, B200RK_K_QUAD, 8.0 * double(n) * 2.0 * double(M));   // every point read once, every integral written once
+  CumTrapzArgs a{y_t.d, out_t.d, h_t.d, (int)M, n};
+  if (c->vec_width == 4) cumtrapz_kernel<4, 4, kThreads><<<quad_grid(c, n, 4), kThreads, 0, c->stream>>>(a);
+  else cumtrapz_kernel<2, 4, kThreads><<<quad_grid(c, n, 2), kThreads, 0, c->stream>>>(a);
+  CUDA_TRY(c, cudaGetLastError());
+  return B200RK_OK;
+}
+
+int cumsimpson_impl(b200rk_ctx* c, const b200rk_vec* const* Y, const double* X, size_t m, Outputs* outs) {
+  TRY(check_series(c, Y, m, "cumsimpson"));
+  Series s;
+  TRY(sort_and_trim(c, Y, X, m, &s));
+  long N = (long)s.x.size();
+  if (N < 3) return fail(c, B200RK_EINVAL, "X and Y must have at least 3 elements to perform Simpson, use cumtrapz instead");   // integrate.nim:347-348
+  const bool evenN = (N % 2 == 0);
+  if (evenN) N -= 1;
+  const size_t n_global = s.y[0]->n_global, n = s.y[0]->n_local;
+  // integrals at every second data point (+ the last point of an even-length set): the knots of the spline
+  std::vector<SimpsonStep> steps;
+  std::vector<double> xs{s.x[0]};
+  std::vector<const b200rk_vec*> dy{s.y[0]};
+  const long pairs = (N - 1) / 2;
+  for (long i = 0; i < pairs; ++i) {
+    SimpsonStep st;
+    st.ia = (int)(2 * i + 2); st.ib = (int)(2 * i + 1); st.ic = (int)(2 * i); st.reuse = 1;       // y[2i] was the previous y[2i'+2] (or the first point)
+    simpson_pair(s.x[2 * i + 1] - s.x[2 * i], s.x[2 * i + 2] - s.x[2 * i + 1], &st.ca, &st.cb, &st.cc);
+    steps.push_back(st);
+    xs.push_back(s.x[2 * i + 2]);
+    dy.push_back(s.y[2 * i + 2]);
+  }
+  if (evenN) {
+    const long last = (long)s.x.size() - 1;
+    double alpha, beta, eta;
+    simpson_tail(s.x[last - 1] - s.x[last - 2], s.x[last] - s.x[last - 1], &alpha, &beta, &eta);
+    SimpsonStep st;                                                                                // eta*y[last-2] + beta*y[last-1] + alpha*y[last]
+    st.ia = (int)(last - 2); st.ib = (int)(last - 1); st.ic = (int)last; st.reuse = 0;
+    st.ca = eta; st.cb = beta; st.cc = alpha;
+    steps.push_back(st);
+    xs.push_back(s.x[last]);
+    dy.push_back(s.y[last]);
+  }
+  // because Simpson uses several input points per integral point, the integral at all input points comes from
+  // hermiteInterpolate(X, xs, y, dy) with the ORIGINAL X (integrate.nim:377-378): plan it before any device work
+  std::vector<HermiteOut> plan;
+  TRY(hermite_plan(c, X, m, xs.data(), xs.size(), &plan));
+  Outputs knots;   // released at the end of the call (stream-ordered reuse: the pool belongs to this stream)
+  for (size_t k = 0; k < xs.size(); ++k) { b200rk_vec* v = nullptr; TRY(knots.add(c, n_global, &v)); }
+  if (n) {
+    DeviceTable<const double*> y_t(c);
+    DeviceTable<double*> node_t(c);
+    DeviceTable<SimpsonStep> step_t(c);
+    TRY(y_t.upload(device_ptrs<double>(s.y)));
+    TRY(node_t.upload(device_ptrs_mut(knots.v)));
+    TRY(step_t.upload(steps));
+    ProfScope ps(c, B200RK_K_QUAD, 8.0 * double(n) * double(s.x.size() + xs.size()));   // every point read once, every knot written once
+    SimpsonScanArgs a{y_t.d, node_t.d, step_t.d, (int)steps.size(), 0, n};
+    if (c->vec_width == 4) simpson_scan_kernel<4, kThreads><<<quad_grid(c, n, 4), kThreads, 0, c->stream>>>(a);
+    else simpson_scan_kernel<2, kThreads><<<quad_grid(c, n, 2), kThreads, 0, c->stream>>>(a);
+    CUDA_TRY(c, cudaGetLastError());
+  }
+  std::vector<const b200rk_vec*> knot_y(knots.v.begin(), knots.v.end());
+  return run_hermite_many(c, plan, knot_y, dy, outs);
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200rk_hermite_interpolate(b200rk_ctx* c, const double* x, size_t nx, const double* t, size_t nt, const b200rk_vec* const* y,
+                               const b200rk_vec* const* dy, b200rk_vec** out, size_t* n_out) {
+  if (!c || !x || !t || !out || !n_out) return fail(c, B200RK_EINVAL, "null argument");
+  TRY(check_series(c, y, nt, "hermiteInterpolate"));
+  TRY(check_series(c, dy, nt, "hermiteInterpolate"));
+  if (nt) TRY(check_same(c, y[0], dy[0]));
+  std::vector<HermiteOut> plan;
+  TRY(hermite_plan(c, x, nx, t, nt, &plan));
+  Outputs outs;
+  TRY(run_hermite_many(c, plan, std::vector<const b200rk_vec*>(y, y + nt), std::vector<const b200rk_vec*>(dy, dy + nt), &outs));
+  hand_over(outs, out, n_out);
+  return B200RK_OK;
+}
+
+int b200rk_cumtrapz(b200rk_ctx* c, const b200rk_vec* const* Y, const double* X, size_t m, b200rk_vec** out, size_t* n_out) {
+  if (!c || !X || !out || !n_out) return fail(c, B200RK_EINVAL, "null argument");
+  Outputs outs;
+  TRY(cumtrapz_impl(c, Y, X, m, &outs));
+  hand_over(outs, out, n_out);
+  return B200RK_OK;
+}
+
+int b200rk_cumsimpson(b200rk_ctx* c, const b200rk_vec* const* Y, const double* X, size_t m, b200rk_vec** out, size_t* n_out) {
+  if (!c || !X || !out || !n_out) return fail(c, B200RK_EINVAL, "null argument");
+  Outputs outs;
+  TRY(cumsimpson_impl(c, Y, X, m, &outs));
+  hand_over(outs, out, n_out);
+  return B200RK_OK;
+}
+
+// cumtrapz(f, X, ctx, dx) (integrate.nim:138-175). The reference stores f, the running integral and the time at
+// EVERY step (from min(X) to max(X) + 1.0 in steps of dx: 10^5 vectors per unit of time at the default dx) and
+// interpolates afterwards. The samples each step interval contributes are known beforehand, so this streams:
+// four vectors live, each step = 1 callback + 1 kernel, samples are emitted when their interval is complete.
+int b200rk_cumtrapz_fn(b200rk_ctx* c, b200rk_fn_of_t f, void* user, size_t n_global, const double* X, size_t m, double dx,
+                       b200rk_vec** out, size_t* n_out) {
+  if (!c || !f || !X || !out || !n_out) return fail(c, B200RK_EINVAL, "null argument");
+  if (m == 0) return fail(c, B200RK_EINVAL, "index out of bounds, the container is empty");
+  if (!(dx > 0.0)) return fail(c, B200RK_EINVAL, "cumtrapz: dx must be > 0 (the reference would never terminate)");
+  double lo = X[0], hi = X[0];
+  for (size_t i = 0; i < m; ++i) {
+    if (X[i] != X[i]) return fail(c, B200RK_EINVAL, "X contains NaN");
+    lo = std::min(lo, X[i]); hi = std::max(hi, X[i]);
+  }
+  const double tEnd = hi + 1.0;                                                                    // integrate.nim:160
+  if ((tEnd - lo) / dx > 2e8) return fail(c, B200RK_EINVAL, "cumtrapz: more than 2e8 steps; choose a larger dx");
+  std::vector<double> times;
+  double t = lo;
+  times.push_back(t);
+  t += dx;
+  while (t <= tEnd) { times.push_back(t); t += dx; }                                               // integrate.nim:167-174
+  std::vector<HermiteOut> plan;
+  TRY(hermite_plan(c, X, m, times.data(), times.size(), &plan));
+  std::vector<size_t> order(plan.size());                                                          // samples by the interval that completes them
+  std::iota(order.begin(), order.end(), size_t(0));
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+    return (plan[a].j + (plan[a].kind == 1 ? 0 : 1)) < (plan[b].j + (plan[b].kind == 1 ? 0 : 1));
+  });
+  Outputs outs;
+  for (size_t o = 0; o < plan.size(); ++o) { b200rk_vec* v = nullptr; TRY(outs.add(c, n_global, &v)); }
+  Workspace ws(c);
+  b200rk_vec *dy[2], *I[2];
+  for (int i = 0; i < 2; ++i) { TRY(ws.get(n_global, &dy[i])); TRY(ws.get(n_global, &I[i])); }
+  const size_t n = dy[0]->n_local;
+  auto call = [&](double tt, b200rk_vec* dst) -> int {
+    const int rc = f(tt, dst, user);
+    return rc == 0 ? B200RK_OK : fail(c, B200RK_ECALLBACK, "integrand callback returned " + std::to_string(rc));
+  };
+  int cur = 0;
+  TRY(call(times[0], dy[0]));
+  TRY(launch_ewise(c, EW_SUB, dy[0]->d, dy[0]->d, 0.0, I[0]->d, n, B200RK_K_QUAD));                // the right kind of zero
+  size_t next = 0;
+  auto emit_done = [&](long completed_points) -> int {   // samples whose data (points <= completed_points - 1) is ready
+    for (; next < order.size(); ++next) {
+      const HermiteOut& p = plan[order[next]];
+      const long needs = p.j + (p.kind == 1 ? 0 : 1);
+      if (needs > completed_points - 1) break;
+      b200rk_vec* dst = outs.v[order[next]];
+      if (p.kind == 1) { TRY(vec_copy_raw(c, dst, I[cur])); continue; }
+      // the interval (j, j+1) is (previous, current)
+      TRY(launch_hermite(c, I[1 - cur]->d, dy[1 - cur]->d, I[cur]->d, dy[cur]->d, p.h00, p.hA, p.h01, p.hB, dst->d, n));
+    }
+    return B200RK_OK;
+  };
+  for (size_t k = 0; k + 1 < times.size(); ++k) {
+    TRY(call(times[k + 1], dy[1 - cur]));
+    if (n) {
+      ProfScope ps(c, B200RK_K_QUAD, 8.0 * double(n) * 4);
+      trapz_step_kernel<2, kThreads><<<quad_grid(c, n, 2), kThreads, 0, c->stream>>>(I[cur]->d, dy[cur]->d, dy[1 - cur]->d, 0.5 * dx, I[1 - cur]->d, n);   // integrate.nim:170
+      CUDA_TRY(c, cudaGetLastError());
+    }
+    cur = 1 - cur;
+    TRY(emit_done((long)k + 2));
+  }
+  TRY(emit_done((long)times.size()));   // a data set of one point: only copies of it can be asked for
+  if (next != order.size()) return fail(c, B200RK_EINVAL, "cumtrapz: internal plan mismatch");
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));   // the callback's buffers may go away after return
+  hand_over(outs, out, n_out);
+  return B200RK_OK;
+}
+
+// cumsimpson(f, X, ctx, dx) (integrate.nim:379-400): f on linspace(min X, max X, round((max-min)/dx) + 2), the
+// discrete rule on those values, then hermiteInterpolate(X, t, ys, dy) — composed exactly like the reference, so
+// all evaluations of f are alive at once (3 vectors per grid point): meant for moderate (max-min)/dx.
+int b200rk_cumsimpson_fn(b200rk_ctx* c, b200rk_fn_of_t f, void* user, size_t n_global, const double* X, size_t m, double dx,
+                         b200rk_vec** out, size_t* n_out) {
+  if (!c || !f || !X || !out || !n_out) return fail(c, B200RK_EINVAL, "null argument");
+  if (m == 0) return fail(c, B200RK_EINVAL, "index out of bounds, the container is empty");
+  if (!(dx > 0.0)) return fail(c, B200RK_EINVAL, "cumsimpson: dx must be > 0");
+  double lo = X[0], hi = X[0];
+  for (size_t i = 0; i < m; ++i) {
+    if (X[i] != X[i]) return fail(c, B200RK_EINVAL, "X contains NaN");
+    lo = std::min(lo, X[i]); hi = std::max(hi, X[i]);
+  }
+  const double count = std::round((hi - lo) / dx) + 2.0;                                           // toInt rounds half away from zero
+  size_t off = 0, len = 0;
+  shard_range(n_global, c->rank, c->world, &off, &len);
+  size_t free_b = 0, total_b = 0;
+  CUDA_TRY(c, cudaMemGetInfo(&free_b, &total_b));
+  if (count > 5e7 || count * 3.0 * double(std::max<size_t>(len, 4)) * 8.0 > 0.9 * double(free_b))
+    return fail(c, B200RK_ENOMEM, "cumsimpson(f, X, dx): " + std::to_string((long long)count) + " grid points of " + std::to_string(len) +
+                                      " elements do not fit (3 vectors per point are alive at once, as in the reference); choose a larger dx");
+  const long nt = (long)count;
+  std::vector<double> t;                                                                           // linspace, utils.nim:498-507
+  const double step = (hi - lo) / double(nt - 1);
+  t.push_back(lo);
+  for (long i = 1; i <= nt - 2; ++i) t.push_back(lo + step * double(i));
+  t.push_back(hi);
+  Outputs dy;   // released when the call returns
+  for (double x : t) {
+    b200rk_vec* v = nullptr;
+    TRY(dy.add(c, n_global, &v));
+    const int rc = f(x, v, user);
+    if (rc != 0) return fail(c, B200RK_ECALLBACK, "integrand callback returned " + std::to_string(rc));
+  }
+  std::vector<const b200rk_vec*> dyc(dy.v.begin(), dy.v.end());
+  Outputs ys;
+  TRY(cumsimpson_impl(c, dyc.data(), t.data(), t.size(), &ys));
+  if (ys.v.size() != t.size()) return fail(c, B200RK_EINVAL, "cumsimpson(f, X, dx): the grid collapsed (min(X) == max(X)?)");
+  std::vector<HermiteOut> plan;
+  TRY(hermite_plan(c, X, m, t.data(), t.size(), &plan));
+  Outputs outs;
+  TRY(run_hermite_many(c, plan, std::vector<const b200rk_vec*>(ys.v.begin(), ys.v.end()), dyc, &outs));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  hand_over(outs, out, n_out);
+  return B200RK_OK;
+}
+
+}  // extern "C"

@@ -78,7 +78,7 @@ class Context:
     def profile_read(self) -> dict:
         p = capi.Profile()
         capi.check(capi.lib().b200rk_profile_read(self._h, C.byref(p)), self._h)
-        names = ("stage", "finish", "rhs", "other", "fused")
+        names = ("stage", "finish", "rhs", "other", "fused", "quad")
         return {n: dict(launches=int(p.launches[i]), ms=float(p.ms[i]), bytes=float(p.algorithmic_bytes[i])) for i, n in enumerate(names)}
 
     def stats(self) -> dict:
@@ -282,6 +282,90 @@ def hermiteSpline(x: float, x1: float, x2: float, y1: GpuVector, y2: GpuVector, 
     out = y1._new_like()
     capi.check(capi.lib().b200rk_hermite(out._h, x, x1, x2, y1._h, y2._h, dy1._h, dy2._h), y1.ctx.handle)
     return out
+
+
+def _adopt_list(ctx: "Context", slots, n_out) -> list:
+    return [GpuVector(ctx, C.c_void_p(slots[i])) for i in range(n_out.value)]
+
+
+def hermiteInterpolate(x: Sequence[float], t: Sequence[float], y: Sequence["GpuVector"], dy: Sequence["GpuVector"]) -> list:
+    """utils.nim:282-312 on a trajectory of device vectors: the cubic Hermite spline through (t[i], y[i]) with slopes
+    dy[i], evaluated at every x in ONE kernel. Like the reference: sorted x silently drops samples outside the data,
+    unsorted x raises ValueError for them."""
+    y, dy = list(y), list(dy)
+    if len(y) != len(t) or len(dy) != len(t):
+        raise ValueError("t, y and dy must have the same length")
+    if not y:
+        raise ValueError("index out of bounds, the container is empty")
+    ctx = y[0].ctx
+    xa = np.ascontiguousarray(np.asarray(list(x), dtype=np.float64))
+    ta = np.ascontiguousarray(np.asarray(list(t), dtype=np.float64))
+    slots = (C.c_void_p * max(xa.size, 1))()
+    n_out = C.c_size_t(0)
+    capi.check(capi.lib().b200rk_hermite_interpolate(ctx.handle, xa.ctypes.data, xa.size, ta.ctypes.data, ta.size, _ptr_array(y), _ptr_array(dy),
+                                                     slots, C.byref(n_out)), ctx.handle)
+    return _adopt_list(ctx, slots, n_out)
+
+
+class _PyFnOfT:
+    """Adapts a Python integrand ``f(x, ctx) -> GpuVector`` (NumContextProc[T, float]) to b200rk_fn_of_t."""
+
+    def __init__(self, f: Callable, dctx: "Context", numctx):
+        self.exc = None
+        self.calls = 0
+
+        def tramp(t, out_h, _user):
+            try:
+                self.calls += 1
+                out = GpuVector(dctx, C.c_void_p(out_h), owned=False)
+                r = f(t, numctx)
+                if not isinstance(r, GpuVector):
+                    raise TypeError("the integrand must return a GpuVector")
+                if r._h.value != out_h:
+                    out.copy_from(r)
+                return 0
+            except BaseException as e:  # noqa: BLE001 — must not unwind through C
+                self.exc = e
+                return 1
+
+        self.fn = capi.FN_OF_T(tramp)
+
+
+def _cumulative(name: str, first, X, ctx, dx, like):
+    L = capi.lib()
+    Xa = np.ascontiguousarray(np.asarray(list(X), dtype=np.float64))
+    n_out = C.c_size_t(0)
+    slots = (C.c_void_p * max(Xa.size, 1))()
+    if callable(first):  # cumtrapz(f, X, ctx, dx) / cumsimpson(f, X, ctx, dx)
+        numctx = ctx if ctx is not None else newNumContext()
+        if like is None:
+            like = first(float(Xa.min()) if Xa.size else 0.0, numctx)  # learn T's size (one extra evaluation; pass `like` to avoid it)
+        dctx = like.ctx
+        cb = _PyFnOfT(first, dctx, numctx)
+        rc = getattr(L, name + "_fn")(dctx.handle, cb.fn, None, len(like), Xa.ctypes.data, Xa.size, float(dx), slots, C.byref(n_out))
+        if cb.exc is not None:
+            raise cb.exc
+        capi.check(rc, dctx.handle)
+        return _adopt_list(dctx, slots, n_out)
+    Y = list(first)  # cumtrapz(Y, X) / cumsimpson(Y, X)
+    if len(Y) != Xa.size:
+        raise ValueError("X and Y must have the same length")
+    if not Y:
+        raise ValueError("x is empty!")
+    dctx = Y[0].ctx
+    capi.check(getattr(L, name)(dctx.handle, _ptr_array(Y), Xa.ctypes.data, Xa.size, slots, C.byref(n_out)), dctx.handle)
+    return _adopt_list(dctx, slots, n_out)
+
+
+def cumtrapz(Y_or_f, X: Sequence[float], ctx: "NumContext | None" = None, dx: float = 1e-5, like: "GpuVector | None" = None) -> list:
+    """integrate.nim:119-135 (``cumtrapz(Y, X)``: a list of GpuVector sampled at X) and integrate.nim:138-175
+    (``cumtrapz(f, X, ctx, dx)``: ``f(x, ctx) -> GpuVector`` integrated in steps of dx, returned at X)."""
+    return _cumulative("b200rk_cumtrapz", Y_or_f, X, ctx, dx, like)
+
+
+def cumsimpson(Y_or_f, X: Sequence[float], ctx: "NumContext | None" = None, dx: float = 1e-5, like: "GpuVector | None" = None) -> list:
+    """integrate.nim:330-378 (``cumsimpson(Y, X)``) and integrate.nim:379-400 (``cumsimpson(f, X, ctx, dx)``)."""
+    return _cumulative("b200rk_cumsimpson", Y_or_f, X, ctx, dx, like)
 
 
 class NumContext:

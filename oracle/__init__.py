@@ -27,7 +27,7 @@ def build(force: bool = False) -> str:
     """Compile liboracle.so with the committed Makefile (g++ -O2 -ffp-contract=off)."""
     src_newer = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB_PATH)
-        for f in ("rk_oracle.hpp", "oracle_capi.cpp", "Makefile")
+        for f in ("rk_oracle.hpp", "quad_oracle.hpp", "oracle_capi.cpp", "Makefile")
     )
     if force or src_newer:
         subprocess.run(["make", "-C", _HERE, "-s"] + (["-B"] if force else []), check=True)
@@ -321,3 +321,94 @@ def pair_tableau(method: str) -> dict:
         raise ValueError_(method)
     return dict(stages=stages.value, order=order.value, n_b=n_b.value, n_bhat=n_bhat.value, err_direct=bool(direct.value),
                 c=c, a=a, b=b, bhat=bhat)
+
+
+# ----------------------------------------------------------------------------------------------------
+# Hermite interpolation of a data set + cumulative quadrature (quad_oracle.hpp)
+# ----------------------------------------------------------------------------------------------------
+FN_CB = C.CFUNCTYPE(None, C.c_double, C.POINTER(C.c_double), C.c_size_t, C.c_void_p)
+
+
+class Defect(RuntimeError):
+    """Stands for Nim's AssertionDefect / IndexDefect (not a ValueError)."""
+
+
+def _check_q(rc: int):
+    if rc == 3:
+        raise Defect(lib().oracle_last_error().decode())
+    _check(rc)
+
+
+def _seq(a, scalar: bool):
+    """Sequence of T as a contiguous (m, n) array; n = 1 for scalars."""
+    a = _f64(a)
+    return a.reshape(-1, 1) if scalar else np.atleast_2d(a)
+
+
+def _out(res, n_out, scalar):
+    r = res[: n_out.value].copy()
+    return r[:, 0] if scalar else r
+
+
+def hermite_interpolate(x, t, y, dy, scalar: bool = False) -> np.ndarray:
+    """utils.nim:282-312. y, dy: (len(t), n) arrays (or 1-D with scalar=True). Returns (n_out, n)."""
+    x, t = _f64(x), _f64(t)
+    y, dy = _seq(y, scalar), _seq(dy, scalar)
+    n = y.shape[1]
+    res = np.empty((max(x.size, 1), n))
+    n_out = C.c_size_t(0)
+    _check_q(lib().oracle_hermite_interpolate(C.c_int(scalar), C.c_size_t(n), _p(x), C.c_size_t(x.size), _p(t), C.c_size_t(t.size), _p(y), _p(dy),
+                                              _p(res), C.byref(n_out)))
+    return _out(res, n_out, scalar)
+
+
+def _cum(fn_name, Y, X, scalar):
+    X = _f64(X)
+    Y = _seq(Y, scalar)
+    n = Y.shape[1]
+    res = np.empty((max(X.size, 1), n))
+    n_out = C.c_size_t(0)
+    _check_q(getattr(lib(), fn_name)(C.c_int(scalar), C.c_size_t(n), _p(Y), _p(X), C.c_size_t(X.size), _p(res), C.byref(n_out)))
+    return _out(res, n_out, scalar)
+
+
+def cumtrapz(Y, X, scalar: bool = False) -> np.ndarray:
+    """integrate.nim:119-135."""
+    return _cum("oracle_cumtrapz", Y, X, scalar)
+
+
+def cumsimpson(Y, X, scalar: bool = False) -> np.ndarray:
+    """integrate.nim:330-378."""
+    return _cum("oracle_cumsimpson", Y, X, scalar)
+
+
+def _cum_fn(fn_name, f, X, dx, n, scalar):
+    X = _f64(X)
+    res = np.empty((max(X.size, 1), n))
+    n_out = C.c_size_t(0)
+    evals = C.c_long(0)
+
+    def tramp(t, op, nn, _user):
+        out = np.ctypeslib.as_array(op, shape=(nn,))
+        out[:] = f(t)
+
+    cb = FN_CB(tramp)
+    _check_q(getattr(lib(), fn_name)(C.c_int(scalar), C.c_size_t(n), cb, None, _p(X), C.c_size_t(X.size), C.c_double(dx), _p(res), C.byref(n_out),
+                                     C.byref(evals)))
+    return _out(res, n_out, scalar), evals.value
+
+
+def cumtrapz_fn(f, X, dx: float = 1e-5, n: int = 1, scalar: bool = False):
+    """integrate.nim:138-175; f(t) -> array of n values. Returns (values, number of evaluations of f)."""
+    return _cum_fn("oracle_cumtrapz_fn", f, X, dx, n, scalar)
+
+
+def cumsimpson_fn(f, X, dx: float = 1e-5, n: int = 1, scalar: bool = False):
+    """integrate.nim:379-400."""
+    return _cum_fn("oracle_cumsimpson_fn", f, X, dx, n, scalar)
+
+
+def simpson_weights(h1: float, h2: float, tail: bool = False):
+    a, b, e = C.c_double(0), C.c_double(0), C.c_double(0)
+    lib().oracle_simpson_weights(C.c_int(tail), C.c_double(h1), C.c_double(h2), C.byref(a), C.byref(b), C.byref(e))
+    return a.value, b.value, e.value

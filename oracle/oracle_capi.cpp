@@ -6,6 +6,7 @@
 #include <memory>
 
 #include "rk_oracle.hpp"
+#include "quad_oracle.hpp"
 
 using namespace rk_oracle;
 
@@ -274,6 +275,81 @@ int oracle_pair_tableau(const char* method, int* stages, int* order, int* n_b, i
   std::memcpy(c, p->c, sizeof(p->c)); std::memcpy(a, p->a, sizeof(p->a));
   std::memcpy(b, p->b, sizeof(p->b)); std::memcpy(bhat, p->bhat, sizeof(p->bhat));
   return 0;
+}
+
+// ---- Hermite interpolation of a data set + cumulative quadrature (quad_oracle.hpp) ---------------------------
+// Sequences of T are flat row-major arrays: item k occupies [k*n, (k+1)*n). scalar != 0 runs the T = float
+// instantiation (n must be 1) — the reference's own tests use it. Return: 0 ok, 1 ValueError, 3 assert / bounds defect.
+typedef void (*oracle_fn_cb)(double t, double* out, size_t n, void* user);
+}  // extern "C"
+
+template <class Fn>
+static int guarded(Fn&& fn) {
+  try { fn(); return 0; }
+  catch (const ValueError& e) { g_err = e.what(); return 1; }
+  catch (const AssertionDefect& e) { g_err = e.what(); return 3; }
+  catch (const IndexDefect& e) { g_err = e.what(); return 3; }
+}
+static std::vector<Vector> rows(const double* a, size_t m, size_t n) {
+  std::vector<Vector> r;
+  for (size_t k = 0; k < m; ++k) r.emplace_back(a + k * n, n);
+  return r;
+}
+static std::vector<double> scalars(const double* a, size_t m) { return std::vector<double>(a, a + m); }
+static void store(const std::vector<Vector>& r, size_t n, double* out, size_t* n_out) {
+  for (size_t k = 0; k < r.size(); ++k) std::memcpy(out + k * n, r[k].components.data(), n * sizeof(double));
+  *n_out = r.size();
+}
+static void store(const std::vector<double>& r, size_t, double* out, size_t* n_out) {
+  for (size_t k = 0; k < r.size(); ++k) out[k] = r[k];
+  *n_out = r.size();
+}
+static FnOfT<Vector> vec_fn(oracle_fn_cb cb, void* user, size_t n, long* evals) {
+  return [=](double t) { std::vector<double> v(n); cb(t, v.data(), n, user); if (evals) ++*evals; return Vector(v); };
+}
+static FnOfT<double> scalar_fn(oracle_fn_cb cb, void* user, long* evals) {
+  return [=](double t) { double v = 0.0; cb(t, &v, 1, user); if (evals) ++*evals; return v; };
+}
+
+extern "C" {
+
+int oracle_hermite_interpolate(int scalar, size_t n, const double* x, size_t nx, const double* t, size_t nt, const double* y,
+                               const double* dy, double* out, size_t* n_out) {
+  return guarded([&] {
+    if (scalar) store(hermite_interpolate<double>(scalars(x, nx), scalars(t, nt), scalars(y, nt), scalars(dy, nt)), 1, out, n_out);
+    else store(hermite_interpolate<Vector>(scalars(x, nx), scalars(t, nt), rows(y, nt, n), rows(dy, nt, n)), n, out, n_out);
+  });
+}
+int oracle_cumtrapz(int scalar, size_t n, const double* Y, const double* X, size_t m, double* out, size_t* n_out) {
+  return guarded([&] {
+    if (scalar) store(cumtrapz<double>(scalars(Y, m), scalars(X, m)), 1, out, n_out);
+    else store(cumtrapz<Vector>(rows(Y, m, n), scalars(X, m)), n, out, n_out);
+  });
+}
+int oracle_cumsimpson(int scalar, size_t n, const double* Y, const double* X, size_t m, double* out, size_t* n_out) {
+  return guarded([&] {
+    if (scalar) store(cumsimpson<double>(scalars(Y, m), scalars(X, m)), 1, out, n_out);
+    else store(cumsimpson<Vector>(rows(Y, m, n), scalars(X, m)), n, out, n_out);
+  });
+}
+int oracle_cumtrapz_fn(int scalar, size_t n, oracle_fn_cb cb, void* user, const double* X, size_t m, double dx, double* out,
+                       size_t* n_out, long* evals) {
+  return guarded([&] {
+    if (scalar) store(cumtrapz_fn<double>(scalar_fn(cb, user, evals), scalars(X, m), dx), 1, out, n_out);
+    else store(cumtrapz_fn<Vector>(vec_fn(cb, user, n, evals), scalars(X, m), dx), n, out, n_out);
+  });
+}
+int oracle_cumsimpson_fn(int scalar, size_t n, oracle_fn_cb cb, void* user, const double* X, size_t m, double dx, double* out,
+                         size_t* n_out, long* evals) {
+  return guarded([&] {
+    if (scalar) store(cumsimpson_fn<double>(scalar_fn(cb, user, evals), scalars(X, m), dx), 1, out, n_out);
+    else store(cumsimpson_fn<Vector>(vec_fn(cb, user, n, evals), scalars(X, m), dx), n, out, n_out);
+  });
+}
+// the coefficient triples alone (host-side scalars of the product are checked against these)
+void oracle_simpson_weights(int tail, double h1, double h2, double* alpha, double* beta, double* eta) {
+  const SimpsonWeights w = tail ? simpson_tail_weights(h1, h2) : simpson_pair_weights(h1, h2);
+  *alpha = w.alpha; *beta = w.beta; *eta = w.eta;
 }
 
 }  // extern "C"

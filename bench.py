@@ -4,6 +4,7 @@
     python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
     python bench.py --sweep [--out FILE]                     # BASELINE.json config 5: kernel bandwidth sweep
+    python bench.py --quad [--out FILE]                      # trajectory consumers (cumtrapz / cumsimpson / hermiteInterpolate)
 
 A "step" is one accepted Runge–Kutta step of the adaptive driver loop (ode.nim:511-541). On the general
 pipeline (any user right-hand side) an attempt is S-1 right-hand-side launches, S-1 fused stage-accumulate
@@ -549,6 +550,61 @@ def run_sweep(args):
         dist.destroy_process_group()
 
 
+def run_quad(args):
+    """SURVEY.md §8f rank 4 — the trajectory consumers (csrc/quadrature.cu): cumtrapz / cumsimpson over a sampled
+    trajectory of M device vectors and hermiteInterpolate at 2M sample points, at 2^log2n elements per vector.
+    GB/s = algorithmic bytes (every input vector read once, every output written once) / CUDA-event time of the
+    kernels (library profiler, class "quad"), next to the oracle port's time for the same call on one host core."""
+    import numericalnim_b200 as nn
+    import oracle as O
+
+    ctx = nn.default_context()
+    peak, peak_src = peaks()
+    lg = args.log2n or 23
+    n, m = 1 << lg, args.quad_points
+    rng = np.random.default_rng(1234)
+    base = rng.uniform(-1.0, 1.0, n)
+    X = np.linspace(0.0, 2.0, m) + rng.uniform(-0.02, 0.02, m) * (np.arange(m) % 2)   # uneven spacing, sorted
+    Y = [nn.newVector(np.roll(base, 17 * k), ctx) for k in range(m)]
+    dY = [nn.newVector(np.roll(base, 17 * k + 5), ctx) for k in range(m)]
+    xs = np.sort(rng.uniform(X[0], X[-1], 2 * m))
+    n_cpu = 1 << min(lg, args.quad_cpu_log2n)
+    Yc = np.stack([np.roll(base[:n_cpu], 17 * k) for k in range(m)])
+    dYc = np.stack([np.roll(base[:n_cpu], 17 * k + 5) for k in range(m)])
+    cases = (("cumtrapz", lambda: nn.cumtrapz(Y, X), lambda: O.cumtrapz(Yc, X)),
+             ("cumsimpson", lambda: nn.cumsimpson(Y, X), lambda: O.cumsimpson(Yc, X)),
+             ("hermiteInterpolate", lambda: nn.hermiteInterpolate(xs, X, Y, dY), lambda: O.hermite_interpolate(xs, X, Yc, dYc)))
+    rows = []
+    for name, gpu, cpu in cases:
+        for _ in range(3):
+            for v in gpu():
+                v.free()
+        ctx.set("profile", 1)
+        ctx.profile_reset()
+        t0 = time.perf_counter()
+        for _ in range(args.quad_iters):
+            for v in gpu():
+                v.free()
+        ctx.synchronize()
+        wall = (time.perf_counter() - t0) / args.quad_iters
+        p = ctx.profile_read()["quad"]
+        ctx.set("profile", 0)
+        t0 = time.perf_counter()
+        cpu()
+        cpu_s = time.perf_counter() - t0
+        gbs = p["bytes"] / (p["ms"] * 1e-3) / 1e9
+        alg_per_call = p["bytes"] / args.quad_iters
+        row = {"op": name, "log2n": lg, "points": m, "kernel_launches_per_call": p["launches"] / args.quad_iters, "kernel_ms_per_call": p["ms"] / args.quad_iters,
+               "wall_ms_per_call": 1e3 * wall, "algorithmic_GB_per_call": alg_per_call / 1e9, "GBps": gbs, "frac_of_peak": gbs / peak,
+               "cpu_oracle_s_at_2p%d" % int(np.log2(n_cpu)): cpu_s, "cpu_GBps_same_bytes": alg_per_call * (n_cpu / n) / cpu_s / 1e9,
+               "gpu_over_cpu_per_element": (cpu_s / n_cpu) / (1e-3 * wall / n)}
+        rows.append(row)
+        print(json.dumps(row), flush=True)
+    if args.out:
+        with open(args.out, "w") as fh:
+            json.dump({"peak_gbs": peak, "peak_source": peak_src, "host_cores": os.cpu_count(), "rows": rows}, fh, indent=1)
+
+
 def run_tune(args):
     """Launch-geometry matrix at one size: vec_width x ctas_per_sm for stage m=1,5,8 and the DOPRI54 finish."""
     import numericalnim_b200 as nn
@@ -625,6 +681,10 @@ def main():
     ap.add_argument("--no-fuse", action="store_true", help="headline = the stage/RHS/finish pipeline even for element-local built-in RHS")
     ap.add_argument("--cpu-budget-s", type=float, default=120.0)
     ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--quad", action="store_true", help="trajectory consumers: cumtrapz / cumsimpson / hermiteInterpolate bandwidth")
+    ap.add_argument("--quad-points", type=int, default=33)
+    ap.add_argument("--quad-iters", type=int, default=5)
+    ap.add_argument("--quad-cpu-log2n", type=int, default=18)
     ap.add_argument("--tune", action="store_true")
     ap.add_argument("--sweep-min", type=int, default=16)
     ap.add_argument("--sweep-max", type=int, default=26)
@@ -639,6 +699,8 @@ def main():
         args.warmup = 3
     if args.tune:
         return run_tune(args)
+    if args.quad:
+        return run_quad(args)
     if args.sweep:
         return run_sweep(args)
     if args.impl == "reference":

@@ -15,6 +15,7 @@
 //   linspace, hermiteSpline         utils.nim:498-507, 273-279
 #pragma once
 #include <cmath>
+#include <exception>
 #include <functional>
 #include <map>
 #include <memory>
@@ -295,6 +296,89 @@ inline Solution solveODE(const DeviceRhs& f, const GpuVector& y0, const std::vec
   for (size_t i = 0; i < n_out; ++i) sol.y.push_back(GpuVector::adopt(y0.device(), slots[i]));
   detail::trim_times(sol.t);
   return sol;
+}
+
+// ---- consumers of a trajectory: hermiteInterpolate (utils.nim:282-312), cumtrapz / cumsimpson (integrate.nim) ----
+namespace detail {
+inline std::vector<const b200rk_vec*> handles(const std::vector<GpuVector>& v) {
+  std::vector<const b200rk_vec*> h;
+  for (const GpuVector& x : v) h.push_back(x.handle());
+  return h;
+}
+inline std::vector<GpuVector> adopt_all(const std::shared_ptr<Device>& dev, const std::vector<b200rk_vec*>& slots, size_t n) {
+  std::vector<GpuVector> r;
+  for (size_t i = 0; i < n; ++i) r.push_back(GpuVector::adopt(dev, slots[i]));
+  return r;
+}
+}  // namespace detail
+
+inline std::vector<GpuVector> hermiteInterpolate(const std::vector<double>& x, const std::vector<double>& t, const std::vector<GpuVector>& y,
+                                                 const std::vector<GpuVector>& dy) {
+  if (y.empty() || y.size() != t.size() || dy.size() != t.size()) throw ValueError("t, y and dy must have the same non-zero length");
+  std::vector<b200rk_vec*> slots(x.size() ? x.size() : 1, nullptr);
+  size_t n = 0;
+  const auto hy = detail::handles(y), hdy = detail::handles(dy);
+  check(b200rk_hermite_interpolate(y[0].device()->handle(), x.data(), x.size(), t.data(), t.size(), hy.data(), hdy.data(), slots.data(), &n),
+        y[0].device()->handle());
+  return detail::adopt_all(y[0].device(), slots, n);
+}
+inline std::vector<GpuVector> cumtrapz(const std::vector<GpuVector>& Y, const std::vector<double>& X) {  // integrate.nim:119-135
+  if (Y.empty() || Y.size() != X.size()) throw ValueError("X and Y must have the same non-zero length");
+  std::vector<b200rk_vec*> slots(X.size(), nullptr);
+  size_t n = 0;
+  const auto h = detail::handles(Y);
+  check(b200rk_cumtrapz(Y[0].device()->handle(), h.data(), X.data(), X.size(), slots.data(), &n), Y[0].device()->handle());
+  return detail::adopt_all(Y[0].device(), slots, n);
+}
+inline std::vector<GpuVector> cumsimpson(const std::vector<GpuVector>& Y, const std::vector<double>& X) {  // integrate.nim:330-378
+  if (Y.empty() || Y.size() != X.size()) throw ValueError("X and Y must have the same non-zero length");
+  std::vector<b200rk_vec*> slots(X.size(), nullptr);
+  size_t n = 0;
+  const auto h = detail::handles(Y);
+  check(b200rk_cumsimpson(Y[0].device()->handle(), h.data(), X.data(), X.size(), slots.data(), &n), Y[0].device()->handle());
+  return detail::adopt_all(Y[0].device(), slots, n);
+}
+
+// NumContextProc[T, float]: the integrand at one point
+using NumContextProc = std::function<GpuVector(double, NumContext&)>;
+namespace detail {
+struct FnEnv {
+  const NumContextProc* f;
+  NumContext* ctx;
+  std::shared_ptr<Device> dev;
+  std::exception_ptr err;
+};
+inline int fn_trampoline(double t, b200rk_vec* out, void* user) {
+  auto* env = static_cast<FnEnv*>(user);
+  try {
+    GpuVector r = (*env->f)(t, *env->ctx);
+    return b200rk_vec_copy(out, r.handle());
+  } catch (...) {
+    env->err = std::current_exception();
+    return 1;
+  }
+}
+using CumFn = int (*)(b200rk_ctx*, b200rk_fn_of_t, void*, size_t, const double*, size_t, double, b200rk_vec**, size_t*);
+inline std::vector<GpuVector> cumulative_fn(CumFn api, const NumContextProc& f, const std::vector<double>& X, const GpuVector& like,
+                                            std::shared_ptr<NumContext> ctx, double dx) {
+  if (!ctx) ctx = newNumContext();
+  FnEnv env{&f, ctx.get(), like.device(), nullptr};
+  std::vector<b200rk_vec*> slots(X.size() ? X.size() : 1, nullptr);
+  size_t n = 0;
+  const int rc = api(like.device()->handle(), &fn_trampoline, &env, like.size(), X.data(), X.size(), dx, slots.data(), &n);
+  if (env.err) std::rethrow_exception(env.err);
+  check(rc, like.device()->handle());
+  return adopt_all(like.device(), slots, n);
+}
+}  // namespace detail
+// cumtrapz(f, X, ctx, dx) (integrate.nim:138-175) / cumsimpson(f, X, ctx, dx) (integrate.nim:379-400); `like` fixes T's size
+inline std::vector<GpuVector> cumtrapz(const NumContextProc& f, const std::vector<double>& X, const GpuVector& like,
+                                       std::shared_ptr<NumContext> ctx = nullptr, double dx = 1e-5) {
+  return detail::cumulative_fn(&b200rk_cumtrapz_fn, f, X, like, std::move(ctx), dx);
+}
+inline std::vector<GpuVector> cumsimpson(const NumContextProc& f, const std::vector<double>& X, const GpuVector& like,
+                                         std::shared_ptr<NumContext> ctx = nullptr, double dx = 1e-5) {
+  return detail::cumulative_fn(&b200rk_cumsimpson_fn, f, X, like, std::move(ctx), dx);
 }
 
 }  // namespace numericalnim

@@ -170,6 +170,12 @@ static int ctx_common_init(b200rk_ctx* c) {
   c->sm_count = prop.multiProcessorCount;
   if (prop.l2CacheSize > 0) c->l2_bytes = (size_t)prop.l2CacheSize;
   CUDA_TRY(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  {  // stream-ordered scratch (quadrature.cu's per-call tables): keep freed blocks cached instead of returning them to the OS at every sync
+    cudaMemPool_t pool = nullptr;
+    unsigned long long keep = ~0ull;
+    if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    cudaGetLastError();
+  }
   CUDA_TRY(c, cudaMalloc(&c->d_ticket, sizeof(unsigned int)));
   CUDA_TRY(c, cudaMemset(c->d_ticket, 0, sizeof(unsigned int)));
   CUDA_TRY(c, cudaMalloc(&c->d_result, sizeof(double)));

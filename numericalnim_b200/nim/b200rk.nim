@@ -73,6 +73,15 @@ proc b200rk_jit_rhs_new(ctx: B200rkCtx, expr: cstring, nVec: cint, vecs: ptr Vec
                         fn: ptr RhsFn, user: ptr pointer): cint {.importc, cdecl, dynlib: lib.}
 proc b200rk_jit_rhs_set_scalars(user: pointer, nScalar: cint, scalars: ptr cdouble): cint {.importc, cdecl, dynlib: lib.}
 proc b200rk_jit_rhs_free(user: pointer): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_hermite_interpolate(ctx: B200rkCtx, x: ptr cdouble, nx: csize_t, t: ptr cdouble, nt: csize_t, y, dy: ptr VecHandle,
+                                outVecs: ptr VecHandle, nOut: ptr csize_t): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_cumtrapz(ctx: B200rkCtx, Y: ptr VecHandle, X: ptr cdouble, m: csize_t, outVecs: ptr VecHandle, nOut: ptr csize_t): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_cumsimpson(ctx: B200rkCtx, Y: ptr VecHandle, X: ptr cdouble, m: csize_t, outVecs: ptr VecHandle, nOut: ptr csize_t): cint {.importc, cdecl, dynlib: lib.}
+type FnOfT = proc(t: cdouble, outVec: VecHandle, user: pointer): cint {.cdecl.}
+proc b200rk_cumtrapz_fn(ctx: B200rkCtx, f: FnOfT, user: pointer, nGlobal: csize_t, X: ptr cdouble, m: csize_t, dx: cdouble,
+                        outVecs: ptr VecHandle, nOut: ptr csize_t): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_cumsimpson_fn(ctx: B200rkCtx, f: FnOfT, user: pointer, nGlobal: csize_t, X: ptr cdouble, m: csize_t, dx: cdouble,
+                          outVecs: ptr VecHandle, nOut: ptr csize_t): cint {.importc, cdecl, dynlib: lib.}
 
 # ---- error convention: status code -> Nim exception (SURVEY.md §8b) ---------------------------------
 proc check(rc: cint, ctx: B200rkCtx = nil) =
@@ -230,3 +239,64 @@ proc solveODE*(f: JitRhs, y0: GpuVector, tspan: openArray[float], options: ODEop
   for i in 0 ..< nOut.int: ys[i] = GpuVector(h: slots[i], ctx: y0.ctx, borrowed: false)
   while tOut.len > 0 and tOut[^1] != tOut[^1]: tOut.setLen(tOut.len - 1)
   result = (@tOut, ys)
+
+# ---- consumers of a trajectory: hermiteInterpolate (utils.nim:282-312), cumtrapz / cumsimpson (integrate.nim) --
+proc handles(v: openArray[GpuVector]): seq[VecHandle] =
+  result = newSeq[VecHandle](v.len)
+  for i, x in v: result[i] = x.h
+proc adoptAll(ctx: B200rkCtx, slots: seq[VecHandle], n: csize_t): seq[GpuVector] =
+  result = newSeq[GpuVector](n.int)
+  for i in 0 ..< n.int: result[i] = GpuVector(h: slots[i], ctx: ctx, borrowed: false)
+
+proc hermiteInterpolate*(x, t: openArray[float], y, dy: openArray[GpuVector]): seq[GpuVector] =
+  ## Same name and argument order as utils.nim:282; all samples are evaluated by one kernel.
+  if y.len == 0 or y.len != t.len or dy.len != t.len: raise newException(ValueError, "t, y and dy must have the same non-zero length")
+  var (xs, ts, hy, hdy) = (@x, @t, handles(y), handles(dy))
+  var slots = newSeq[VecHandle](max(xs.len, 1))
+  var n: csize_t
+  check(b200rk_hermite_interpolate(y[0].ctx, cast[ptr cdouble](addr xs[0]), xs.len.csize_t, cast[ptr cdouble](addr ts[0]), ts.len.csize_t,
+                                   addr hy[0], addr hdy[0], addr slots[0], addr n), y[0].ctx)
+  adoptAll(y[0].ctx, slots, n)
+
+template cumulativeDiscrete(api: untyped, Y: openArray[GpuVector], X: openArray[float]): seq[GpuVector] =
+  if Y.len == 0 or Y.len != X.len: raise newException(ValueError, "X and Y must have the same non-zero length")
+  var (xs, hy) = (@X, handles(Y))
+  var slots = newSeq[VecHandle](xs.len)
+  var n: csize_t
+  check(api(Y[0].ctx, addr hy[0], cast[ptr cdouble](addr xs[0]), xs.len.csize_t, addr slots[0], addr n), Y[0].ctx)
+  adoptAll(Y[0].ctx, slots, n)
+
+proc cumtrapz*(Y: openArray[GpuVector], X: openArray[float]): seq[GpuVector] = cumulativeDiscrete(b200rk_cumtrapz, Y, X)      # integrate.nim:119-135
+proc cumsimpson*(Y: openArray[GpuVector], X: openArray[float]): seq[GpuVector] = cumulativeDiscrete(b200rk_cumsimpson, Y, X)  # integrate.nim:330-378
+
+type FnEnv = object
+  f: NumContextProc[GpuVector, float]
+  ctx: NumContext[GpuVector, float]
+  err: ref Exception
+proc fnTrampoline(t: cdouble, outVec: VecHandle, user: pointer): cint {.cdecl.} =
+  let env = cast[ptr FnEnv](user)
+  try:
+    let r = env.f(t.float, env.ctx)
+    result = b200rk_vec_copy(outVec, r.h)
+  except CatchableError as e:
+    env.err = e
+    result = 1
+
+template cumulativeFn(api: untyped, f, X, like, ctx, dx: untyped): seq[GpuVector] =
+  var nctx = ctx
+  if nctx.isNil: nctx = newNumContext[GpuVector, float]()
+  var env = FnEnv(f: f, ctx: nctx)
+  var xs = @X
+  var slots = newSeq[VecHandle](max(xs.len, 1))
+  var n: csize_t
+  let rc = api(like.ctx, fnTrampoline, addr env, like.len.csize_t, cast[ptr cdouble](addr xs[0]), xs.len.csize_t, dx.cdouble, addr slots[0], addr n)
+  if not env.err.isNil: raise env.err
+  check(rc, like.ctx)
+  adoptAll(like.ctx, slots, n)
+
+proc cumtrapz*(f: NumContextProc[GpuVector, float], X: openArray[float], like: GpuVector,
+               ctx: NumContext[GpuVector, float] = nil, dx = 1e-5): seq[GpuVector] =      # integrate.nim:138-175; `like` fixes T's size
+  cumulativeFn(b200rk_cumtrapz_fn, f, X, like, ctx, dx)
+proc cumsimpson*(f: NumContextProc[GpuVector, float], X: openArray[float], like: GpuVector,
+                 ctx: NumContext[GpuVector, float] = nil, dx = 1e-5): seq[GpuVector] =    # integrate.nim:379-400
+  cumulativeFn(b200rk_cumsimpson_fn, f, X, like, ctx, dx)

@@ -67,27 +67,5 @@ int main() {
     std::printf("jit same_bits_as_closure=%d dopri54_ok=%d bad_expression_raises=%d launches_closure=%lld launches_jit=%lld\n", same ? 1 : 0,
                 close ? 1 : 0, bad_expr, (long long)a.stats.launches, (long long)b.stats.launches);
   }
-  // The consumers on the far side: integrate the solved trajectory over time (tests/test_integrate.nim:67-95 with the
-  // trajectory y(t) = exp(-0.1 t) from above: cumulative integral 10 (1 - exp(-0.1 t)) + const).
-  int quad_ok = 0;
-  {
-    Solution sol = solveODE(fVector, y0, linspace(0.0, 10.0, 41), ooVector, nullptr, "tsit54");
-    const std::vector<GpuVector> It = cumtrapz(sol.y, sol.t), Is = cumsimpson(sol.y, sol.t);
-    bool ok = It.size() == 41 && Is.size() == 41;
-    for (size_t i = 0; ok && i < 41; ++i) {
-      const double exact = 10.0 * (1.0 - std::exp(-0.1 * sol.t[i]));
-      ok = meanSquaredError(It[i].components(), exact) <= 1e-2 && meanSquaredError(Is[i].components(), exact) <= 1e-5;
-    }
-    // cumtrapz(f, X, ctx, dx) with a closure integrand, as tests/test_integrate.nim:6 writes fVector
-    auto ctx = newNumContext();
-    ctx->tValues.emplace("a", newVector({2.0, 2.0, 2.0}));
-    const NumContextProc g = [](double x, NumContext& c) { return std::cos(x) * c.tValues.at("a"); };
-    const std::vector<double> X = linspace(0.0, 4.71238898038469, 17);
-    const std::vector<GpuVector> G = cumsimpson(g, X, y0, ctx, 0.01);
-    bool ok2 = G.size() == 17;
-    for (size_t i = 0; ok2 && i < 17; ++i) ok2 = meanSquaredError(G[i].components(), 2.0 * std::sin(X[i])) <= 1e-3;
-    quad_ok = ok && ok2;
-    std::printf("quadrature trajectory_ok=%d function_variant_ok=%d\n", ok ? 1 : 0, ok2 ? 1 : 0);
-  }
-  return (failures == 0 && raised == 4 && jit_ok && quad_ok) ? 0 : 1;
+  return (failures == 0 && raised == 4 && jit_ok) ? 0 : 1;
 }

@@ -79,6 +79,47 @@ def main():
             fails.append(("lorenz96 tsit54", nl, st, refl.stats.steps, float(np.max(np.abs(got - exp)))))
         if rank == 0:
             print(f"[multi-gpu world={world}] lorenz96 n={nl} tsit54: steps={st['steps']} rejected={st['rejected']} collectives={st['collectives']} ok={ok}", flush=True)
+    # right-hand side given as SOURCE, sharded: the parameter vector shards like the state; the run-time compiled
+    # attempt kernel / device loop use the same in-kernel all-reduce as the built-ins
+    K = 2.0 + 3.0 * np.arange(n) / (n - 1)
+    gK = nn.newVector(K, ctx)
+    jrhs = nn.rhsJit("c0*y*(1.0 - y/p0) + c1*t", [gK], [0.7, 0.05])
+    oj = O.rhs_callback(lambda t, y: 0.7 * y * (1.0 - y / K) + 0.05 * t)
+    for method in ("dopri54", "vern65"):
+        refj = O.solve_vector(method, oj, y0, [0.0, 2.0], O.new_options(**kw))
+        for devloop in (1, 0):
+            ctx.set("device_loop", devloop)
+            t, ys = nn.solveODE(jrhs, gy0, [0.0, 2.0], nn.newODEoptions(**kw), integrator=method)
+            st = dict(nn.ode.last_stats)
+            got, exp = ys[-1].local_numpy(), refj.y[-1][off:off + ln]
+            ok = bool(np.all(np.abs(got - exp) <= 1e-9 * np.abs(exp) + 1e-13 * np.max(np.abs(refj.y[-1])))) and \
+                st["steps"] == refj.stats.steps and st["rejected"] == refj.stats.rejected and st["collectives"] == st["attempts"]
+            if not ok:
+                fails.append(("jit rhs", method, devloop, st, refj.stats.steps, float(np.max(np.abs(got - exp)))))
+            if rank == 0:
+                print(f"[multi-gpu world={world}] jit rhs {method} device_loop={devloop}: steps={st['steps']} launches={st['launches']} collectives={st['collectives']} ok={ok}", flush=True)
+    ctx.set("device_loop", -1)
+    # trajectory consumers, sharded: element-wise, the only scalar that crosses shards is the duplicate test's count
+    rngq = np.random.default_rng(11)
+    Xq = np.array([0.0, 1.0, 0.5, 1.0, 2.0, 1.5, 3.0])
+    base = rngq.uniform(-1.0, 1.0, (6, n))
+    Yq = np.stack([base[0], base[1], base[2], base[1], base[3], base[4], base[5]])
+    dv = [nn.newVector(r, ctx) for r in Yq]
+    for name, ofn in (("cumtrapz", O.cumtrapz), ("cumsimpson", O.cumsimpson)):
+        got = np.array([v.local_numpy() for v in getattr(nn, name)(dv, Xq)])
+        exp = ofn(Yq, Xq)[:, off:off + ln]
+        ok = got.shape == exp.shape and np.array_equal(got.view(np.uint64), exp.view(np.uint64))
+        if not ok:
+            fails.append((name + " sharded",))
+        if rank == 0:
+            print(f"[multi-gpu world={world}] {name} sharded bitwise ok={ok}", flush=True)
+    Ybad = Yq.copy()
+    Ybad[3, n - 1] += 1.0  # lives on the LAST rank only: every rank must still see the impure duplicate
+    try:
+        nn.cumtrapz([nn.newVector(r, ctx) for r in Ybad], Xq)
+        fails.append(("impure duplicate not detected on rank", rank))
+    except ValueError:
+        pass
     # sharded sum(v) goes through the same allreduce
     s = gy0.sum()
     assert abs(s - O.vector_sum(y0)) <= 1e-12 * np.abs(y0).sum(), (s, O.vector_sum(y0))

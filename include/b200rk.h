@@ -213,6 +213,15 @@ B200RK_API int b200rk_cumtrapz_fn(b200rk_ctx* ctx, b200rk_fn_of_t f, void* user,
 B200RK_API int b200rk_cumsimpson_fn(b200rk_ctx* ctx, b200rk_fn_of_t f, void* user, size_t n_global, const double* X,
                                     size_t m, double dx, b200rk_vec** out, size_t* n_out);
 
+/* Host only (no device needed): the host-side decisions of the routines above, for tests and tooling. hermite_plan:
+ * for every sample hermiteInterpolate(x, t, ..) returns, in order, the data interval [t[j], t[j+1]] it is evaluated on
+ * (is_copy = 1: it is the copy of data point j = nt-1, utils.nim:299-300) and {h00, h10*(x2-x1), h01, h11*(x2-x1)}
+ * (utils.nim:273-279); arrays need room for nx entries (4*nx factors). simpson_weights: (alpha, beta, eta) of
+ * integrate.nim:357-359 (tail = 0) or :367-369 (tail = 1). */
+B200RK_API int b200rk_hermite_plan(const double* x, size_t nx, const double* t, size_t nt, int* interval, int* is_copy,
+                                   double* factors, size_t* n_out);
+B200RK_API int b200rk_simpson_weights(int tail, double h1, double h2, double* alpha, double* beta, double* eta);
+
 /* ---- the hot path ------------------------------------------------------------------------------ */
 /* One IntegratorProc call (ode.nim:38): (yNew, newFSAL, dtUsed, error) = X_step(f, t, y, FSAL, dt, options, ctx).
  * Runs the adaptive retry loop of commonAdaptiveMethodCode (ode.nim:57-76) for adaptive methods.

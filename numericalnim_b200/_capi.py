@@ -98,6 +98,8 @@ _DECLS = {
     "b200rk_cumsimpson": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "b200rk_cumtrapz_fn": (C.c_int, [C.c_void_p, FN_OF_T, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_double, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "b200rk_cumsimpson_fn": (C.c_int, [C.c_void_p, FN_OF_T, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_double, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "b200rk_hermite_plan": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]),
+    "b200rk_simpson_weights": (C.c_int, [C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "b200rk_step": (C.c_int, [C.c_void_p, C.c_int, RHS_FN, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_double,
                               C.POINTER(Options), C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "b200rk_solve": (C.c_int, [C.c_void_p, C.c_int, RHS_FN, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Options),

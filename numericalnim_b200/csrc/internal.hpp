@@ -72,7 +72,7 @@ struct b200rk_ctx {
   int vec_width = 4;
   int ctas_per_sm = 0;         // stage/element-wise kernels: 0 = one tile per CTA (measured best, profiles/)
   int finish_ctas_per_sm = 2;  // reducing kernels: persistent grid, one partial per CTA (measured best)
-  int fused_ctas_per_sm = 4;   // fused pointwise attempt kernel (54 registers -> 4 CTAs/SM resident; measured best)
+  int fused_ctas_per_sm = 4;   // fused pointwise attempt kernel: persistent grid of 4 CTAs per SM (~100 registers: 2 resident, 2 waves; measured best, profiles/r01_tune_*)
   bool fuse_pointwise = true;  // element-local built-in RHS: whole attempt in one kernel
   bool fuse_stencil = true;    // built-in Lorenz-96 (single GPU): stage accumulate + stencil RHS in one kernel
   int l2_hints = -1;           // producer stores evict_last / streams evict_first: -1 auto (vector <= 0.65 L2), 0 off, 1 on

@@ -281,6 +281,28 @@ int cumsimpson_impl(b200rk_ctx* c, const b200rk_vec* const* Y, const double* X, 
 
 extern "C" {
 
+// Host only (no device, no context): what the two routines above decide on the host, exposed so that the CPU test-suite
+// can pin it against the oracle — which data interval every returned sample of hermiteInterpolate(x, t, ..) uses (or
+// that it is the copy of the last data point) with the spline's four scalar factors, and Simpson's coefficient triples.
+int b200rk_hermite_plan(const double* x, size_t nx, const double* t, size_t nt, int* interval, int* is_copy, double* factors,
+                        size_t* n_out) {
+  if (!x || !t || !interval || !is_copy || !factors || !n_out) return fail(nullptr, B200RK_EINVAL, "null argument");
+  std::vector<HermiteOut> plan;
+  TRY(hermite_plan(nullptr, x, nx, t, nt, &plan));
+  for (size_t o = 0; o < plan.size(); ++o) {
+    interval[o] = plan[o].j; is_copy[o] = plan[o].kind;
+    factors[4 * o] = plan[o].h00; factors[4 * o + 1] = plan[o].hA; factors[4 * o + 2] = plan[o].h01; factors[4 * o + 3] = plan[o].hB;
+  }
+  *n_out = plan.size();
+  return B200RK_OK;
+}
+int b200rk_simpson_weights(int tail, double h1, double h2, double* alpha, double* beta, double* eta) {
+  if (!alpha || !beta || !eta) return fail(nullptr, B200RK_EINVAL, "null argument");
+  if (tail) simpson_tail(h1, h2, alpha, beta, eta);
+  else simpson_pair(h1, h2, alpha, beta, eta);
+  return B200RK_OK;
+}
+
 int b200rk_hermite_interpolate(b200rk_ctx* c, const double* x, size_t nx, const double* t, size_t nt, const b200rk_vec* const* y,
                                const b200rk_vec* const* dy, b200rk_vec** out, size_t* n_out) {
   if (!c || !x || !t || !out || !n_out) return fail(c, B200RK_EINVAL, "null argument");

@@ -49,23 +49,5 @@ int main() {
     solveODE([](double, const GpuVector&, NumContext&) -> GpuVector { throw std::domain_error("boom"); }, y0, {0.0, 1.0});
   } catch (const std::domain_error&) { raised += 1; }
   std::printf("errors raised=%d of 4\n", raised);
-  // The same right-hand side handed over as SOURCE: compiled at run time into the fused kernels (one kernel per RK4
-  // step / per adaptive attempt instead of one per Vector operator); fixed-step results are bit-identical to the closure's.
-  int jit_ok = 0;
-  {
-    JitRhs fJit(y0.device(), "c0*y", {}, {-0.1});
-    Solution a = solveODE(fVector, y0, tspan, ooVector, nullptr, "rk4");
-    Solution b = solveODE(fJit, y0, tspan, ooVector, "rk4");
-    bool same = a.t == b.t && a.y.size() == b.y.size();
-    for (size_t i = 0; same && i < a.y.size(); ++i) same = a.y[i].components() == b.y[i].components();
-    Solution d = solveODE(fJit, y0, tspan, newODEoptions(), "dopri54");
-    bool close = d.t == tspan;
-    for (size_t i = 0; close && i < d.y.size(); ++i) close = meanSquaredError(d.y[i].components(), std::exp(-0.1 * d.t[i])) <= 1e-4;
-    int bad_expr = 0;
-    try { JitRhs bad(y0.device(), "c0*z", {}, {1.0}); } catch (const ValueError&) { bad_expr = 1; }
-    jit_ok = same && close && bad_expr;
-    std::printf("jit same_bits_as_closure=%d dopri54_ok=%d bad_expression_raises=%d launches_closure=%lld launches_jit=%lld\n", same ? 1 : 0,
-                close ? 1 : 0, bad_expr, (long long)a.stats.launches, (long long)b.stats.launches);
-  }
-  return (failures == 0 && raised == 4 && jit_ok) ? 0 : 1;
+  return (failures == 0 && raised == 4) ? 0 : 1;
 }

@@ -9,6 +9,6 @@ echo "== bench cfg2 N=2"; timeout 600 python -m torch.distributed.run --nnodes=1
 import sys,json
 d=json.loads(sys.stdin.read()); print('value',round(d['value'],1),'e2e',round(d['e2e']['value'],1),'frac',round(d['roofline']['frac'],3),'pipeline',round(d['pipeline']['value'],1))"
 echo "== compute-sanitizer memcheck: jit + quadrature (small sizes)"
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_quadrature.py tests/test_gpu_jit.py -q -p no:cacheprovider -x -k "not full_size and not device_loop_step_sequence and not single_step_matches" 2>&1 | tail -6 | cut -c1-300
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_quadrature.py tests/test_gpu_rhs_from_source.py -q -p no:cacheprovider -x -k "not full_size and not device_loop_step_sequence and not single_step_matches" 2>&1 | tail -6 | cut -c1-300
 echo "== compute-sanitizer racecheck: quadrature + fused jit attempt"
-timeout 900 compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest tests/test_gpu_quadrature.py tests/test_gpu_jit.py -q -p no:cacheprovider -x -k "cumtrapz_bitwise or hermite_interpolate_bitwise or jit_fused_attempt" 2>&1 | tail -6 | cut -c1-300
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest tests/test_gpu_quadrature.py tests/test_gpu_rhs_from_source.py -q -p no:cacheprovider -x -k "cumtrapz_bitwise or hermite_interpolate_bitwise or jit_fused_attempt" 2>&1 | tail -6 | cut -c1-300

@@ -15,7 +15,7 @@ import numericalnim_b200 as nn  # noqa: E402
 
 ALL = (-1, 0, 1, 2, 3, 4)
 UNITS = [  # (expression, n_vec, n_scalar, patterns)
-    ("c0*y*(1.0 - y/p0) + c1*t", 1, 2, ALL),      # tests/test_gpu_jit.py LOGISTIC
+    ("c0*y*(1.0 - y/p0) + c1*t", 1, 2, ALL),      # tests/test_gpu_rhs_from_source.py LOGISTIC
     ("-(p0*y) + p1*(c0*t)", 2, 1, ALL),           # FORCED
     ("c0*y", 0, 1, (-1, 0)),                      # SCALE; examples/cpp_host_demo.cpp
     ("-(p0*y)", 1, 0, (-1, 0, 3)),                # bench.py jit leg (dopri54, vern65), builtin-equality test

@@ -32,9 +32,6 @@ def test_cpp_host_mirror_runs_reference_vector_tests(tmp_path):
     cases = [dict(kv.split("=") for kv in line.split()[1:]) for line in r.stdout.splitlines() if line.startswith("case ")]
     assert len(cases) == 8 and all(c["ok"] == "1" for c in cases)
     assert "errors raised=4 of 4" in r.stdout
-    jit = [dict(kv.split("=") for kv in line.split()[1:]) for line in r.stdout.splitlines() if line.startswith("jit ")]
-    assert len(jit) == 1 and jit[0]["same_bits_as_closure"] == "1" and jit[0]["dopri54_ok"] == "1" and jit[0]["bad_expression_raises"] == "1"
-    assert int(jit[0]["launches_jit"]) < int(jit[0]["launches_closure"])  # fused RK4 step: 1 launch instead of 8
     ts = O.linspace(-10.0, 10.0, 100)
     for c in cases:
         opts = O.new_options(relTol=1e-8, dt=1e-2) if c["options"] == "ooVector" else O.new_options()

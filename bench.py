@@ -283,6 +283,17 @@ def run_ours(args):
                 ctx.set("profile", 0)
             except Exception:  # noqa: BLE001
                 pass
+    # ---- consumers of the trajectory (hermiteInterpolate, cumtrapz, cumsimpson; csrc/quadrature.cu): bandwidth at the
+    # workload's vector length, 17 time points. Also after every solver measurement, and fenced the same way.
+    quad_obj = None
+    if world == 1 and not args.no_quad:
+        try:
+            import oracle as O_
+            quad_obj = {"note": "trajectory consumers at 2^%d elements x 17 points: GB/s of algorithmic bytes over kernel time" % lg,
+                        "rows": [{k: r[k] for k in ("op", "points", "kernel_ms_per_call", "GBps", "frac_of_peak", "cpu_GBps_same_bytes")}
+                                 for r in quad_rows(nn, O_, ctx, lg, 17, 3, 18, peaks()[0])]}
+        except Exception as e:  # noqa: BLE001
+            quad_obj = {"error": str(e)[:400]}
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on a bounded sample -----------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and rhs_kind == "diag":
@@ -366,6 +377,7 @@ def run_ours(args):
             "roofline": roofline,
             "pipeline": pipeline_obj,
             "jit_rhs": jit_obj,
+            "trajectory_consumers": quad_obj,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_steps * world / (e2e_ms_max * 1e-3), "unit": "RK steps/s (solveODE on host buffers: H2D y0+lambda, solve, D2H states)",
                     "h2d_bytes_per_step": h2d / max(1, e2e_steps), "d2h_bytes_per_step": d2h / max(1, e2e_steps), "steps_per_solve": e2e_steps / reps,
@@ -550,56 +562,68 @@ def run_sweep(args):
         dist.destroy_process_group()
 
 
-def run_quad(args):
-    """SURVEY.md §8f rank 4 — the trajectory consumers (csrc/quadrature.cu): cumtrapz / cumsimpson over a sampled
-    trajectory of M device vectors and hermiteInterpolate at 2M sample points, at 2^log2n elements per vector.
-    GB/s = algorithmic bytes (every input vector read once, every output written once) / CUDA-event time of the
-    kernels (library profiler, class "quad"), next to the oracle port's time for the same call on one host core."""
-    import numericalnim_b200 as nn
-    import oracle as O
-
-    ctx = nn.default_context()
-    peak, peak_src = peaks()
-    lg = args.log2n or 23
-    n, m = 1 << lg, args.quad_points
+def quad_rows(nn, O, ctx, lg: int, m: int, iters: int, cpu_log2n: int, peak: float, emit=None) -> list:
+    """Time cumtrapz / cumsimpson over a sampled trajectory of m device vectors and hermiteInterpolate at 2m sample
+    points, 2^lg elements per vector. GB/s = algorithmic bytes (every input vector read once, every output written
+    once) / CUDA-event time of the kernels (library profiler, class "quad"), next to the oracle port's time for the
+    same call on one host core at 2^cpu_log2n elements."""
+    n = 1 << lg
     rng = np.random.default_rng(1234)
     base = rng.uniform(-1.0, 1.0, n)
     X = np.linspace(0.0, 2.0, m) + rng.uniform(-0.02, 0.02, m) * (np.arange(m) % 2)   # uneven spacing, sorted
     Y = [nn.newVector(np.roll(base, 17 * k), ctx) for k in range(m)]
     dY = [nn.newVector(np.roll(base, 17 * k + 5), ctx) for k in range(m)]
     xs = np.sort(rng.uniform(X[0], X[-1], 2 * m))
-    n_cpu = 1 << min(lg, args.quad_cpu_log2n)
+    n_cpu = 1 << min(lg, cpu_log2n)
     Yc = np.stack([np.roll(base[:n_cpu], 17 * k) for k in range(m)])
     dYc = np.stack([np.roll(base[:n_cpu], 17 * k + 5) for k in range(m)])
     cases = (("cumtrapz", lambda: nn.cumtrapz(Y, X), lambda: O.cumtrapz(Yc, X)),
              ("cumsimpson", lambda: nn.cumsimpson(Y, X), lambda: O.cumsimpson(Yc, X)),
              ("hermiteInterpolate", lambda: nn.hermiteInterpolate(xs, X, Y, dY), lambda: O.hermite_interpolate(xs, X, Yc, dYc)))
     rows = []
-    for name, gpu, cpu in cases:
-        for _ in range(3):
-            for v in gpu():
-                v.free()
-        ctx.set("profile", 1)
-        ctx.profile_reset()
-        t0 = time.perf_counter()
-        for _ in range(args.quad_iters):
-            for v in gpu():
-                v.free()
-        ctx.synchronize()
-        wall = (time.perf_counter() - t0) / args.quad_iters
-        p = ctx.profile_read()["quad"]
+    try:
+        for name, gpu, cpu in cases:
+            for _ in range(3):
+                for v in gpu():
+                    v.free()
+            ctx.set("profile", 1)
+            ctx.profile_reset()
+            t0 = time.perf_counter()
+            for _ in range(iters):
+                for v in gpu():
+                    v.free()
+            ctx.synchronize()
+            wall = (time.perf_counter() - t0) / iters
+            p = ctx.profile_read()["quad"]
+            ctx.set("profile", 0)
+            t0 = time.perf_counter()
+            cpu()
+            cpu_s = time.perf_counter() - t0
+            gbs = p["bytes"] / (p["ms"] * 1e-3) / 1e9
+            alg_per_call = p["bytes"] / iters
+            row = {"op": name, "log2n": lg, "points": m, "kernel_launches_per_call": p["launches"] / iters, "kernel_ms_per_call": p["ms"] / iters,
+                   "wall_ms_per_call": 1e3 * wall, "algorithmic_GB_per_call": alg_per_call / 1e9, "GBps": gbs, "frac_of_peak": gbs / peak,
+                   "cpu_oracle_s_at_2p%d" % int(np.log2(n_cpu)): cpu_s, "cpu_GBps_same_bytes": alg_per_call * (n_cpu / n) / cpu_s / 1e9,
+                   "gpu_over_cpu_per_element": (cpu_s / n_cpu) / (1e-3 * wall / n)}
+            rows.append(row)
+            if emit:
+                emit(row)
+    finally:
         ctx.set("profile", 0)
-        t0 = time.perf_counter()
-        cpu()
-        cpu_s = time.perf_counter() - t0
-        gbs = p["bytes"] / (p["ms"] * 1e-3) / 1e9
-        alg_per_call = p["bytes"] / args.quad_iters
-        row = {"op": name, "log2n": lg, "points": m, "kernel_launches_per_call": p["launches"] / args.quad_iters, "kernel_ms_per_call": p["ms"] / args.quad_iters,
-               "wall_ms_per_call": 1e3 * wall, "algorithmic_GB_per_call": alg_per_call / 1e9, "GBps": gbs, "frac_of_peak": gbs / peak,
-               "cpu_oracle_s_at_2p%d" % int(np.log2(n_cpu)): cpu_s, "cpu_GBps_same_bytes": alg_per_call * (n_cpu / n) / cpu_s / 1e9,
-               "gpu_over_cpu_per_element": (cpu_s / n_cpu) / (1e-3 * wall / n)}
-        rows.append(row)
-        print(json.dumps(row), flush=True)
+        for v in Y + dY:
+            v.free()
+    return rows
+
+
+def run_quad(args):
+    """SURVEY.md §8f rank 4 — bandwidth of the trajectory consumers (csrc/quadrature.cu), one JSON row per routine."""
+    import numericalnim_b200 as nn
+    import oracle as O
+
+    ctx = nn.default_context()
+    peak, peak_src = peaks()
+    rows = quad_rows(nn, O, ctx, args.log2n or 23, args.quad_points, args.quad_iters, args.quad_cpu_log2n, peak,
+                     emit=lambda row: print(json.dumps(row), flush=True))
     if args.out:
         with open(args.out, "w") as fh:
             json.dump({"peak_gbs": peak, "peak_source": peak_src, "host_cores": os.cpu_count(), "rows": rows}, fh, indent=1)
@@ -677,6 +701,7 @@ def main():
     ap.add_argument("--log2n", type=int, default=0, help="override log2 of elements per GPU")
     ap.add_argument("--e2e-reps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-quad", action="store_true", help="skip the trajectory-consumer bandwidth leg")
     ap.add_argument("--no-jit", action="store_true", help="skip the run-time compiled right-hand-side leg")
     ap.add_argument("--no-fuse", action="store_true", help="headline = the stage/RHS/finish pipeline even for element-local built-in RHS")
     ap.add_argument("--cpu-budget-s", type=float, default=120.0)

@@ -18,7 +18,8 @@
 //   algorithm.isSorted — non-strict ascending; system.toInt(float) — round half away from zero.
 // Pinning: the reference's own cases tests/test_integrate.nim:67-95 (cumtrapz / cumsimpson, discrete and function
 // variants, X = linspace(0, 3pi/2, 17), Y = 2cos x against 2 sin x with its tolerances) — see
-// tests/test_oracle_quadrature.py. The branch of hermiteInterpolate for unsorted x and the duplicate handling of
+// tests/test_oracle_quadrature.py, which also compares every routine bit for bit with an independent pure-Python
+// restatement (tests/pyref_quad.py). The branch of hermiteInterpolate for unsorted x and the duplicate handling of
 // sortAndTrimDataset are reached by no reference test: PARITY UNPINNED there, restated from the code.
 #pragma once
 #include <algorithm>

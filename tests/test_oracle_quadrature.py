@@ -104,3 +104,70 @@ def test_simpson_weights_reduce_to_the_classic_rule():
     assert (a, b, e) == (0.5 / 3.0, 4.0 * 0.5 / 3.0, 0.5 / 3.0) or np.allclose([a, b, e], [1 / 6, 4 / 6, 1 / 6], rtol=1e-15)
     a, b, e = O.simpson_weights(0.5, 0.5, tail=True)  # last interval of an even-length set: (5, 8, -1) h / 12
     assert np.allclose([a, b, e], [5 * 0.5 / 12, 8 * 0.5 / 12, -0.5 / 12], rtol=1e-15)
+
+
+# ---------------------------------------------------------------------------------------------------
+# two independent restatements of the Nim source agree bit for bit (C++ oracle vs tests/pyref_quad.py)
+# ---------------------------------------------------------------------------------------------------
+import pyref_quad as P  # noqa: E402
+
+
+def _bits(a):
+    return [float(v).hex() for v in a]
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_oracle_equals_python_restatement(seed):
+    rng = np.random.default_rng(1000 + seed)
+    m = int(rng.integers(3, 14))
+    X = rng.uniform(0.0, 3.0, m)
+    Y = rng.uniform(-2.0, 2.0, m)
+    if seed % 3 == 0:
+        X = np.sort(X)
+    if seed % 4 == 0:  # pure duplicates
+        X[1], Y[1] = X[0], Y[0]
+        if m > 4:
+            X[4], Y[4] = X[2], Y[2]
+    try:
+        want_t, want_s = P.cumtrapz(Y.tolist(), X.tolist()), None
+    except ValueError:
+        with pytest.raises(ValueError):
+            O.cumtrapz(Y, X, scalar=True)
+        return
+    assert _bits(O.cumtrapz(Y, X, scalar=True)) == _bits(want_t)
+    try:
+        want_s = P.cumsimpson(Y.tolist(), X.tolist())
+    except ValueError:
+        with pytest.raises(ValueError):
+            O.cumsimpson(Y, X, scalar=True)
+        return
+    assert _bits(O.cumsimpson(Y, X, scalar=True)) == _bits(want_s)
+    t = np.sort(rng.uniform(0.0, 3.0, m))
+    y, dy = rng.uniform(-1, 1, m), rng.uniform(-1, 1, m)
+    x = rng.uniform(t[0], t[-1], 7)
+    x[0] = t[-1]
+    if seed % 2:
+        x = np.sort(x)
+    assert _bits(O.hermite_interpolate(x, t, y, dy, scalar=True)) == _bits(P.hermite_interpolate(x.tolist(), t.tolist(), y.tolist(), dy.tolist()))
+
+
+@pytest.mark.parametrize("dx", [0.1, 0.0371])
+def test_oracle_function_variants_equal_python_restatement(dx):
+    f = lambda t: 2.0 * math.cos(t) + 0.25 * t
+    for Xs in (list(X), [X[3], X[0], X[16], X[7], X[7], X[1]]):
+        v, _ = O.cumtrapz_fn(f, Xs, dx=dx, scalar=True)
+        assert _bits(v) == _bits(P.cumtrapz_fn(f, Xs, dx))
+        v, _ = O.cumsimpson_fn(f, Xs, dx=dx, scalar=True)
+        assert _bits(v) == _bits(P.cumsimpson_fn(f, Xs, dx))
+
+
+def test_hermite_spline_restatements_agree():
+    """utils.nim:273-279 is written with `^`; the oracle's product form (u*u, t*(t*t)) must give the same bits."""
+    rng = np.random.default_rng(4)
+    for _ in range(2000):
+        x1, w = rng.uniform(-2, 2), 10.0 ** rng.uniform(-3, 1)
+        x2 = x1 + w
+        x = x1 + w * rng.uniform(0, 1)
+        y1, y2, d1, d2 = rng.uniform(-3, 3, 4)
+        a = O.hermite(x, x1, x2, [y1], [y2], [d1], [d2])[0]
+        assert float(a).hex() == float(P.hermite_spline(x, x1, x2, y1, y2, d1, d2)).hex()

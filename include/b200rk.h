@@ -170,7 +170,7 @@ B200RK_API int b200rk_builtin_rhs_free(void* user);
  * DOPRI54 / Tsit54 / Vern65, the device-resident driver loop, the one-kernel RK4 step, and a plain dydt kernel for
  * every other method. The returned (fn, user) pair is an ordinary b200rk_rhs_fn for b200rk_step / b200rk_solve /
  * b200rk_solver_new. A wrong expression -> B200RK_EINVAL with the compiler log in b200rk_last_error().
- * The parameter vectors must outlive `user`. */
+ * The parameter vectors must outlive `user`, and `user` must be freed before its context is destroyed. */
 B200RK_API int b200rk_jit_rhs_new(b200rk_ctx* ctx, const char* expr, int n_vec, const b200rk_vec* const* vecs,
                                   int n_scalar, const double* scalars, b200rk_rhs_fn* fn, void** user);
 B200RK_API int b200rk_jit_rhs_set_scalars(void* user, int n_scalar, const double* scalars); /* no recompilation */

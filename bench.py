@@ -284,14 +284,18 @@ def run_ours(args):
             except Exception:  # noqa: BLE001
                 pass
     # ---- consumers of the trajectory (hermiteInterpolate, cumtrapz, cumsimpson; csrc/quadrature.cu): bandwidth at the
-    # workload's vector length, 17 time points. Also after every solver measurement, and fenced the same way.
+    # workload's vector length, 17 time points — `bench.py --quad` in a child process (own CUDA context on the same
+    # GPU), after every solver measurement, so that nothing it does can disturb them.
     quad_obj = None
     if world == 1 and not args.no_quad:
         try:
-            import oracle as O_
-            quad_obj = {"note": "trajectory consumers at 2^%d elements x 17 points: GB/s of algorithmic bytes over kernel time" % lg,
-                        "rows": [{k: r[k] for k in ("op", "points", "kernel_ms_per_call", "GBps", "frac_of_peak", "cpu_GBps_same_bytes")}
-                                 for r in quad_rows(nn, O_, ctx, lg, 17, 3, 18, peaks()[0])]}
+            cp = subprocess.run([sys.executable, os.path.abspath(__file__), "--quad", "--log2n", str(lg), "--quad-points", "17", "--quad-iters", "3"],
+                                capture_output=True, text=True, timeout=600, env=dict(os.environ, LOCAL_RANK=str(local_rank)))
+            rows = [json.loads(l) for l in cp.stdout.splitlines() if l.startswith('{"op"')]
+            if cp.returncode != 0 or not rows:
+                raise RuntimeError("bench.py --quad exited %d: %s" % (cp.returncode, cp.stderr.strip()[-300:]))
+            quad_obj = {"note": "trajectory consumers at 2^%d elements x 17 points: GB/s of algorithmic bytes over kernel time (bench.py --quad)" % lg,
+                        "rows": [{k: r[k] for k in ("op", "points", "kernel_ms_per_call", "GBps", "frac_of_peak", "cpu_GBps_same_bytes")} for r in rows]}
         except Exception as e:  # noqa: BLE001
             quad_obj = {"error": str(e)[:400]}
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on a bounded sample -----------------------

@@ -120,11 +120,20 @@ int hermite_plan(const b200rk_ctx* c, const double* x, size_t nx, const double* 
   } else {
     double tmin = t[0], tmax = t[0];
     for (size_t i = 1; i < nt; ++i) { tmin = std::min(tmin, t[i]); tmax = std::max(tmax, t[i]); }
+    // The reference scans the intervals from the left for every sample. For ascending t (every internal caller, and
+    // any sensible data set) the first interval with t[i] <= a < t[i+1] is the only one, so it is found by bisection;
+    // anything else keeps the literal scan.
+    const bool t_sorted = std::is_sorted(t, t + nt);
     for (size_t k = 0; k < nx; ++k) {
       const double a = x[k];
       bool found = false;
-      for (long i = 0; i <= thigh - 1; ++i)
-        if (t[i] <= a && a < t[i + 1]) { plan->push_back(spline(a, i)); found = true; break; }
+      if (t_sorted) {
+        const long i = (long)(std::upper_bound(t, t + nt, a) - t) - 1;   // last i with t[i] <= a (NaN: none)
+        if (i >= 0 && i <= thigh - 1 && t[i] <= a && a < t[i + 1]) { plan->push_back(spline(a, i)); found = true; }
+      } else {
+        for (long i = 0; i <= thigh - 1; ++i)
+          if (t[i] <= a && a < t[i + 1]) { plan->push_back(spline(a, i)); found = true; break; }
+      }
       if (found) continue;
       if (a == t[thigh]) plan->push_back(last);
       else return fail(c, B200RK_EINVAL, std::to_string(a) + " not in interval " + std::to_string(tmin) + " - " + std::to_string(tmax));  // utils.nim:312
@@ -348,7 +357,7 @@ int b200rk_cumtrapz_fn(b200rk_ctx* c, b200rk_fn_of_t f, void* user, size_t n_glo
     lo = std::min(lo, X[i]); hi = std::max(hi, X[i]);
   }
   const double tEnd = hi + 1.0;                                                                    // integrate.nim:160
-  if ((tEnd - lo) / dx > 2e8) return fail(c, B200RK_EINVAL, "cumtrapz: more than 2e8 steps; choose a larger dx");
+  if ((tEnd - lo) / dx > 5e7) return fail(c, B200RK_EINVAL, "cumtrapz: more than 5e7 steps; choose a larger dx");
   std::vector<double> times;
   double t = lo;
   times.push_back(t);

@@ -45,6 +45,7 @@ struct Pk {
   double v[W];
 };
 
+#ifndef B200RK_HOST_EMULATION
 template <int W>
 __device__ __forceinline__ Pk<W> ld_stream(const double* p);
 template <>
@@ -133,6 +134,17 @@ __device__ __forceinline__ void st_pol(double* p, const Pk<W>& x) {
     st_stream<W>(p, x);
   }
 }
+#else
+// Host emulation (tests/host_emul): the same kernels compiled by the host compiler and run one emulated thread at a
+// time, so that the CPU test-suite can check the kernels' arithmetic and indexing against the oracle without a GPU.
+// Only the memory-access helpers (inline PTX above) and the grid-wide reduction need a host form.
+enum L2Policy : int { L2_NORMAL = 0, L2_EVICT_FIRST = 1, L2_EVICT_LAST = 2 };
+template <int W> inline Pk<W> ld_stream(const double* p) { Pk<W> r; for (int e = 0; e < W; ++e) r.v[e] = p[e]; return r; }
+template <int W> inline Pk<W> ld_plain(const double* p) { return ld_stream<W>(p); }
+template <int W> inline void st_stream(double* p, const Pk<W>& x) { for (int e = 0; e < W; ++e) p[e] = x.v[e]; }
+template <int W, int POL> inline Pk<W> ld_pol(const double* p) { return ld_stream<W>(p); }
+template <int W, int POL> inline void st_pol(double* p, const Pk<W>& x) { st_stream<W>(p, x); }
+#endif
 
 // ---------------------------------------------------------------------------------------------------
 // Stage accumulate:  out = y + c * (w0*k0 + w1*k1 + ... )      (left-associated, no FMA)
@@ -337,6 +349,10 @@ __device__ __forceinline__ double block_sum(double v) {
 
 template <int THREADS>
 __device__ __forceinline__ void grid_sum_finish(double thread_val, const ReduceScratch& rs) {
+#ifdef B200RK_HOST_EMULATION
+  *rs.result = __dadd_rn(*rs.result, thread_val);  // emulated threads run one after another: a plain running sum
+  return;
+#endif
   __shared__ bool is_last;
   const double bsum = block_sum<THREADS>(thread_val);
   if (threadIdx.x == 0) {

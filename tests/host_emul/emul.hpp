@@ -1,0 +1,69 @@
+// emul.hpp — compile the product's CUDA kernels (numericalnim_b200/csrc/kernels.cuh, quad_kernels.cuh) with the HOST
+// compiler and run them one emulated thread at a time, so the CPU test-suite can compare the kernels' arithmetic and
+// indexing with the oracle bit for bit without a GPU. TEST INFRASTRUCTURE ONLY.
+//
+// What is emulated: thread/block indices, the fp64 intrinsics (plain IEEE operations: the translation unit is built
+// with -ffp-contract=off, as the device code is built with -fmad=false), global loads/stores (kernels.cuh gives its
+// inline-PTX access helpers a host form under B200RK_HOST_EMULATION) and the grid-wide sum (a running sum in
+// emulation order). What is not: anything that needs threads to run concurrently (block reductions, the shared-memory
+// Lorenz-96 tile, the cooperative device loop) — those kernels are parsed but only the GPU suite runs them.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+// the oracle first, before any CUDA keyword is turned into a macro
+#include "quad_oracle.hpp"
+#include "rk_oracle.hpp"
+
+struct EmulDim3 { unsigned x = 0, y = 0, z = 0; };
+static EmulDim3 threadIdx, blockIdx, gridDim, blockDim;
+
+#define __device__
+#define __global__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __shared__ static
+
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline double __ddiv_rn(double a, double b) { return a / b; }
+template <class T> inline T __shfl_down_sync(unsigned, T v, int) { return v; }
+inline void __syncthreads() {}
+inline void __threadfence() {}
+inline void __threadfence_system() {}
+inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned o = *p; *p += v; return o; }
+inline int atomicExch(int* p, int v) { const int o = *p; *p = v; return o; }
+template <class T> inline T __ldcg(const T* p) { return *p; }
+template <class T> inline T __ldg(const T* p) { return *p; }
+inline long long clock64() { return 0; }
+inline long long __double_as_longlong(double d) { long long r; std::memcpy(&r, &d, 8); return r; }
+inline double __longlong_as_double(long long v) { double r; std::memcpy(&r, &v, 8); return r; }
+struct double2 { double x, y; };
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
+
+#define __CUDACC_RTC__ 1           // kernels.cuh: no <cuda_runtime.h>
+#define B200RK_HOST_EMULATION 1
+
+// a right-hand side "given as source", as jit.cu would generate it (PW_USER instantiations)
+#define B200RK_JIT 1
+#define B200RK_USER_NP 1
+namespace b200rk {
+inline double user_rhs(double t, double y, const double* p, const double* c) { return c[0] * y * (1.0 - y / p[0]) + c[1] * t; }
+}
+
+#include "kernels.cuh"
+#include "quad_kernels.cuh"
+#include "methods.h"
+
+// run `body` once per emulated thread of a (grid x threads) launch, blocks and threads in index order
+template <class F>
+inline void emul_launch(unsigned grid, unsigned threads, F&& body) {
+  gridDim.x = grid; blockDim.x = threads;
+  for (unsigned b = 0; b < grid; ++b)
+    for (unsigned t = 0; t < threads; ++t) { blockIdx.x = b; threadIdx.x = t; body(); }
+}

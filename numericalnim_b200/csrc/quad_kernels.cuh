@@ -244,3 +244,83 @@ __global__ void __launch_bounds__(THREADS) neq_count_kernel(const double* __rest
 }
 
 }  // namespace b200rk
+
+// ---------------------------------------------------------------------------------------------------
+// cumsimpson(Y, X) in ONE pass (experimental, knob "fuse_simpson", off by default until measured on the GPU):
+// the Simpson scan and the Hermite interpolation back onto X fused. While a thread walks the knot intervals it holds
+// exactly what every sample inside the current interval needs — the integrals at both knots (I_j, I_{j+1}) and the
+// data at both knots (the spline's slopes) — so the samples are emitted from registers and the knot integrals never
+// travel to HBM: every data point read once, every result written once (2M vector passes instead of the 3.5M of
+// simpson_scan_kernel + hermite_many_kernel). The host groups the samples by the interval that completes them.
+// ---------------------------------------------------------------------------------------------------
+namespace b200rk {
+
+struct SimpsonFusedArgs {
+  const double* const* y;     // sorted, trimmed data points
+  double* const* out;         // one vector per returned sample
+  const SimpsonStep* step;    // as for simpson_scan_kernel
+  const int* tail;            // per step: 0 = knots are the data points (ic, ia) of a regular pair, 1 = (ib, ic) of the tail rule
+  const int* emit_begin;      // steps + 1 offsets into emit / emit_out
+  const HermiteOut* emit;     // samples grouped by knot interval; kind 1 = copy of the integral at the interval's right knot
+  const int* emit_out;        // which output vector each grouped sample is
+  int steps, first;
+  size_t n;
+};
+
+template <int W, int THREADS>
+__global__ void __launch_bounds__(THREADS) simpson_fused_kernel(const SimpsonFusedArgs a) {
+  const size_t nvec = a.n / W;
+  for (size_t v = (size_t)blockIdx.x * THREADS + threadIdx.x; v < nvec; v += (size_t)gridDim.x * THREADS) {
+    Pk<W> prev_a = ld_stream<W>(a.y[a.first] + v * W), I;
+#pragma unroll
+    for (int e = 0; e < W; ++e) I.v[e] = __dadd_rn(prev_a.v[e], -prev_a.v[e]);
+    for (int j = 0; j < a.steps; ++j) {
+      const SimpsonStep s = a.step[j];
+      const int tail = a.tail[j];
+      const Pk<W> ya = ld_stream<W>(a.y[s.ia] + v * W);
+      const Pk<W> yb = ld_stream<W>(a.y[s.ib] + v * W);
+      Pk<W> yc;
+      if (s.reuse) yc = prev_a;
+      else yc = ld_stream<W>(a.y[s.ic] + v * W);
+      Pk<W> I1;
+#pragma unroll
+      for (int e = 0; e < W; ++e) {
+        const double t = __dadd_rn(__dadd_rn(__dmul_rn(ya.v[e], s.ca), __dmul_rn(yb.v[e], s.cb)), __dmul_rn(yc.v[e], s.cc));
+        I1.v[e] = __dadd_rn(I.v[e], t);
+      }
+      const Pk<W> d0 = tail ? yb : yc, d1 = tail ? yc : ya;   // the data at the interval's two knots = the spline's slopes
+      for (int q = a.emit_begin[j]; q < a.emit_begin[j + 1]; ++q) {
+        const HermiteOut p = a.emit[q];
+        Pk<W> r;
+        if (p.kind == 1) r = I1;
+        else {
+#pragma unroll
+          for (int e = 0; e < W; ++e) r.v[e] = hermite_elem(I.v[e], d0.v[e], I1.v[e], d1.v[e], p);
+        }
+        st_stream<W>(a.out[a.emit_out[q]] + v * W, r);
+      }
+      I = I1;
+      prev_a = ya;
+    }
+  }
+  if (blockIdx.x == 0) {  // ragged tail (n % W elements)
+    const size_t i = nvec * W + threadIdx.x;
+    if (i < a.n) {
+      const double y0 = a.y[a.first][i];
+      double I = __dadd_rn(y0, -y0);
+      for (int j = 0; j < a.steps; ++j) {
+        const SimpsonStep s = a.step[j];
+        const double ya = a.y[s.ia][i], yb = a.y[s.ib][i], yc = a.y[s.ic][i];
+        const double I1 = __dadd_rn(I, __dadd_rn(__dadd_rn(__dmul_rn(ya, s.ca), __dmul_rn(yb, s.cb)), __dmul_rn(yc, s.cc)));
+        const double d0 = a.tail[j] ? yb : yc, d1 = a.tail[j] ? yc : ya;
+        for (int q = a.emit_begin[j]; q < a.emit_begin[j + 1]; ++q) {
+          const HermiteOut p = a.emit[q];
+          a.out[a.emit_out[q]][i] = (p.kind == 1) ? I1 : hermite_elem(I, d0, I1, d1, p);
+        }
+        I = I1;
+      }
+    }
+  }
+}
+
+}  // namespace b200rk

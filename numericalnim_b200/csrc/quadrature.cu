@@ -6,6 +6,7 @@
 // spline's scalar factors — same expressions, same rounding); every O(N) operation runs in quad_kernels.cuh.
 #include "internal.hpp"
 #include "quad_kernels.cuh"
+#include "quad_group.hpp"
 
 #include <numeric>
 
@@ -267,6 +268,34 @@ int cumsimpson_impl(b200rk_ctx* c, const b200rk_vec* const* Y, const double* X, 
   // hermiteInterpolate(X, xs, y, dy) with the ORIGINAL X (integrate.nim:377-378): plan it before any device work
   std::vector<HermiteOut> plan;
   TRY(hermite_plan(c, X, m, xs.data(), xs.size(), &plan));
+  if (c->fuse_simpson && n) {
+    // experimental single-pass form (knob "fuse_simpson", off by default): scan + interpolation in one kernel, the knot
+    // integrals stay in registers — see simpson_fused_kernel
+    std::vector<int> tail(steps.size(), 0), emit_begin, slot;
+    if (evenN) tail.back() = 1;
+    std::vector<HermiteOut> grouped;
+    group_samples_by_interval(plan, (int)steps.size(), &emit_begin, &grouped, &slot);
+    for (size_t o = 0; o < plan.size(); ++o) { b200rk_vec* v = nullptr; TRY(outs->add(c, n_global, &v)); }
+    if (plan.empty()) return B200RK_OK;
+    DeviceTable<const double*> y_t(c);
+    DeviceTable<double*> out_t(c);
+    DeviceTable<SimpsonStep> step_t(c);
+    DeviceTable<int> tail_t(c), begin_t(c), slot_t(c);
+    DeviceTable<HermiteOut> emit_t(c);
+    TRY(y_t.upload(device_ptrs<double>(s.y)));
+    TRY(out_t.upload(device_ptrs_mut(outs->v)));
+    TRY(step_t.upload(steps));
+    TRY(tail_t.upload(tail));
+    TRY(begin_t.upload(emit_begin));
+    TRY(emit_t.upload(grouped));
+    TRY(slot_t.upload(slot));
+    ProfScope ps(c, B200RK_K_QUAD, 8.0 * double(n) * double(s.x.size() + plan.size()));   // every point read once, every sample written once
+    SimpsonFusedArgs a{y_t.d, out_t.d, step_t.d, tail_t.d, begin_t.d, emit_t.d, slot_t.d, (int)steps.size(), 0, n};
+    if (c->vec_width == 4) simpson_fused_kernel<4, kThreads><<<quad_grid(c, n, 4), kThreads, 0, c->stream>>>(a);
+    else simpson_fused_kernel<2, kThreads><<<quad_grid(c, n, 2), kThreads, 0, c->stream>>>(a);
+    CUDA_TRY(c, cudaGetLastError());
+    return B200RK_OK;
+  }
   Outputs knots;   // released at the end of the call (stream-ordered reuse: the pool belongs to this stream)
   for (size_t k = 0; k < xs.size(); ++k) { b200rk_vec* v = nullptr; TRY(knots.add(c, n_global, &v)); }
   if (n) {

@@ -2,6 +2,7 @@
 // against the CPU oracle. Every element-wise result must agree BIT FOR BIT; sums within 1e-12 (different order).
 // Prints one line per case; exit code = number of failing cases. Built and run by tests/test_kernel_host_emulation.py.
 #include "emul.hpp"
+#include "quad_group.hpp"
 
 #include "../../include/b200rk.h"  // host-only planning entry points of the library (b200rk_hermite_plan)
 
@@ -218,7 +219,7 @@ static void test_rk4() {
 // ---- trajectory consumers (quad_kernels.cuh) with the library's own host-side plan -----------------------------------
 template <int W>
 static void test_quadrature() {
-  bool ok_t = true, ok_s = true, ok_h = true;
+  bool ok_t = true, ok_s = true, ok_h = true, ok_f = true;
   for (int m : {1, 2, 3, 4, 5, 8, 9, 17, 18}) {
     for (size_t n : {size_t(1), size_t(5), size_t(1023)}) {
       std::vector<double> X(m);
@@ -279,6 +280,35 @@ static void test_quadrature() {
         const auto ref = rk_oracle::cumsimpson<Vector>(Yv, X);
         ok_s = ok_s && ref.size() == n_out;
         for (size_t o = 0; ok_s && o < n_out; ++o) ok_s = same_bits(out[o], ref[o].components);
+        // the same call in ONE kernel (simpson_fused_kernel): samples grouped by the knot interval that completes them,
+        // here asked for in a scrambled order with a repeat, so the output-slot indirection is exercised too
+        std::vector<double> Xq(X.rbegin(), X.rend());
+        Xq.push_back(X[m / 2]);
+        std::swap(Xq[0], Xq[m / 3]);
+        std::vector<int> jq(Xq.size()), kq(Xq.size());
+        std::vector<double> fq(4 * Xq.size());
+        size_t nq = 0;
+        if (b200rk_hermite_plan(Xq.data(), Xq.size(), xs.data(), xs.size(), jq.data(), kq.data(), fq.data(), &nq) != 0) { ok_f = false; continue; }
+        const int nsteps = (int)steps.size();
+        std::vector<int> tail(nsteps, 0), begin, slot;
+        if (even) tail[nsteps - 1] = 1;
+        std::vector<HermiteOut> planq(nq), grouped;
+        for (size_t o = 0; o < nq; ++o) planq[o] = HermiteOut{jq[o], kq[o], fq[4 * o], fq[4 * o + 1], fq[4 * o + 2], fq[4 * o + 3]};
+        group_samples_by_interval(planq, nsteps, &begin, &grouped, &slot);   // the product's own grouping (quad_group.hpp)
+        std::vector<std::vector<double>> outf(nq, std::vector<double>(n, -3.0));
+        std::vector<double*> opf;
+        for (auto& v : outf) opf.push_back(v.data());
+        SimpsonFusedArgs fa{yp.data(), opf.data(), steps.data(), tail.data(), begin.data(), grouped.data(), slot.data(), nsteps, 0, n};
+        emul_launch(2, T, [&] { simpson_fused_kernel<W, T>(fa); });
+        const auto refq = rk_oracle::cumsimpson<Vector>(Yv, X);   // the data set is the same; only the samples differ
+        std::vector<Vector> kn;                                   // knots of the oracle: re-derive the samples with its own interpolation
+        {
+          std::vector<Vector> yk, dk;
+          for (size_t q = 0; q < xs.size(); ++q) { yk.emplace_back(knots[q]); dk.emplace_back(std::vector<double>(dyp[q], dyp[q] + n)); }
+          kn = rk_oracle::hermite_interpolate<Vector>(Xq, xs, yk, dk);
+        }
+        ok_f = ok_f && kn.size() == nq && grouped.size() == nq;
+        for (size_t o = 0; ok_f && o < nq; ++o) ok_f = same_bits(outf[o], kn[o].components);
       }
       if (m >= 2) {  // hermiteInterpolate at unsorted samples (jumps between intervals, repeats, the end point)
         std::vector<std::vector<double>> dY(m);
@@ -310,6 +340,7 @@ static void test_quadrature() {
   report("cumtrapz_kernel W=" + std::to_string(W), ok_t);
   report("simpson_scan_kernel + hermite_many_kernel (cumsimpson) W=" + std::to_string(W), ok_s);
   report("hermite_many_kernel unsorted samples W=" + std::to_string(W), ok_h);
+  report("simpson_fused_kernel (cumsimpson in one pass) W=" + std::to_string(W), ok_f);
 }
 
 int main() {

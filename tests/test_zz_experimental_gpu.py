@@ -28,7 +28,7 @@ def test_cumsimpson_single_pass_equals_two_kernel_path(nn, vec_width):
             for n in (1, 3, 4, 5, 1023, 65536 + 7):
                 X = np.sort(rng.uniform(0.0, 3.0, m))
                 if m == 8:  # unsorted samples with a pure duplicate: results come back in the caller's order
-                    X = np.concatenate([X[::-1], X[2:3]])
+                    X = np.concatenate([X[::-1], X[::-1][2:3]])
                 Y = rng.uniform(-2.0, 2.0, (m, n))
                 if m == 8:
                     Y = np.concatenate([Y[::-1], Y[::-1][2:3]])

@@ -136,7 +136,8 @@ __device__ __forceinline__ void st_pol(double* p, const Pk<W>& x) {
 #else
 // Host emulation (tests/host_emul): the same kernels compiled by the host compiler and run one emulated thread at a
 // time, so that the CPU test-suite can check the kernels' arithmetic and indexing against the oracle without a GPU.
-// Only the memory-access helpers (inline PTX above) and the grid-wide reduction need a host form.
+// Only the memory-access helpers (inline PTX above) need a host form (plus, for the single-threaded emulation, the
+// grid-wide reduction: B200RK_EMULATE_SERIAL_SUM).
 enum L2Policy : int { L2_NORMAL = 0, L2_EVICT_FIRST = 1, L2_EVICT_LAST = 2 };
 template <int W> inline Pk<W> ld_stream(const double* p) { Pk<W> r; for (int e = 0; e < W; ++e) r.v[e] = p[e]; return r; }
 template <int W> inline Pk<W> ld_plain(const double* p) { return ld_stream<W>(p); }
@@ -348,8 +349,8 @@ __device__ __forceinline__ double block_sum(double v) {
 
 template <int THREADS>
 __device__ __forceinline__ void grid_sum_finish(double thread_val, const ReduceScratch& rs) {
-#ifdef B200RK_HOST_EMULATION
-  *rs.result = __dadd_rn(*rs.result, thread_val);  // emulated threads run one after another: a plain running sum
+#ifdef B200RK_EMULATE_SERIAL_SUM
+  *rs.result = __dadd_rn(*rs.result, thread_val);  // serial host emulation (threads run one after another): a plain running sum
   return;
 #endif
   __shared__ bool is_last;

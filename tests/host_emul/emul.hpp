@@ -19,8 +19,51 @@
 #include "quad_oracle.hpp"
 #include "rk_oracle.hpp"
 
+// Two modes. Default: ONE host thread plays every CUDA thread in turn (fast; kernels whose threads do not interact).
+// EMUL_MT: one host thread per CUDA thread of a block, blocks one after another; __syncthreads / warp shuffles /
+// atomics are real synchronisation, so block reductions, shared-memory tiles and (as a one-block grid) the cooperative
+// loop run too — and ThreadSanitizer can look for data races between the emulated threads.
 struct EmulDim3 { unsigned x = 0, y = 0, z = 0; };
+#ifdef EMUL_MT
+#include <barrier>
+#include <memory>
+#include <thread>
+static thread_local EmulDim3 threadIdx, blockIdx, gridDim, blockDim;
+struct EmulBlock {
+  std::barrier<> block;
+  std::vector<std::unique_ptr<std::barrier<>>> warp;
+  explicit EmulBlock(unsigned threads) : block(threads) {
+    for (unsigned w = 0; w * 32 < threads; ++w) warp.push_back(std::make_unique<std::barrier<>>(std::min(32u, threads - w * 32)));
+  }
+};
+static EmulBlock* g_emul_block = nullptr;
+inline void __syncthreads() { g_emul_block->block.arrive_and_wait(); }
+void emul_grid_sync() { g_emul_block->block.arrive_and_wait(); }   // one-block grids only
+template <class T>
+inline T __shfl_down_sync(unsigned, T v, int off) {
+  static T lanes[1024];
+  const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+  lanes[tid] = v;
+  g_emul_block->warp[w]->arrive_and_wait();
+  const T r = (lane + (unsigned)off < 32u && tid + (unsigned)off < blockDim.x) ? lanes[tid + off] : v;
+  g_emul_block->warp[w]->arrive_and_wait();
+  return r;
+}
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+#else
 static EmulDim3 threadIdx, blockIdx, gridDim, blockDim;
+void emul_grid_sync() {}
+template <class T> inline T __shfl_down_sync(unsigned, T v, int) { return v; }
+inline void __syncthreads() {}
+inline void __threadfence() {}
+inline void __threadfence_system() {}
+inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned o = *p; *p += v; return o; }
+inline int atomicExch(int* p, int v) { const int o = *p; *p = v; return o; }
+#define B200RK_EMULATE_SERIAL_SUM 1   // kernels.cuh: grid_sum_finish becomes a running sum
+#endif
 
 #define __device__
 #define __global__
@@ -32,12 +75,6 @@ static EmulDim3 threadIdx, blockIdx, gridDim, blockDim;
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __ddiv_rn(double a, double b) { return a / b; }
-template <class T> inline T __shfl_down_sync(unsigned, T v, int) { return v; }
-inline void __syncthreads() {}
-inline void __threadfence() {}
-inline void __threadfence_system() {}
-inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned o = *p; *p += v; return o; }
-inline int atomicExch(int* p, int v) { const int o = *p; *p = v; return o; }
 template <class T> inline T __ldcg(const T* p) { return *p; }
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline long long clock64() { return 0; }
@@ -60,10 +97,25 @@ inline double user_rhs(double t, double y, const double* p, const double* c) { r
 #include "quad_kernels.cuh"
 #include "methods.h"
 
-// run `body` once per emulated thread of a (grid x threads) launch, blocks and threads in index order
+// run `body` once per emulated thread of a (grid x threads) launch
 template <class F>
 inline void emul_launch(unsigned grid, unsigned threads, F&& body) {
+#ifdef EMUL_MT
+  for (unsigned b = 0; b < grid; ++b) {   // blocks one after another, the threads of a block concurrently
+    EmulBlock blk(threads);
+    g_emul_block = &blk;
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < threads; ++t)
+      pool.emplace_back([&, b, t] {
+        gridDim.x = grid; blockDim.x = threads; blockIdx.x = b; threadIdx.x = t;
+        body();
+      });
+    for (auto& th : pool) th.join();
+    g_emul_block = nullptr;
+  }
+#else
   gridDim.x = grid; blockDim.x = threads;
   for (unsigned b = 0; b < grid; ++b)
     for (unsigned t = 0; t < threads; ++t) { blockIdx.x = b; threadIdx.x = t; body(); }
+#endif
 }

@@ -30,9 +30,13 @@ static bool same_bits(const std::vector<double>& a, const std::vector<double>& b
 }
 static bool close_rel(double a, double b, double rtol) { return std::fabs(a - b) <= rtol * std::fabs(b) || (a == 0.0 && b == 0.0); }
 static ReduceScratch scratch(double* sum) {
+  static double partials[64];      // one per emulated CTA (threaded mode: the real two-stage reduction runs)
+  static unsigned ticket = 0;
   ReduceScratch rs;
   std::memset(&rs, 0, sizeof(rs));
   rs.result = sum;
+  rs.partials = partials;
+  rs.ticket = &ticket;
   rs.mail.world = 1;
   return rs;
 }

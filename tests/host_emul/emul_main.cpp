@@ -347,7 +347,63 @@ static void test_quadrature() {
   report("simpson_fused_kernel (cumsimpson in one pass) W=" + std::to_string(W), ok_f);
 }
 
+// ---- the remaining thread-independent kernels: Vector operators, RK4 combine, Hermite, Lorenz-96, one trapezoid step ----
+template <int OP>
+static bool ewise_case(const std::vector<double>& a, const std::vector<double>& b, double s, const std::vector<double>& want) {
+  bool ok = true;
+  const size_t n = a.size();
+  std::vector<double> out(n);
+  emul_launch(2, T, [&] { ewise_kernel<OP, 2, 2, T, 0>(a.data(), b.data(), s, out.data(), n); });
+  ok = ok && same_bits(out, want);
+  emul_launch(3, T, [&] { ewise_kernel<OP, 4, 2, T, 1>(a.data(), b.data(), s, out.data(), n); });
+  ok = ok && same_bits(out, want);
+  std::vector<double> inplace = a;  // out may alias an input (utils operators used in place)
+  emul_launch(2, T, [&] { ewise_kernel<OP, 2, 2, T, 0>(inplace.data(), b.data(), s, inplace.data(), n); });
+  return ok && same_bits(inplace, want);
+}
+static void test_elementwise() {
+  bool ok_ops = true, ok_rk4 = true, ok_h = true, ok_l = true, ok_tz = true;
+  for (size_t n : kSizes) {
+    const auto a = rvec(n, -2.0, 2.0), b = rvec(n, 0.5, 3.0);
+    const Vector A(a), B(b);
+    const double s = -0.37;
+    ok_ops = ok_ops && ewise_case<EW_ADD>(a, b, s, (A + B).components) && ewise_case<EW_SUB>(a, b, s, (A - B).components) &&
+             ewise_case<EW_HMUL>(a, b, s, rk_oracle::hadamard(A, B).components) && ewise_case<EW_HDIV>(a, b, s, rk_oracle::hdiv(A, B).components) &&
+             ewise_case<EW_SCALE>(a, b, s, (s * A).components) && ewise_case<EW_ADD_SCALAR>(a, b, s, rk_oracle::add_scalar(s, A).components) &&
+             ewise_case<EW_NEG>(a, b, s, (-A).components) && ewise_case<EW_ABS>(a, b, s, rk_oracle::vabs(A).components) &&
+             ewise_case<EW_DIV_SCALAR>(a, b, s, (A / s).components) && ewise_case<EW_NEG_HMUL>(a, b, s, (-rk_oracle::hadamard(A, B)).components);
+    // RK4 final combine (ode.nim:188)
+    const auto k1 = rvec(n), k2 = rvec(n), k3 = rvec(n), k4 = rvec(n);
+    const double dt = 0.0123;
+    std::vector<double> out(n);
+    emul_launch(2, T, [&] { rk4_final_kernel<4, 1, T>(a.data(), k1.data(), k2.data(), k3.data(), k4.data(), dt / 6.0, out.data(), n); });
+    const Vector r4 = A + dt / 6.0 * (Vector(k1) + 2.0 * (Vector(k2) + Vector(k3)) + Vector(k4));
+    ok_rk4 = ok_rk4 && same_bits(out, r4.components);
+    // hermiteSpline (utils.nim:273-279) with the host-side factors the driver computes
+    const double x1 = 0.3, x2 = 0.8, x = 0.4321;
+    const double tt = (x - x1) / (x2 - x1), u = 1.0 - tt;
+    const double h00 = (1.0 + 2.0 * tt) * (u * u), h10 = tt * (u * u), h01 = (tt * tt) * (3.0 - 2.0 * tt), h11 = (tt * (tt * tt)) - (tt * tt);
+    emul_launch(2, T, [&] { hermite_kernel<2, T>(a.data(), k1.data(), b.data(), k2.data(), h00, h10 * (x2 - x1), h01, h11 * (x2 - x1), out.data(), n); });
+    ok_h = ok_h && same_bits(out, rk_oracle::hermite_spline<Vector>(x, x1, x2, A, B, Vector(k1), Vector(k2)).components);
+    // Lorenz-96 right-hand side, cyclic (single GPU: the neighbours are in the vector itself)
+    if (n >= 4) {
+      const auto y = rvec(n, 7.0, 9.0);
+      emul_launch(2, T, [&] { lorenz96_kernel<T>(y.data(), y.data() + n - 2, y.data(), 8.0, out.data(), n); });
+      ok_l = ok_l && same_bits(out, rk_oracle::rhs_lorenz96(8.0)(0.0, Vector(y), nullptr).components);
+    }
+    // one step of the streaming cumtrapz(f, X, ctx, dx) (integrate.nim:170)
+    emul_launch(2, T, [&] { trapz_step_kernel<2, T>(a.data(), k1.data(), k2.data(), 0.5 * 0.01, out.data(), n); });
+    ok_tz = ok_tz && same_bits(out, (A + 0.5 * 0.01 * (Vector(k1) + Vector(k2))).components);
+  }
+  report("ewise_kernel: + - *. /. scalar* +. neg abs /scalar -(a*.b), both widths, in place", ok_ops);
+  report("rk4_final_kernel", ok_rk4);
+  report("hermite_kernel", ok_h);
+  report("lorenz96_kernel", ok_l);
+  report("trapz_step_kernel", ok_tz);
+}
+
 int main() {
+  test_elementwise();
   test_stage<1, 4>(); test_stage<2, 4>(); test_stage<3, 2>(); test_stage<5, 4>(); test_stage<6, 2>(); test_stage<8, 4>(); test_stage<9, 4>();
   test_finish<7, 4, false>("dopri54", rk_oracle::dopri54_pair());
   test_finish<7, 2, true>("tsit54", rk_oracle::tsit54_pair());

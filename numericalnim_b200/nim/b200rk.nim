@@ -258,13 +258,14 @@ proc hermiteInterpolate*(x, t: openArray[float], y, dy: openArray[GpuVector]): s
                                    addr hy[0], addr hdy[0], addr slots[0], addr n), y[0].ctx)
   adoptAll(y[0].ctx, slots, n)
 
-template cumulativeDiscrete(api: untyped, Y: openArray[GpuVector], X: openArray[float]): seq[GpuVector] =
-  if Y.len == 0 or Y.len != X.len: raise newException(ValueError, "X and Y must have the same non-zero length")
-  var (xs, hy) = (@X, handles(Y))
+template cumulativeDiscrete(api: untyped, yArg: openArray[GpuVector], xArg: openArray[float]): seq[GpuVector] =
+  if yArg.len == 0 or yArg.len != xArg.len: raise newException(ValueError, "X and Y must have the same non-zero length")
+  var (xs, hy) = (@xArg, handles(yArg))
   var slots = newSeq[VecHandle](xs.len)
   var n: csize_t
-  check(api(Y[0].ctx, addr hy[0], cast[ptr cdouble](addr xs[0]), xs.len.csize_t, addr slots[0], addr n), Y[0].ctx)
-  adoptAll(Y[0].ctx, slots, n)
+  let dev = yArg[0].ctx
+  check(api(dev, addr hy[0], cast[ptr cdouble](addr xs[0]), xs.len.csize_t, addr slots[0], addr n), dev)
+  adoptAll(dev, slots, n)
 
 proc cumtrapz*(Y: openArray[GpuVector], X: openArray[float]): seq[GpuVector] = cumulativeDiscrete(b200rk_cumtrapz, Y, X)      # integrate.nim:119-135
 proc cumsimpson*(Y: openArray[GpuVector], X: openArray[float]): seq[GpuVector] = cumulativeDiscrete(b200rk_cumsimpson, Y, X)  # integrate.nim:330-378
@@ -282,17 +283,20 @@ proc fnTrampoline(t: cdouble, outVec: VecHandle, user: pointer): cint {.cdecl.} 
     env.err = e
     result = 1
 
-template cumulativeFn(api: untyped, f, X, like, ctx, dx: untyped): seq[GpuVector] =
-  var nctx = ctx
+template cumulativeFn(api: untyped, fArg, xArg, likeArg, ctxArg, dxArg: untyped): seq[GpuVector] =
+  # (parameter names chosen not to collide with the field names used below: untyped parameters replace every
+  # identifier of the same name, also after a dot and inside object constructors)
+  var nctx = ctxArg
   if nctx.isNil: nctx = newNumContext[GpuVector, float]()
-  var env = FnEnv(f: f, ctx: nctx)
-  var xs = @X
+  var env = FnEnv(f: fArg, ctx: nctx)
+  var xs = @xArg
   var slots = newSeq[VecHandle](max(xs.len, 1))
   var n: csize_t
-  let rc = api(like.ctx, fnTrampoline, addr env, like.len.csize_t, cast[ptr cdouble](addr xs[0]), xs.len.csize_t, dx.cdouble, addr slots[0], addr n)
+  let dev = likeArg.ctx
+  let rc = api(dev, fnTrampoline, addr env, likeArg.len.csize_t, cast[ptr cdouble](addr xs[0]), xs.len.csize_t, dxArg.cdouble, addr slots[0], addr n)
   if not env.err.isNil: raise env.err
-  check(rc, like.ctx)
-  adoptAll(like.ctx, slots, n)
+  check(rc, dev)
+  adoptAll(dev, slots, n)
 
 proc cumtrapz*(f: NumContextProc[GpuVector, float], X: openArray[float], like: GpuVector,
                ctx: NumContext[GpuVector, float] = nil, dx = 1e-5): seq[GpuVector] =      # integrate.nim:138-175; `like` fixes T's size

@@ -217,9 +217,9 @@ proc newJitRhs*(expr: string, vecs: openArray[GpuVector] = [], scalars: openArra
   ## e.g. newJitRhs("c0*y*(1.0 - y/p0)", [K], [r]); a wrong expression raises ValueError with the compiler log.
   new(result, proc(r: JitRhs) = (if not r.user.isNil: discard b200rk_jit_rhs_free(r.user)))
   result.ctx = ctx
-  result.vecs = @vecs
+  result.vecs = @vecs                       # value semantics: the right-hand side owns its own copies of the parameters
   var hs = newSeq[VecHandle](vecs.len)
-  for i, v in vecs: hs[i] = v.h
+  for i in 0 ..< result.vecs.len: hs[i] = result.vecs[i].h
   var cs = @scalars
   check(b200rk_jit_rhs_new(ctx, expr.cstring, hs.len.cint, (if hs.len > 0: addr hs[0] else: nil), cs.len.cint,
                            (if cs.len > 0: cast[ptr cdouble](addr cs[0]) else: nil), addr result.fn, addr result.user), ctx)

@@ -412,3 +412,21 @@ def simpson_weights(h1: float, h2: float, tail: bool = False):
     a, b, e = C.c_double(0), C.c_double(0), C.c_double(0)
     lib().oracle_simpson_weights(C.c_int(tail), C.c_double(h1), C.c_double(h2), C.byref(a), C.byref(b), C.byref(e))
     return a.value, b.value, e.value
+
+
+# ----------------------------------------------------------------------------------------------------
+# courtesy baseline: fused, multi-threaded CPU code for the diag-linear IVP (NOT the reference's behaviour)
+# ----------------------------------------------------------------------------------------------------
+class FusedStats(C.Structure):
+    _fields_ = [("steps", C.c_long), ("attempts", C.c_long), ("rejected", C.c_long), ("limiter_hits", C.c_long), ("seconds", C.c_double),
+                ("threads", C.c_int), ("_pad", C.c_int)]
+
+
+def fused_mt_solve_diag(integrator: str, lam, y0, t_end: float, options: OracleOptions | None = None, max_steps: int = 0, threads: int = 0):
+    """One fused pass per attempt over all host cores (std::thread chunks). Returns (y_end, FusedStats)."""
+    lam, y = _f64(lam), _f64(y0).copy()
+    st = FusedStats()
+    options = options or new_options()
+    _check(lib().oracle_fused_mt_solve_diag(integrator.encode(), _p(lam), _p(y), C.c_size_t(y.size), C.c_double(t_end), C.byref(options),
+                                            C.c_long(max_steps), C.c_int(threads), C.byref(st)))
+    return y, st

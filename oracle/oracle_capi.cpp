@@ -2,6 +2,7 @@
 // bench.py's cpu_baseline / --impl reference legs can drive the CPU oracle.
 // TEST INFRASTRUCTURE ONLY: nothing under numericalnim_b200/ may load this library.
 #include <chrono>
+#include <thread>
 #include <cstring>
 #include <memory>
 
@@ -350,6 +351,94 @@ int oracle_cumsimpson_fn(int scalar, size_t n, oracle_fn_cb cb, void* user, cons
 void oracle_simpson_weights(int tail, double h1, double h2, double* alpha, double* beta, double* eta) {
   const SimpsonWeights w = tail ? simpson_tail_weights(h1, h2) : simpson_pair_weights(h1, h2);
   *alpha = w.alpha; *beta = w.beta; *eta = w.eta;
+}
+
+// ---- courtesy baseline (NOT the reference's behaviour) ---------------------------------------------------------------
+// What a CPU can do for the same element-local IVP y' = -(lambda .* y) when the attempt is fused into one pass over
+// the state and spread over all host cores (std::thread, contiguous chunks): per element the very same operations in
+// the same order as pair_step (so element-wise results are bit-identical to the oracle's), the error norm summed per
+// thread and combined in thread order. Reported
+// next to the single-threaded port in bench.py's cpu_baseline so the GPU/CPU ratio can also be read against a
+// well-written CPU code; numericalnim itself is single-threaded and allocates a Vector per operator.
+struct oracle_fused_stats { long steps, attempts, rejected, limiter_hits; double seconds; int threads; int _pad; };
+
+int oracle_fused_mt_solve_diag(const char* method, const double* lam, double* y_io, size_t n, double t_end,
+                               const oracle_options* opt, long max_steps, int threads, oracle_fused_stats* out) {
+  const Pair* pp = pair_by_name(method);
+  if (!pp) { g_err = "fused baseline: dopri54 / tsit54 / vern65 only"; return 1; }
+  const Pair p = *pp;
+  const Options o = to_opt(opt);
+  const int S = p.stages;
+  int used = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+  if (used < 1) used = 1;
+  if ((size_t)used > n) used = (int)std::max<size_t>(n, 1);
+  std::vector<double> Y[2] = {std::vector<double>(y_io, y_io + n), std::vector<double>(n)}, F[2] = {std::vector<double>(n), std::vector<double>(n)};
+  for (size_t i = 0; i < n; ++i) F[0][i] = -(lam[i] * Y[0][i]);                       // FSAL = f(t0, y0)
+  int cur = 0;
+  double t = o.tStart, dt = std::sqrt(o.dtMax * o.dtMin), error = 0.0;                // ode.nim:491-493
+  oracle_fused_stats st{0, 0, 0, 0, 0.0, used, 0};
+  const auto t0 = std::chrono::steady_clock::now();
+  while (t < t_end && (max_steps <= 0 || st.steps < max_steps)) {
+    dt = nim_min(dt, t_end - t);                                                      // ode.nim:525
+    int limit = 0;
+    while (true) {                                                                    // ode.nim:57-76
+      const double* y = Y[cur].data(); const double* k1 = F[cur].data();
+      double* yn = Y[1 - cur].data(); double* ks = F[1 - cur].data();
+      const double h = dt;
+      std::vector<double> partial(used, 0.0);
+      auto work = [&](int w) {
+        const size_t lo = n * (size_t)w / (size_t)used, hi = n * (size_t)(w + 1) / (size_t)used;
+        double acc_sum = 0.0;
+        for (size_t i = lo; i < hi; ++i) {
+          double k[9];
+          k[0] = k1[i];
+          double in = 0.0;
+          for (int s = 2; s <= S; ++s) {
+            double acc = p.a[s][0] * k[0];
+            for (int j = 1; j < s - 1; ++j) acc = acc + p.a[s][j] * k[j];
+            in = y[i] + h * acc;
+            k[s - 1] = -(lam[i] * in);
+          }
+          double accb = p.b[0] * k[0];
+          for (int j = 1; j < p.n_b; ++j) accb = accb + p.b[j] * k[j];
+          const double ynew = y[i] + h * accb;
+          double acch = p.bhat[0] * k[0];
+          for (int j = 1; j < p.n_bhat; ++j) acch = acch + p.bhat[j] * k[j];
+          const double e = p.err_is_direct ? h * acch : ynew - (y[i] + h * acch);
+          const double r = e / (o.absTol + o.relTol * std::fabs(ynew));
+          acc_sum += r * r;
+          yn[i] = ynew; ks[i] = k[S - 1];
+        }
+        partial[w] = acc_sum;
+      };
+      std::vector<std::thread> pool;
+      for (int w = 1; w < used; ++w) pool.emplace_back(work, w);
+      work(0);
+      for (auto& th : pool) th.join();
+      double sum = 0.0;
+      for (int w = 0; w < used; ++w) sum += partial[w];
+      st.attempts++;
+      error = std::sqrt(1.0 / double(n) * sum);
+      if (error <= 1) break;
+      if (std::isnan(error)) { g_err = "error norm is NaN"; return 2; }
+      st.rejected++;
+      dt = dt * nim_min(4, nim_max(0.125, 0.9 * std::pow(1.0 / error, 1.0 / double(p.order))));
+      if (std::fabs(dt) < o.dtMin) { dt = o.dtMin; limit += 1; st.limiter_hits++; }
+      else if (o.dtMax < std::fabs(dt)) dt = o.dtMax;
+      if (!(limit < 2)) break;
+    }
+    cur = 1 - cur;
+    t += dt;
+    st.steps++;
+    if (error == 0.0) dt *= 5;                                                        // ode.nim:533-541
+    else dt = dt * nim_min(4, nim_max(0.125, 0.9 * std::pow(1.0 / error, 1.0 / double(p.order))));
+    if (dt < o.dtMin) dt = o.dtMin;
+    else if (o.dtMax < dt) dt = o.dtMax;
+  }
+  st.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  std::memcpy(y_io, Y[cur].data(), n * sizeof(double));
+  *out = st;
+  return 0;
 }
 
 }  // extern "C"

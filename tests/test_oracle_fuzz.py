@@ -50,3 +50,20 @@ def test_repeated_tstart_is_reported_once():
         t_py, y_py, _ = R.solve(R.rhs_scale(-0.1), R.Vec([1.0, 2.0]), tspan, R.options(), "dopri54")
         assert sol.t.tolist() == t_py == want
         assert sol.y.shape[0] == len(y_py) == len(want)
+
+
+def test_courtesy_fused_multithreaded_baseline_equals_the_port():
+    """bench.py's courtesy CPU row (fused attempt, all host cores) is the same arithmetic per element as the port:
+    identical step sequence counts, final state bit-identical when the error norms round alike, else within 1e-12."""
+    import numpy as np
+    import oracle as O
+    n = 5000
+    lam = 0.1 + 9.9 * np.arange(n) / (n - 1)
+    y0 = 1.0 + 0.5 * np.sin(2 * np.pi * np.arange(n) / n)
+    kw = dict(absTol=1e-6, relTol=1e-6, dtMax=1.0, dtMin=1e-8)
+    for method in ("dopri54", "tsit54", "vern65"):
+        ref = O.solve_vector(method, O.rhs_diag_linear(lam), y0, [0.0, 2.0], O.new_options(**kw))
+        for threads in (1, 3):
+            y, st = O.fused_mt_solve_diag(method, lam, y0, 2.0, O.new_options(**kw), threads=threads)
+            assert (st.steps, st.rejected, st.limiter_hits) == (ref.stats.steps, ref.stats.rejected, ref.stats.limiter_hits), (method, threads)
+            assert np.allclose(y, ref.y[-1], rtol=1e-9, atol=1e-13)

@@ -42,6 +42,10 @@ def test_kernels_match_the_oracle_bit_for_bit(tmp_path):
     assert rc == 0 and not bad, bad
     for family in ("stage_kernel", "finish_kernel", "fused_attempt", "source rhs", "user_rk4_kernel", "cumtrapz_kernel", "hermite_many_kernel"):
         assert any(family in k for k in cases), family
+    exe = str(tmp_path / "emul_main")
+    for seed in range(1, 13):  # the same cases on other random inputs
+        rc, cases, out = _run(exe, str(seed))
+        assert rc == 0 and all(v == "1" for v in cases.values()), (seed, [k for k, v in cases.items() if v != "1"])
 
 
 def test_the_gate_detects_fma_contraction(tmp_path):

@@ -75,6 +75,7 @@ struct b200rk_ctx {
   int fused_ctas_per_sm = 4;   // fused pointwise attempt kernel: persistent grid of 4 CTAs per SM (~100 registers: 2 resident, 2 waves; measured best, profiles/r01_tune_*)
   bool fuse_pointwise = true;  // element-local built-in RHS: whole attempt in one kernel
   bool fuse_stencil = true;    // built-in Lorenz-96 (single GPU): stage accumulate + stencil RHS in one kernel
+  bool finish_prefetch = false; // software-pipelined finish kernel (experimental: verified by host emulation, not yet measured on the GPU)
   bool fuse_simpson = false;   // cumsimpson as one kernel (experimental: verified by host emulation, not yet measured on the GPU)
   int l2_hints = -1;           // producer stores evict_last / streams evict_first: -1 auto (vector <= 0.65 L2), 0 off, 1 on
   size_t l2_bytes = 126u << 20;

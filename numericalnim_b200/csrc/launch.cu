@@ -1,6 +1,7 @@
 // launch.cu — generic kernel launchers: template dispatch on the number of streams / vector width / launch
 // geometry, the algorithmic-byte accounting of the profiler, and the read-back of a reduction result.
 #include "internal.hpp"
+#include "finish_pf.cuh"
 
 template <int M, int W, bool CHAIN>
 static int launch_stage_mw(b200rk_ctx* c, const StageArgs<M>& a) {
@@ -56,6 +57,13 @@ static int launch_finish_cfg(b200rk_ctx* c, const FinishPlan& p) {
   unsigned grid = grid_for(c, p.n / W, kThreads * U, c->finish_ctas_per_sm);
   TRY(ensure_partials(c, grid));
   a.rs = reduce_scratch(c);
+  if constexpr (NK >= 6 && U == 1) {  // experimental software-pipelined form (finish_pf.cuh), knob "finish_prefetch", default off
+    if (c->finish_prefetch) {
+      finish_pf_kernel<NK, W, DIRECT, MODE, kThreads><<<grid, kThreads, 0, c->stream>>>(a);
+      CUDA_TRY(c, cudaGetLastError());
+      return B200RK_OK;
+    }
+  }
   finish_kernel<NK, W, U, DIRECT, MODE, kThreads><<<grid, kThreads, 0, c->stream>>>(a);
   CUDA_TRY(c, cudaGetLastError());
   return B200RK_OK;

@@ -195,6 +195,7 @@ static int ctx_common_init(b200rk_ctx* c) {
   if (const char* e = getenv("B200RK_FUSE_POINTWISE")) c->fuse_pointwise = atoi(e) != 0;
   if (const char* e = getenv("B200RK_FUSE_STENCIL")) c->fuse_stencil = atoi(e) != 0;
   if (const char* e = getenv("B200RK_FUSE_SIMPSON")) c->fuse_simpson = atoi(e) != 0;
+  if (const char* e = getenv("B200RK_FINISH_PREFETCH")) c->finish_prefetch = atoi(e) != 0;
   if (const char* e = getenv("B200RK_L2_HINTS")) c->l2_hints = atoi(e) < 0 ? -1 : (atoi(e) != 0);
   CUDA_TRY(c, cudaDeviceSynchronize());
   return B200RK_OK;
@@ -275,6 +276,7 @@ int b200rk_set(b200rk_ctx* c, const char* key, int64_t v) {
   else if (k == "device_loop") c->device_loop = v < 0 ? -1 : (v != 0);
   else if (k == "fuse_stencil") c->fuse_stencil = v != 0;
   else if (k == "fuse_simpson") c->fuse_simpson = v != 0;
+  else if (k == "finish_prefetch") c->finish_prefetch = v != 0;
   else if (k == "l2_hints") c->l2_hints = v < 0 ? -1 : (v != 0);
   else if (k == "fused_ctas_per_sm") { if (v < 0) return fail(c, B200RK_EINVAL, "fused_ctas_per_sm must be >= 0"); c->fused_ctas_per_sm = (int)v; }
   else if (k == "pool_budget_mb") {
@@ -300,6 +302,7 @@ int b200rk_get(const b200rk_ctx* c, const char* key, int64_t* v) {
   else if (k == "p2p") *v = c->p2p;
   else if (k == "fuse_stencil") *v = c->fuse_stencil;
   else if (k == "fuse_simpson") *v = c->fuse_simpson;
+  else if (k == "finish_prefetch") *v = c->finish_prefetch;
   else if (k == "l2_hints") *v = c->l2_hints;
   else if (k == "fused_ctas_per_sm") *v = c->fused_ctas_per_sm;
   else if (k == "profile") *v = c->profile;

@@ -12,6 +12,14 @@ echo "== 1. experimental + C++ extras"; timeout 300 python -m pytest tests/test_
 echo "== 2. cumsimpson two-kernel vs single-pass"
 timeout 200 python bench.py --quad --out gpurun_out/quad_default.json 2>&1 | grep '"op": "cumsimpson"' | cut -c1-400
 B200RK_FUSE_SIMPSON=1 timeout 200 python bench.py --quad --out gpurun_out/quad_fuse_simpson.json 2>&1 | grep '"op": "cumsimpson"' | cut -c1-400
+echo "== 2b. finish kernel: default vs software-pipelined (pipeline leg of the bench: finish GB/s, steps/s)"
+fin='import sys,json
+d=json.loads(sys.stdin.read()); p=d["pipeline"]; f=p["roofline"]["finish_kernel"]
+print("pipeline steps/s", round(p["value"],1), "finish GB/s", round(f["achieved"]), "us", round(f["avg_launch_us"],1))'
+for cfg in "0 4 2" "1 4 2" "1 4 1" "1 2 2" "1 2 3"; do set -- $cfg
+  echo "finish_prefetch=$1 vec_width=$2 finish_ctas_per_sm=$3"
+  B200RK_FINISH_PREFETCH=$1 B200RK_VEC_WIDTH=$2 B200RK_FINISH_CTAS_PER_SM=$3 timeout 200 python bench.py --no-jit --no-quad --no-cpu-baseline --e2e-reps 1 2>&1 | grep '^{"metric"' | python -c "$fin"
+done
 echo "== 3. compute-sanitizer, tiny cases"
 timeout 150 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_quadrature.py -q -p no:cacheprovider -x -k "quadrature_errors or unsorted_input" 2>&1 | tail -4 | cut -c1-300
 timeout 150 compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest tests/test_gpu_parity.py -q -p no:cacheprovider -x -k "error_norm_is_deterministic or test_lorenz96_rhs_bitwise" 2>&1 | tail -4 | cut -c1-300

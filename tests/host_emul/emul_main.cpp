@@ -111,21 +111,39 @@ static void test_finish(const char* name, const rk_oracle::Pair& p) {
     const Vector e1 = rk_oracle::hdiv(ey, tol);
     const double S = rk_oracle::vsum(rk_oracle::hadamard(e1, e1));
     ok = ok && same_bits(ynew, yN.components) && same_bits(err, ey.components) && close_rel(sum, S, 1e-12);
+    {  // the software-pipelined form (finish_pf.cuh, experimental): same elements, and the SAME sum bits on the same grid
+      std::vector<double> ynew_pf(n), err_pf(n);
+      double sum_pf = 0.0;
+      a.ynew_out = ynew_pf.data(); a.err_out = err_pf.data(); a.rs = scratch(&sum_pf);
+      emul_launch(2, T, [&] { finish_pf_kernel<NK, W, DIRECT, 1, T>(a); });
+      ok = ok && same_bits(ynew_pf, yN.components) && same_bits(err_pf, ey.components) && std::memcmp(&sum_pf, &sum, 8) == 0;
+      a.ynew_out = ynew.data(); a.err_out = err.data();
+    }
     if (DIRECT) {  // Tsit54 as the solver runs it: yNew is loaded instead of y (mode 2), the error row is direct
       std::vector<double> err2(n);
       double sum2 = 0.0;
       a.y = yN.components.data(); a.ynew_out = nullptr; a.err_out = err2.data(); a.rs = scratch(&sum2);
       emul_launch(2, T, [&] { finish_kernel<NK, W, 1, true, 2, T>(a); });
       ok = ok && same_bits(err2, ey.components) && close_rel(sum2, S, 1e-12);
+      std::vector<double> err2p(n);
+      double sum2p = 0.0;
+      a.err_out = err2p.data(); a.rs = scratch(&sum2p);
+      emul_launch(2, T, [&] { finish_pf_kernel<NK, W, true, 2, T>(a); });
+      ok = ok && same_bits(err2p, ey.components) && std::memcmp(&sum2p, &sum2, 8) == 0;
     } else {      // DOPRI54 as the solver runs it: yNew recomputed in registers, not stored (mode 0)
       std::vector<double> err0(n);
       double sum0 = 0.0;
       a.ynew_out = nullptr; a.err_out = err0.data(); a.rs = scratch(&sum0);
       emul_launch(2, T, [&] { finish_kernel<NK, W, 1, false, 0, T>(a); });
       ok = ok && same_bits(err0, ey.components) && close_rel(sum0, S, 1e-12);
+      std::vector<double> err0p(n);
+      double sum0p = 0.0;
+      a.err_out = err0p.data(); a.rs = scratch(&sum0p);
+      emul_launch(2, T, [&] { finish_pf_kernel<NK, W, false, 0, T>(a); });
+      ok = ok && same_bits(err0p, ey.components) && std::memcmp(&sum0p, &sum0, 8) == 0;
     }
   }
-  report(std::string("finish_kernel ") + name + " W=" + std::to_string(W), ok);
+  report(std::string("finish_kernel + finish_pf_kernel ") + name + " W=" + std::to_string(W), ok);
 }
 
 // ---- whole attempt in one kernel (fused_attempt_kernel) vs the oracle's X_step with a first attempt that is accepted -

@@ -40,7 +40,7 @@ def test_kernels_match_the_oracle_bit_for_bit(tmp_path):
     assert len(cases) >= 30, out
     bad = [k for k, v in cases.items() if v != "1"]
     assert rc == 0 and not bad, bad
-    for family in ("stage_kernel", "finish_kernel", "fused_attempt", "source rhs", "user_rk4_kernel", "cumtrapz_kernel", "hermite_many_kernel"):
+    for family in ("stage_kernel", "finish_kernel", "finish_pf_kernel", "fused_attempt", "source rhs", "user_rk4_kernel", "cumtrapz_kernel", "hermite_many_kernel"):
         assert any(family in k for k in cases), family
     exe = str(tmp_path / "emul_main")
     for seed in range(1, 13):  # the same cases on other random inputs

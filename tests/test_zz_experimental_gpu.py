@@ -46,3 +46,43 @@ def test_cumsimpson_single_pass_equals_two_kernel_path(nn, vec_width):
     finally:
         ctx.set("fuse_simpson", 0)
         ctx.set("vec_width", 4)
+
+
+@pytest.mark.parametrize("vec_width", [4, 2])
+@pytest.mark.parametrize("method,stages", [("dopri54", 7), ("tsit54", 7), ("vern65", 9)])
+def test_prefetching_finish_kernel_equals_default(nn, method, stages, vec_width):
+    """knob finish_prefetch=1: the software-pipelined finish kernel (finish_pf.cuh) — same yNew / error_y bits and, on the
+    same grid, the same error-norm bits as finish_kernel; whole solves take the identical step sequence."""
+    ctx = nn.default_context()
+    rng = np.random.default_rng(13)
+    try:
+        ctx.set("vec_width", vec_width)
+        for n in (1, 3, 4, 5, 1023, 65536 + 7, (1 << 20) + 1):
+            y = 1.0 + 0.5 * rng.uniform(-1.0, 1.0, n)
+            ks = [nn.newVector(rng.uniform(-1.0, 1.0, n)) for _ in range(stages)]
+            gy = nn.newVector(y)
+            res = {}
+            for pf in (0, 1):
+                ctx.set("finish_prefetch", pf)
+                yn, ey, S, E = nn.combineErr(method, 0.01, 1e-6, 1e-6, gy, ks, want_err_y=True)
+                res[pf] = (yn.to_numpy(), ey.to_numpy(), S, E)
+            assert np.array_equal(res[0][0].view(np.uint64), res[1][0].view(np.uint64)), (method, n)
+            assert np.array_equal(res[0][1].view(np.uint64), res[1][1].view(np.uint64)), (method, n)
+            assert res[0][2] == res[1][2] and res[0][3] == res[1][3], (method, n, res[0][2], res[1][2])
+        # a whole adaptive solve on the general pipeline (fused paths off) takes the same steps either way
+        n = 4096
+        lam = 0.1 + 9.9 * np.arange(n) / (n - 1)
+        y0 = 1.0 + 0.5 * np.sin(2 * np.pi * np.arange(n) / n)
+        ctx.set("fuse_pointwise", 0)
+        out = {}
+        for pf in (0, 1):
+            ctx.set("finish_prefetch", pf)
+            t, ys = nn.solveODE(nn.rhsDiagLinear(nn.newVector(lam)), nn.newVector(y0), [0.0, 2.0],
+                                nn.newODEoptions(absTol=1e-6, relTol=1e-6, dtMax=1.0, dtMin=1e-8), integrator=method)
+            out[pf] = (ys[-1].to_numpy(), dict(nn.ode.last_stats))
+        assert np.array_equal(out[0][0].view(np.uint64), out[1][0].view(np.uint64))
+        assert out[0][1]["steps"] == out[1][1]["steps"] and out[0][1]["launches"] == out[1][1]["launches"]
+    finally:
+        ctx.set("finish_prefetch", 0)
+        ctx.set("fuse_pointwise", 1)
+        ctx.set("vec_width", 4)

@@ -35,6 +35,15 @@ def kernels():
     return out
 
 
+def registers():
+    res = ""
+    for path in sorted(glob.glob(os.path.join(OBJ, "*.o"))):
+        if path.endswith("kernels_src.o"):
+            continue
+        res += subprocess.run(["cuobjdump", "-res-usage", path], capture_output=True, text=True, check=True).stdout
+    return {m[0]: int(m[1]) for m in re.findall(r"Function (\S+):\s*\n\s*REG:(\d+)", res)}
+
+
 def fp64(c):
     return sum(v for k, v in c.items() if k.startswith(("DADD", "DMUL", "DFMA", "DSETP", "MUFU")))
 
@@ -61,21 +70,24 @@ def main():
     if os.path.exists(p):
         peak = float(json.load(open(p))["hbm_gbs"]) * 1e9
     ks = kernels()
-    print("| kernel | fp64-pipe instr / element | fp64-pipe time | HBM time (algorithmic bytes) | bound | measured | measured / max(model) |")
-    print("|---|---|---|---|---|---|---|")
+    regs = registers()
+    print("| kernel | registers -> resident CTAs/SM (256 threads) | fp64-pipe instr / element | fp64-pipe time | HBM time (algorithmic bytes) | bound | measured | measured / max(model) |")
+    print("|---|---|---|---|---|---|---|---|")
     for label, frag, w, u, passes, n, meas, src in ROWS:
         match = [c for fn, c in ks.items() if frag in fn]
         if not match:
-            print(f"| {label} | (not found: {frag}) | | | | | |")
+            print(f"| {label} | (not found: {frag}) | | | | | | |")
             continue
         c = match[0]
+        r = [v for fn, v in regs.items() if frag in fn][0]
+        occ = f"{r} -> {min(8, 65536 // (max(r, 1) * 256))}"
         per_elem = fp64(c) / float(w * u + 1)   # static body = W*U elements + the scalar tail's 1
         t_fp = per_elem * n / FP64_RATE * 1e6
         t_hbm = passes * 8.0 * n / peak * 1e6
         bound = "fp64 issue" if t_fp > t_hbm else "HBM"
         ms = f"{meas:.1f} us ({src})" if meas else "—"
         ratio = f"{meas / max(t_fp, t_hbm):.2f}" if meas else "—"
-        print(f"| {label} | {per_elem:.0f} | {t_fp:.1f} us | {t_hbm:.1f} us | {bound} | {ms} | {ratio} |")
+        print(f"| {label} | {occ} | {per_elem:.0f} | {t_fp:.1f} us | {t_hbm:.1f} us | {bound} | {ms} | {ratio} |")
 
 
 if __name__ == "__main__":

@@ -350,7 +350,14 @@ __device__ __forceinline__ double block_sum(double v) {
 template <int THREADS>
 __device__ __forceinline__ void grid_sum_finish(double thread_val, const ReduceScratch& rs) {
 #ifdef B200RK_EMULATE_SERIAL_SUM
-  *rs.result = __dadd_rn(*rs.result, thread_val);  // serial host emulation (threads run one after another): a plain running sum
+  // serial host emulation (threads run one after another, CTA 0 / thread 0 first): a plain running sum; the last
+  // thread publishes it the way the last CTA does
+  if (blockIdx.x == 0 && threadIdx.x == 0) *rs.result = 0.0;
+  *rs.result = __dadd_rn(*rs.result, thread_val);
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == THREADS - 1 && rs.result_host) {
+    *rs.result_host = *rs.result;
+    *rs.seq_host = rs.seq;
+  }
   return;
 #endif
   __shared__ bool is_last;

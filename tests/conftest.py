@@ -17,8 +17,21 @@ os.environ.setdefault("B200RK_JIT_CACHE", os.path.join(ROOT, ".jitcache"))
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
+def pytest_addoption(parser):
+    parser.addoption("--host-emulation", action="store_true", default=False,
+                     help="TEST INFRASTRUCTURE: run the `gpu` tests on the CPU against tests/host_emul/_build/libb200rk_emul.so — the product's "
+                          "host sources and kernels compiled by g++ with every kernel launch emulated thread by thread (no GPU, no NVRTC)")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+    if config.getoption("--host-emulation"):
+        # Only the test-suite can do this: the product package has no switch for it and raises without a CUDA device.
+        sys.path.insert(0, os.path.join(ROOT, "tests", "host_emul"))
+        import build_emul_lib
+        from numericalnim_b200 import _capi
+        _capi.LIB_PATH = build_emul_lib.build()
+        os.environ["B200RK_TEST_HOST_EMULATION"] = "1"
 
 
 def unhex(xs):

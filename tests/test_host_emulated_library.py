@@ -1,0 +1,44 @@
+"""The GPU parity suites, run on the CPU against the HOST-EMULATED library (tests/host_emul/build_emul_lib.py): the
+product's own host sources (drivers, planners, launch code) and kernels compiled by g++ — the only source change is the
+`<<<grid, threads>>>` launch syntax, which becomes a loop over emulated threads (a real thread team with barriers for
+the shared-memory Lorenz-96 kernel and the cooperative device loop); CUDA runtime calls resolve to a fake runtime whose
+"device" memory is host memory. It is what lets a change to host logic or kernel arithmetic be checked end to end
+against the oracle before any GPU time is spent — and what verified, this round, everything written after the GPU budget
+ran out (including the experimental default-off paths, which XPASS here).
+
+TEST INFRASTRUCTURE ONLY: the library is built under tests/, selected by a pytest option, and the product package has no
+way to load it (numericalnim_b200 still raises without a CUDA device; tests/test_capi_host.py checks that). What it
+cannot cover: NVRTC / module loading (right-hand sides from source), multi-CTA concurrency, peer mailboxes, performance."""
+import importlib.util
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SUITES = ["tests/test_gpu_parity.py", "tests/test_gpu_fuzz.py", "tests/test_gpu_quadrature.py", "tests/test_gpu_device_loop.py",
+          "tests/test_zz_experimental_gpu.py"]
+
+
+def test_gpu_suites_pass_under_host_emulation():
+    cmd = [sys.executable, "-m", "pytest", *SUITES, "-q", "-m", "gpu", "--host-emulation", "-p", "no:cacheprovider"]
+    if importlib.util.find_spec("xdist") is not None:
+        cmd += ["-n", str(min(6, os.cpu_count() or 1))]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=3000, cwd=ROOT)
+    tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-2000:]
+    counts = {k: int(v) for v, k in re.findall(r"(\d+) (passed|failed|error|errors|xpassed|xfailed|skipped)", tail)}
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+    assert counts.get("failed", 0) == 0 and counts.get("error", 0) == 0 and counts.get("errors", 0) == 0, tail
+    assert counts.get("passed", 0) >= 199, tail            # parity 147 + fuzz 3 + quadrature 40 + device loop 9
+    assert counts.get("xpassed", 0) + counts.get("xfailed", 0) == 8, tail
+    assert counts.get("xpassed", 0) == 8, "an experimental (default-off) path fails under host emulation: " + tail
+
+
+def test_emulated_library_is_not_reachable_from_the_product():
+    """No CPU fallback: the package names neither the emulated library nor the switch that selects it."""
+    pkg = os.path.join(ROOT, "numericalnim_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".nim")) and "lib" + os.sep + "obj" not in dirpath:
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "b200rk_emul" not in src and "host_emul" not in src.replace("tests/host_emul", "") and "--host-emulation" not in src, f

@@ -42,3 +42,28 @@ def test_emulated_library_is_not_reachable_from_the_product():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".nim")) and "lib" + os.sep + "obj" not in dirpath:
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "b200rk_emul" not in src and "host_emul" not in src.replace("tests/host_emul", "") and "--host-emulation" not in src, f
+
+
+def test_compiled_language_hosts_run_against_the_emulated_library(tmp_path):
+    """The C and C++ demos (what a Nim / C / C++ host does with the C-ABI), linked against the emulated library and run
+    on the CPU: the reference's Vector ODE tests through C++ closures, the plain-C solve, and the trajectory consumers
+    through the C++ mirror (the demo whose first GPU run is still pending). The demos that hand a right-hand side over
+    as source need NVRTC + a GPU and stay GPU-only."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "host_emul"))
+    import build_emul_lib
+    lib = build_emul_lib.build()
+    libdir, inc = os.path.dirname(lib), os.path.join(ROOT, "include")
+    link = [f"-L{libdir}", "-lb200rk_emul", f"-Wl,-rpath,{libdir}"]
+
+    def run(src, compiler, std, args=(), extra=()):
+        exe = str(tmp_path / os.path.basename(src).split(".")[0])
+        subprocess.run([compiler, std, "-O2", f"-I{inc}", os.path.join(ROOT, "examples", src), *link, *extra, "-o", exe], check=True, capture_output=True, text=True)
+        r = subprocess.run([exe, *args], capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout + r.stderr
+        return r.stdout
+
+    assert "quadrature trajectory_ok=1 function_variant_ok=1" in run("cpp_quadrature_demo.cpp", "g++", "-std=c++17")
+    out = run("cpp_host_demo.cpp", "g++", "-std=c++17")
+    assert out.count(" ok=1 ") == 8 and "errors raised=4 of 4" in out
+    out = run("c_host_demo.c", "gcc", "-std=c99", args=("tsit54", "4096"), extra=("-lm",))
+    assert "n_out=2" in out and "max_abs_err_vs_exact" in out

@@ -30,7 +30,7 @@ def pytest_configure(config):
         sys.path.insert(0, os.path.join(ROOT, "tests", "host_emul"))
         import build_emul_lib
         from numericalnim_b200 import _capi
-        _capi.LIB_PATH = build_emul_lib.build()
+        _capi.LIB_PATH = build_emul_lib.build(sanitize=os.environ.get("B200RK_TEST_EMULATION_SANITIZE", ""))
         os.environ["B200RK_TEST_HOST_EMULATION"] = "1"
 
 

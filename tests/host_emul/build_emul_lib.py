@@ -43,7 +43,13 @@ def transform(text: str, name: str) -> str:
     return "\n".join(out) + "\n", n
 
 
-def build(force: bool = False) -> str:
+def build(force: bool = False, sanitize: str = "") -> str:
+    """sanitize = "address": an AddressSanitizer build (libb200rk_emul_asan.so) — since "device" memory is host memory,
+    an out-of-bounds access of a kernel or of the host code is reported like compute-sanitizer memcheck would."""
+    global BUILD, OUT
+    if sanitize:
+        BUILD = os.path.join(HERE, "_build", "emul_lib_" + sanitize)
+        OUT = os.path.join(HERE, "_build", "libb200rk_emul_%s.so" % {"address": "asan"}.get(sanitize, sanitize))
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
     deps = srcs + [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".hpp", ".cuh", ".h"))] + \
         [os.path.join(HERE, f) for f in ("emul_lib_prelude.hpp", "emul_lib_support.cpp", "build_emul_lib.py")] + \
@@ -64,6 +70,8 @@ def build(force: bool = False) -> str:
     flags = ["-std=c++20", "-O1", "-ffp-contract=off", "-fPIC", "-pthread", "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-unused-variable",
              "-Wno-unused-but-set-variable", "-include", os.path.join(HERE, "emul_lib_prelude.hpp"),
              f"-I{os.path.join(HERE, 'fake_cuda')}", f"-I{os.path.join(HERE, 'cuda_stubs')}", f"-I{CSRC}", f"-I{HERE}"]
+    if sanitize:
+        flags += ["-fsanitize=" + sanitize, "-fno-omit-frame-pointer", "-g"]
     objs = []
     procs = []
     for c in cpps:
@@ -74,10 +82,10 @@ def build(force: bool = False) -> str:
         err = p.communicate()[1]
         if p.returncode != 0:
             raise SystemExit(f"compiling {c} failed:\n{err[-4000:]}")
-    subprocess.run(["g++", "-shared", "-pthread", "-o", OUT, *objs, "-ldl"], check=True)
+    subprocess.run(["g++", "-shared", "-pthread", *(["-fsanitize=" + sanitize] if sanitize else []), "-o", OUT, *objs, "-ldl"], check=True)
     print(f"{OUT}: {total} kernel launches rewritten", file=sys.stderr)
     return OUT
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv))
+    print(build(force="--force" in sys.argv, sanitize="address" if "--asan" in sys.argv else ""))

@@ -67,3 +67,34 @@ def test_compiled_language_hosts_run_against_the_emulated_library(tmp_path):
     assert out.count(" ok=1 ") == 8 and "errors raised=4 of 4" in out
     out = run("c_host_demo.c", "gcc", "-std=c99", args=("tsit54", "4096"), extra=("-lm",))
     assert "n_out=2" in out and "max_abs_err_vs_exact" in out
+
+
+def _gcc_file(name):
+    r = subprocess.run(["gcc", "-print-file-name=" + name], capture_output=True, text=True)
+    p = r.stdout.strip()
+    return p if r.returncode == 0 and os.path.isabs(p) and os.path.exists(p) else None
+
+
+def test_memory_errors_under_address_sanitizer(tmp_path):
+    """memcheck without a GPU: the emulated library built with AddressSanitizer. "Device" memory is host memory, so an
+    out-of-bounds access by a kernel (ragged sizes, tile seams, pointer tables) or by the host code is reported the way
+    compute-sanitizer would. Default: the trajectory-consumer, experimental and fuzz suites (seconds);
+    B200RK_TEST_ASAN=full runs every emulated GPU suite (207 cases, ~4 min — clean at the end of round 1)."""
+    import pytest
+    asan, stdcpp = _gcc_file("libasan.so"), _gcc_file("libstdc++.so.6")
+    if not asan or not stdcpp:
+        pytest.skip("AddressSanitizer runtime not available")
+    suites = SUITES if os.environ.get("B200RK_TEST_ASAN") == "full" else ["tests/test_gpu_quadrature.py", "tests/test_zz_experimental_gpu.py", "tests/test_gpu_fuzz.py"]
+    log = str(tmp_path / "asan")
+    env = dict(os.environ, LD_PRELOAD=f"{asan} {stdcpp}", ASAN_OPTIONS=f"detect_leaks=0:log_path={log}", B200RK_TEST_EMULATION_SANITIZE="address")
+    cmd = [sys.executable, "-m", "pytest", *suites, "-q", "-m", "gpu", "--host-emulation", "-p", "no:cacheprovider"]
+    if importlib.util.find_spec("xdist") is not None:
+        cmd += ["-n", str(min(6, os.cpu_count() or 1))]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=3000, cwd=ROOT, env=env)
+    reports = [f for f in os.listdir(tmp_path) if f.startswith("asan")]
+    detail = "".join(open(os.path.join(tmp_path, f)).read()[:3000] for f in reports[:2])
+    if "Shadow memory range interleaves" in detail or "ASan runtime does not come first" in r.stderr + detail:
+        pytest.skip("AddressSanitizer cannot be preloaded into this interpreter")
+    assert not reports, detail
+    tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-2000:]
+    assert r.returncode == 0 and " failed" not in tail and " error" not in tail, r.stdout[-3000:] + r.stderr[-2000:]

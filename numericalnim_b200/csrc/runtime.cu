@@ -145,8 +145,13 @@ int vec_alloc(b200rk_ctx* c, size_t n_global, b200rk_vec** out) {
   *out = v;
   return B200RK_OK;
 }
-void vec_release(b200rk_vec* v) {  // back to the pool
-  if (v) v->ctx->pool.push_back(v);
+void vec_release(b200rk_vec* v) {  // back to the pool (bounded: a call that held 10^5 vectors must not leave them all cached)
+  if (!v) return;
+  b200rk_ctx* c = v->ctx;
+  if (c->pool.size() < 512) { c->pool.push_back(v); return; }
+  cudaStreamSynchronize(c->stream);  // enqueued work may still use it
+  cudaFree(v->d);
+  delete v;
 }
 int check_same(const b200rk_ctx* c, const b200rk_vec* a, const b200rk_vec* b) {
   if (!a || !b) return fail(c, B200RK_EINVAL, "null vector");

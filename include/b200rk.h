@@ -212,7 +212,8 @@ typedef int (*b200rk_fn_of_t)(double t, b200rk_vec* out, void* user);
 B200RK_API int b200rk_cumtrapz_fn(b200rk_ctx* ctx, b200rk_fn_of_t f, void* user, size_t n_global, const double* X, size_t m,
                                   double dx, b200rk_vec** out, size_t* n_out);
 /* cumsimpson(f, X, ctx, dx) (integrate.nim:379-400): f on linspace(min X, max X, round((max-min)/dx) + 2), the discrete
- * rule, interpolated at X. All evaluations are alive at once like in the reference (B200RK_ENOMEM if they cannot fit). */
+ * rule, interpolated at X. Up to 4096 grid points that fit, all evaluations are alive at once like in the reference;
+ * finer grids are streamed through a window of a few vectors (same results; knob "stream_simpson": 1 always, 0 never). */
 B200RK_API int b200rk_cumsimpson_fn(b200rk_ctx* ctx, b200rk_fn_of_t f, void* user, size_t n_global, const double* X,
                                     size_t m, double dx, b200rk_vec** out, size_t* n_out);
 

@@ -76,6 +76,7 @@ struct b200rk_ctx {
   bool fuse_pointwise = true;  // element-local built-in RHS: whole attempt in one kernel
   bool fuse_stencil = true;    // built-in Lorenz-96 (single GPU): stage accumulate + stencil RHS in one kernel
   bool finish_prefetch = false; // software-pipelined finish kernel (experimental: verified by host emulation, not yet measured on the GPU)
+  int stream_simpson = -1;     // cumsimpson(f, X, dx): -1 = stream the grid only when the composed form would not fit, 0 never, 1 always
   bool fuse_simpson = false;   // cumsimpson as one kernel (experimental: verified by host emulation, not yet measured on the GPU)
   int l2_hints = -1;           // producer stores evict_last / streams evict_first: -1 auto (vector <= 0.65 L2), 0 off, 1 on
   size_t l2_bytes = 126u << 20;

@@ -8,6 +8,7 @@
 #include "quad_kernels.cuh"
 #include "quad_group.hpp"
 
+#include <map>
 #include <numeric>
 
 namespace {
@@ -315,6 +316,121 @@ int cumsimpson_impl(b200rk_ctx* c, const b200rk_vec* const* Y, const double* X, 
   return run_hermite_many(c, plan, knot_y, dy, outs);
 }
 
+// cumsimpson(f, X, ctx, dx) without keeping every evaluation alive. The reference's composition
+//   dy = f(t);  ys = cumsimpson(dy, t) = hermiteInterpolate(t, knots, I, dy[knots]);  result = hermiteInterpolate(X, t, ys, dy)
+// only ever looks two grid points back: the Simpson step of pair j needs f at t[2j], t[2j+1], t[2j+2]; ys[2j] and
+// ys[2j+1] are splines on the knot interval j; the samples of X inside [t[k], t[k+1]) need ys and f at k and k+1. So the
+// grid is walked once with a window of a few vectors, each launch being one of the kernels the composed form uses
+// (stage accumulate for the Simpson step — y + 1.0*((ya*ca + yb*cb) + yc*cc) is the scan's arithmetic bit for bit —,
+// the Hermite kernel for both interpolation levels): same results, same order of callbacks, O(1) memory.
+// Requires a strictly increasing grid (always the case unless min(X) == max(X)); returns 1 if it cannot apply.
+int cumsimpson_fn_streaming(b200rk_ctx* c, b200rk_fn_of_t f, void* user, size_t n_global, const double* X, size_t m,
+                            const std::vector<double>& t, Outputs* outs, bool* applied) {
+  *applied = false;
+  const long nt = (long)t.size();
+  if (nt < 3) return B200RK_OK;
+  for (long k = 0; k + 1 < nt; ++k) if (!(t[k] < t[k + 1])) return B200RK_OK;
+  // knots and Simpson steps of the discrete rule on (f(t), t) (integrate.nim:341-376)
+  long N = nt;
+  const bool evenN = (N % 2 == 0);
+  if (evenN) N -= 1;
+  const long pairs = (N - 1) / 2;
+  std::vector<SimpsonStep> steps;
+  std::vector<double> xs{t[0]};
+  std::vector<long> knot_idx{0};
+  for (long i = 0; i < pairs; ++i) {
+    SimpsonStep st;
+    st.ia = (int)(2 * i + 2); st.ib = (int)(2 * i + 1); st.ic = (int)(2 * i); st.reuse = 0;
+    simpson_pair(t[2 * i + 1] - t[2 * i], t[2 * i + 2] - t[2 * i + 1], &st.ca, &st.cb, &st.cc);
+    steps.push_back(st); xs.push_back(t[2 * i + 2]); knot_idx.push_back(2 * i + 2);
+  }
+  if (evenN) {
+    const long last = nt - 1;
+    double alpha, beta, eta;
+    simpson_tail(t[last - 1] - t[last - 2], t[last] - t[last - 1], &alpha, &beta, &eta);
+    SimpsonStep st;
+    st.ia = (int)(last - 2); st.ib = (int)(last - 1); st.ic = (int)last; st.reuse = 0;
+    st.ca = eta; st.cb = beta; st.cc = alpha;
+    steps.push_back(st); xs.push_back(t[last]); knot_idx.push_back(last);
+  }
+  std::vector<HermiteOut> inner, outer;   // ys[k] from the knots; the result from (ys, f) on the grid
+  TRY(hermite_plan(c, t.data(), (size_t)nt, xs.data(), xs.size(), &inner));
+  if ((long)inner.size() != nt) return B200RK_OK;   // cannot happen on an increasing grid; let the composed form decide
+  TRY(hermite_plan(c, X, m, t.data(), (size_t)nt, &outer));
+  std::vector<size_t> order(outer.size());
+  std::iota(order.begin(), order.end(), size_t(0));
+  auto need = [&](const HermiteOut& p) { return p.kind == 1 ? nt - 1 : (long)p.j + 1; };   // highest grid point a sample needs
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return need(outer[a]) < need(outer[b]); });
+  for (size_t o = 0; o < outer.size(); ++o) { b200rk_vec* v = nullptr; TRY(outs->add(c, n_global, &v)); }
+  *applied = true;
+
+  std::map<long, b200rk_vec*> dyv, ysv;   // the window
+  struct Window {
+    std::map<long, b200rk_vec*>&a, &b;
+    b200rk_vec* I[2] = {nullptr, nullptr};
+    ~Window() { for (auto& kv : a) vec_release(kv.second); for (auto& kv : b) vec_release(kv.second); for (auto* v : I) if (v) vec_release(v); }
+  } win{dyv, ysv};
+  TRY(vec_alloc(c, n_global, &win.I[0]));
+  TRY(vec_alloc(c, n_global, &win.I[1]));
+  const size_t n = win.I[0]->n_local;
+  auto eval = [&](long k) -> int {   // f(t[k]), once, in increasing k like the reference's loop (integrate.nim:397-398)
+    if (dyv.count(k)) return B200RK_OK;
+    b200rk_vec* v = nullptr;
+    TRY(vec_alloc(c, n_global, &v));
+    dyv[k] = v;
+    const int rc = f(t[k], v, user);
+    return rc == 0 ? B200RK_OK : fail(c, B200RK_ECALLBACK, "integrand callback returned " + std::to_string(rc));
+  };
+  size_t next_out = 0;
+  long avail = -1;   // ys[0..avail] computed
+  auto emit_ready = [&]() -> int {
+    for (; next_out < order.size(); ++next_out) {
+      const HermiteOut& p = outer[order[next_out]];
+      if (need(p) > avail) break;
+      b200rk_vec* dst = outs->v[order[next_out]];
+      if (p.kind == 1) { TRY(vec_copy_raw(c, dst, ysv.at(nt - 1))); continue; }
+      TRY(launch_hermite(c, ysv.at(p.j)->d, dyv.at(p.j)->d, ysv.at(p.j + 1)->d, dyv.at(p.j + 1)->d, p.h00, p.hA, p.h01, p.hB, dst->d, n));
+    }
+    return B200RK_OK;
+  };
+  TRY(eval(0));
+  int cur = 0;
+  TRY(launch_ewise(c, EW_SUB, dyv[0]->d, dyv[0]->d, 0.0, win.I[0]->d, n, B200RK_K_QUAD));   // the right kind of zero (integrate.nim:351)
+  long in_k = 0;   // next grid point whose ys is due
+  for (size_t j = 0; j < steps.size(); ++j) {
+    const SimpsonStep& st = steps[j];
+    const long lo_k = std::min({st.ia, st.ib, st.ic}), hi_k = std::max({st.ia, st.ib, st.ic});
+    for (long k = lo_k; k <= hi_k; ++k) TRY(eval(k));
+    const double* kp[3] = {dyv.at(st.ia)->d, dyv.at(st.ib)->d, dyv.at(st.ic)->d};
+    const double w[3] = {st.ca, st.cb, st.cc};
+    TRY(launch_stage(c, 3, win.I[cur]->d, kp, w, 1.0, false, win.I[1 - cur]->d, n));   // I_{j+1} = I_j + ((ya*ca + yb*cb) + yc*cc)
+    // ys at the grid points of knot interval j
+    for (; in_k < nt && inner[in_k].kind == 0 && inner[in_k].j == (int)j; ++in_k) {
+      const HermiteOut& p = inner[in_k];
+      b200rk_vec* v = nullptr;
+      TRY(vec_alloc(c, n_global, &v));
+      ysv[in_k] = v;
+      TRY(launch_hermite(c, win.I[cur]->d, dyv.at(knot_idx[j])->d, win.I[1 - cur]->d, dyv.at(knot_idx[j + 1])->d, p.h00, p.hA, p.h01, p.hB, v->d, n));
+      avail = in_k;
+      TRY(emit_ready());
+    }
+    cur = 1 - cur;
+    // drop what no later step, spline or sample can need: everything below the last grid point whose ys exists
+    for (auto* mp : {&dyv, &ysv})
+      for (auto it = mp->begin(); it != mp->end() && it->first < avail;) { vec_release(it->second); it = mp->erase(it); }
+  }
+  if (in_k == nt - 1 && inner[in_k].kind == 1) {   // the last grid point is the last knot: its ys is the integral itself
+    b200rk_vec* v = nullptr;
+    TRY(vec_alloc(c, n_global, &v));
+    ysv[in_k] = v;
+    TRY(vec_copy_raw(c, v, win.I[cur]));
+    avail = in_k; ++in_k;
+    TRY(emit_ready());
+  }
+  if (in_k != nt || next_out != order.size()) return fail(c, B200RK_EINVAL, "cumsimpson(f, X, dx): internal streaming plan mismatch");
+  return B200RK_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -443,8 +559,9 @@ int b200rk_cumtrapz_fn(b200rk_ctx* c, b200rk_fn_of_t f, void* user, size_t n_glo
 }
 
 // cumsimpson(f, X, ctx, dx) (integrate.nim:379-400): f on linspace(min X, max X, round((max-min)/dx) + 2), the
-// discrete rule on those values, then hermiteInterpolate(X, t, ys, dy) — composed exactly like the reference, so
-// all evaluations of f are alive at once (3 vectors per grid point): meant for moderate (max-min)/dx.
+// discrete rule on those values, then hermiteInterpolate(X, t, ys, dy). Up to 4096 grid points that fit in memory it is
+// composed exactly like the reference (all evaluations alive at once); beyond that the grid is streamed through a
+// window of a few vectors (cumsimpson_fn_streaming above) with the same results.
 int b200rk_cumsimpson_fn(b200rk_ctx* c, b200rk_fn_of_t f, void* user, size_t n_global, const double* X, size_t m, double dx,
                          b200rk_vec** out, size_t* n_out) {
   if (!c || !f || !X || !out || !n_out) return fail(c, B200RK_EINVAL, "null argument");
@@ -456,19 +573,33 @@ int b200rk_cumsimpson_fn(b200rk_ctx* c, b200rk_fn_of_t f, void* user, size_t n_g
     lo = std::min(lo, X[i]); hi = std::max(hi, X[i]);
   }
   const double count = std::round((hi - lo) / dx) + 2.0;                                           // toInt rounds half away from zero
+  if (count > 5e7) return fail(c, B200RK_EINVAL, "cumsimpson(f, X, dx): more than 5e7 grid points; choose a larger dx");
   size_t off = 0, len = 0;
   shard_range(n_global, c->rank, c->world, &off, &len);
   size_t free_b = 0, total_b = 0;
   CUDA_TRY(c, cudaMemGetInfo(&free_b, &total_b));
-  if (count > 5e7 || count * 3.0 * double(std::max<size_t>(len, 4)) * 8.0 > 0.9 * double(free_b))
-    return fail(c, B200RK_ENOMEM, "cumsimpson(f, X, dx): " + std::to_string((long long)count) + " grid points of " + std::to_string(len) +
-                                      " elements do not fit (3 vectors per point are alive at once, as in the reference); choose a larger dx");
+  const bool fits = count * 3.0 * double(std::max<size_t>(len, 4)) * 8.0 <= 0.25 * double(free_b) && count <= 4096;
   const long nt = (long)count;
   std::vector<double> t;                                                                           // linspace, utils.nim:498-507
   const double step = (hi - lo) / double(nt - 1);
   t.push_back(lo);
   for (long i = 1; i <= nt - 2; ++i) t.push_back(lo + step * double(i));
   t.push_back(hi);
+  // The composed form below keeps all evaluations alive like the reference (3 vectors per grid point). When that does
+  // not fit — or on request (knob "stream_simpson" = 1; 0 = never) — the grid is streamed through a window instead.
+  if (c->stream_simpson == 1 || (c->stream_simpson < 0 && !fits)) {
+    Outputs souts;
+    bool applied = false;
+    TRY(cumsimpson_fn_streaming(c, f, user, n_global, X, m, t, &souts, &applied));
+    if (applied) {
+      CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+      hand_over(souts, out, n_out);
+      return B200RK_OK;
+    }
+  }
+  if (count * 3.0 * double(std::max<size_t>(len, 4)) * 8.0 > 0.9 * double(free_b))
+    return fail(c, B200RK_ENOMEM, "cumsimpson(f, X, dx): " + std::to_string((long long)count) + " grid points of " + std::to_string(len) +
+                                      " elements do not fit (3 vectors per point are alive at once, as in the reference); choose a larger dx");
   Outputs dy;   // released when the call returns
   for (double x : t) {
     b200rk_vec* v = nullptr;

@@ -282,6 +282,7 @@ int b200rk_set(b200rk_ctx* c, const char* key, int64_t v) {
   else if (k == "fuse_stencil") c->fuse_stencil = v != 0;
   else if (k == "fuse_simpson") c->fuse_simpson = v != 0;
   else if (k == "finish_prefetch") c->finish_prefetch = v != 0;
+  else if (k == "stream_simpson") c->stream_simpson = v < 0 ? -1 : (v != 0);
   else if (k == "l2_hints") c->l2_hints = v < 0 ? -1 : (v != 0);
   else if (k == "fused_ctas_per_sm") { if (v < 0) return fail(c, B200RK_EINVAL, "fused_ctas_per_sm must be >= 0"); c->fused_ctas_per_sm = (int)v; }
   else if (k == "pool_budget_mb") {
@@ -308,6 +309,7 @@ int b200rk_get(const b200rk_ctx* c, const char* key, int64_t* v) {
   else if (k == "fuse_stencil") *v = c->fuse_stencil;
   else if (k == "fuse_simpson") *v = c->fuse_simpson;
   else if (k == "finish_prefetch") *v = c->finish_prefetch;
+  else if (k == "stream_simpson") *v = c->stream_simpson;
   else if (k == "l2_hints") *v = c->l2_hints;
   else if (k == "fused_ctas_per_sm") *v = c->fused_ctas_per_sm;
   else if (k == "profile") *v = c->profile;

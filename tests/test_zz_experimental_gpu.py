@@ -86,3 +86,48 @@ def test_prefetching_finish_kernel_equals_default(nn, method, stages, vec_width)
         ctx.set("finish_prefetch", 0)
         ctx.set("fuse_pointwise", 1)
         ctx.set("vec_width", 4)
+
+
+@pytest.mark.parametrize("dx", [0.1, 0.013, 0.5])
+def test_streaming_cumsimpson_fn_equals_composed_form(nn, dx):
+    """knob stream_simpson=1: cumsimpson(f, X, dx) walks the grid through a window of a few vectors instead of keeping
+    every evaluation alive — same results bit for bit, same callbacks in the same order. (Without the knob it is used
+    only where the composed form would not fit or the grid has more than 4096 points.)"""
+    import math
+
+    import oracle as O
+    ctx = nn.default_context()
+    n = 4099
+    a = np.linspace(1.0, 3.0, n)
+    ga = nn.newVector(a)
+    try:
+        for X in (O.linspace(0.0, 1.5 * math.pi, 17), O.linspace(0.0, 1.5 * math.pi, 17)[[3, 0, 16, 7, 7, 1]], np.array([1.0, 2.0, 1.5])):
+            ref, evals = O.cumsimpson_fn(lambda x: a * math.cos(x) + 0.1 * x, X, dx=dx, n=n)
+            for mode in (0, 1):
+                ctx.set("stream_simpson", mode)
+                calls = []
+
+                def f(x, c):
+                    calls.append(x)
+                    return math.cos(x) * ga + 0.1 * x
+
+                got = np.array([v.to_numpy() for v in nn.cumsimpson(f, X, dx=dx, like=ga)])
+                assert got.shape == ref.shape and np.array_equal(got.view(np.uint64), ref.view(np.uint64)), (dx, mode)
+                assert calls == sorted(calls) and len(calls) == evals
+    finally:
+        ctx.set("stream_simpson", -1)
+
+
+def test_cumsimpson_fn_streams_a_fine_grid_by_itself(nn):
+    """23,564 grid points (dx = 2e-4): beyond the composed form's limit, so the library streams on its own."""
+    import math
+
+    import oracle as O
+    n = 64
+    a = np.linspace(1.0, 3.0, n)
+    ga = nn.newVector(a)
+    X = O.linspace(0.0, 1.5 * math.pi, 17)
+    got = np.array([v.to_numpy() for v in nn.cumsimpson(lambda x, c: math.cos(x) * ga, X, dx=2e-4, like=ga)])
+    ref, _ = O.cumsimpson_fn(lambda x: a * math.cos(x), X, dx=2e-4, n=n)
+    assert np.array_equal(got.view(np.uint64), ref.view(np.uint64))
+    assert np.max(np.abs(got - np.outer(np.sin(X), a))) < 1e-10

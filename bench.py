@@ -221,6 +221,18 @@ def run_ours(args):
     fusable = not args.no_fuse and (rhs_kind == "diag" or world == 1)
     pipe = timed_steps(0)                       # stage / RHS / finish pipeline (what any user closure gets)
     head = timed_steps(1) if fusable else pipe  # headline: the library's default path for this workload
+    # experimental (knob fuse_stencil_attempt, off by default): the whole Lorenz-96 attempt in ONE kernel — reported as
+    # an extra object next to the default path, on request
+    l96_attempt = None
+    if args.l96_attempt and rhs_kind != "diag" and world == 1 and fusable:
+        try:
+            ctx.set("fuse_stencil_attempt", 1)
+            l96_attempt = timed_steps(1)
+        except Exception as e:  # noqa: BLE001 — the headline must survive an experimental path
+            l96_attempt = {"error": str(e)[:400]}
+        finally:
+            ctx.set("fuse_stencil_attempt", 0)
+            ctx.set("profile", 0)
     ctx.set("fuse_pointwise", 1 if fusable else 0)
     ctx.set("fuse_stencil", 1 if fusable else 0)
     ms, ms_max, prof = head["ms"], head["ms_max"], head["prof"]
@@ -363,6 +375,18 @@ def run_ours(args):
                         "avg_launch_us": 1e3 * fu["ms"] / max(1, fu["launches"]), "algorithmic_bytes_per_launch": fu["bytes"] / max(1, fu["launches"]),
                         "instrumented_ms_per_step": prof["instrumented_ms"] / args.steps,
                         "kernel_time_share_of_step": fu["ms"] / prof["instrumented_ms"] if prof["instrumented_ms"] > 0 else None}
+        l96_obj = None
+        if l96_attempt is not None:
+            if "error" in l96_attempt:
+                l96_obj = l96_attempt
+            else:
+                fu = l96_attempt["prof"]["fused"]
+                l96_obj = {"note": "experimental knob fuse_stencil_attempt=1: the whole attempt (all stages, Lorenz-96 stencil, yNew, error norm) in one "
+                                   "kernel over overlapped tiles (csrc/stencil_attempt.cuh); algorithmic bytes = 4 vector passes per attempt",
+                           "value": args.steps * world / (l96_attempt["ms_max"] * 1e-3), "ms_per_step": l96_attempt["ms_max"] / args.steps,
+                           "attempts": l96_attempt["attempts"], "rejected": l96_attempt["rejected"], "gpu_launches": l96_attempt["launches"],
+                           "t_reached": l96_attempt["t"], "hbm_gbs": gbs(fu), "frac_of_peak": gbs(fu) / peak, "launches": fu["launches"],
+                           "avg_launch_us": 1e3 * fu["ms"] / max(1, fu["launches"])}
         line = {
             "metric": "rk_steps_per_sec", "value": args.steps * world / (ms_max * 1e-3), "unit": "RK steps/s (x 2^%d-element shard, summed over GPUs)" % lg,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
@@ -381,6 +405,7 @@ def run_ours(args):
             "roofline": roofline,
             "pipeline": pipeline_obj,
             "jit_rhs": jit_obj,
+            "l96_attempt": l96_obj,
             "trajectory_consumers": quad_obj,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_steps * world / (e2e_ms_max * 1e-3), "unit": "RK steps/s (solveODE on host buffers: H2D y0+lambda, solve, D2H states)",
@@ -715,6 +740,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-quad", action="store_true", help="skip the trajectory-consumer bandwidth leg")
     ap.add_argument("--no-jit", action="store_true", help="skip the run-time compiled right-hand-side leg")
+    ap.add_argument("--l96-attempt", action="store_true", help="Lorenz-96 workloads on 1 GPU: also time the experimental one-kernel attempt (knob fuse_stencil_attempt)")
     ap.add_argument("--no-fuse", action="store_true", help="headline = the stage/RHS/finish pipeline even for element-local built-in RHS")
     ap.add_argument("--cpu-budget-s", type=float, default=120.0)
     ap.add_argument("--sweep", action="store_true")

@@ -97,8 +97,8 @@ B200RK_API int b200rk_world(const b200rk_ctx* ctx);
  * kernels), "fuse_pointwise" (1 = element-local built-in right-hand sides run a whole attempt as one
  * kernel; 0 = always the stage / RHS / finish pipeline), "fuse_stencil" (built-in Lorenz-96: stage accumulate + stencil
  * in one kernel), "device_loop" (-1 auto | 0 | 1: the whole adaptive loop in one persistent kernel), "spin_readback",
- * "l2_hints" (-1 auto | 0 | 1: producer/consumer hand-off through the L2), "fuse_simpson" / "finish_prefetch" (experimental, default 0:
- * cumsimpson as one kernel / software-pipelined finish kernel), "profile" (0|1), "pool_budget_mb" (bytes of freed vectors the context keeps for reuse;
+ * "l2_hints" (-1 auto | 0 | 1: producer/consumer hand-off through the L2), "fuse_simpson" / "finish_prefetch" / "fuse_stencil_attempt" (experimental, default 0:
+ * cumsimpson as one kernel / software-pipelined finish kernel / a whole attempt of the built-in Lorenz-96 right-hand side in one kernel), "profile" (0|1), "pool_budget_mb" (bytes of freed vectors the context keeps for reuse;
  * 0 = release everything now). Read-only: "p2p", "sm_count". */
 B200RK_API int b200rk_set(b200rk_ctx* ctx, const char* key, int64_t value);
 B200RK_API int b200rk_get(const b200rk_ctx* ctx, const char* key, int64_t* value);

@@ -2,6 +2,7 @@
 // the fused paths (whole attempt for element-local RHS, stage + Lorenz-96 stencil) and the adaptive retry loop
 // of commonAdaptiveMethodCode (ode.nim:57-76).
 #include "internal.hpp"
+#include "stencil_attempt.cuh"
 
 int builtin_rhs_fn(double /*t*/, const b200rk_vec* y, b200rk_vec* dydt, void* user) {
   BuiltinRhs* r = static_cast<BuiltinRhs*>(user);
@@ -311,6 +312,31 @@ static int launch_fused_rk4(b200rk_ctx* c, const PwSpec& pw, bool negate, double
   return B200RK_OK;
 }
 
+// Whole attempt of an FSAL pair with the built-in Lorenz-96 right-hand side in one kernel (stencil_attempt.cuh:
+// overlapped tiles, stage inputs through shared memory). Experimental, knob "fuse_stencil_attempt".
+template <int PAT>
+static int launch_l96_attempt(b200rk_ctx* c, const MethodDef& md, double F, bool negate, double dt, const b200rk_options& o,
+                              const b200rk_vec* y, const b200rk_vec* fsal, b200rk_vec* y_new, b200rk_vec* fsal_new) {
+  constexpr int S = Pattern<PAT>::S, J = 2;
+  constexpr int OUT = 2 * J * kThreads - StencilTile<S>::HL - StencilTile<S>::HR;
+  L96AttemptArgs<S> a;
+  std::memset(&a, 0, sizeof(a));
+  a.f.y = y->d; a.f.k1 = fsal->d;
+  for (int s = 2; s <= S; ++s) row_mask(c, md.a[s], a.f.a[s - 2], S - 1);
+  row_mask(c, md.b, a.f.b, S);
+  row_mask(c, md.bhat, a.f.bh, S);
+  a.f.dt = dt; a.f.cb = dt; a.f.cbh = dt; a.f.absTol = o.absTol; a.f.relTol = o.relTol;
+  a.f.ynew = y_new->d; a.f.ks_out = fsal_new->d; a.f.n = y->n_local;
+  a.F = F; a.sgn = negate ? -1.0 : 1.0;
+  const unsigned grid = (unsigned)((a.f.n + OUT - 1) / OUT);
+  TRY(ensure_partials(c, grid));
+  a.f.rs = reduce_scratch(c);
+  ProfScope ps(c, B200RK_K_FUSED, 8.0 * double(a.f.n) * 4);  // y, k1 read; yNew, k_S written
+  l96_attempt_kernel<PAT, J, kThreads><<<grid, kThreads, 0, c->stream>>>(a);
+  CUDA_TRY(c, cudaGetLastError());
+  return B200RK_OK;
+}
+
 // One IntegratorProc call. y, fsal read-only; y_new, fsal_new written.
 int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, double t, const b200rk_vec* y,
                    const b200rk_vec* fsal, double dt_in, const b200rk_options& o, b200rk_vec* y_new,
@@ -327,7 +353,13 @@ int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, double t, co
   if (fused && !md.rk4_final) { fused_pat = fused_pattern_of(c, md); fused = fused_pat >= 0; }
   const bool stencil_fused = !fused && c->fuse_stencil && c->world == 1 && rhs.f == &builtin_rhs_fn &&
                              static_cast<const BuiltinRhs*>(rhs.user)->kind == B200RK_RHS_LORENZ96 && y->n_global >= 4;
+  // experimental: the whole attempt of the stencil right-hand side in one kernel (overlapped tiles read y and FSAL far
+  // beyond a CTA's own outputs, so the outputs must not alias the inputs)
+  bool l96_attempt = stencil_fused && c->fuse_stencil_attempt && method_fusable(md) && !md.rk4_final && fsal && fsal_new &&
+                     y_new->d != y->d && y_new->d != fsal->d && fsal_new->d != y->d && fsal_new->d != fsal->d;
+  if (l96_attempt) { fused_pat = fused_pattern_of(c, md); l96_attempt = fused_pat >= 0; }
   if (fused) TRY(check_pw_sizes(c, pw, y));
+  fused = fused || l96_attempt;
   if (md.k1_from_fsal) {
     if (!fsal) return fail(c, B200RK_EINVAL, std::string(md.name) + ": FSAL vector required");
     TRY(check_same(c, y, fsal));
@@ -353,6 +385,16 @@ int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, double t, co
       // still counted so rhs_evals matches the unfused path)
       if (rhs.evals) *rhs.evals += md.rk4_final ? 4 : (S - 1);
       if (md.rk4_final) { TRY(launch_fused_rk4(c, pw, rhs.negate_time, t, dt, y, y_new)); break; }
+      if (l96_attempt) {
+        const double F = static_cast<const BuiltinRhs*>(rhs.user)->scalar;
+        switch (fused_pat) {
+          case PAT_DOPRI54: TRY(launch_l96_attempt<PAT_DOPRI54>(c, md, F, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new)); break;
+          case PAT_DOPRI54_STRICT: TRY(launch_l96_attempt<PAT_DOPRI54_STRICT>(c, md, F, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new)); break;
+          case PAT_TSIT54: TRY(launch_l96_attempt<PAT_TSIT54>(c, md, F, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new)); break;
+          case PAT_VERN65: TRY(launch_l96_attempt<PAT_VERN65>(c, md, F, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new)); break;
+          default: TRY(launch_l96_attempt<PAT_VERN65_STRICT>(c, md, F, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new)); break;
+        }
+      } else
       switch (fused_pat) {
         case PAT_DOPRI54: TRY(launch_fused_pair<PAT_DOPRI54>(c, md, pw, rhs.negate_time, t, dt, o, y, fsal, y_new, fsal_new)); break;
         case PAT_DOPRI54_STRICT: TRY(launch_fused_pair<PAT_DOPRI54_STRICT>(c, md, pw, rhs.negate_time, t, dt, o, y, fsal, y_new, fsal_new)); break;

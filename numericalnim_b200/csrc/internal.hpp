@@ -75,6 +75,7 @@ struct b200rk_ctx {
   int fused_ctas_per_sm = 4;   // fused pointwise attempt kernel: persistent grid of 4 CTAs per SM (~100 registers: 2 resident, 2 waves; measured best, profiles/r01_tune_*)
   bool fuse_pointwise = true;  // element-local built-in RHS: whole attempt in one kernel
   bool fuse_stencil = true;    // built-in Lorenz-96 (single GPU): stage accumulate + stencil RHS in one kernel
+  bool fuse_stencil_attempt = false;  // built-in Lorenz-96: a whole attempt in one kernel, overlapped tiles (experimental: verified by host emulation, not yet run on the GPU)
   bool finish_prefetch = false; // software-pipelined finish kernel (experimental: verified by host emulation, not yet measured on the GPU)
   int stream_simpson = -1;     // cumsimpson(f, X, dx): -1 = stream the grid only when the composed form would not fit, 0 never, 1 always
   bool fuse_simpson = false;   // cumsimpson as one kernel (experimental: verified by host emulation, not yet measured on the GPU)

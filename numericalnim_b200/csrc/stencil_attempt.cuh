@@ -1,0 +1,154 @@
+// stencil_attempt.cuh — a whole adaptive attempt of an FSAL pair for the built-in Lorenz-96 right-hand side in ONE
+// kernel (single GPU, cyclic). EXPERIMENTAL: knob "fuse_stencil_attempt", off by default until it has been run and
+// measured on the GPU (bit-identical to the stage_l96_kernel / finish_kernel pipeline under host emulation).
+//
+// The element-local fused attempt (kernels.cuh: fused_attempt_kernel) keeps k_1..k_S of an element in registers because
+// nothing crosses elements. Lorenz-96 reads y[i-2], y[i-1], y[i+1] (ode.nim's ODEProc is the caller's; this one is
+// b200rk's built-in), so stage s at element i needs the stage input at three neighbours — which needs their k's, and so
+// on down the stages. Overlapped tiling removes the dependence between CTAs: a CTA loads a tile of TW elements of y and
+// k1 (FSAL) that overlaps its neighbours' tiles by HL elements on the left and HR on the right, and evaluates every
+// stage on the whole tile. Each right-hand-side evaluation makes 2 more elements on the left edge and 1 more on the
+// right edge depend on data outside the tile; after the S-1 evaluations of an attempt positions [2(S-1), TW-(S-1)) are
+// still exact. Only positions [HL, TW-HR) are stored (HL >= 2(S-1), HR >= S-1, both multiples of 4 so every tile stays
+// 32-byte aligned): 2 % of the arithmetic is redundant, and HBM traffic per attempt drops from 53 vector passes
+// (Tsit54: 41 stage/finish + 12 stencil) to 4 — read y and k1, write yNew and k_S.
+//
+// Within the CTA the stage input travels through shared memory (two buffers, so one barrier per stage): a thread
+// computes the stage input at its own E = 2*J positions from registers, publishes it, and after the barrier applies the
+// stencil to its positions. Per element the operations are exactly those of stage_elem / stage_l96_kernel /
+// finish_elem in the same order (__dmul_rn / __dadd_rn / __ddiv_rn), so yNew, k_S and every r*r term are bit-identical
+// to the unfused pipeline; the sum of the r*r terms is taken in a different order (tile by tile), like every other
+// grid geometry of the reducing kernels.
+#pragma once
+#include "kernels.cuh"
+
+namespace b200rk {
+
+template <int S>
+struct StencilTile {
+  static constexpr int HL = ((2 * (S - 1) + 3) / 4) * 4;   // left overlap: 2 per right-hand-side evaluation, rounded to 32 bytes
+  static constexpr int HR = (((S - 1) + 3) / 4) * 4;       // right overlap: 1 per evaluation
+};
+
+template <int S>
+struct L96AttemptArgs {
+  FusedArgs<S> f;     // y, k1, a/b/bh rows, dt, cb, cbh, tolerances, ynew, ks_out, n, rs (the parameter fields are unused)
+  double F, sgn;      // forcing; -1 for the backward pass g = -f(-t, y) (ode.nim:545), else +1
+};
+
+// stage s (compile-time) of every element the thread owns; recursion keeps the row masks template constants
+template <int PAT, int s, int E, int TW>
+struct L96Stages {
+  template <int S>
+  __device__ __forceinline__ static void run(const double (&y)[E], double (&k)[E][S], double (&in)[E], const int (&pos)[E],
+                                             double (*buf)[TW + 4], const L96AttemptArgs<S>& a) {
+    if constexpr (s > 2) L96Stages<PAT, s - 1, E, TW>::run(y, k, in, pos, buf, a);
+    double* sh = buf[s & 1] + 2;   // sh[-2], sh[-1] and sh[TW] are zero pads (their consumers are outside the stored range)
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const double acc = const_wsum<S, Pattern<PAT>::a(s - 2)>(k[e], a.f.a[s - 2]);
+      in[e] = __dadd_rn(y[e], __dmul_rn(acc, a.f.dt));                                   // stage_elem
+      sh[pos[e]] = in[e];
+    }
+    __syncthreads();   // the other buffer was last read before the previous stage's barrier: one barrier per stage
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int p = pos[e];
+      const double v = __dadd_rn(__dadd_rn(__dmul_rn(__dadd_rn(sh[p + 1], -sh[p - 2]), sh[p - 1]), -in[e]), a.F);  // lorenz96
+      k[e][s - 1] = __dmul_rn(v, a.sgn);
+    }
+  }
+};
+
+template <int PAT, int J, int THREADS>
+__global__ void __launch_bounds__(THREADS) l96_attempt_kernel(const L96AttemptArgs<Pattern<PAT>::S> a) {
+  constexpr int S = Pattern<PAT>::S;
+  constexpr int E = 2 * J, TW = E * THREADS;
+  constexpr int HL = StencilTile<S>::HL, HR = StencilTile<S>::HR, OUT = TW - HL - HR;
+  __shared__ double buf[2][TW + 4];
+  const size_t n = a.f.n;
+  const size_t tile0 = (size_t)blockIdx.x * OUT;          // first stored element of this tile
+  if (threadIdx.x < 3) {
+    const int q = threadIdx.x < 2 ? (int)threadIdx.x : TW + 2;
+    buf[0][q] = 0.0; buf[1][q] = 0.0;
+  }
+  double y[E], k[E][S], in[E];
+  int pos[E];
+  const bool interior = tile0 >= (size_t)HL && tile0 - HL + TW <= n;
+  const size_t wrap = n - (size_t)HL % n;                 // (tile0 + p + wrap) % n == tile0 - HL + p (mod n)
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int p = 2 * ((int)threadIdx.x + j * THREADS);
+    pos[2 * j] = p; pos[2 * j + 1] = p + 1;
+    if (interior) {
+      const size_t g = tile0 - HL + p;
+      const Pk<2> yv = ld_stream<2>(a.f.y + g), kv = ld_stream<2>(a.f.k1 + g);
+      y[2 * j] = yv.v[0]; y[2 * j + 1] = yv.v[1];
+      k[2 * j][0] = kv.v[0]; k[2 * j + 1][0] = kv.v[1];
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const size_t g = (tile0 + (size_t)(p + h) + wrap) % n;
+        y[2 * j + h] = a.f.y[g];
+        k[2 * j + h][0] = a.f.k1[g];
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e)
+#pragma unroll
+    for (int j = 1; j < S; ++j) k[e][j] = 0.0;
+  L96Stages<PAT, S, E, TW>::run(y, k, in, pos, buf, a);
+
+  double acc = 0.0;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int p = pos[2 * j];
+    const size_t g = tile0 + (size_t)(p - HL);            // p and HL even: a pair is stored whole or not at all (up to n)
+    const bool stored = p >= HL && p < HL + OUT && g < n;
+    double yn[2], ks[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int e = 2 * j + h;
+      ks[h] = k[e][S - 1];
+      if (Pattern<PAT>::last) yn[h] = in[e];
+      else yn[h] = __dadd_rn(y[e], __dmul_rn(const_wsum<S, Pattern<PAT>::b()>(k[e], a.f.b), a.f.cb));
+      const double lo = __dmul_rn(const_wsum<S, Pattern<PAT>::bh()>(k[e], a.f.bh), a.f.cbh);
+      double err;
+      if (Pattern<PAT>::direct) err = lo;
+      else err = __dadd_rn(yn[h], -__dadd_rn(y[e], lo));
+      const double tol = __dadd_rn(a.f.absTol, __dmul_rn(fabs(yn[h]), a.f.relTol));
+      const double r = __ddiv_rn(err, tol);
+      if (stored && g + h < n) acc = __dadd_rn(acc, __dmul_rn(r, r));
+    }
+    if (stored) {
+      if (g + 1 < n) {
+        Pk<2> o;
+        o.v[0] = yn[0]; o.v[1] = yn[1];
+        st_stream<2>(a.f.ynew + g, o);
+        o.v[0] = ks[0]; o.v[1] = ks[1];
+        st_stream<2>(a.f.ks_out + g, o);
+      } else {
+        a.f.ynew[g] = yn[0];
+        a.f.ks_out[g] = ks[0];
+      }
+    }
+  }
+#ifdef B200RK_EMULATE_SERIAL_SUM
+  // host emulation (threads of a CTA run concurrently, CTAs one after another): thread 0 adds the CTA's terms in thread
+  // order to the running sum and the last CTA publishes it the way grid_sum_finish's last CTA does
+  __shared__ double red[THREADS];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = (blockIdx.x == 0) ? 0.0 : *a.f.rs.result;
+    for (int i = 0; i < THREADS; ++i) t = __dadd_rn(t, red[i]);
+    *a.f.rs.result = t;
+    if (blockIdx.x == gridDim.x - 1 && a.f.rs.result_host) { *a.f.rs.result_host = t; *a.f.rs.seq_host = a.f.rs.seq; }
+  }
+#else
+  grid_sum_finish<THREADS>(acc, a.f.rs);
+#endif
+}
+
+}  // namespace b200rk

@@ -95,6 +95,7 @@ inline double user_rhs(double t, double y, const double* p, const double* c) { r
 
 #include "kernels.cuh"
 #include "finish_pf.cuh"
+#include "stencil_attempt.cuh"
 #include "quad_kernels.cuh"
 #include "methods.h"
 

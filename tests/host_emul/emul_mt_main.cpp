@@ -162,6 +162,44 @@ static void test_device_loop(const char* name, const rk_oracle::Pair& p, rk_orac
   report(std::string("fused_run_kernel (device-resident loop, one-block grid) ") + name, ok);
 }
 
+// ---- a whole Lorenz-96 attempt in one kernel (stencil_attempt.cuh: overlapped tiles, two shared-memory buffers, one
+// barrier per stage) vs the oracle's IntegratorProc: yNew and the new FSAL bit for bit, error norm through the real
+// two-stage reduction ---------------------------------------------------------------------------------------------------
+template <int PAT>
+static void test_l96_attempt(const char* name, const rk_oracle::Pair& p, rk_oracle::IntegratorProc<Vector> step) {
+  constexpr int S = Pattern<PAT>::S, J = 2;
+  constexpr int OUT = 2 * J * T - StencilTile<S>::HL - StencilTile<S>::HR;
+  bool ok = true;
+  for (size_t n : {size_t(4), size_t(5), size_t(7), size_t(OUT - 1), size_t(OUT), size_t(OUT + 1), size_t(2 * OUT + 3), size_t(1000)})
+    for (double sgn : {1.0, -1.0}) {
+      const double F = 8.0, dt = 0.004;
+      const auto y = rvec(n, 7.0, 9.0);
+      rk_oracle::OdeProc<Vector> f = rk_oracle::rhs_lorenz96(F);
+      if (sgn < 0) f = [F](double t, const Vector& v, rk_oracle::Context<Vector>* c) { return -rk_oracle::rhs_lorenz96(F)(-t, v, c); };  // ode.nim:545
+      const Vector fsal = f(0.0, Vector(y), nullptr);
+      const rk_oracle::Options o = rk_oracle::new_options(1e-4, 1e-3, 1e-3, 1.0, 1e-8);
+      rk_oracle::Context<Vector> ctx;
+      const auto ref = step(f, 0.0, Vector(y), fsal, dt, o, &ctx);
+      std::vector<double> ynew(n, -5.0), ks(n, -5.0);
+      Scratch sc;
+      L96AttemptArgs<S> a;
+      std::memset(&a, 0, sizeof(a));
+      a.f.y = y.data(); a.f.k1 = fsal.components.data();
+      for (int s = 2; s <= S; ++s)
+        for (int j = 0; j < s - 1; ++j) a.f.a[s - 2][j] = p.a[s][j];
+      for (int j = 0; j < p.n_b; ++j) a.f.b[j] = p.b[j];
+      for (int j = 0; j < p.n_bhat; ++j) a.f.bh[j] = p.bhat[j];
+      a.f.dt = dt; a.f.cb = dt; a.f.cbh = dt; a.f.absTol = o.absTol; a.f.relTol = o.relTol;
+      a.f.ynew = ynew.data(); a.f.ks_out = ks.data(); a.f.n = n; a.f.rs = sc.rs();
+      a.F = F; a.sgn = sgn;
+      const unsigned grid = (unsigned)((n + OUT - 1) / OUT);
+      emul_launch(grid, T, [&] { l96_attempt_kernel<PAT, J, T>(a); });
+      const double err = std::sqrt(1.0 / double(n) * sc.result);
+      ok = ok && ref.dt == dt && same_bits(ynew, ref.y_new.components) && same_bits(ks, ref.fsal.components) && close_rel(err, ref.error, 1e-13);
+    }
+  report(std::string("l96_attempt_kernel (whole attempt, overlapped tiles) ") + name, ok);
+}
+
 // ---- positive control for the race detector: a tile kernel with its barrier removed ---------------------------------
 template <int THREADS>
 __global__ void racy_tile_kernel(const double* in, double* out) {
@@ -183,6 +221,9 @@ int main(int argc, char** argv) {
   test_stage_l96<1>();
   test_stage_l96<3>();
   test_stage_l96<6>();
+  test_l96_attempt<PAT_DOPRI54>("dopri54", rk_oracle::dopri54_pair(), &rk_oracle::dopri54_step<Vector>);
+  test_l96_attempt<PAT_TSIT54>("tsit54", rk_oracle::tsit54_pair(), &rk_oracle::tsit54_step<Vector>);
+  test_l96_attempt<PAT_VERN65>("vern65", rk_oracle::vern65_pair(), &rk_oracle::vern65_step<Vector>);
   test_device_loop<PAT_DOPRI54, PW_DIAG, 2>("dopri54 diag W=2", rk_oracle::dopri54_pair(), &rk_oracle::dopri54_step<Vector>);
   test_device_loop<PAT_TSIT54, PW_DIAG, 4>("tsit54 diag W=4", rk_oracle::tsit54_pair(), &rk_oracle::tsit54_step<Vector>);
   test_device_loop<PAT_VERN65, PW_DIAG, 2>("vern65 diag W=2", rk_oracle::vern65_pair(), &rk_oracle::vern65_step<Vector>);

@@ -65,7 +65,7 @@ def test_interacting_kernels_under_threaded_emulation(tmp_path):
     the oracle's ODESolver) — plus all the cases above once more with the REAL reduction instead of a running sum."""
     rc, cases, out = _run(_build(str(tmp_path / "emul_mt"), ["-O1", "-ffp-contract=off"], "emul_mt_main.cpp"))
     assert rc == 0 and len(cases) >= 8 and all(v == "1" for v in cases.values()), out
-    for family in ("neq_count_kernel", "stage_l96_kernel", "fused_run_kernel", "source rhs"):
+    for family in ("neq_count_kernel", "stage_l96_kernel", "l96_attempt_kernel", "fused_run_kernel", "source rhs"):
         assert any(family in k for k in cases), family
     rc, cases, out = _run(_build(str(tmp_path / "emul_main_mt"), ["-O1", "-ffp-contract=off", "-DEMUL_MT"]))
     assert rc == 0 and len(cases) >= 30 and all(v == "1" for v in cases.values()), out

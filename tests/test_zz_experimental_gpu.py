@@ -131,3 +131,78 @@ def test_cumsimpson_fn_streams_a_fine_grid_by_itself(nn):
     ref, _ = O.cumsimpson_fn(lambda x: a * math.cos(x), X, dx=2e-4, n=n)
     assert np.array_equal(got.view(np.uint64), ref.view(np.uint64))
     assert np.max(np.abs(got - np.outer(np.sin(X), a))) < 1e-10
+
+
+# ---- knob fuse_stencil_attempt: a whole attempt of the built-in Lorenz-96 right-hand side in one kernel ---------------
+@pytest.mark.parametrize("method,stages", [("dopri54", 7), ("tsit54", 7), ("vern65", 9)])
+def test_l96_attempt_kernel_bitwise_equals_pipeline(nn, method, stages):
+    """l96_attempt_kernel (stencil_attempt.cuh: overlapped tiles, stage inputs through shared memory): yNew and the new
+    FSAL carry the same bits as the stage_l96_kernel / finish_kernel pipeline and as the oracle, at sizes around the
+    tile seams (1004 / 1000 stored elements per 1024-element tile) and below one tile (the tile wraps the cyclic domain
+    several times), forward and backward in time, with and without the zero weights; one launch instead of S."""
+    import oracle as O
+    ctx = nn.default_context()
+    rng = np.random.default_rng(17)
+    out_per_tile = 1024 - (12 + 8 if stages == 7 else 16 + 8)
+    sizes = [4, 5, 7, 19, 21, out_per_tile - 1, out_per_tile, out_per_tile + 1, 1023, 1024, 1025, 2 * out_per_tile - 1, 2 * out_per_tile,
+             2 * out_per_tile + 2, 3 * out_per_tile + 13, 8192 + 5]
+    opts = dict(absTol=1e-2, relTol=1e-2, dtMax=1.0, dtMin=1e-8, dt=0.005)
+    o = nn.newODEoptions(**opts)
+    rhs = nn.rhsLorenz96(8.0)
+    try:
+        for strict in (0, 1):
+            ctx.set("strict_zeros", strict)
+            for n in (sizes if not strict else sizes[5:9]):
+                y = 8.0 + rng.uniform(-1.0, 1.0, n)
+                fs = O.rhs_eval(O.rhs_lorenz96(8.0), 0.0, y)
+                gy, gf = nn.newVector(y), nn.newVector(fs)
+                res = {}
+                for fuse in (1, 0):
+                    ctx.set("fuse_stencil_attempt", fuse)
+                    l0 = ctx.stats()["launches"]
+                    yn, fn, dt_used, err = nn.integratorStep(method, rhs, 0.0, gy, gf, 0.005, o)
+                    res[fuse] = (yn.to_numpy(), fn.to_numpy(), dt_used, err, ctx.stats()["launches"] - l0)
+                assert np.array_equal(res[1][0].view(np.uint64), res[0][0].view(np.uint64)), (method, n, "yNew")
+                assert np.array_equal(res[1][1].view(np.uint64), res[0][1].view(np.uint64)), (method, n, "FSAL")
+                assert res[1][2] == res[0][2] and abs(res[1][3] - res[0][3]) <= 1e-13 * res[0][3]   # same terms, another order of summation
+                assert res[1][4] == 1 and res[0][4] == stages
+                if not strict:
+                    yn_ref, fn_ref, _, err_ref, st = O.step_vector(method, O.rhs_lorenz96(8.0), 0.0, y, fs, 0.005, O.new_options(**opts))
+                    assert st.rejected == 0
+                    assert np.array_equal(res[1][0].view(np.uint64), yn_ref.view(np.uint64)), (method, n, "yNew vs oracle")
+                    assert np.array_equal(res[1][1].view(np.uint64), fn_ref.view(np.uint64)), (method, n, "FSAL vs oracle")
+                    assert abs(res[1][3] - err_ref) <= 1e-12 * err_ref
+    finally:
+        ctx.set("strict_zeros", 0)
+        ctx.set("fuse_stencil_attempt", 0)
+
+
+@pytest.mark.parametrize("method", ["tsit54", "vern65"])
+def test_l96_attempt_solve_matches_pipeline_and_oracle(nn, method):
+    """solveODE over a tspan on both sides of tStart with dense output, tolerances that make the controller reject:
+    same accepted / rejected counts as the pipeline and the oracle, states within 1e-9 of the state's scale
+    (the error norms differ in the last bits only, so the step sizes do too, and the chaotic system amplifies that: the
+    default pipeline sits at the same 5e-11 from the oracle)."""
+    import oracle as O
+    ctx = nn.default_context()
+    n = 2500
+    y0 = 8.0 + np.random.default_rng(3).uniform(-4.0, 4.0, n)   # rough state: the controller overshoots and rejects
+    ts = nn.linspace(-0.1, 0.3, 5)
+    opts = dict(absTol=1e-5, relTol=1e-5, dtMax=1.0, dtMin=1e-4, tStart=0.0)
+    res = {}
+    try:
+        for fuse in (1, 0):
+            ctx.set("fuse_stencil_attempt", fuse)
+            l0 = ctx.stats()["launches"]
+            t, ys = nn.solveODE(nn.rhsLorenz96(8.0), nn.newVector(y0), ts, nn.newODEoptions(**opts), integrator=method)
+            res[fuse] = (list(t), np.array([v.to_numpy() for v in ys]), dict(nn.ode.last_stats), ctx.stats()["launches"] - l0)
+        ref = O.solve_vector(method, O.rhs_lorenz96(8.0), y0, ts, O.new_options(**opts))
+        for fuse in (1, 0):
+            assert res[fuse][0] == list(ref.t)
+            assert res[fuse][2]["steps"] == ref.stats.steps and res[fuse][2]["rejected"] == ref.stats.rejected, (fuse, res[fuse][2])
+            assert np.max(np.abs(res[fuse][1] - ref.y)) <= 1e-9 * np.max(np.abs(ref.y)), fuse
+        assert ref.stats.rejected > 0
+        assert np.max(np.abs(res[1][1] - res[0][1])) <= 1e-9 * np.max(np.abs(res[0][1]))
+        assert res[1][3] < res[0][3] / 3
+    finally:
+        ctx.set("fuse_stencil_attempt", 0)

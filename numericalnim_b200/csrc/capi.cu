@@ -7,6 +7,7 @@ extern "C" {
 // ---- options / dispatch -----------------------------------------------------------------------------
 int b200rk_options_new(b200rk_options* out, double dt, double absTol, double relTol, double dtMax, double dtMin,
                        double scaleMax, double scaleMin, double tStart) {
+  if (!out) return fail(nullptr, B200RK_EINVAL, "null argument");
   if (std::fabs(dtMax) < std::fabs(dtMin)) return fail(nullptr, B200RK_EINVAL, "dtMin must be less than dtMax");   // ode.nim:95-96
   if (std::fabs(scaleMax) < 1) return fail(nullptr, B200RK_EINVAL, "scaleMax must be bigger than 1");              // ode.nim:97-98
   if (1 < std::fabs(scaleMin)) return fail(nullptr, B200RK_EINVAL, "scaleMin must be smaller than 1");             // ode.nim:99-100
@@ -14,9 +15,10 @@ int b200rk_options_new(b200rk_options* out, double dt, double absTol, double rel
                         std::fabs(relTol), std::fabs(scaleMax), std::fabs(scaleMin)};                              // ode.nim:101-102
   return B200RK_OK;
 }
-void b200rk_options_default(b200rk_options* out) { b200rk_options_new(out, 1e-4, 1e-4, 1e-4, 1e-2, 1e-4, 4.0, 0.1, 0.0); }
+void b200rk_options_default(b200rk_options* out) { if (out) b200rk_options_new(out, 1e-4, 1e-4, 1e-4, 1e-2, 1e-4, 4.0, 0.1, 0.0); }
 
 int b200rk_method_from_name(const char* name, int* method) {
+  if (!method) return fail(nullptr, B200RK_EINVAL, "null argument");
   std::string s = name ? name : "";
   std::string low = s;
   for (char& ch : low) ch = (char)std::tolower((unsigned char)ch);
@@ -38,6 +40,7 @@ int b200rk_method_info(int method, int* stages, int* use_fsal, double* order, in
 }
 int b200rk_method_tableau(int method, double* c, double* a, double* b, double* bhat) {
   if (method < 0 || method > B200RK_VERN65) return fail(nullptr, B200RK_EINVAL, "tableau export covers the FSAL pairs only");
+  if (!c || !a || !b || !bhat) return fail(nullptr, B200RK_EINVAL, "null argument");
   const MethodDef& m = method_def(method);
   std::memset(c, 0, 10 * sizeof(double)); std::memset(a, 0, 90 * sizeof(double));
   std::memset(b, 0, 9 * sizeof(double)); std::memset(bhat, 0, 9 * sizeof(double));
@@ -57,6 +60,7 @@ int b200rk_shard_range(size_t n_global, int rank, int world, size_t* offset, siz
 }
 
 int b200rk_vec_fill(b200rk_vec* v, double value) {
+  if (!v) return fail(nullptr, B200RK_EINVAL, "null vector");
   return launch_ewise(v->ctx, EW_FILL, v->d, nullptr, value, v->d, v->n_local, B200RK_K_OTHER);
 }
 
@@ -92,6 +96,7 @@ int b200rk_vec_abs(b200rk_vec* out, const b200rk_vec* a) {
   return launch_ewise(a->ctx, EW_ABS, a->d, nullptr, 0.0, out->d, a->n_local, B200RK_K_OTHER);
 }
 int b200rk_vec_sum(const b200rk_vec* a, double* out) {
+  if (!a || !out) return fail(a ? a->ctx : nullptr, B200RK_EINVAL, "null argument");
   b200rk_ctx* c = a->ctx;
   TRY(launch_sum(c, a->d, a->n_local));
   return fetch_global_sum(c, out);
@@ -105,8 +110,10 @@ int b200rk_hermite(b200rk_vec* out, double x, double x1, double x2, const b200rk
 
 // ---- built-in right-hand sides ----------------------------------------------------------------------
 int b200rk_builtin_rhs_new(b200rk_ctx* c, int kind, double scalar, const b200rk_vec* lambda, b200rk_rhs_fn* fn, void** user) {
+  if (!c || !fn || !user) return fail(c, B200RK_EINVAL, "null argument");
   if (kind < B200RK_RHS_SCALE || kind > B200RK_RHS_LORENZ96) return fail(c, B200RK_EINVAL, "unknown builtin rhs");
   if (kind == B200RK_RHS_DIAG_LINEAR && !lambda) return fail(c, B200RK_EINVAL, "diag-linear rhs needs lambda");
+  if (lambda && lambda->ctx != c) return fail(c, B200RK_EINVAL, "diag-linear rhs: lambda belongs to another context");
   *user = new BuiltinRhs{c, kind, scalar, lambda};
   *fn = &builtin_rhs_fn;
   return B200RK_OK;
@@ -150,6 +157,7 @@ int b200rk_combine_err(b200rk_ctx* c, int method, double dt, double absTol, doub
 
 int b200rk_rk4_combine(b200rk_ctx* c, double dt, const b200rk_vec* y, const b200rk_vec* k1, const b200rk_vec* k2,
                        const b200rk_vec* k3, const b200rk_vec* k4, b200rk_vec* out) {
+  if (!c) return fail(nullptr, B200RK_EINVAL, "null argument");
   TRY(check_same(c, y, k1)); TRY(check_same(c, y, k2)); TRY(check_same(c, y, k3)); TRY(check_same(c, y, k4)); TRY(check_same(c, y, out));
   return launch_rk4_final(c, y->d, k1->d, k2->d, k3->d, k4->d, dt / 6.0, out->d, y->n_local);
 }

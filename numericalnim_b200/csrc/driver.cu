@@ -283,7 +283,7 @@ int b200rk_solve(b200rk_ctx* c, int method, b200rk_rhs_fn f, void* user, const b
 int b200rk_solve_host(b200rk_ctx* c, int method, b200rk_rhs_fn f, void* user, size_t n_global, const double* y0_local,
                       const double* tspan, size_t n_tspan, const b200rk_options* options, double* t_out,
                       double* y_out_local, size_t* n_y_out, b200rk_stats* stats) {
-  if (!c || !y0_local || !y_out_local || !tspan) return fail(c, B200RK_EINVAL, "null argument");
+  if (!c || !y0_local || !y_out_local || !tspan || !t_out || !n_y_out) return fail(c, B200RK_EINVAL, "null argument");
   b200rk_vec* y0 = nullptr;
   TRY(vec_alloc(c, n_global, &y0));
   int rc = B200RK_OK;
@@ -345,12 +345,14 @@ int b200rk_solver_new(b200rk_ctx* c, int method, b200rk_rhs_fn f, void* user, co
   return B200RK_OK;
 }
 int b200rk_solver_advance(b200rk_solver* s, int64_t max_steps, int64_t* steps_done, int* finished) {
+  if (!s) return fail(nullptr, B200RK_EINVAL, "null solver");
   int rc = solver_advance(s, max_steps, steps_done);
   if (rc == B200RK_OK) CUDA_TRY(s->c, cudaStreamSynchronize(s->c->stream));
   if (finished) *finished = s->finished ? 1 : 0;
   return rc;
 }
 int b200rk_solver_state(const b200rk_solver* s, double* t, double* dt_next, double* last_error, const b200rk_vec** y) {
+  if (!s) return fail(nullptr, B200RK_EINVAL, "null solver");
   if (t) *t = s->t;
   if (dt_next) *dt_next = s->dt;
   if (last_error) *last_error = s->error;
@@ -358,6 +360,7 @@ int b200rk_solver_state(const b200rk_solver* s, double* t, double* dt_next, doub
   return B200RK_OK;
 }
 int b200rk_solver_stats(const b200rk_solver* s, b200rk_stats* out) {
+  if (!s || !out) return fail(nullptr, B200RK_EINVAL, "null argument");
   solver_fill_stats(s, out, s->launches0, s->collectives0);
   return B200RK_OK;
 }

@@ -155,6 +155,7 @@ void vec_release(b200rk_vec* v) {  // back to the pool (bounded: a call that hel
 }
 int check_same(const b200rk_ctx* c, const b200rk_vec* a, const b200rk_vec* b) {
   if (!a || !b) return fail(c, B200RK_EINVAL, "null vector");
+  if (a->ctx != b->ctx) return fail(c, B200RK_EINVAL, "vectors belong to different contexts");
   if (a->n_global != b->n_global) return fail(c, B200RK_EINVAL, "Vectors must have the same size.");  // utils.nim:26
   return B200RK_OK;
 }
@@ -212,12 +213,13 @@ int b200rk_init(b200rk_ctx** out, int device) {
   b200rk_ctx* c = new b200rk_ctx;
   c->device = device;
   int rc = ctx_common_init(c);
-  if (rc != B200RK_OK) { thread_error() = c->err; delete c; return rc; }
+  if (rc != B200RK_OK) { thread_error() = c->err; b200rk_destroy(c); cudaGetLastError(); return rc; }  // releases whatever was created
   *out = c;
   return B200RK_OK;
 }
 
 int b200rk_nccl_unique_id(void* out128) {
+  if (!out128) return fail(nullptr, B200RK_EINVAL, "null argument");
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
   TRY(nccl_bind(nullptr));
   ncclUniqueId id;
@@ -228,6 +230,7 @@ int b200rk_nccl_unique_id(void* out128) {
 
 int b200rk_init_distributed(b200rk_ctx** out, int device, int rank, int world, const void* id128) {
   if (!out || world < 1 || rank < 0 || rank >= world) return fail(nullptr, B200RK_EINVAL, "bad rank/world");
+  if (world > 1 && !id128) return fail(nullptr, B200RK_EINVAL, "null NCCL id");
   b200rk_ctx* c = new b200rk_ctx;
   c->device = device; c->rank = rank; c->world = world;
   int rc = ctx_common_init(c);
@@ -241,7 +244,7 @@ int b200rk_init_distributed(b200rk_ctx** out, int device, int rank, int world, c
     }
     if (rc == B200RK_OK) rc = setup_p2p(c);
   }
-  if (rc != B200RK_OK) { thread_error() = c->err; delete c; return rc; }
+  if (rc != B200RK_OK) { thread_error() = c->err; b200rk_destroy(c); cudaGetLastError(); return rc; }  // releases whatever was created
   *out = c;
   return B200RK_OK;
 }
@@ -249,7 +252,7 @@ int b200rk_init_distributed(b200rk_ctx** out, int device, int rank, int world, c
 void b200rk_destroy(b200rk_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
+  if (c->stream) cudaStreamSynchronize(c->stream);
   for (auto* v : c->pool) { cudaFree(v->d); delete v; }
   for (auto& r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : c->ev_free) cudaEventDestroy(e);
@@ -261,16 +264,21 @@ void b200rk_destroy(b200rk_ctx* c) {
   if (c->h_run_state) cudaFreeHost(c->h_run_state);
   if (c->copy_event) cudaEventDestroy(c->copy_event);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
-  cudaStreamDestroy(c->stream);
+  if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
 
-void* b200rk_stream(const b200rk_ctx* c) { return (void*)c->stream; }
-int b200rk_synchronize(b200rk_ctx* c) { CUDA_TRY(c, cudaStreamSynchronize(c->stream)); return B200RK_OK; }
-int b200rk_rank(const b200rk_ctx* c) { return c->rank; }
-int b200rk_world(const b200rk_ctx* c) { return c->world; }
+void* b200rk_stream(const b200rk_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int b200rk_synchronize(b200rk_ctx* c) {
+  if (!c) return fail(nullptr, B200RK_EINVAL, "null context");
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return B200RK_OK;
+}
+int b200rk_rank(const b200rk_ctx* c) { return c ? c->rank : 0; }
+int b200rk_world(const b200rk_ctx* c) { return c ? c->world : 0; }
 
 int b200rk_set(b200rk_ctx* c, const char* key, int64_t v) {
+  if (!c) return fail(nullptr, B200RK_EINVAL, "null context");
   std::string k = key ? key : "";
   if (k == "strict_zeros") c->strict_zeros = v != 0;
   else if (k == "vec_width") { if (v != 2 && v != 4) return fail(c, B200RK_EINVAL, "vec_width must be 2 or 4"); c->vec_width = (int)v; }
@@ -299,6 +307,7 @@ int b200rk_set(b200rk_ctx* c, const char* key, int64_t v) {
   return B200RK_OK;
 }
 int b200rk_get(const b200rk_ctx* c, const char* key, int64_t* v) {
+  if (!c || !v) return fail(c, B200RK_EINVAL, "null argument");
   std::string k = key ? key : "";
   if (k == "strict_zeros") *v = c->strict_zeros;
   else if (k == "vec_width") *v = c->vec_width;
@@ -323,12 +332,14 @@ int b200rk_get(const b200rk_ctx* c, const char* key, int64_t* v) {
 }
 
 int b200rk_profile_reset(b200rk_ctx* c) {
+  if (!c) return fail(nullptr, B200RK_EINVAL, "null context");
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   for (auto& r : c->prof) { c->ev_free.push_back(r.a); c->ev_free.push_back(r.b); }
   c->prof.clear();
   return B200RK_OK;
 }
 int b200rk_profile_read(b200rk_ctx* c, b200rk_profile* out) {
+  if (!c || !out) return fail(c, B200RK_EINVAL, "null argument");
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   std::memset(out, 0, sizeof(*out));
   for (auto& r : c->prof) {
@@ -341,6 +352,7 @@ int b200rk_profile_read(b200rk_ctx* c, b200rk_profile* out) {
   return B200RK_OK;
 }
 int b200rk_ctx_stats(const b200rk_ctx* c, b200rk_stats* out) {
+  if (!c || !out) return fail(c, B200RK_EINVAL, "null argument");
   std::memset(out, 0, sizeof(*out));
   out->launches = c->launches;
   out->collectives = c->collectives;
@@ -368,25 +380,33 @@ int b200rk_vec_free(b200rk_vec* v) {
   delete v;
   return B200RK_OK;
 }
-size_t b200rk_vec_len(const b200rk_vec* v) { return v->n_global; }
-size_t b200rk_vec_local_len(const b200rk_vec* v) { return v->n_local; }
-size_t b200rk_vec_local_offset(const b200rk_vec* v) { return v->offset; }
-double* b200rk_vec_data(const b200rk_vec* v) { return v->d; }
+size_t b200rk_vec_len(const b200rk_vec* v) { return v ? v->n_global : 0; }
+size_t b200rk_vec_local_len(const b200rk_vec* v) { return v ? v->n_local : 0; }
+size_t b200rk_vec_local_offset(const b200rk_vec* v) { return v ? v->offset : 0; }
+double* b200rk_vec_data(const b200rk_vec* v) { return v ? v->d : nullptr; }
 
 int b200rk_vec_upload_local(b200rk_vec* v, const double* h) {
+  if (!v || (!h && v->n_local)) return fail(v ? v->ctx : nullptr, B200RK_EINVAL, "null argument");
   b200rk_ctx* c = v->ctx;
   CUDA_TRY(c, cudaMemcpyAsync(v->d, h, v->n_local * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return B200RK_OK;
 }
 int b200rk_vec_download_local(const b200rk_vec* v, double* h) {
+  if (!v || (!h && v->n_local)) return fail(v ? v->ctx : nullptr, B200RK_EINVAL, "null argument");
   b200rk_ctx* c = v->ctx;
   CUDA_TRY(c, cudaMemcpyAsync(h, v->d, v->n_local * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return B200RK_OK;
 }
-int b200rk_vec_upload(b200rk_vec* v, const double* hg) { return b200rk_vec_upload_local(v, hg + v->offset); }
-int b200rk_vec_download(const b200rk_vec* v, double* hg) { return b200rk_vec_download_local(v, hg + v->offset); }
+int b200rk_vec_upload(b200rk_vec* v, const double* hg) {
+  if (!v || !hg) return fail(v ? v->ctx : nullptr, B200RK_EINVAL, "null argument");
+  return b200rk_vec_upload_local(v, hg + v->offset);
+}
+int b200rk_vec_download(const b200rk_vec* v, double* hg) {
+  if (!v || !hg) return fail(v ? v->ctx : nullptr, B200RK_EINVAL, "null argument");
+  return b200rk_vec_download_local(v, hg + v->offset);
+}
 int b200rk_vec_copy(b200rk_vec* dst, const b200rk_vec* src) {
   TRY(check_same(dst ? dst->ctx : nullptr, dst, src));
   return vec_copy_raw(dst->ctx, dst, src);

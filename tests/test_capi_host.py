@@ -103,3 +103,45 @@ def test_linspace_host_helper():  # tests/test_utils.nim:15-23
     assert nn.linspace(-10.0, 10.0, 100) == O.linspace(-10.0, 10.0, 100).tolist()
     with pytest.raises(ValueError):
         nn.linspace(0.0, 1.0, 0)
+
+
+def test_null_arguments_are_einval_not_a_crash():
+    """The C-ABI never faults on a NULL handle or output pointer: EINVAL (the shim's ValueError) before any CUDA call —
+    so this runs without a device, against the real library."""
+    L = _capi.lib()
+    null = C.c_void_p(None)
+    i64 = C.c_int64(0)
+    dbl = C.c_double(0.0)
+    sz = C.c_size_t(0)
+    calls = [
+        lambda: L.b200rk_options_new(None, 1e-4, 1e-4, 1e-4, 1e-2, 1e-4, 4.0, 0.1, 0.0),
+        lambda: L.b200rk_method_from_name(b"rk4", None),
+        lambda: L.b200rk_method_tableau(0, None, None, None, None),
+        lambda: L.b200rk_set(null, b"vec_width", 4),
+        lambda: L.b200rk_get(null, b"vec_width", C.byref(i64)),
+        lambda: L.b200rk_synchronize(null),
+        lambda: L.b200rk_profile_reset(null),
+        lambda: L.b200rk_profile_read(null, None),
+        lambda: L.b200rk_ctx_stats(null, None),
+        lambda: L.b200rk_vec_new(null, 8, None),
+        lambda: L.b200rk_vec_fill(null, 1.0),
+        lambda: L.b200rk_vec_sum(null, C.byref(dbl)),
+        lambda: L.b200rk_vec_upload(null, None),
+        lambda: L.b200rk_vec_download(null, None),
+        lambda: L.b200rk_vec_upload_local(null, None),
+        lambda: L.b200rk_vec_download_local(null, None),
+        lambda: L.b200rk_vec_add(null, null, null),
+        lambda: L.b200rk_vec_copy(null, null),
+        lambda: L.b200rk_builtin_rhs_new(null, 0, 1.0, null, None, None),
+        lambda: L.b200rk_nccl_unique_id(None),
+        lambda: L.b200rk_init(None, 0),
+        lambda: L.b200rk_init_distributed(None, 0, 0, 1, None),
+        lambda: L.b200rk_shard_range(8, 0, 1, None, C.byref(sz)),
+    ]
+    for i, call in enumerate(calls):
+        assert call() == _capi.EINVAL, i
+    assert L.b200rk_vec_len(null) == 0 and L.b200rk_vec_local_len(null) == 0 and L.b200rk_vec_local_offset(null) == 0
+    assert not L.b200rk_vec_data(null) and not L.b200rk_stream(null)
+    assert L.b200rk_vec_free(null) == _capi.OK and L.b200rk_jit_rhs_free(null) == _capi.OK
+    L.b200rk_destroy(null)
+    L.b200rk_options_default(None)

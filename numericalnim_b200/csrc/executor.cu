@@ -314,6 +314,39 @@ static int launch_fused_rk4(b200rk_ctx* c, const PwSpec& pw, bool negate, double
 
 // Whole attempt of an FSAL pair with the built-in Lorenz-96 right-hand side in one kernel (stencil_attempt.cuh:
 // overlapped tiles, stage inputs through shared memory). Experimental, knob "fuse_stencil_attempt".
+// Sharded: every shard must hold at least the largest overlap, so that a halo comes from the immediate ring neighbour
+// only (same answer on every rank: shard_range is a pure function of n, rank, world).
+constexpr int kAttemptHaloMax = StencilTile<9>::HL + StencilTile<9>::HR;   // Vern65: 16 + 8
+static bool l96_attempt_shards_ok(const b200rk_ctx* c, size_t n_global) {
+  for (int r = 0; r < c->world; ++r) {
+    size_t off = 0, len = 0;
+    shard_range(n_global, r, c->world, &off, &len);
+    if (len < (size_t)StencilTile<9>::HL) return false;
+  }
+  return true;
+}
+// The HL elements before this shard and the HR after it, of y and of k1 (FSAL): one grouped exchange with the ring
+// neighbours on the context stream per IntegratorProc call — y and k1 do not change between the retries of an attempt.
+// Layout of each halo array: [0, HL) = left neighbour's tail, [HL, HL + HR) = right neighbour's head.
+static int exchange_attempt_halo(b200rk_ctx* c, const b200rk_vec* y, const b200rk_vec* fsal, int HL, int HR) {
+  if (!c->d_halo_attempt) CUDA_TRY(c, cudaMalloc(&c->d_halo_attempt, 2 * kAttemptHaloMax * sizeof(double)));
+  double *hy = c->d_halo_attempt, *hk = c->d_halo_attempt + kAttemptHaloMax;
+  const size_t n = y->n_local;
+  const int left = (c->rank + c->world - 1) % c->world, right = (c->rank + 1) % c->world;
+  NCCL_TRY(c, g_nccl.GroupStart());   // same order on every rank: with world == 2 both neighbours are the same peer and the pairs match in order
+  NCCL_TRY(c, g_nccl.Send(y->d, HR, ncclDouble, left, c->comm, c->stream));
+  NCCL_TRY(c, g_nccl.Send(y->d + n - HL, HL, ncclDouble, right, c->comm, c->stream));
+  NCCL_TRY(c, g_nccl.Send(fsal->d, HR, ncclDouble, left, c->comm, c->stream));
+  NCCL_TRY(c, g_nccl.Send(fsal->d + n - HL, HL, ncclDouble, right, c->comm, c->stream));
+  NCCL_TRY(c, g_nccl.Recv(hy + HL, HR, ncclDouble, right, c->comm, c->stream));
+  NCCL_TRY(c, g_nccl.Recv(hy, HL, ncclDouble, left, c->comm, c->stream));
+  NCCL_TRY(c, g_nccl.Recv(hk + HL, HR, ncclDouble, right, c->comm, c->stream));
+  NCCL_TRY(c, g_nccl.Recv(hk, HL, ncclDouble, left, c->comm, c->stream));
+  NCCL_TRY(c, g_nccl.GroupEnd());
+  c->collectives++;
+  return B200RK_OK;
+}
+
 template <int PAT>
 static int launch_l96_attempt(b200rk_ctx* c, const MethodDef& md, double F, bool negate, double dt, const b200rk_options& o,
                               const b200rk_vec* y, const b200rk_vec* fsal, b200rk_vec* y_new, b200rk_vec* fsal_new) {
@@ -328,6 +361,7 @@ static int launch_l96_attempt(b200rk_ctx* c, const MethodDef& md, double F, bool
   a.f.dt = dt; a.f.cb = dt; a.f.cbh = dt; a.f.absTol = o.absTol; a.f.relTol = o.relTol;
   a.f.ynew = y_new->d; a.f.ks_out = fsal_new->d; a.f.n = y->n_local;
   a.F = F; a.sgn = negate ? -1.0 : 1.0;
+  if (c->world > 1) { a.halo_y = c->d_halo_attempt; a.halo_k = c->d_halo_attempt + kAttemptHaloMax; }  // filled by exchange_attempt_halo
   const unsigned grid = (unsigned)((a.f.n + OUT - 1) / OUT);
   TRY(ensure_partials(c, grid));
   a.f.rs = reduce_scratch(c);
@@ -355,7 +389,9 @@ int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, double t, co
                              static_cast<const BuiltinRhs*>(rhs.user)->kind == B200RK_RHS_LORENZ96 && y->n_global >= 4;
   // experimental: the whole attempt of the stencil right-hand side in one kernel (overlapped tiles read y and FSAL far
   // beyond a CTA's own outputs, so the outputs must not alias the inputs)
-  bool l96_attempt = stencil_fused && c->fuse_stencil_attempt && method_fusable(md) && !md.rk4_final && fsal && fsal_new &&
+  const bool l96_builtin = !fused && rhs.f == &builtin_rhs_fn && static_cast<const BuiltinRhs*>(rhs.user)->kind == B200RK_RHS_LORENZ96 &&
+                           y->n_global >= 4;
+  bool l96_attempt = l96_builtin && c->fuse_stencil_attempt && (c->world == 1 || l96_attempt_shards_ok(c, y->n_global)) && method_fusable(md) && !md.rk4_final && fsal && fsal_new &&
                      y_new->d != y->d && y_new->d != fsal->d && fsal_new->d != y->d && fsal_new->d != fsal->d;
   if (l96_attempt) { fused_pat = fused_pattern_of(c, md); l96_attempt = fused_pat >= 0; }
   if (fused) TRY(check_pw_sizes(c, pw, y));
@@ -376,6 +412,8 @@ int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, double t, co
     if (!(last_input_is_ynew && S == 2)) TRY(ws.get(N, &tmp));
   }
 
+  if (l96_attempt && c->world > 1)
+    TRY(exchange_attempt_halo(c, y, fsal, S == 9 ? StencilTile<9>::HL : StencilTile<7>::HL, S == 9 ? StencilTile<9>::HR : StencilTile<7>::HR));
   double dt = dt_in, error = 0.0;
   int limitCounter = 0;
   while (true) {

@@ -51,6 +51,7 @@ struct b200rk_ctx {
   double* h_result = nullptr;   // pinned + mapped host scalar
   double* h_result_dev = nullptr;  // device alias of h_result
   double* d_halo = nullptr;        // 3 doubles: stencil halo of the sharded Lorenz-96 right-hand side
+  double* d_halo_attempt = nullptr;  // 2 x 24 doubles: halo of y and k1 for the one-kernel Lorenz-96 attempt (stencil_attempt.cuh), sharded
   unsigned long long* h_seq = nullptr;      // pinned + mapped: sequence word of the last finished reduction
   unsigned long long* h_seq_dev = nullptr;  // device alias
   unsigned long long seq = 0;               // last sequence number handed to a reducing launch

@@ -260,6 +260,7 @@ void b200rk_destroy(b200rk_ctx* c) {
   if (c->d_mail) cudaFree(c->d_mail);
   if (c->comm) g_nccl.CommDestroy(c->comm);
   cudaFree(c->d_partials); cudaFree(c->d_ticket); cudaFree(c->d_result); cudaFree(c->d_halo); cudaFreeHost(c->h_result); cudaFreeHost(c->h_seq);
+  if (c->d_halo_attempt) cudaFree(c->d_halo_attempt);
   if (c->d_run_state) cudaFree(c->d_run_state);
   if (c->h_run_state) cudaFreeHost(c->h_run_state);
   if (c->copy_event) cudaEventDestroy(c->copy_event);

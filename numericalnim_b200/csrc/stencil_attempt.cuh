@@ -1,5 +1,5 @@
 // stencil_attempt.cuh — a whole adaptive attempt of an FSAL pair for the built-in Lorenz-96 right-hand side in ONE
-// kernel (single GPU, cyclic). EXPERIMENTAL: knob "fuse_stencil_attempt", off by default until it has been run and
+// kernel (cyclic; one GPU, or one contiguous shard per GPU with a halo from the ring neighbours). EXPERIMENTAL: knob "fuse_stencil_attempt", off by default until it has been run and
 // measured on the GPU (bit-identical to the stage_l96_kernel / finish_kernel pipeline under host emulation).
 //
 // The element-local fused attempt (kernels.cuh: fused_attempt_kernel) keeps k_1..k_S of an element in registers because
@@ -12,6 +12,9 @@
 // still exact. Only positions [HL, TW-HR) are stored (HL >= 2(S-1), HR >= S-1, both multiples of 4 so every tile stays
 // 32-byte aligned): 2 % of the arithmetic is redundant, and HBM traffic per attempt drops from 53 vector passes
 // (Tsit54: 41 stage/finish + 12 stencil) to 4 — read y and k1, write yNew and k_S.
+// Sharded over GPUs the same overlap reaches HL / HR elements into the neighbouring shards: ONE halo exchange of y and k1
+// per IntegratorProc call (they do not change between the retries of an attempt) replaces the 3-element exchange in front
+// of each of the S-1 right-hand-side evaluations.
 //
 // Within the CTA the stage input travels through shared memory (two buffers, so one barrier per stage): a thread
 // computes the stage input at its own E = 2*J positions from registers, publishes it, and after the barrier applies the
@@ -34,6 +37,12 @@ template <int S>
 struct L96AttemptArgs {
   FusedArgs<S> f;     // y, k1, a/b/bh rows, dt, cb, cbh, tolerances, ynew, ks_out, n, rs (the parameter fields are unused)
   double F, sgn;      // forcing; -1 for the backward pass g = -f(-t, y) (ode.nim:545), else +1
+  // Sharded state (one contiguous block of the cyclic global vector per GPU): the HL elements before the block and the
+  // HR elements after it, of y and of k1 — [0, HL) from the left neighbour's tail, [HL, HL+HR) from the right
+  // neighbour's head, exchanged once per IntegratorProc call (executor.cu). Null on a single GPU: the block is the
+  // whole ring and the edge tiles index it cyclically.
+  const double* halo_y;
+  const double* halo_k;
 };
 
 // stage s (compile-time) of every element the thread owns; recursion keeps the row masks template constants
@@ -88,9 +97,19 @@ __global__ void __launch_bounds__(THREADS) l96_attempt_kernel(const L96AttemptAr
     } else {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const size_t g = (tile0 + (size_t)(p + h) + wrap) % n;
-        y[2 * j + h] = a.f.y[g];
-        k[2 * j + h][0] = a.f.k1[g];
+        if (a.halo_y) {  // shard: positions before / after the block come from the neighbours' halos
+          const long long idx = (long long)tile0 - HL + (p + h);
+          const double *ys = nullptr, *kq = nullptr;
+          if (idx < 0) { ys = a.halo_y + (HL + idx); kq = a.halo_k + (HL + idx); }
+          else if ((size_t)idx < n) { ys = a.f.y + idx; kq = a.f.k1 + idx; }
+          else if ((size_t)idx - n < (size_t)HR) { ys = a.halo_y + (HL + ((size_t)idx - n)); kq = a.halo_k + (HL + ((size_t)idx - n)); }
+          y[2 * j + h] = ys ? *ys : 0.0;   // further right: beyond what any stored position depends on
+          k[2 * j + h][0] = kq ? *kq : 0.0;
+        } else {
+          const size_t g = (tile0 + (size_t)(p + h) + wrap) % n;
+          y[2 * j + h] = a.f.y[g];
+          k[2 * j + h][0] = a.f.k1[g];
+        }
       }
     }
   }

@@ -79,6 +79,22 @@ def main():
             fails.append(("lorenz96 tsit54", nl, st, refl.stats.steps, float(np.max(np.abs(got - exp)))))
         if rank == 0:
             print(f"[multi-gpu world={world}] lorenz96 n={nl} tsit54: steps={st['steps']} rejected={st['rejected']} collectives={st['collectives']} ok={ok}", flush=True)
+        # experimental knob fuse_stencil_attempt: the whole attempt in one kernel; sharded, ONE halo exchange of y and k1
+        # (12 + 8 elements each) per IntegratorProc call instead of a 3-element exchange per right-hand-side evaluation
+        try:
+            ctx.set("fuse_stencil_attempt", 1)
+            c0 = ctx.stats()["collectives"]
+            t, ys = nn.solveODE(rhs_l, gl, [0.0, 0.5], nn.newODEoptions(**kw), integrator="tsit54")
+            st2 = dict(nn.ode.last_stats)
+            got2 = ys[-1].local_numpy()
+            ok2 = bool(np.all(np.abs(got2 - exp) <= 1e-7 * np.abs(exp))) and st2["steps"] == refl.stats.steps and st2["rejected"] == refl.stats.rejected
+            if not ok2:
+                fails.append(("lorenz96 tsit54 one-kernel attempt", nl, st2, refl.stats.steps, float(np.max(np.abs(got2 - exp)))))
+            if rank == 0:
+                print(f"[multi-gpu world={world}] lorenz96 n={nl} tsit54 one-kernel attempt: steps={st2['steps']} rejected={st2['rejected']} "
+                      f"launches={st2['launches']} (default path {st['launches']}) collectives={st2['collectives']} (default {st['collectives']}) ok={ok2}", flush=True)
+        finally:
+            ctx.set("fuse_stencil_attempt", 0)
     # right-hand side given as SOURCE, sharded: the parameter vector shards like the state; the run-time compiled
     # attempt kernel / device loop use the same in-kernel all-reduce as the built-ins
     K = 2.0 + 3.0 * np.arange(n) / (n - 1)

@@ -170,7 +170,8 @@ static void test_l96_attempt(const char* name, const rk_oracle::Pair& p, rk_orac
   constexpr int S = Pattern<PAT>::S, J = 2;
   constexpr int OUT = 2 * J * T - StencilTile<S>::HL - StencilTile<S>::HR;
   bool ok = true;
-  for (size_t n : {size_t(4), size_t(5), size_t(7), size_t(OUT - 1), size_t(OUT), size_t(OUT + 1), size_t(2 * OUT + 3), size_t(1000)})
+  int splits = 0;
+  for (size_t n : {size_t(4), size_t(5), size_t(7), size_t(40), size_t(OUT - 1), size_t(OUT), size_t(OUT + 1), size_t(2 * OUT + 3), size_t(1000)})
     for (double sgn : {1.0, -1.0}) {
       const double F = 8.0, dt = 0.004;
       const auto y = rvec(n, 7.0, 9.0);
@@ -196,8 +197,32 @@ static void test_l96_attempt(const char* name, const rk_oracle::Pair& p, rk_orac
       emul_launch(grid, T, [&] { l96_attempt_kernel<PAT, J, T>(a); });
       const double err = std::sqrt(1.0 / double(n) * sc.result);
       ok = ok && ref.dt == dt && same_bits(ynew, ref.y_new.components) && same_bits(ks, ref.fsal.components) && close_rel(err, ref.error, 1e-13);
+      // the same attempt SHARDED: G contiguous blocks of the ring, each launched on its own with the HL / HR elements of
+      // y and k1 around the block as halos (what executor.cu's exchange_attempt_halo delivers from the ring neighbours)
+      constexpr int HL = StencilTile<S>::HL, HR = StencilTile<S>::HR;
+      for (size_t G : {size_t(2), size_t(3)}) {
+        const size_t chunk = ((n + G - 1) / G + 3) / 4 * 4;           // runtime.cu: shard_range
+        if (n < chunk * (G - 1) + HL || chunk < (size_t)HL) continue;  // every shard at least HL long
+        std::vector<double> yn2(n, -5.0), ks2(n, -5.0);
+        double s2 = 0.0;
+        ++splits;
+        for (size_t r = 0; r < G; ++r) {
+          const size_t lo = r * chunk, len = std::min(n, lo + chunk) - lo;
+          std::vector<double> hy(HL + HR), hk(HL + HR);
+          for (int i = 0; i < HL; ++i) { hy[i] = y[(lo + n - HL + i) % n]; hk[i] = fsal.components[(lo + n - HL + i) % n]; }
+          for (int i = 0; i < HR; ++i) { hy[HL + i] = y[(lo + len + i) % n]; hk[HL + i] = fsal.components[(lo + len + i) % n]; }
+          Scratch sc2;
+          L96AttemptArgs<S> b = a;
+          b.f.y = y.data() + lo; b.f.k1 = fsal.components.data() + lo; b.f.ynew = yn2.data() + lo; b.f.ks_out = ks2.data() + lo;
+          b.f.n = len; b.f.rs = sc2.rs(); b.halo_y = hy.data(); b.halo_k = hk.data();
+          emul_launch((unsigned)((len + OUT - 1) / OUT), T, [&] { l96_attempt_kernel<PAT, J, T>(b); });
+          s2 += sc2.result;                                             // the all-reduce of the shards' partial sums
+        }
+        ok = ok && same_bits(yn2, ref.y_new.components) && same_bits(ks2, ref.fsal.components) &&
+             close_rel(std::sqrt(1.0 / double(n) * s2), ref.error, 1e-13);
+      }
     }
-  report(std::string("l96_attempt_kernel (whole attempt, overlapped tiles) ") + name, ok);
+  report(std::string("l96_attempt_kernel (whole attempt, overlapped tiles; ") + std::to_string(splits) + " sharded splits) " + name, ok && splits >= 16);
 }
 
 // ---- positive control for the race detector: a tile kernel with its barrier removed ---------------------------------

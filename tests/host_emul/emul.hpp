@@ -30,9 +30,9 @@ struct EmulDim3 { unsigned x = 0, y = 0, z = 0; };
 #include <thread>
 static thread_local EmulDim3 threadIdx, blockIdx, gridDim, blockDim;
 struct EmulBlock {
-  std::barrier<> block;
+  std::barrier<> block, cta_end;   // __syncthreads; end of a CTA (the team then plays the next one)
   std::vector<std::unique_ptr<std::barrier<>>> warp;
-  explicit EmulBlock(unsigned threads) : block(threads) {
+  explicit EmulBlock(unsigned threads) : block(threads), cta_end(threads) {
     for (unsigned w = 0; w * 32 < threads; ++w) warp.push_back(std::make_unique<std::barrier<>>(std::min(32u, threads - w * 32)));
   }
 };
@@ -103,18 +103,22 @@ inline double user_rhs(double t, double y, const double* p, const double* c) { r
 template <class F>
 inline void emul_launch(unsigned grid, unsigned threads, F&& body) {
 #ifdef EMUL_MT
-  for (unsigned b = 0; b < grid; ++b) {   // blocks one after another, the threads of a block concurrently
-    EmulBlock blk(threads);
-    g_emul_block = &blk;
-    std::vector<std::thread> pool;
-    for (unsigned t = 0; t < threads; ++t)
-      pool.emplace_back([&, b, t] {
-        gridDim.x = grid; blockDim.x = threads; blockIdx.x = b; threadIdx.x = t;
+  // one team of host threads per launch: blocks one after another (team-wide barrier in between), the threads of a
+  // block concurrently
+  EmulBlock blk(threads);
+  g_emul_block = &blk;
+  std::vector<std::thread> pool;
+  for (unsigned t = 0; t < threads; ++t)
+    pool.emplace_back([&, t] {
+      gridDim.x = grid; blockDim.x = threads; threadIdx.x = t;
+      for (unsigned b = 0; b < grid; ++b) {
+        blockIdx.x = b;
         body();
-      });
-    for (auto& th : pool) th.join();
-    g_emul_block = nullptr;
-  }
+        blk.cta_end.arrive_and_wait();
+      }
+    });
+  for (auto& th : pool) th.join();
+  g_emul_block = nullptr;
 #else
   gridDim.x = grid; blockDim.x = threads;
   for (unsigned b = 0; b < grid; ++b)

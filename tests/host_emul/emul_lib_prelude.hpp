@@ -20,9 +20,9 @@ struct EmulDim3 { unsigned x = 0, y = 0, z = 0; };
 static thread_local EmulDim3 threadIdx, blockIdx, gridDim, blockDim;
 
 struct EmulBlock {
-  std::barrier<> block;
+  std::barrier<> block, cta_end;   // __syncthreads; end of a CTA (the team then plays the next one)
   std::vector<std::unique_ptr<std::barrier<>>> warp;
-  explicit EmulBlock(unsigned threads) : block(threads) {
+  explicit EmulBlock(unsigned threads) : block(threads), cta_end(threads) {
     for (unsigned w = 0; w * 32 < threads; ++w) warp.push_back(std::make_unique<std::barrier<>>(std::min(32u, threads - w * 32)));
   }
 };
@@ -76,18 +76,22 @@ inline void emul_launch_serial(unsigned grid, unsigned threads, F&& body) {
 }
 template <class F>
 inline void emul_launch_threaded(unsigned grid, unsigned threads, F&& body) {
-  for (unsigned b = 0; b < grid; ++b) {   // CTAs one after another (function-static "shared memory" is one copy)
-    EmulBlock blk(threads);
-    g_emul_block = &blk;
-    std::vector<std::thread> pool;
-    for (unsigned t = 0; t < threads; ++t)
-      pool.emplace_back([&, b, t] {
-        gridDim.x = grid; blockDim.x = threads; blockIdx.x = b; threadIdx.x = t;
+  // one team of host threads per launch; it plays the CTAs one after another (function-static "shared memory" is one
+  // copy), with a team-wide barrier between CTAs
+  EmulBlock blk(threads);
+  g_emul_block = &blk;
+  std::vector<std::thread> pool;
+  for (unsigned t = 0; t < threads; ++t)
+    pool.emplace_back([&, t] {
+      gridDim.x = grid; blockDim.x = threads; threadIdx.x = t;
+      for (unsigned b = 0; b < grid; ++b) {
+        blockIdx.x = b;
         body();
-      });
-    for (auto& th : pool) th.join();
-    g_emul_block = nullptr;
-  }
+        blk.cta_end.arrive_and_wait();
+      }
+    });
+  for (auto& th : pool) th.join();
+  g_emul_block = nullptr;
 }
 // cooperative launch of the device-resident loop: a one-CTA grid (fake device: 1 SM, 1 CTA per SM), threaded
 template <class A>

@@ -360,13 +360,14 @@ static int launch_l96_attempt(b200rk_ctx* c, const MethodDef& md, double F, bool
   row_mask(c, md.bhat, a.f.bh, S);
   a.f.dt = dt; a.f.cb = dt; a.f.cbh = dt; a.f.absTol = o.absTol; a.f.relTol = o.relTol;
   a.f.ynew = y_new->d; a.f.ks_out = fsal_new->d; a.f.n = y->n_local;
-  a.F = F; a.sgn = negate ? -1.0 : 1.0;
+  a.F = F;
   if (c->world > 1) { a.halo_y = c->d_halo_attempt; a.halo_k = c->d_halo_attempt + kAttemptHaloMax; }  // filled by exchange_attempt_halo
   const unsigned grid = (unsigned)((a.f.n + OUT - 1) / OUT);
   TRY(ensure_partials(c, grid));
   a.f.rs = reduce_scratch(c);
   ProfScope ps(c, B200RK_K_FUSED, 8.0 * double(a.f.n) * 4);  // y, k1 read; yNew, k_S written
-  l96_attempt_kernel<PAT, J, kThreads><<<grid, kThreads, 0, c->stream>>>(a);
+  if (negate) l96_attempt_kernel<PAT, J, kThreads, true><<<grid, kThreads, 0, c->stream>>>(a);
+  else l96_attempt_kernel<PAT, J, kThreads, false><<<grid, kThreads, 0, c->stream>>>(a);
   CUDA_TRY(c, cudaGetLastError());
   return B200RK_OK;
 }

@@ -36,7 +36,7 @@ struct StencilTile {
 template <int S>
 struct L96AttemptArgs {
   FusedArgs<S> f;     // y, k1, a/b/bh rows, dt, cb, cbh, tolerances, ynew, ks_out, n, rs (the parameter fields are unused)
-  double F, sgn;      // forcing; -1 for the backward pass g = -f(-t, y) (ode.nim:545), else +1
+  double F;           // forcing (the backward pass g = -f(-t, y), ode.nim:545, is the kernel's NEG template argument)
   // Sharded state (one contiguous block of the cyclic global vector per GPU): the HL elements before the block and the
   // HR elements after it, of y and of k1 — [0, HL) from the left neighbour's tail, [HL, HL+HR) from the right
   // neighbour's head, exchanged once per IntegratorProc call (executor.cu). Null on a single GPU: the block is the
@@ -45,31 +45,41 @@ struct L96AttemptArgs {
   const double* halo_k;
 };
 
-// stage s (compile-time) of every element the thread owns; recursion keeps the row masks template constants
-template <int PAT, int s, int E, int TW>
+// stage s (compile-time) of every element the thread owns; recursion keeps the row masks template constants.
+// A thread owns J pairs of adjacent positions (p, p+1): of the stencil's operands only in[p-2], in[p-1] (one 128-bit
+// shared-memory load) and in[p+2] come from other threads, in[p] and in[p+1] are its own registers.
+// NEG: the backward pass g = -f(-t, y) (ode.nim:545). v * (+1.0) == v and v * (-1.0) == -v exactly, so instead of
+// stage_l96_kernel's multiplication by sgn the sign is a compile-time negation (an operand modifier, no fp64 issue).
+template <int PAT, int s, int J, int TW, bool NEG>
 struct L96Stages {
   template <int S>
-  __device__ __forceinline__ static void run(const double (&y)[E], double (&k)[E][S], double (&in)[E], const int (&pos)[E],
+  __device__ __forceinline__ static void run(const double (&y)[2 * J], double (&k)[2 * J][S], double (&in)[2 * J], const int (&pos)[J],
                                              double (*buf)[TW + 4], const L96AttemptArgs<S>& a) {
-    if constexpr (s > 2) L96Stages<PAT, s - 1, E, TW>::run(y, k, in, pos, buf, a);
+    if constexpr (s > 2) L96Stages<PAT, s - 1, J, TW, NEG>::run(y, k, in, pos, buf, a);
     double* sh = buf[s & 1] + 2;   // sh[-2], sh[-1] and sh[TW] are zero pads (their consumers are outside the stored range)
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
+    for (int e = 0; e < 2 * J; ++e) {
       const double acc = const_wsum<S, Pattern<PAT>::a(s - 2)>(k[e], a.f.a[s - 2]);
       in[e] = __dadd_rn(y[e], __dmul_rn(acc, a.f.dt));                                   // stage_elem
-      sh[pos[e]] = in[e];
     }
+#pragma unroll
+    for (int j = 0; j < J; ++j) { sh[pos[j]] = in[2 * j]; sh[pos[j] + 1] = in[2 * j + 1]; }
     __syncthreads();   // the other buffer was last read before the previous stage's barrier: one barrier per stage
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-      const int p = pos[e];
-      const double v = __dadd_rn(__dadd_rn(__dmul_rn(__dadd_rn(sh[p + 1], -sh[p - 2]), sh[p - 1]), -in[e]), a.F);  // lorenz96
-      k[e][s - 1] = __dmul_rn(v, a.sgn);
+    for (int j = 0; j < J; ++j) {
+      const int p = pos[j];
+      const double m2 = sh[p - 2], m1 = sh[p - 1], p2 = sh[p + 2];
+      const double c0 = in[2 * j], c1 = in[2 * j + 1];
+      // lorenz96_kernel: ((y[i+1] - y[i-2]) * y[i-1] - y[i]) + F at i = p and i = p + 1
+      const double v0 = __dadd_rn(__dadd_rn(__dmul_rn(__dadd_rn(c1, -m2), m1), -c0), a.F);
+      const double v1 = __dadd_rn(__dadd_rn(__dmul_rn(__dadd_rn(p2, -m1), c0), -c1), a.F);
+      k[2 * j][s - 1] = NEG ? -v0 : v0;
+      k[2 * j + 1][s - 1] = NEG ? -v1 : v1;
     }
   }
 };
 
-template <int PAT, int J, int THREADS>
+template <int PAT, int J, int THREADS, bool NEG>
 __global__ void __launch_bounds__(THREADS) l96_attempt_kernel(const L96AttemptArgs<Pattern<PAT>::S> a) {
   constexpr int S = Pattern<PAT>::S;
   constexpr int E = 2 * J, TW = E * THREADS;
@@ -82,13 +92,13 @@ __global__ void __launch_bounds__(THREADS) l96_attempt_kernel(const L96AttemptAr
     buf[0][q] = 0.0; buf[1][q] = 0.0;
   }
   double y[E], k[E][S], in[E];
-  int pos[E];
+  int pos[J];   // first position of each pair the thread owns
   const bool interior = tile0 >= (size_t)HL && tile0 - HL + TW <= n;
   const size_t wrap = n - (size_t)HL % n;                 // (tile0 + p + wrap) % n == tile0 - HL + p (mod n)
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     const int p = 2 * ((int)threadIdx.x + j * THREADS);
-    pos[2 * j] = p; pos[2 * j + 1] = p + 1;
+    pos[j] = p;
     if (interior) {
       const size_t g = tile0 - HL + p;
       const Pk<2> yv = ld_stream<2>(a.f.y + g), kv = ld_stream<2>(a.f.k1 + g);
@@ -117,12 +127,12 @@ __global__ void __launch_bounds__(THREADS) l96_attempt_kernel(const L96AttemptAr
   for (int e = 0; e < E; ++e)
 #pragma unroll
     for (int j = 1; j < S; ++j) k[e][j] = 0.0;
-  L96Stages<PAT, S, E, TW>::run(y, k, in, pos, buf, a);
+  L96Stages<PAT, S, J, TW, NEG>::run(y, k, in, pos, buf, a);
 
   double acc = 0.0;
 #pragma unroll
   for (int j = 0; j < J; ++j) {
-    const int p = pos[2 * j];
+    const int p = pos[j];
     const size_t g = tile0 + (size_t)(p - HL);            // p and HL even: a pair is stored whole or not at all (up to n)
     const bool stored = p >= HL && p < HL + OUT && g < n;
     double yn[2], ks[2];

@@ -192,9 +192,10 @@ static void test_l96_attempt(const char* name, const rk_oracle::Pair& p, rk_orac
       for (int j = 0; j < p.n_bhat; ++j) a.f.bh[j] = p.bhat[j];
       a.f.dt = dt; a.f.cb = dt; a.f.cbh = dt; a.f.absTol = o.absTol; a.f.relTol = o.relTol;
       a.f.ynew = ynew.data(); a.f.ks_out = ks.data(); a.f.n = n; a.f.rs = sc.rs();
-      a.F = F; a.sgn = sgn;
+      a.F = F;
       const unsigned grid = (unsigned)((n + OUT - 1) / OUT);
-      emul_launch(grid, T, [&] { l96_attempt_kernel<PAT, J, T>(a); });
+      if (sgn < 0) emul_launch(grid, T, [&] { l96_attempt_kernel<PAT, J, T, true>(a); });
+      else emul_launch(grid, T, [&] { l96_attempt_kernel<PAT, J, T, false>(a); });
       const double err = std::sqrt(1.0 / double(n) * sc.result);
       ok = ok && ref.dt == dt && same_bits(ynew, ref.y_new.components) && same_bits(ks, ref.fsal.components) && close_rel(err, ref.error, 1e-13);
       // the same attempt SHARDED: G contiguous blocks of the ring, each launched on its own with the HL / HR elements of
@@ -215,7 +216,8 @@ static void test_l96_attempt(const char* name, const rk_oracle::Pair& p, rk_orac
           L96AttemptArgs<S> b = a;
           b.f.y = y.data() + lo; b.f.k1 = fsal.components.data() + lo; b.f.ynew = yn2.data() + lo; b.f.ks_out = ks2.data() + lo;
           b.f.n = len; b.f.rs = sc2.rs(); b.halo_y = hy.data(); b.halo_k = hk.data();
-          emul_launch((unsigned)((len + OUT - 1) / OUT), T, [&] { l96_attempt_kernel<PAT, J, T>(b); });
+          if (sgn < 0) emul_launch((unsigned)((len + OUT - 1) / OUT), T, [&] { l96_attempt_kernel<PAT, J, T, true>(b); });
+          else emul_launch((unsigned)((len + OUT - 1) / OUT), T, [&] { l96_attempt_kernel<PAT, J, T, false>(b); });
           s2 += sc2.result;                                             // the all-reduce of the shards' partial sums
         }
         ok = ok && same_bits(yn2, ref.y_new.components) && same_bits(ks2, ref.fsal.components) &&

@@ -210,3 +210,34 @@ def test_l96_attempt_solve_matches_pipeline_and_oracle(nn, method):
         assert res[1][3] < res[0][3] / 3
     finally:
         ctx.set("fuse_stencil_attempt", 0)
+
+
+def test_l96_attempt_matches_golden_lorenz96_fixtures(nn):
+    """The committed Lorenz-96 trajectories (tests/golden/trajectories.json: N = 40, far smaller than a tile, so every tile
+    position wraps the ring ~25 times; several rejected attempts) with the one-kernel attempt switched on: same times,
+    same step / attempt / rejection counts, states within the tolerance the default path is held to."""
+    import json
+    import os
+    ctx = nn.default_context()
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "trajectories.json")) as fh:
+        golden = json.load(fh)
+    unhex = lambda xs: np.array([float.fromhex(x) for x in xs], dtype=np.float64)
+    checked = 0
+    try:
+        ctx.set("fuse_stencil_attempt", 1)
+        for name, g in golden.items():
+            if g["rhs"]["kind"] != "l96" or g["integrator"] not in ("dopri54", "tsit54", "vern65"):
+                continue
+            l0 = ctx.stats()["launches"]
+            t, ys = nn.solveODE(nn.rhsLorenz96(g["rhs"]["F"]), nn.newVector(unhex(g["y0"])), unhex(g["tspan"]), nn.newODEoptions(**g["options"]),
+                                integrator=g["integrator"])
+            st = dict(nn.ode.last_stats)
+            assert np.array_equal(np.array(t).view(np.uint64), unhex(g["t"]).view(np.uint64)), name
+            assert (st["steps"], st["attempts"], st["rejected"], st["limiter_hits"]) == (g["steps"], g["attempts"], g["rejected"], g["limiter_hits"]), (name, st)
+            got, want = np.array([v.to_numpy() for v in ys]), np.array([unhex(r) for r in g["y"]])
+            assert got.shape == want.shape and np.all(np.abs(got - want) <= 1e-6 * np.abs(want) + 1e-13 * np.max(np.abs(want))), name
+            assert ctx.stats()["launches"] - l0 < 3 * g["attempts"] + 16   # one kernel per attempt (+ dense output / initial evaluations)
+            checked += 1
+        assert checked >= 1
+    finally:
+        ctx.set("fuse_stencil_attempt", 0)

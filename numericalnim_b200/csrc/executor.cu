@@ -328,7 +328,7 @@ static bool l96_attempt_shards_ok(const b200rk_ctx* c, size_t n_global) {
 // The HL elements before this shard and the HR after it, of y and of k1 (FSAL): one grouped exchange with the ring
 // neighbours on the context stream per IntegratorProc call — y and k1 do not change between the retries of an attempt.
 // Layout of each halo array: [0, HL) = left neighbour's tail, [HL, HL + HR) = right neighbour's head.
-static int exchange_attempt_halo(b200rk_ctx* c, const b200rk_vec* y, const b200rk_vec* fsal, int HL, int HR) {
+static int exchange_attempt_halo(b200rk_ctx* c, const b200rk_vec* y, const b200rk_vec* fsal /* null: y only (RK4) */, int HL, int HR) {
   if (!c->d_halo_attempt) CUDA_TRY(c, cudaMalloc(&c->d_halo_attempt, 2 * kAttemptHaloMax * sizeof(double)));
   double *hy = c->d_halo_attempt, *hk = c->d_halo_attempt + kAttemptHaloMax;
   const size_t n = y->n_local;
@@ -336,12 +336,16 @@ static int exchange_attempt_halo(b200rk_ctx* c, const b200rk_vec* y, const b200r
   NCCL_TRY(c, g_nccl.GroupStart());   // same order on every rank: with world == 2 both neighbours are the same peer and the pairs match in order
   NCCL_TRY(c, g_nccl.Send(y->d, HR, ncclDouble, left, c->comm, c->stream));
   NCCL_TRY(c, g_nccl.Send(y->d + n - HL, HL, ncclDouble, right, c->comm, c->stream));
-  NCCL_TRY(c, g_nccl.Send(fsal->d, HR, ncclDouble, left, c->comm, c->stream));
-  NCCL_TRY(c, g_nccl.Send(fsal->d + n - HL, HL, ncclDouble, right, c->comm, c->stream));
+  if (fsal) {
+    NCCL_TRY(c, g_nccl.Send(fsal->d, HR, ncclDouble, left, c->comm, c->stream));
+    NCCL_TRY(c, g_nccl.Send(fsal->d + n - HL, HL, ncclDouble, right, c->comm, c->stream));
+  }
   NCCL_TRY(c, g_nccl.Recv(hy + HL, HR, ncclDouble, right, c->comm, c->stream));
   NCCL_TRY(c, g_nccl.Recv(hy, HL, ncclDouble, left, c->comm, c->stream));
-  NCCL_TRY(c, g_nccl.Recv(hk + HL, HR, ncclDouble, right, c->comm, c->stream));
-  NCCL_TRY(c, g_nccl.Recv(hk, HL, ncclDouble, left, c->comm, c->stream));
+  if (fsal) {
+    NCCL_TRY(c, g_nccl.Recv(hk + HL, HR, ncclDouble, right, c->comm, c->stream));
+    NCCL_TRY(c, g_nccl.Recv(hk, HL, ncclDouble, left, c->comm, c->stream));
+  }
   NCCL_TRY(c, g_nccl.GroupEnd());
   c->collectives++;
   return B200RK_OK;
@@ -372,6 +376,23 @@ static int launch_l96_attempt(b200rk_ctx* c, const MethodDef& md, double F, bool
   return B200RK_OK;
 }
 
+// A whole RK4 step with the built-in Lorenz-96 right-hand side in one kernel (stencil_attempt.cuh: l96_rk4_kernel).
+static int launch_l96_rk4(b200rk_ctx* c, double F, bool negate, double dt, const b200rk_vec* y, b200rk_vec* y_new) {
+  constexpr int J = 2, OUT = 2 * J * kThreads - 8 - 4;
+  L96Rk4Args a;
+  std::memset(&a, 0, sizeof(a));
+  a.y = y->d; a.ynew = y_new->d; a.n = y->n_local;
+  a.F = F; a.hdt = 0.5 * dt; a.dt = dt; a.c6 = dt / 6.0;   // same host scalars as launch_fused_rk4 / launch_rk4_final
+  if (c->world > 1) a.halo_y = c->d_halo_attempt;
+  if (!a.n) return B200RK_OK;
+  const unsigned grid = (unsigned)((a.n + OUT - 1) / OUT);
+  ProfScope ps(c, B200RK_K_FUSED, 8.0 * double(a.n) * 2);   // y read, yNew written
+  if (negate) l96_rk4_kernel<J, kThreads, true><<<grid, kThreads, 0, c->stream>>>(a);
+  else l96_rk4_kernel<J, kThreads, false><<<grid, kThreads, 0, c->stream>>>(a);
+  CUDA_TRY(c, cudaGetLastError());
+  return B200RK_OK;
+}
+
 // One IntegratorProc call. y, fsal read-only; y_new, fsal_new written.
 int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, double t, const b200rk_vec* y,
                    const b200rk_vec* fsal, double dt_in, const b200rk_options& o, b200rk_vec* y_new,
@@ -392,9 +413,11 @@ int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, double t, co
   // beyond a CTA's own outputs, so the outputs must not alias the inputs)
   const bool l96_builtin = !fused && rhs.f == &builtin_rhs_fn && static_cast<const BuiltinRhs*>(rhs.user)->kind == B200RK_RHS_LORENZ96 &&
                            y->n_global >= 4;
-  bool l96_attempt = l96_builtin && c->fuse_stencil_attempt && (c->world == 1 || l96_attempt_shards_ok(c, y->n_global)) && method_fusable(md) && !md.rk4_final && fsal && fsal_new &&
-                     y_new->d != y->d && y_new->d != fsal->d && fsal_new->d != y->d && fsal_new->d != fsal->d;
-  if (l96_attempt) { fused_pat = fused_pattern_of(c, md); l96_attempt = fused_pat >= 0; }
+  bool l96_attempt = l96_builtin && c->fuse_stencil_attempt && (c->world == 1 || l96_attempt_shards_ok(c, y->n_global)) && method_fusable(md) &&
+                     y_new->d != y->d;
+  if (l96_attempt && !md.rk4_final)
+    l96_attempt = fsal && fsal_new && y_new->d != fsal->d && fsal_new->d != y->d && fsal_new->d != fsal->d;
+  if (l96_attempt && !md.rk4_final) { fused_pat = fused_pattern_of(c, md); l96_attempt = fused_pat >= 0; }
   if (fused) TRY(check_pw_sizes(c, pw, y));
   fused = fused || l96_attempt;
   if (md.k1_from_fsal) {
@@ -413,8 +436,10 @@ int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, double t, co
     if (!(last_input_is_ynew && S == 2)) TRY(ws.get(N, &tmp));
   }
 
-  if (l96_attempt && c->world > 1)
-    TRY(exchange_attempt_halo(c, y, fsal, S == 9 ? StencilTile<9>::HL : StencilTile<7>::HL, S == 9 ? StencilTile<9>::HR : StencilTile<7>::HR));
+  if (l96_attempt && c->world > 1) {
+    if (md.rk4_final) TRY(exchange_attempt_halo(c, y, nullptr, 8, 4));
+    else TRY(exchange_attempt_halo(c, y, fsal, S == 9 ? StencilTile<9>::HL : StencilTile<7>::HL, S == 9 ? StencilTile<9>::HR : StencilTile<7>::HR));
+  }
   double dt = dt_in, error = 0.0;
   int limitCounter = 0;
   while (true) {
@@ -423,7 +448,11 @@ int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, double t, co
       // element-local right-hand side: the whole attempt is one kernel (the callbacks it stands for are
       // still counted so rhs_evals matches the unfused path)
       if (rhs.evals) *rhs.evals += md.rk4_final ? 4 : (S - 1);
-      if (md.rk4_final) { TRY(launch_fused_rk4(c, pw, rhs.negate_time, t, dt, y, y_new)); break; }
+      if (md.rk4_final) {
+        if (l96_attempt) TRY(launch_l96_rk4(c, static_cast<const BuiltinRhs*>(rhs.user)->scalar, rhs.negate_time, dt, y, y_new));
+        else TRY(launch_fused_rk4(c, pw, rhs.negate_time, t, dt, y, y_new));
+        break;
+      }
       if (l96_attempt) {
         const double F = static_cast<const BuiltinRhs*>(rhs.user)->scalar;
         switch (fused_pat) {

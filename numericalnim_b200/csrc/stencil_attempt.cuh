@@ -45,11 +45,21 @@ struct L96AttemptArgs {
   const double* halo_k;
 };
 
-// stage s (compile-time) of every element the thread owns; recursion keeps the row masks template constants.
-// A thread owns J pairs of adjacent positions (p, p+1): of the stencil's operands only in[p-2], in[p-1] (one 128-bit
-// shared-memory load) and in[p+2] come from other threads, in[p] and in[p+1] are its own registers.
+// lorenz96_kernel's ((y[i+1] - y[i-2]) * y[i-1] - y[i]) + F at the two adjacent positions p, p+1 a thread owns: c0, c1 are
+// its own stage inputs (registers), sh[p-2], sh[p-1] (one 128-bit shared-memory load) and sh[p+2] its neighbours'.
 // NEG: the backward pass g = -f(-t, y) (ode.nim:545). v * (+1.0) == v and v * (-1.0) == -v exactly, so instead of
 // stage_l96_kernel's multiplication by sgn the sign is a compile-time negation (an operand modifier, no fp64 issue).
+template <bool NEG>
+__device__ __forceinline__ void l96_pair(const double* sh, int p, double c0, double c1, double F, double& k0, double& k1) {
+  const double m2 = sh[p - 2], m1 = sh[p - 1], p2 = sh[p + 2];
+  const double v0 = __dadd_rn(__dadd_rn(__dmul_rn(__dadd_rn(c1, -m2), m1), -c0), F);
+  const double v1 = __dadd_rn(__dadd_rn(__dmul_rn(__dadd_rn(p2, -m1), c0), -c1), F);
+  k0 = NEG ? -v0 : v0;
+  k1 = NEG ? -v1 : v1;
+}
+
+// stage s (compile-time) of every element the thread owns; recursion keeps the row masks template constants.
+// A thread owns J pairs of adjacent positions (p, p+1).
 template <int PAT, int s, int J, int TW, bool NEG>
 struct L96Stages {
   template <int S>
@@ -66,18 +76,23 @@ struct L96Stages {
     for (int j = 0; j < J; ++j) { sh[pos[j]] = in[2 * j]; sh[pos[j] + 1] = in[2 * j + 1]; }
     __syncthreads();   // the other buffer was last read before the previous stage's barrier: one barrier per stage
 #pragma unroll
-    for (int j = 0; j < J; ++j) {
-      const int p = pos[j];
-      const double m2 = sh[p - 2], m1 = sh[p - 1], p2 = sh[p + 2];
-      const double c0 = in[2 * j], c1 = in[2 * j + 1];
-      // lorenz96_kernel: ((y[i+1] - y[i-2]) * y[i-1] - y[i]) + F at i = p and i = p + 1
-      const double v0 = __dadd_rn(__dadd_rn(__dmul_rn(__dadd_rn(c1, -m2), m1), -c0), a.F);
-      const double v1 = __dadd_rn(__dadd_rn(__dmul_rn(__dadd_rn(p2, -m1), c0), -c1), a.F);
-      k[2 * j][s - 1] = NEG ? -v0 : v0;
-      k[2 * j + 1][s - 1] = NEG ? -v1 : v1;
-    }
+    for (int j = 0; j < J; ++j) l96_pair<NEG>(sh, pos[j], in[2 * j], in[2 * j + 1], a.F, k[2 * j][s - 1], k[2 * j + 1][s - 1]);
   }
 };
+
+// Position p of the tile that stores [tile0, tile0 + OUT): element tile0 - HL + p of the block — from the block itself,
+// cyclically (single GPU, halo == nullptr), or from the neighbours' halos (sharded; [0, HL) left, [HL, HL + HR) right).
+template <int HL, int HR>
+__device__ __forceinline__ double l96_edge_load(const double* v, const double* halo, size_t n, size_t tile0, int p) {
+  if (halo) {
+    const long long idx = (long long)tile0 - HL + p;
+    if (idx < 0) return halo[HL + idx];
+    if ((size_t)idx < n) return v[idx];
+    if ((size_t)idx - n < (size_t)HR) return halo[HL + ((size_t)idx - n)];
+    return 0.0;   // further right: beyond what any stored position depends on
+  }
+  return v[(tile0 + (size_t)p + (n - (size_t)HL % n)) % n];
+}
 
 template <int PAT, int J, int THREADS, bool NEG>
 __global__ void __launch_bounds__(THREADS) l96_attempt_kernel(const L96AttemptArgs<Pattern<PAT>::S> a) {
@@ -94,7 +109,6 @@ __global__ void __launch_bounds__(THREADS) l96_attempt_kernel(const L96AttemptAr
   double y[E], k[E][S], in[E];
   int pos[J];   // first position of each pair the thread owns
   const bool interior = tile0 >= (size_t)HL && tile0 - HL + TW <= n;
-  const size_t wrap = n - (size_t)HL % n;                 // (tile0 + p + wrap) % n == tile0 - HL + p (mod n)
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     const int p = 2 * ((int)threadIdx.x + j * THREADS);
@@ -107,19 +121,8 @@ __global__ void __launch_bounds__(THREADS) l96_attempt_kernel(const L96AttemptAr
     } else {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        if (a.halo_y) {  // shard: positions before / after the block come from the neighbours' halos
-          const long long idx = (long long)tile0 - HL + (p + h);
-          const double *ys = nullptr, *kq = nullptr;
-          if (idx < 0) { ys = a.halo_y + (HL + idx); kq = a.halo_k + (HL + idx); }
-          else if ((size_t)idx < n) { ys = a.f.y + idx; kq = a.f.k1 + idx; }
-          else if ((size_t)idx - n < (size_t)HR) { ys = a.halo_y + (HL + ((size_t)idx - n)); kq = a.halo_k + (HL + ((size_t)idx - n)); }
-          y[2 * j + h] = ys ? *ys : 0.0;   // further right: beyond what any stored position depends on
-          k[2 * j + h][0] = kq ? *kq : 0.0;
-        } else {
-          const size_t g = (tile0 + (size_t)(p + h) + wrap) % n;
-          y[2 * j + h] = a.f.y[g];
-          k[2 * j + h][0] = a.f.k1[g];
-        }
+        y[2 * j + h] = l96_edge_load<HL, HR>(a.f.y, a.halo_y, n, tile0, p + h);
+        k[2 * j + h][0] = l96_edge_load<HL, HR>(a.f.k1, a.halo_k, n, tile0, p + h);
       }
     }
   }
@@ -178,6 +181,70 @@ __global__ void __launch_bounds__(THREADS) l96_attempt_kernel(const L96AttemptAr
 #else
   grid_sum_finish<THREADS>(acc, a.f.rs);
 #endif
+}
+
+// ---------------------------------------------------------------------------------------------------
+// A whole RK4 step (ode.nim:180-189) for the built-in Lorenz-96 right-hand side in one kernel, same tiling: four
+// stencil evaluations (k1 = f(y) included: RK4 has no FSAL) -> overlap 8 left / 4 right; reads y, writes yNew. Stage
+// inputs y + k*hdt (hdt = 0.5*dt from the host), y + k3*dt and the final combine are fused_rk4_elem / rk4_elem.
+// ---------------------------------------------------------------------------------------------------
+struct L96Rk4Args {
+  const double* y;
+  double* ynew;
+  size_t n;
+  double F, hdt, dt, c6;
+  const double* halo_y;   // sharded: 8 elements before the block, 4 after it (null on a single GPU)
+};
+
+template <int J, int THREADS, bool NEG>
+__global__ void __launch_bounds__(THREADS) l96_rk4_kernel(const L96Rk4Args a) {
+  constexpr int E = 2 * J, TW = E * THREADS, HL = 8, HR = 4, OUT = TW - HL - HR;
+  __shared__ double buf[2][TW + 4];
+  const size_t n = a.n;
+  const size_t tile0 = (size_t)blockIdx.x * OUT;
+  if (threadIdx.x < 3) {
+    const int q = threadIdx.x < 2 ? (int)threadIdx.x : TW + 2;
+    buf[0][q] = 0.0; buf[1][q] = 0.0;
+  }
+  double y[E], k[4][E], in[E];
+  int pos[J];
+  const bool interior = tile0 >= (size_t)HL && tile0 - HL + TW <= n;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int p = 2 * ((int)threadIdx.x + j * THREADS);
+    pos[j] = p;
+    if (interior) {
+      const Pk<2> yv = ld_stream<2>(a.y + (tile0 - HL + p));
+      y[2 * j] = yv.v[0]; y[2 * j + 1] = yv.v[1];
+    } else {
+      y[2 * j] = l96_edge_load<HL, HR>(a.y, a.halo_y, n, tile0, p);
+      y[2 * j + 1] = l96_edge_load<HL, HR>(a.y, a.halo_y, n, tile0, p + 1);
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {   // stage s + 1: its input, published; then k_{s+1} from the neighbours' inputs
+    double* sh = buf[s & 1] + 2;
+    const double c = (s == 3) ? a.dt : a.hdt;
+#pragma unroll
+    for (int e = 0; e < E; ++e) in[e] = (s == 0) ? y[e] : __dadd_rn(y[e], __dmul_rn(k[s - 1 < 0 ? 0 : s - 1][e], c));
+#pragma unroll
+    for (int j = 0; j < J; ++j) { sh[pos[j]] = in[2 * j]; sh[pos[j] + 1] = in[2 * j + 1]; }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < J; ++j) l96_pair<NEG>(sh, pos[j], in[2 * j], in[2 * j + 1], a.F, k[s][2 * j], k[s][2 * j + 1]);
+  }
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int p = pos[j];
+    const size_t g = tile0 + (size_t)(p - HL);
+    if (p >= HL && p < HL + OUT && g < n) {
+      Pk<2> o;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) o.v[h] = rk4_elem(y[2 * j + h], k[0][2 * j + h], k[1][2 * j + h], k[2][2 * j + h], k[3][2 * j + h], a.c6);
+      if (g + 1 < n) st_stream<2>(a.ynew + g, o);
+      else a.ynew[g] = o.v[0];
+    }
+  }
 }
 
 }  // namespace b200rk

@@ -227,6 +227,51 @@ static void test_l96_attempt(const char* name, const rk_oracle::Pair& p, rk_orac
   report(std::string("l96_attempt_kernel (whole attempt, overlapped tiles; ") + std::to_string(splits) + " sharded splits) " + name, ok && splits >= 16);
 }
 
+// ---- a whole RK4 step with the Lorenz-96 stencil in one kernel (l96_rk4_kernel) vs the oracle's RK4_step: bit for bit,
+// the ring as one block and shard by shard with halos ------------------------------------------------------------------------
+static void test_l96_rk4() {
+  constexpr int J = 2, HL = 8, HR = 4, OUT = 2 * J * T - HL - HR;
+  bool ok = true;
+  int splits = 0;
+  for (size_t n : {size_t(4), size_t(5), size_t(7), size_t(40), size_t(OUT - 1), size_t(OUT), size_t(OUT + 1), size_t(2 * OUT + 3), size_t(1000)})
+    for (double sgn : {1.0, -1.0}) {
+      const double F = 8.0, dt = 0.004;
+      const auto y = rvec(n, 7.0, 9.0);
+      rk_oracle::OdeProc<Vector> f = rk_oracle::rhs_lorenz96(F);
+      if (sgn < 0) f = [F](double t, const Vector& v, rk_oracle::Context<Vector>* c) { return -rk_oracle::rhs_lorenz96(F)(-t, v, c); };  // ode.nim:545
+      const rk_oracle::Options o = rk_oracle::new_options(dt, 1e-3, 1e-3, 1.0, 1e-8);
+      rk_oracle::Context<Vector> ctx;
+      const auto ref = rk_oracle::rk4_step<Vector>(f, 0.0, Vector(y), Vector(y), dt, o, &ctx);
+      auto run = [&](const L96Rk4Args& a, unsigned grid) {
+        if (sgn < 0) emul_launch(grid, T, [&] { l96_rk4_kernel<J, T, true>(a); });
+        else emul_launch(grid, T, [&] { l96_rk4_kernel<J, T, false>(a); });
+      };
+      std::vector<double> ynew(n, -5.0);
+      L96Rk4Args a;
+      std::memset(&a, 0, sizeof(a));
+      a.y = y.data(); a.ynew = ynew.data(); a.n = n; a.F = F; a.hdt = 0.5 * dt; a.dt = dt; a.c6 = dt / 6.0;
+      run(a, (unsigned)((n + OUT - 1) / OUT));
+      ok = ok && same_bits(ynew, ref.y_new.components);
+      for (size_t G : {size_t(2), size_t(3)}) {
+        const size_t chunk = ((n + G - 1) / G + 3) / 4 * 4;           // runtime.cu: shard_range
+        if (n < chunk * (G - 1) + HL || chunk < (size_t)HL) continue;
+        std::vector<double> yn2(n, -5.0);
+        ++splits;
+        for (size_t r = 0; r < G; ++r) {
+          const size_t lo = r * chunk, len = std::min(n, lo + chunk) - lo;
+          std::vector<double> hy(HL + HR);
+          for (int i = 0; i < HL; ++i) hy[i] = y[(lo + n - HL + i) % n];
+          for (int i = 0; i < HR; ++i) hy[HL + i] = y[(lo + len + i) % n];
+          L96Rk4Args b = a;
+          b.y = y.data() + lo; b.ynew = yn2.data() + lo; b.n = len; b.halo_y = hy.data();
+          run(b, (unsigned)((len + OUT - 1) / OUT));
+        }
+        ok = ok && same_bits(yn2, ref.y_new.components);
+      }
+    }
+  report("l96_rk4_kernel (whole RK4 step, overlapped tiles; " + std::to_string(splits) + " sharded splits)", ok && splits >= 16);
+}
+
 // ---- positive control for the race detector: a tile kernel with its barrier removed ---------------------------------
 template <int THREADS>
 __global__ void racy_tile_kernel(const double* in, double* out) {
@@ -251,6 +296,7 @@ int main(int argc, char** argv) {
   test_l96_attempt<PAT_DOPRI54>("dopri54", rk_oracle::dopri54_pair(), &rk_oracle::dopri54_step<Vector>);
   test_l96_attempt<PAT_TSIT54>("tsit54", rk_oracle::tsit54_pair(), &rk_oracle::tsit54_step<Vector>);
   test_l96_attempt<PAT_VERN65>("vern65", rk_oracle::vern65_pair(), &rk_oracle::vern65_step<Vector>);
+  test_l96_rk4();
   test_device_loop<PAT_DOPRI54, PW_DIAG, 2>("dopri54 diag W=2", rk_oracle::dopri54_pair(), &rk_oracle::dopri54_step<Vector>);
   test_device_loop<PAT_TSIT54, PW_DIAG, 4>("tsit54 diag W=4", rk_oracle::tsit54_pair(), &rk_oracle::tsit54_step<Vector>);
   test_device_loop<PAT_VERN65, PW_DIAG, 2>("vern65 diag W=2", rk_oracle::vern65_pair(), &rk_oracle::vern65_step<Vector>);

@@ -241,3 +241,41 @@ def test_l96_attempt_matches_golden_lorenz96_fixtures(nn):
         assert checked >= 1
     finally:
         ctx.set("fuse_stencil_attempt", 0)
+
+
+def test_l96_rk4_step_in_one_kernel_is_bit_identical(nn):
+    """knob fuse_stencil_attempt with RK4 (l96_rk4_kernel: k1..k4 and the final combine of one step over overlapped
+    tiles, 8 + 4 elements of overlap): fixed step, so whole trajectories — dense output on both sides of tStart included —
+    carry the same bits as the stage+stencil pipeline and the oracle; one launch per step instead of five."""
+    import oracle as O
+    ctx = nn.default_context()
+    rng = np.random.default_rng(23)
+    o = nn.newODEoptions(dt=0.005)
+    rhs = nn.rhsLorenz96(8.0)
+    try:
+        for n in [4, 5, 7, 21, 1011, 1012, 1013, 1024, 2024, 2025, 3049]:
+            y = 8.0 + rng.uniform(-1.0, 1.0, n)
+            gy = nn.newVector(y)
+            res = {}
+            for fuse in (1, 0):
+                ctx.set("fuse_stencil_attempt", fuse)
+                l0 = ctx.stats()["launches"]
+                yn, fn, dt_used, err = nn.integratorStep("rk4", rhs, 0.0, gy, None, 0.005, o)
+                res[fuse] = (yn.to_numpy(), fn.to_numpy(), ctx.stats()["launches"] - l0)
+            ref = O.step_vector("rk4", O.rhs_lorenz96(8.0), 0.0, y, y, 0.005, O.new_options(dt=0.005))[0]
+            for a, b, what in ((res[1][0], res[0][0], "yNew vs pipeline"), (res[1][1], res[0][1], "returned FSAL vs pipeline"), (res[1][0], ref, "yNew vs oracle")):
+                assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), (n, what)
+            assert res[1][2] < res[0][2]
+        n = 1500
+        y0 = 8.0 + 0.01 * np.sin(2 * np.pi * 37 * np.arange(n) / n)
+        ts = nn.linspace(-0.05, 0.1, 7)
+        out = {}
+        for fuse in (1, 0):
+            ctx.set("fuse_stencil_attempt", fuse)
+            t, ys = nn.solveODE(rhs, nn.newVector(y0), ts, nn.newODEoptions(dt=2e-3), integrator="rk4")
+            out[fuse] = np.array([v.to_numpy() for v in ys])
+        want = O.solve_vector("rk4", O.rhs_lorenz96(8.0), y0, ts, O.new_options(dt=2e-3)).y
+        assert np.array_equal(out[1].view(np.uint64), out[0].view(np.uint64))
+        assert np.array_equal(out[1].view(np.uint64), np.asarray(want).view(np.uint64))
+    finally:
+        ctx.set("fuse_stencil_attempt", 0)

@@ -2,8 +2,14 @@
 verified bit for bit by host emulation (tests/test_kernel_host_emulation.py) but have not run on a B200 yet. The tests
 below compare them with the default (GPU-verified) path; they are non-strict xfail so that their first GPU run is
 reported (XPASS / xfail) without being able to turn the suite red or to mask anything (the file runs last)."""
+import os
+
 import numpy as np
 import pytest
+
+# AddressSanitizer pass of the host-emulated library (tests/test_host_emulated_library.py): the thread-per-CUDA-thread
+# kernels are slow there, a few sizes around the tile seams are enough to catch an out-of-bounds access
+LIGHT = bool(os.environ.get("B200RK_TEST_EMULATION_SANITIZE"))
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.xfail(strict=False, reason="experimental, off by default: verified by host emulation, first GPU run pending")]
@@ -150,13 +156,15 @@ def test_l96_attempt_kernel_bitwise_equals_pipeline(nn, method, stages):
              2 * out_per_tile + 2, 3 * out_per_tile + 13]
     if not os.environ.get("B200RK_TEST_HOST_EMULATION"):
         sizes += [8192 + 5, (1 << 20) + 7]   # on the GPU also sizes with thousands of tiles
+    if LIGHT:
+        sizes = [5, out_per_tile - 1, out_per_tile, out_per_tile + 1, 1025, 2 * out_per_tile + 2]
     opts = dict(absTol=1e-2, relTol=1e-2, dtMax=1.0, dtMin=1e-8, dt=0.005)
     o = nn.newODEoptions(**opts)
     rhs = nn.rhsLorenz96(8.0)
     try:
         for strict in (0, 1):
             ctx.set("strict_zeros", strict)
-            for n in (sizes if not strict else sizes[5:9]):
+            for n in (sizes if not strict else sizes[5:9] if not LIGHT else sizes[2:3]):
                 y = 8.0 + rng.uniform(-1.0, 1.0, n)
                 fs = O.rhs_eval(O.rhs_lorenz96(8.0), 0.0, y)
                 gy, gf = nn.newVector(y), nn.newVector(fs)
@@ -189,9 +197,9 @@ def test_l96_attempt_solve_matches_pipeline_and_oracle(nn, method):
     default pipeline sits at the same 5e-11 from the oracle)."""
     import oracle as O
     ctx = nn.default_context()
-    n = 2500
+    n = 2500 if not LIGHT else 1100
     y0 = 8.0 + np.random.default_rng(3).uniform(-4.0, 4.0, n)   # rough state: the controller overshoots and rejects
-    ts = nn.linspace(-0.1, 0.3, 5)
+    ts = nn.linspace(-0.1, 0.3, 5) if not LIGHT else nn.linspace(-0.05, 0.1, 4)
     opts = dict(absTol=1e-5, relTol=1e-5, dtMax=1.0, dtMin=1e-4, tStart=0.0)
     res = {}
     try:
@@ -205,7 +213,7 @@ def test_l96_attempt_solve_matches_pipeline_and_oracle(nn, method):
             assert res[fuse][0] == list(ref.t)
             assert res[fuse][2]["steps"] == ref.stats.steps and res[fuse][2]["rejected"] == ref.stats.rejected, (fuse, res[fuse][2])
             assert np.max(np.abs(res[fuse][1] - ref.y)) <= 1e-9 * np.max(np.abs(ref.y)), fuse
-        assert ref.stats.rejected > 0
+        assert LIGHT or ref.stats.rejected > 0
         assert np.max(np.abs(res[1][1] - res[0][1])) <= 1e-9 * np.max(np.abs(res[0][1]))
         assert res[1][3] < res[0][3] / 3
     finally:
@@ -253,7 +261,7 @@ def test_l96_rk4_step_in_one_kernel_is_bit_identical(nn):
     o = nn.newODEoptions(dt=0.005)
     rhs = nn.rhsLorenz96(8.0)
     try:
-        for n in [4, 5, 7, 21, 1011, 1012, 1013, 1024, 2024, 2025, 3049]:
+        for n in ([4, 5, 7, 21, 1011, 1012, 1013, 1024, 2024, 2025, 3049] if not LIGHT else [5, 1012, 1013, 2025]):
             y = 8.0 + rng.uniform(-1.0, 1.0, n)
             gy = nn.newVector(y)
             res = {}
@@ -268,7 +276,7 @@ def test_l96_rk4_step_in_one_kernel_is_bit_identical(nn):
             assert res[1][2] < res[0][2]
         n = 1500
         y0 = 8.0 + 0.01 * np.sin(2 * np.pi * 37 * np.arange(n) / n)
-        ts = nn.linspace(-0.05, 0.1, 7)
+        ts = nn.linspace(-0.05, 0.1, 7) if not LIGHT else nn.linspace(-0.01, 0.02, 4)
         out = {}
         for fuse in (1, 0):
             ctx.set("fuse_stencil_attempt", fuse)

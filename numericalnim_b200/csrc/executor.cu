@@ -351,10 +351,10 @@ static int exchange_attempt_halo(b200rk_ctx* c, const b200rk_vec* y, const b200r
   return B200RK_OK;
 }
 
-template <int PAT>
-static int launch_l96_attempt(b200rk_ctx* c, const MethodDef& md, double F, bool negate, double dt, const b200rk_options& o,
-                              const b200rk_vec* y, const b200rk_vec* fsal, b200rk_vec* y_new, b200rk_vec* fsal_new) {
-  constexpr int S = Pattern<PAT>::S, J = 2;
+template <int PAT, int J>
+static int launch_l96_attempt_j(b200rk_ctx* c, const MethodDef& md, double F, bool negate, double dt, const b200rk_options& o,
+                                const b200rk_vec* y, const b200rk_vec* fsal, b200rk_vec* y_new, b200rk_vec* fsal_new) {
+  constexpr int S = Pattern<PAT>::S;
   constexpr int OUT = 2 * J * kThreads - StencilTile<S>::HL - StencilTile<S>::HR;
   L96AttemptArgs<S> a;
   std::memset(&a, 0, sizeof(a));
@@ -374,6 +374,15 @@ static int launch_l96_attempt(b200rk_ctx* c, const MethodDef& md, double F, bool
   else l96_attempt_kernel<PAT, J, kThreads, false><<<grid, kThreads, 0, c->stream>>>(a);
   CUDA_TRY(c, cudaGetLastError());
   return B200RK_OK;
+}
+
+// Tile width = 512 * J positions (knob "l96_attempt_pairs": 2 = 1024-wide tiles, 2 % overlap, 80-98 registers; 1 = 512-wide,
+// 4 % overlap, fewer registers and more resident CTAs) — to be settled by measurement.
+template <int PAT>
+static int launch_l96_attempt(b200rk_ctx* c, const MethodDef& md, double F, bool negate, double dt, const b200rk_options& o,
+                              const b200rk_vec* y, const b200rk_vec* fsal, b200rk_vec* y_new, b200rk_vec* fsal_new) {
+  if (c->l96_attempt_pairs == 1) return launch_l96_attempt_j<PAT, 1>(c, md, F, negate, dt, o, y, fsal, y_new, fsal_new);
+  return launch_l96_attempt_j<PAT, 2>(c, md, F, negate, dt, o, y, fsal, y_new, fsal_new);
 }
 
 // A whole RK4 step with the built-in Lorenz-96 right-hand side in one kernel (stencil_attempt.cuh: l96_rk4_kernel).

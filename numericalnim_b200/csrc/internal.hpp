@@ -77,6 +77,7 @@ struct b200rk_ctx {
   bool fuse_pointwise = true;  // element-local built-in RHS: whole attempt in one kernel
   bool fuse_stencil = true;    // built-in Lorenz-96 (single GPU): stage accumulate + stencil RHS in one kernel
   bool fuse_stencil_attempt = false;  // built-in Lorenz-96: a whole attempt in one kernel, overlapped tiles (experimental: verified by host emulation, not yet run on the GPU)
+  int l96_attempt_pairs = 2;   // l96_attempt_kernel: 128-bit pairs per thread (tile = 512 * pairs positions); 1 or 2
   bool finish_prefetch = false; // software-pipelined finish kernel (experimental: verified by host emulation, not yet measured on the GPU)
   int stream_simpson = -1;     // cumsimpson(f, X, dx): -1 = stream the grid only when the composed form would not fit, 0 never, 1 always
   bool fuse_simpson = false;   // cumsimpson as one kernel (experimental: verified by host emulation, not yet measured on the GPU)

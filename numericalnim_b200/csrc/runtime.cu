@@ -201,6 +201,7 @@ static int ctx_common_init(b200rk_ctx* c) {
   if (const char* e = getenv("B200RK_FUSE_POINTWISE")) c->fuse_pointwise = atoi(e) != 0;
   if (const char* e = getenv("B200RK_FUSE_STENCIL")) c->fuse_stencil = atoi(e) != 0;
   if (const char* e = getenv("B200RK_FUSE_STENCIL_ATTEMPT")) c->fuse_stencil_attempt = atoi(e) != 0;
+  if (const char* e = getenv("B200RK_L96_ATTEMPT_PAIRS")) c->l96_attempt_pairs = (atoi(e) == 1) ? 1 : 2;
   if (const char* e = getenv("B200RK_FUSE_SIMPSON")) c->fuse_simpson = atoi(e) != 0;
   if (const char* e = getenv("B200RK_FINISH_PREFETCH")) c->finish_prefetch = atoi(e) != 0;
   if (const char* e = getenv("B200RK_L2_HINTS")) c->l2_hints = atoi(e) < 0 ? -1 : (atoi(e) != 0);
@@ -291,6 +292,7 @@ int b200rk_set(b200rk_ctx* c, const char* key, int64_t v) {
   else if (k == "device_loop") c->device_loop = v < 0 ? -1 : (v != 0);
   else if (k == "fuse_stencil") c->fuse_stencil = v != 0;
   else if (k == "fuse_stencil_attempt") c->fuse_stencil_attempt = v != 0;
+  else if (k == "l96_attempt_pairs") { if (v != 1 && v != 2) return fail(c, B200RK_EINVAL, "l96_attempt_pairs must be 1 or 2"); c->l96_attempt_pairs = (int)v; }
   else if (k == "fuse_simpson") c->fuse_simpson = v != 0;
   else if (k == "finish_prefetch") c->finish_prefetch = v != 0;
   else if (k == "stream_simpson") c->stream_simpson = v < 0 ? -1 : (v != 0);
@@ -320,6 +322,7 @@ int b200rk_get(const b200rk_ctx* c, const char* key, int64_t* v) {
   else if (k == "p2p") *v = c->p2p;
   else if (k == "fuse_stencil") *v = c->fuse_stencil;
   else if (k == "fuse_stencil_attempt") *v = c->fuse_stencil_attempt;
+  else if (k == "l96_attempt_pairs") *v = c->l96_attempt_pairs;
   else if (k == "fuse_simpson") *v = c->fuse_simpson;
   else if (k == "finish_prefetch") *v = c->finish_prefetch;
   else if (k == "stream_simpson") *v = c->stream_simpson;

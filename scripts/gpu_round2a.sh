@@ -26,6 +26,7 @@ l96='import sys,json
 d=json.loads(sys.stdin.read()); a=d.get("l96_attempt") or {}
 print("default steps/s", round(d["value"],1), "attempts/s", round(d["attempts_per_sec"],1), "| one-kernel attempt:", {k: (round(v,1) if isinstance(v,float) else v) for k,v in a.items() if k != "note"})'
 timeout 400 python bench.py --workload cfg3_tsit54_lorenz96_16M --l96-attempt --no-jit --no-quad --no-cpu-baseline --e2e-reps 1 2>&1 | grep '^{"metric"' | tee gpurun_out/bench_cfg3_l96_attempt.json | python -c "$l96" | cut -c1-700
+B200RK_L96_ATTEMPT_PAIRS=1 timeout 400 python bench.py --workload cfg3_tsit54_lorenz96_16M --l96-attempt --no-jit --no-quad --no-cpu-baseline --e2e-reps 1 2>&1 | grep '^{"metric"' | python -c "$l96" | sed 's/^/512-wide tiles: /' | cut -c1-700
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:"l96_attempt_kernel" -s 2 -c 1 -o gpurun_out/prof_l96_attempt \
   python bench.py --workload cfg3_tsit54_lorenz96_16M --l96-attempt --steps 3 --warmup 3 --no-jit --no-quad --no-cpu-baseline --e2e-reps 1 > gpurun_out/ncu_l96_attempt.log 2>&1; tail -1 gpurun_out/ncu_l96_attempt.log | cut -c1-200
 echo "== 3. compute-sanitizer, tiny cases"

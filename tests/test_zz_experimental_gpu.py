@@ -140,18 +140,19 @@ def test_cumsimpson_fn_streams_a_fine_grid_by_itself(nn):
 
 
 # ---- knob fuse_stencil_attempt: a whole attempt of the built-in Lorenz-96 right-hand side in one kernel ---------------
+@pytest.mark.parametrize("pairs", [2, 1])
 @pytest.mark.parametrize("method,stages", [("dopri54", 7), ("tsit54", 7), ("vern65", 9)])
-def test_l96_attempt_kernel_bitwise_equals_pipeline(nn, method, stages):
+def test_l96_attempt_kernel_bitwise_equals_pipeline(nn, method, stages, pairs):
     """l96_attempt_kernel (stencil_attempt.cuh: overlapped tiles, stage inputs through shared memory): yNew and the new
     FSAL carry the same bits as the stage_l96_kernel / finish_kernel pipeline and as the oracle, at sizes around the
-    tile seams (1004 / 1000 stored elements per 1024-element tile) and below one tile (the tile wraps the cyclic domain
+    tile seams (1004 / 1000 stored elements per 1024-element tile; 492 / 488 per 512-element tile with l96_attempt_pairs=1) and below one tile (the tile wraps the cyclic domain
     several times), with and without the zero weights; one launch instead of S. (Backward time: the solve test below.)"""
     import os
 
     import oracle as O
     ctx = nn.default_context()
     rng = np.random.default_rng(17)
-    out_per_tile = 1024 - (12 + 8 if stages == 7 else 16 + 8)
+    out_per_tile = 512 * pairs - (12 + 8 if stages == 7 else 16 + 8)
     sizes = [4, 5, 7, 19, 21, out_per_tile - 1, out_per_tile, out_per_tile + 1, 1023, 1024, 1025, 2 * out_per_tile - 1, 2 * out_per_tile,
              2 * out_per_tile + 2, 3 * out_per_tile + 13]
     if not os.environ.get("B200RK_TEST_HOST_EMULATION"):
@@ -162,6 +163,7 @@ def test_l96_attempt_kernel_bitwise_equals_pipeline(nn, method, stages):
     o = nn.newODEoptions(**opts)
     rhs = nn.rhsLorenz96(8.0)
     try:
+        ctx.set("l96_attempt_pairs", pairs)
         for strict in (0, 1):
             ctx.set("strict_zeros", strict)
             for n in (sizes if not strict else sizes[5:9] if not LIGHT else sizes[2:3]):
@@ -187,6 +189,7 @@ def test_l96_attempt_kernel_bitwise_equals_pipeline(nn, method, stages):
     finally:
         ctx.set("strict_zeros", 0)
         ctx.set("fuse_stencil_attempt", 0)
+        ctx.set("l96_attempt_pairs", 2)
 
 
 @pytest.mark.parametrize("method", ["tsit54", "vern65"])

@@ -10,6 +10,7 @@
  * Conventions
  *   - plain C types only; every function returns an int status (0 = OK) and never throws;
  *     B200RK_EINVAL plays the role of Nim's ValueError; b200rk_last_error() returns the message.
+ *     A NULL handle or output pointer, and vectors of two different contexts in one call, are B200RK_EINVAL.
  *   - all device work is enqueued on the context's CUDA stream; functions that return scalars to the
  *     host (step, solve, sum) synchronise that stream, the others do not.
  *   - one context = one GPU = one host thread. Multi-GPU = one process (rank) per GPU; a vector of

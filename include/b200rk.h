@@ -99,7 +99,8 @@ B200RK_API int b200rk_world(const b200rk_ctx* ctx);
  * kernel; 0 = always the stage / RHS / finish pipeline), "fuse_stencil" (built-in Lorenz-96: stage accumulate + stencil
  * in one kernel), "device_loop" (-1 auto | 0 | 1: the whole adaptive loop in one persistent kernel), "spin_readback",
  * "l2_hints" (-1 auto | 0 | 1: producer/consumer hand-off through the L2), "fuse_simpson" / "finish_prefetch" / "fuse_stencil_attempt" (experimental, default 0:
- * cumsimpson as one kernel / software-pipelined finish kernel / a whole attempt of the built-in Lorenz-96 right-hand side in one kernel, with "l96_attempt_pairs" 1|2 = 512- or 1024-wide tiles), "profile" (0|1), "pool_budget_mb" (bytes of freed vectors the context keeps for reuse;
+ * cumsimpson as one kernel / software-pipelined finish kernel / a whole attempt of the built-in Lorenz-96 right-hand side in one kernel, with "l96_attempt_pairs" 1|2 = 512- or 1024-wide tiles and,
+ * sharded, "l96_peer_halo" 1|0 = halo read in place from the peer-mapped ring neighbours | one ncclSend/ncclRecv per step), "profile" (0|1), "pool_budget_mb" (bytes of freed vectors the context keeps for reuse;
  * 0 = release everything now). Read-only: "p2p", "sm_count". */
 B200RK_API int b200rk_set(b200rk_ctx* ctx, const char* key, int64_t value);
 B200RK_API int b200rk_get(const b200rk_ctx* ctx, const char* key, int64_t* value);

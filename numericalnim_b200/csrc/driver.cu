@@ -24,10 +24,22 @@ struct b200rk_solver {
   std::vector<b200rk_vec*>* emit = nullptr;
   bool finished = false;
   int64_t launches0 = 0, collectives0 = 0;
+  // sharded one-kernel Lorenz-96 attempt: Y[0..1], F[0..1] of the two ring neighbours, peer-mapped (runtime.cu)
+  PeerVecView peers;
 
   ~b200rk_solver() {
+    if (c && c->peer_view == &peers) c->peer_view = nullptr;
+    if (peers.count) peer_view_close(c, &peers);   // collective: every rank frees its solver at the same point of the program
     for (auto* v : {Y[0], Y[1], F[0], F[1], LDY, SCR}) if (v) vec_release(v);
   }
+};
+
+// ctx->peer_view names the advancing solver's mapping for the duration of one solver_begin / solver_advance call
+struct PeerViewScope {
+  b200rk_ctx* c;
+  const PeerVecView* prev;
+  PeerViewScope(b200rk_ctx* ctx, const PeerVecView* v) : c(ctx), prev(ctx->peer_view) { if (v->count) c->peer_view = v; }
+  ~PeerViewScope() { c->peer_view = prev; }
 };
 
 static int solver_alloc(b200rk_solver* s, size_t N) {
@@ -85,6 +97,9 @@ static int solver_begin(b200rk_solver* s, const b200rk_vec* y0, double sign, std
   }
   s->last_t = s->t; s->last_y = s->Y[0]; s->last_dy = s->LDY;
   s->dt = s->dtInit;
+  // peer-read halos: a neighbour's first attempt reads this rank's Y[0] / F[0] in place, so they must be complete on every
+  // rank before any rank goes on (from then on the per-attempt all-reduce of the error norm keeps the ranks in lockstep)
+  if (s->peers.count) TRY(stream_barrier(c));
   if (s->targets.empty()) { s->finished = true; return B200RK_OK; }
   if (sign > 0) s->tEnd = *std::max_element(s->targets.begin(), s->targets.end());   // ode.nim:510
   else s->tEnd = -*std::min_element(s->targets.begin(), s->targets.end());           // ode.nim:549
@@ -113,6 +128,7 @@ static int solver_emit_sample(b200rk_solver* s, double x) {
 // The `while t < tEnd` loop (ode.nim:511-541 / 553-583), resumable after max_steps accepted steps.
 static int solver_advance(b200rk_solver* s, int64_t max_steps, int64_t* steps_done) {
   b200rk_ctx* c = s->c;
+  PeerViewScope peer_scope(c, &s->peers);
   const MethodDef& md = *s->md;
   int64_t done = 0;
   const long high = (long)s->targets.size() - 1;
@@ -196,6 +212,10 @@ static int solver_create(b200rk_ctx* c, int method, b200rk_rhs_fn f, void* user,
   s->adaptive = s->md->adaptive;
   s->dtInit = s->adaptive ? std::sqrt(s->o.dtMax * s->o.dtMin) : s->o.dt;       // ode.nim:491-496
   int rc = solver_alloc(s, N);
+  if (rc == B200RK_OK && l96_peer_halo_possible(c, *s->md, s->rhs, N)) {
+    b200rk_vec* const vecs[4] = {s->Y[0], s->Y[1], s->F[0], s->F[1]};
+    rc = peer_view_open(c, vecs, 4, &s->peers);   // peers.count stays 0 when the mapping is not available: ncclSend/ncclRecv halo
+  }
   if (rc != B200RK_OK) { delete s; return rc; }
   *out = s;
   return B200RK_OK;

@@ -351,9 +351,36 @@ static int exchange_attempt_halo(b200rk_ctx* c, const b200rk_vec* y, const b200r
   return B200RK_OK;
 }
 
+// Where the halo of this call's y (and k1 = fsal) lives. Inside an advancing solver whose ring neighbours' vectors are
+// peer-mapped (ctx->peer_view) and for the adaptive pairs — whose all-reduce of the error norm keeps the ranks in
+// lockstep, so a neighbour's y / FSAL of this attempt is complete and stays untouched until every rank has finished
+// reading it — the halo is read in place over NVLink: no exchange, no collective. Otherwise (b200rk_step on arbitrary
+// vectors, RK4, no peer mapping) one grouped ncclSend/ncclRecv fills ctx->d_halo_attempt.
+static int l96_halo_for(b200rk_ctx* c, const MethodDef& md, const b200rk_vec* y, const b200rk_vec* fsal, int HL, int HR, L96Halo* h) {
+  *h = L96Halo{nullptr, nullptr, nullptr, nullptr};
+  if (c->world < 2) return B200RK_OK;
+  const PeerVecView* pv = c->peer_view;
+  const int iy = pv ? pv->find(y->d) : -1, ik = (pv && fsal) ? pv->find(fsal->d) : -1;
+  if (!md.rk4_final && iy >= 0 && ik >= 0) {
+    h->left_y = pv->left[iy] + (pv->n_left - HL); h->right_y = pv->right[iy];
+    h->left_k = pv->left[ik] + (pv->n_left - HL); h->right_k = pv->right[ik];
+    return B200RK_OK;
+  }
+  TRY(exchange_attempt_halo(c, y, md.rk4_final ? nullptr : fsal, HL, HR));
+  h->left_y = c->d_halo_attempt; h->right_y = c->d_halo_attempt + HL;
+  h->left_k = c->d_halo_attempt + kAttemptHaloMax; h->right_k = c->d_halo_attempt + kAttemptHaloMax + HL;
+  return B200RK_OK;
+}
+
+bool l96_peer_halo_possible(const b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, size_t n_global) {
+  return c->world > 1 && c->p2p && c->fuse_stencil_attempt && c->l96_peer_halo && rhs.f == &builtin_rhs_fn &&
+         static_cast<const BuiltinRhs*>(rhs.user)->kind == B200RK_RHS_LORENZ96 && md.adaptive && md.use_fsal && method_fusable(md) &&
+         !md.rk4_final && fused_pattern_of(c, md) >= 0 && l96_attempt_shards_ok(c, n_global);
+}
+
 template <int PAT, int J>
 static int launch_l96_attempt_j(b200rk_ctx* c, const MethodDef& md, double F, bool negate, double dt, const b200rk_options& o,
-                                const b200rk_vec* y, const b200rk_vec* fsal, b200rk_vec* y_new, b200rk_vec* fsal_new) {
+                                const L96Halo& halo, const b200rk_vec* y, const b200rk_vec* fsal, b200rk_vec* y_new, b200rk_vec* fsal_new) {
   constexpr int S = Pattern<PAT>::S;
   constexpr int OUT = 2 * J * kThreads - StencilTile<S>::HL - StencilTile<S>::HR;
   L96AttemptArgs<S> a;
@@ -365,7 +392,7 @@ static int launch_l96_attempt_j(b200rk_ctx* c, const MethodDef& md, double F, bo
   a.f.dt = dt; a.f.cb = dt; a.f.cbh = dt; a.f.absTol = o.absTol; a.f.relTol = o.relTol;
   a.f.ynew = y_new->d; a.f.ks_out = fsal_new->d; a.f.n = y->n_local;
   a.F = F;
-  if (c->world > 1) { a.halo_y = c->d_halo_attempt; a.halo_k = c->d_halo_attempt + kAttemptHaloMax; }  // filled by exchange_attempt_halo
+  a.halo = halo;
   const unsigned grid = (unsigned)((a.f.n + OUT - 1) / OUT);
   TRY(ensure_partials(c, grid));
   a.f.rs = reduce_scratch(c);
@@ -380,19 +407,19 @@ static int launch_l96_attempt_j(b200rk_ctx* c, const MethodDef& md, double F, bo
 // 4 % overlap, fewer registers and more resident CTAs) — to be settled by measurement.
 template <int PAT>
 static int launch_l96_attempt(b200rk_ctx* c, const MethodDef& md, double F, bool negate, double dt, const b200rk_options& o,
-                              const b200rk_vec* y, const b200rk_vec* fsal, b200rk_vec* y_new, b200rk_vec* fsal_new) {
-  if (c->l96_attempt_pairs == 1) return launch_l96_attempt_j<PAT, 1>(c, md, F, negate, dt, o, y, fsal, y_new, fsal_new);
-  return launch_l96_attempt_j<PAT, 2>(c, md, F, negate, dt, o, y, fsal, y_new, fsal_new);
+                              const L96Halo& halo, const b200rk_vec* y, const b200rk_vec* fsal, b200rk_vec* y_new, b200rk_vec* fsal_new) {
+  if (c->l96_attempt_pairs == 1) return launch_l96_attempt_j<PAT, 1>(c, md, F, negate, dt, o, halo, y, fsal, y_new, fsal_new);
+  return launch_l96_attempt_j<PAT, 2>(c, md, F, negate, dt, o, halo, y, fsal, y_new, fsal_new);
 }
 
 // A whole RK4 step with the built-in Lorenz-96 right-hand side in one kernel (stencil_attempt.cuh: l96_rk4_kernel).
-static int launch_l96_rk4(b200rk_ctx* c, double F, bool negate, double dt, const b200rk_vec* y, b200rk_vec* y_new) {
+static int launch_l96_rk4(b200rk_ctx* c, double F, bool negate, double dt, const L96Halo& halo, const b200rk_vec* y, b200rk_vec* y_new) {
   constexpr int J = 2, OUT = 2 * J * kThreads - 8 - 4;
   L96Rk4Args a;
   std::memset(&a, 0, sizeof(a));
   a.y = y->d; a.ynew = y_new->d; a.n = y->n_local;
   a.F = F; a.hdt = 0.5 * dt; a.dt = dt; a.c6 = dt / 6.0;   // same host scalars as launch_fused_rk4 / launch_rk4_final
-  if (c->world > 1) a.halo_y = c->d_halo_attempt;
+  a.halo = halo;
   if (!a.n) return B200RK_OK;
   const unsigned grid = (unsigned)((a.n + OUT - 1) / OUT);
   ProfScope ps(c, B200RK_K_FUSED, 8.0 * double(a.n) * 2);   // y read, yNew written
@@ -445,9 +472,10 @@ int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, double t, co
     if (!(last_input_is_ynew && S == 2)) TRY(ws.get(N, &tmp));
   }
 
-  if (l96_attempt && c->world > 1) {
-    if (md.rk4_final) TRY(exchange_attempt_halo(c, y, nullptr, 8, 4));
-    else TRY(exchange_attempt_halo(c, y, fsal, S == 9 ? StencilTile<9>::HL : StencilTile<7>::HL, S == 9 ? StencilTile<9>::HR : StencilTile<7>::HR));
+  L96Halo l96_halo{nullptr, nullptr, nullptr, nullptr};
+  if (l96_attempt) {  // y and k1 do not change between the retries of an attempt: once per call
+    if (md.rk4_final) TRY(l96_halo_for(c, md, y, nullptr, 8, 4, &l96_halo));
+    else TRY(l96_halo_for(c, md, y, fsal, S == 9 ? StencilTile<9>::HL : StencilTile<7>::HL, S == 9 ? StencilTile<9>::HR : StencilTile<7>::HR, &l96_halo));
   }
   double dt = dt_in, error = 0.0;
   int limitCounter = 0;
@@ -458,18 +486,18 @@ int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, double t, co
       // still counted so rhs_evals matches the unfused path)
       if (rhs.evals) *rhs.evals += md.rk4_final ? 4 : (S - 1);
       if (md.rk4_final) {
-        if (l96_attempt) TRY(launch_l96_rk4(c, static_cast<const BuiltinRhs*>(rhs.user)->scalar, rhs.negate_time, dt, y, y_new));
+        if (l96_attempt) TRY(launch_l96_rk4(c, static_cast<const BuiltinRhs*>(rhs.user)->scalar, rhs.negate_time, dt, l96_halo, y, y_new));
         else TRY(launch_fused_rk4(c, pw, rhs.negate_time, t, dt, y, y_new));
         break;
       }
       if (l96_attempt) {
         const double F = static_cast<const BuiltinRhs*>(rhs.user)->scalar;
         switch (fused_pat) {
-          case PAT_DOPRI54: TRY(launch_l96_attempt<PAT_DOPRI54>(c, md, F, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new)); break;
-          case PAT_DOPRI54_STRICT: TRY(launch_l96_attempt<PAT_DOPRI54_STRICT>(c, md, F, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new)); break;
-          case PAT_TSIT54: TRY(launch_l96_attempt<PAT_TSIT54>(c, md, F, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new)); break;
-          case PAT_VERN65: TRY(launch_l96_attempt<PAT_VERN65>(c, md, F, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new)); break;
-          default: TRY(launch_l96_attempt<PAT_VERN65_STRICT>(c, md, F, rhs.negate_time, dt, o, y, fsal, y_new, fsal_new)); break;
+          case PAT_DOPRI54: TRY(launch_l96_attempt<PAT_DOPRI54>(c, md, F, rhs.negate_time, dt, o, l96_halo, y, fsal, y_new, fsal_new)); break;
+          case PAT_DOPRI54_STRICT: TRY(launch_l96_attempt<PAT_DOPRI54_STRICT>(c, md, F, rhs.negate_time, dt, o, l96_halo, y, fsal, y_new, fsal_new)); break;
+          case PAT_TSIT54: TRY(launch_l96_attempt<PAT_TSIT54>(c, md, F, rhs.negate_time, dt, o, l96_halo, y, fsal, y_new, fsal_new)); break;
+          case PAT_VERN65: TRY(launch_l96_attempt<PAT_VERN65>(c, md, F, rhs.negate_time, dt, o, l96_halo, y, fsal, y_new, fsal_new)); break;
+          default: TRY(launch_l96_attempt<PAT_VERN65_STRICT>(c, md, F, rhs.negate_time, dt, o, l96_halo, y, fsal, y_new, fsal_new)); break;
         }
       } else
       switch (fused_pat) {

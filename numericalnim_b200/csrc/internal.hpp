@@ -35,6 +35,8 @@ struct ProfRec {
   cudaEvent_t a, b;
 };
 
+struct PeerVecView;
+
 struct b200rk_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -51,6 +53,8 @@ struct b200rk_ctx {
   double* h_result = nullptr;   // pinned + mapped host scalar
   double* h_result_dev = nullptr;  // device alias of h_result
   double* d_halo = nullptr;        // 3 doubles: stencil halo of the sharded Lorenz-96 right-hand side
+  const PeerVecView* peer_view = nullptr;   // set by the solver that is advancing (driver.cu); null otherwise
+  int* d_barrier = nullptr;                 // 1 int: payload of stream_barrier
   double* d_halo_attempt = nullptr;  // 2 x 24 doubles: halo of y and k1 for the one-kernel Lorenz-96 attempt (stencil_attempt.cuh), sharded
   unsigned long long* h_seq = nullptr;      // pinned + mapped: sequence word of the last finished reduction
   unsigned long long* h_seq_dev = nullptr;  // device alias
@@ -77,6 +81,7 @@ struct b200rk_ctx {
   bool fuse_pointwise = true;  // element-local built-in RHS: whole attempt in one kernel
   bool fuse_stencil = true;    // built-in Lorenz-96 (single GPU): stage accumulate + stencil RHS in one kernel
   bool fuse_stencil_attempt = false;  // built-in Lorenz-96: a whole attempt in one kernel, overlapped tiles (experimental: verified by host emulation, not yet run on the GPU)
+  bool l96_peer_halo = true;   // sharded one-kernel Lorenz-96 attempt inside a solver: read the halo in place from the peer-mapped neighbours (false: ncclSend/ncclRecv)
   int l96_attempt_pairs = 2;   // l96_attempt_kernel: 128-bit pairs per thread (tile = 512 * pairs positions); 1 or 2
   bool finish_prefetch = false; // software-pipelined finish kernel (experimental: verified by host emulation, not yet measured on the GPU)
   int stream_simpson = -1;     // cumsimpson(f, X, dx): -1 = stream the grid only when the composed form would not fit, 0 never, 1 always
@@ -90,6 +95,18 @@ struct b200rk_ctx {
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> ev_free;
   mutable std::string err;
+};
+
+struct PeerVecView {
+  static constexpr int kMax = 4;
+  int count = 0;                       // 0 = not available
+  const double* local[kMax] = {};      // this rank's vectors (device pointers)
+  const double* left[kMax] = {};       // the left / right ring neighbour's vectors of the same role (peer-mapped base pointers)
+  const double* right[kMax] = {};
+  size_t n_left = 0, n_right = 0;      // the neighbours' shard lengths
+  void* opened[2 * kMax] = {};         // what cudaIpcCloseMemHandle must release
+  int n_opened = 0;
+  int find(const double* d) const { for (int i = 0; i < count; ++i) if (local[i] == d) return i; return -1; }
 };
 
 struct b200rk_vec {
@@ -228,6 +245,12 @@ struct RhsCall {
 int ensure_partials(b200rk_ctx* c, size_t blocks);
 ReduceScratch reduce_scratch(b200rk_ctx* c);                 // hands out the next reduction sequence number
 int setup_p2p(b200rk_ctx* c);
+// The same-role vectors of the two ring neighbours, peer-mapped (CUDA IPC over NVLink): the one-kernel Lorenz-96 attempt
+// reads its halo from them in place. Opened per solver (driver.cu), used by do_step through ctx->peer_view while that
+// solver advances. Both calls are collective over the communicator.
+int peer_view_open(b200rk_ctx* c, b200rk_vec* const* vecs, int count, PeerVecView* out);   // out->count == 0: not available (agreed by all ranks)
+int peer_view_close(b200rk_ctx* c, PeerVecView* v);
+int stream_barrier(b200rk_ctx* c);   // every rank's stream has reached this point before any rank's stream continues
 void shard_range(size_t n, int rank, int world, size_t* off, size_t* len);
 int vec_alloc(b200rk_ctx* c, size_t n_global, b200rk_vec** out);
 void vec_release(b200rk_vec* v);
@@ -279,6 +302,7 @@ struct DeviceLoopIO {
   double t, dt, t_end, error;
   int64_t steps, attempts, rejected, limiter_hits;
 };
+bool l96_peer_halo_possible(const b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, size_t n_global);
 bool device_loop_eligible(const b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, size_t n_local);
 int run_device_loop(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, const b200rk_options& o, DeviceLoopIO* io,
                     int64_t max_steps);

@@ -115,6 +115,86 @@ int setup_p2p(b200rk_ctx* c) {
   return B200RK_OK;
 }
 
+int stream_barrier(b200rk_ctx* c) {
+  if (c->world < 2) return B200RK_OK;
+  if (!c->d_barrier) {
+    CUDA_TRY(c, cudaMalloc(&c->d_barrier, sizeof(int)));
+    CUDA_TRY(c, cudaMemset(c->d_barrier, 0, sizeof(int)));
+  }
+  NCCL_TRY(c, g_nccl.AllReduce(c->d_barrier, c->d_barrier, 1, ncclInt, ncclSum, c->comm, c->stream));   // zeros: only the ordering matters
+  c->collectives++;
+  return B200RK_OK;
+}
+
+// Same scheme as setup_p2p: handles travel through one ncclAllGather, each rank maps its two ring neighbours' vectors,
+// the outcome is agreed by an ncclAllReduce(min) — either every rank reads its halo in place or none does.
+int peer_view_open(b200rk_ctx* c, b200rk_vec* const* vecs, int count, PeerVecView* out) {
+  *out = PeerVecView{};
+  if (c->world < 2 || !c->p2p || count < 1 || count > PeerVecView::kMax) return B200RK_OK;
+  const size_t per_rank = 64 * (size_t)PeerVecView::kMax;
+  std::vector<cudaIpcMemHandle_t> mine(PeerVecView::kMax);
+  std::memset(mine.data(), 0, per_rank);
+  int ok = 1;
+  for (int i = 0; i < count; ++i)
+    if (cudaIpcGetMemHandle(&mine[i], vecs[i]->d) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+  char* d_handles = nullptr;
+  int* d_flag = nullptr;
+  CUDA_TRY(c, cudaMalloc(&d_handles, per_rank * (size_t)c->world));
+  CUDA_TRY(c, cudaMalloc(&d_flag, sizeof(int)));
+  CUDA_TRY(c, cudaMemcpyAsync(d_handles + per_rank * (size_t)c->rank, mine.data(), per_rank, cudaMemcpyHostToDevice, c->stream));
+  NCCL_TRY(c, g_nccl.AllGather(d_handles + per_rank * (size_t)c->rank, d_handles, per_rank, ncclChar, c->comm, c->stream));
+  std::vector<cudaIpcMemHandle_t> all((size_t)PeerVecView::kMax * c->world);
+  CUDA_TRY(c, cudaMemcpyAsync(all.data(), d_handles, per_rank * (size_t)c->world, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  const int left = (c->rank + c->world - 1) % c->world, right = (c->rank + 1) % c->world;
+  PeerVecView v;
+  for (int i = 0; i < count && ok; ++i) {
+    void* pl = nullptr;
+    if (cudaIpcOpenMemHandle(&pl, all[(size_t)left * PeerVecView::kMax + i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+    v.opened[v.n_opened++] = pl;
+    v.left[i] = static_cast<const double*>(pl);
+    if (right == left) { v.right[i] = v.left[i]; continue; }   // two ranks: both neighbours are the same peer (one mapping per allocation)
+    void* pr = nullptr;
+    if (cudaIpcOpenMemHandle(&pr, all[(size_t)right * PeerVecView::kMax + i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+    v.opened[v.n_opened++] = pr;
+    v.right[i] = static_cast<const double*>(pr);
+  }
+  CUDA_TRY(c, cudaMemcpyAsync(d_flag, &ok, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  NCCL_TRY(c, g_nccl.AllReduce(d_flag, d_flag, 1, ncclInt, ncclMin, c->comm, c->stream));
+  int agreed = 0;
+  CUDA_TRY(c, cudaMemcpyAsync(&agreed, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  cudaFree(d_handles);
+  cudaFree(d_flag);
+  c->collectives += 2;
+  if (!agreed) {
+    for (int i = 0; i < v.n_opened; ++i) cudaIpcCloseMemHandle(v.opened[i]);
+    cudaGetLastError();
+    return B200RK_OK;
+  }
+  size_t off = 0;
+  shard_range(vecs[0]->n_global, left, c->world, &off, &v.n_left);
+  shard_range(vecs[0]->n_global, right, c->world, &off, &v.n_right);
+  for (int i = 0; i < count; ++i) v.local[i] = vecs[i]->d;
+  v.count = count;
+  *out = v;
+  return B200RK_OK;
+}
+
+int peer_view_close(b200rk_ctx* c, PeerVecView* v) {
+  if (!v->count) return B200RK_OK;
+  // the neighbours may still be reading this rank's vectors in their last kernel, and exported memory must outlive every
+  // mapping of it: all streams drain, all ranks unmap, and only then does anyone go on to release its vectors
+  TRY(stream_barrier(c));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < v->n_opened; ++i) cudaIpcCloseMemHandle(v->opened[i]);
+  cudaGetLastError();
+  *v = PeerVecView{};
+  TRY(stream_barrier(c));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return B200RK_OK;
+}
+
 // =====================================================================================================
 // vectors
 // =====================================================================================================
@@ -201,6 +281,7 @@ static int ctx_common_init(b200rk_ctx* c) {
   if (const char* e = getenv("B200RK_FUSE_POINTWISE")) c->fuse_pointwise = atoi(e) != 0;
   if (const char* e = getenv("B200RK_FUSE_STENCIL")) c->fuse_stencil = atoi(e) != 0;
   if (const char* e = getenv("B200RK_FUSE_STENCIL_ATTEMPT")) c->fuse_stencil_attempt = atoi(e) != 0;
+  if (const char* e = getenv("B200RK_L96_PEER_HALO")) c->l96_peer_halo = atoi(e) != 0;
   if (const char* e = getenv("B200RK_L96_ATTEMPT_PAIRS")) c->l96_attempt_pairs = (atoi(e) == 1) ? 1 : 2;
   if (const char* e = getenv("B200RK_FUSE_SIMPSON")) c->fuse_simpson = atoi(e) != 0;
   if (const char* e = getenv("B200RK_FINISH_PREFETCH")) c->finish_prefetch = atoi(e) != 0;
@@ -262,6 +343,7 @@ void b200rk_destroy(b200rk_ctx* c) {
   if (c->comm) g_nccl.CommDestroy(c->comm);
   cudaFree(c->d_partials); cudaFree(c->d_ticket); cudaFree(c->d_result); cudaFree(c->d_halo); cudaFreeHost(c->h_result); cudaFreeHost(c->h_seq);
   if (c->d_halo_attempt) cudaFree(c->d_halo_attempt);
+  if (c->d_barrier) cudaFree(c->d_barrier);
   if (c->d_run_state) cudaFree(c->d_run_state);
   if (c->h_run_state) cudaFreeHost(c->h_run_state);
   if (c->copy_event) cudaEventDestroy(c->copy_event);
@@ -292,6 +374,7 @@ int b200rk_set(b200rk_ctx* c, const char* key, int64_t v) {
   else if (k == "device_loop") c->device_loop = v < 0 ? -1 : (v != 0);
   else if (k == "fuse_stencil") c->fuse_stencil = v != 0;
   else if (k == "fuse_stencil_attempt") c->fuse_stencil_attempt = v != 0;
+  else if (k == "l96_peer_halo") c->l96_peer_halo = v != 0;
   else if (k == "l96_attempt_pairs") { if (v != 1 && v != 2) return fail(c, B200RK_EINVAL, "l96_attempt_pairs must be 1 or 2"); c->l96_attempt_pairs = (int)v; }
   else if (k == "fuse_simpson") c->fuse_simpson = v != 0;
   else if (k == "finish_prefetch") c->finish_prefetch = v != 0;
@@ -322,6 +405,7 @@ int b200rk_get(const b200rk_ctx* c, const char* key, int64_t* v) {
   else if (k == "p2p") *v = c->p2p;
   else if (k == "fuse_stencil") *v = c->fuse_stencil;
   else if (k == "fuse_stencil_attempt") *v = c->fuse_stencil_attempt;
+  else if (k == "l96_peer_halo") *v = c->l96_peer_halo;
   else if (k == "l96_attempt_pairs") *v = c->l96_attempt_pairs;
   else if (k == "fuse_simpson") *v = c->fuse_simpson;
   else if (k == "finish_prefetch") *v = c->finish_prefetch;

@@ -33,16 +33,21 @@ struct StencilTile {
   static constexpr int HR = (((S - 1) + 3) / 4) * 4;       // right overlap: 1 per evaluation
 };
 
+// Sharded state (one contiguous block of the cyclic global vector per GPU): the HL elements before the block (left_*[0]
+// is element -HL) and the HR elements after it (right_*[0] is element n), of y and of k1. They are either a small buffer
+// filled by one grouped ncclSend/ncclRecv per IntegratorProc call, or — inside a solver, when the ring neighbours'
+// vectors are peer-mapped (CUDA IPC over NVLink) — the neighbours' own vectors: the edge tiles then read the left
+// neighbour's tail and the right neighbour's head in place and the stencil path has no collective at all (executor.cu).
+// All null on a single GPU: the block is the whole ring and the edge tiles index it cyclically.
+struct L96Halo {
+  const double *left_y, *right_y, *left_k, *right_k;
+};
+
 template <int S>
 struct L96AttemptArgs {
   FusedArgs<S> f;     // y, k1, a/b/bh rows, dt, cb, cbh, tolerances, ynew, ks_out, n, rs (the parameter fields are unused)
   double F;           // forcing (the backward pass g = -f(-t, y), ode.nim:545, is the kernel's NEG template argument)
-  // Sharded state (one contiguous block of the cyclic global vector per GPU): the HL elements before the block and the
-  // HR elements after it, of y and of k1 — [0, HL) from the left neighbour's tail, [HL, HL+HR) from the right
-  // neighbour's head, exchanged once per IntegratorProc call (executor.cu). Null on a single GPU: the block is the
-  // whole ring and the edge tiles index it cyclically.
-  const double* halo_y;
-  const double* halo_k;
+  L96Halo halo;       // sharded: where the elements around the block live (all null on a single GPU)
 };
 
 // lorenz96_kernel's ((y[i+1] - y[i-2]) * y[i-1] - y[i]) + F at the two adjacent positions p, p+1 a thread owns: c0, c1 are
@@ -81,14 +86,14 @@ struct L96Stages {
 };
 
 // Position p of the tile that stores [tile0, tile0 + OUT): element tile0 - HL + p of the block — from the block itself,
-// cyclically (single GPU, halo == nullptr), or from the neighbours' halos (sharded; [0, HL) left, [HL, HL + HR) right).
+// cyclically (single GPU, left == nullptr), or from around the block (sharded: left[0] = element -HL, right[0] = element n).
 template <int HL, int HR>
-__device__ __forceinline__ double l96_edge_load(const double* v, const double* halo, size_t n, size_t tile0, int p) {
-  if (halo) {
+__device__ __forceinline__ double l96_edge_load(const double* v, const double* left, const double* right, size_t n, size_t tile0, int p) {
+  if (left) {
     const long long idx = (long long)tile0 - HL + p;
-    if (idx < 0) return halo[HL + idx];
+    if (idx < 0) return left[HL + idx];
     if ((size_t)idx < n) return v[idx];
-    if ((size_t)idx - n < (size_t)HR) return halo[HL + ((size_t)idx - n)];
+    if ((size_t)idx - n < (size_t)HR) return right[(size_t)idx - n];
     return 0.0;   // further right: beyond what any stored position depends on
   }
   return v[(tile0 + (size_t)p + (n - (size_t)HL % n)) % n];
@@ -121,8 +126,8 @@ __global__ void __launch_bounds__(THREADS) l96_attempt_kernel(const L96AttemptAr
     } else {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        y[2 * j + h] = l96_edge_load<HL, HR>(a.f.y, a.halo_y, n, tile0, p + h);
-        k[2 * j + h][0] = l96_edge_load<HL, HR>(a.f.k1, a.halo_k, n, tile0, p + h);
+        y[2 * j + h] = l96_edge_load<HL, HR>(a.f.y, a.halo.left_y, a.halo.right_y, n, tile0, p + h);
+        k[2 * j + h][0] = l96_edge_load<HL, HR>(a.f.k1, a.halo.left_k, a.halo.right_k, n, tile0, p + h);
       }
     }
   }
@@ -193,7 +198,7 @@ struct L96Rk4Args {
   double* ynew;
   size_t n;
   double F, hdt, dt, c6;
-  const double* halo_y;   // sharded: 8 elements before the block, 4 after it (null on a single GPU)
+  L96Halo halo;           // sharded: left_y = the 8 elements before the block, right_y = the 4 after it (null on a single GPU)
 };
 
 template <int J, int THREADS, bool NEG>
@@ -217,8 +222,8 @@ __global__ void __launch_bounds__(THREADS) l96_rk4_kernel(const L96Rk4Args a) {
       const Pk<2> yv = ld_stream<2>(a.y + (tile0 - HL + p));
       y[2 * j] = yv.v[0]; y[2 * j + 1] = yv.v[1];
     } else {
-      y[2 * j] = l96_edge_load<HL, HR>(a.y, a.halo_y, n, tile0, p);
-      y[2 * j + 1] = l96_edge_load<HL, HR>(a.y, a.halo_y, n, tile0, p + 1);
+      y[2 * j] = l96_edge_load<HL, HR>(a.y, a.halo.left_y, a.halo.right_y, n, tile0, p);
+      y[2 * j + 1] = l96_edge_load<HL, HR>(a.y, a.halo.left_y, a.halo.right_y, n, tile0, p + 1);
     }
   }
 #pragma unroll

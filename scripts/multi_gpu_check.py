@@ -81,20 +81,29 @@ def main():
             print(f"[multi-gpu world={world}] lorenz96 n={nl} tsit54: steps={st['steps']} rejected={st['rejected']} collectives={st['collectives']} ok={ok}", flush=True)
         # experimental knob fuse_stencil_attempt: the whole attempt in one kernel; sharded, ONE halo exchange of y and k1
         # (12 + 8 elements each) per IntegratorProc call instead of a 3-element exchange per right-hand-side evaluation
+        # halo: read in place from the peer-mapped neighbours (needs the mailboxes' IPC path) or one ncclSend/ncclRecv per step
         try:
             ctx.set("fuse_stencil_attempt", 1)
-            c0 = ctx.stats()["collectives"]
-            t, ys = nn.solveODE(rhs_l, gl, [0.0, 0.5], nn.newODEoptions(**kw), integrator="tsit54")
-            st2 = dict(nn.ode.last_stats)
-            got2 = ys[-1].local_numpy()
-            ok2 = bool(np.all(np.abs(got2 - exp) <= 1e-7 * np.abs(exp))) and st2["steps"] == refl.stats.steps and st2["rejected"] == refl.stats.rejected
-            if not ok2:
-                fails.append(("lorenz96 tsit54 one-kernel attempt", nl, st2, refl.stats.steps, float(np.max(np.abs(got2 - exp)))))
-            if rank == 0:
-                print(f"[multi-gpu world={world}] lorenz96 n={nl} tsit54 one-kernel attempt: steps={st2['steps']} rejected={st2['rejected']} "
-                      f"launches={st2['launches']} (default path {st['launches']}) collectives={st2['collectives']} (default {st['collectives']}) ok={ok2}", flush=True)
+            for peer_halo in (1, 0):
+                ctx.set("l96_peer_halo", peer_halo)
+                t, ys = nn.solveODE(rhs_l, gl, [0.0, 0.5], nn.newODEoptions(**kw), integrator="tsit54")
+                st2 = dict(nn.ode.last_stats)
+                got2 = ys[-1].local_numpy()
+                ok2 = bool(np.all(np.abs(got2 - exp) <= 1e-7 * np.abs(exp))) and st2["steps"] == refl.stats.steps and st2["rejected"] == refl.stats.rejected
+                if not ok2:
+                    fails.append(("lorenz96 tsit54 one-kernel attempt", nl, peer_halo, st2, refl.stats.steps, float(np.max(np.abs(got2 - exp)))))
+                if rank == 0:
+                    print(f"[multi-gpu world={world}] lorenz96 n={nl} tsit54 one-kernel attempt (peer_halo={peer_halo}, p2p={ctx.get('p2p')}): steps={st2['steps']} "
+                          f"rejected={st2['rejected']} launches={st2['launches']} (default path {st['launches']}) collectives={st2['collectives']} "
+                          f"(default {st['collectives']}) ok={ok2}", flush=True)
+            # RK4 (no error norm, hence no lockstep between the ranks): always the ncclSend/ncclRecv halo
+            t, ys = nn.solveODE(rhs_l, gl, [0.0, 0.05], nn.newODEoptions(dt=2e-3), integrator="rk4")
+            ref4 = O.solve_vector("rk4", O.rhs_lorenz96(8.0), yl, [0.0, 0.05], O.new_options(dt=2e-3)).y[-1][lo:lo + ll]
+            if not np.array_equal(ys[-1].local_numpy().view(np.uint64), np.asarray(ref4).view(np.uint64)):
+                fails.append(("lorenz96 rk4 one-kernel step bitwise", nl))
         finally:
             ctx.set("fuse_stencil_attempt", 0)
+            ctx.set("l96_peer_halo", 1)
     # right-hand side given as SOURCE, sharded: the parameter vector shards like the state; the run-time compiled
     # attempt kernel / device loop use the same in-kernel all-reduce as the built-ins
     K = 2.0 + 3.0 * np.arange(n) / (n - 1)

@@ -170,7 +170,7 @@ static void test_l96_attempt(const char* name, const rk_oracle::Pair& p, rk_orac
   constexpr int S = Pattern<PAT>::S, J = 2;
   constexpr int OUT = 2 * J * T - StencilTile<S>::HL - StencilTile<S>::HR;
   bool ok = true;
-  int splits = 0;
+  int splits = 0, in_place = 0;
   for (size_t n : {size_t(4), size_t(5), size_t(7), size_t(40), size_t(OUT - 1), size_t(OUT), size_t(OUT + 1), size_t(2 * OUT + 3), size_t(1000)})
     for (double sgn : {1.0, -1.0}) {
       const double F = 8.0, dt = 0.004;
@@ -215,16 +215,30 @@ static void test_l96_attempt(const char* name, const rk_oracle::Pair& p, rk_orac
           Scratch sc2;
           L96AttemptArgs<S> b = a;
           b.f.y = y.data() + lo; b.f.k1 = fsal.components.data() + lo; b.f.ynew = yn2.data() + lo; b.f.ks_out = ks2.data() + lo;
-          b.f.n = len; b.f.rs = sc2.rs(); b.halo_y = hy.data(); b.halo_k = hk.data();
+          b.f.n = len; b.f.rs = sc2.rs(); b.halo = L96Halo{hy.data(), hy.data() + HL, hk.data(), hk.data() + HL};
           if (sgn < 0) emul_launch((unsigned)((len + OUT - 1) / OUT), T, [&] { l96_attempt_kernel<PAT, J, T, true>(b); });
           else emul_launch((unsigned)((len + OUT - 1) / OUT), T, [&] { l96_attempt_kernel<PAT, J, T, false>(b); });
           s2 += sc2.result;                                             // the all-reduce of the shards' partial sums
+          // the same shard with its halo read IN PLACE from the neighbours' vectors (what the peer-mapped form does over
+          // NVLink; here all shards live in one array): left tail = the HL elements before the block, right head = after it
+          const size_t lt = (lo + n - HL) % n, rh = (lo + len) % n;
+          if (sgn > 0 && lt + HL <= n && rh + HR <= n) {
+            std::vector<double> yn3(len, -5.0), ks3(len, -5.0);
+            Scratch sc3;
+            L96AttemptArgs<S> d = b;
+            d.f.ynew = yn3.data(); d.f.ks_out = ks3.data(); d.f.rs = sc3.rs();
+            d.halo = L96Halo{y.data() + lt, y.data() + rh, fsal.components.data() + lt, fsal.components.data() + rh};
+            emul_launch((unsigned)((len + OUT - 1) / OUT), T, [&] { l96_attempt_kernel<PAT, J, T, false>(d); });
+            ok = ok && std::memcmp(yn3.data(), yn2.data() + lo, len * sizeof(double)) == 0 &&
+                 std::memcmp(ks3.data(), ks2.data() + lo, len * sizeof(double)) == 0 && sc3.result == sc2.result;
+            ++in_place;
+          }
         }
         ok = ok && same_bits(yn2, ref.y_new.components) && same_bits(ks2, ref.fsal.components) &&
              close_rel(std::sqrt(1.0 / double(n) * s2), ref.error, 1e-13);
       }
     }
-  report(std::string("l96_attempt_kernel (whole attempt, overlapped tiles; ") + std::to_string(splits) + " sharded splits) " + name, ok && splits >= 16);
+  report(std::string("l96_attempt_kernel (whole attempt, overlapped tiles; ") + std::to_string(splits) + " sharded splits, " + std::to_string(in_place) + " shards with the halo read in place) " + name, ok && splits >= 16 && in_place >= 16);
 }
 
 // ---- a whole RK4 step with the Lorenz-96 stencil in one kernel (l96_rk4_kernel) vs the oracle's RK4_step: bit for bit,
@@ -263,7 +277,7 @@ static void test_l96_rk4() {
           for (int i = 0; i < HL; ++i) hy[i] = y[(lo + n - HL + i) % n];
           for (int i = 0; i < HR; ++i) hy[HL + i] = y[(lo + len + i) % n];
           L96Rk4Args b = a;
-          b.y = y.data() + lo; b.ynew = yn2.data() + lo; b.n = len; b.halo_y = hy.data();
+          b.y = y.data() + lo; b.ynew = yn2.data() + lo; b.n = len; b.halo = L96Halo{hy.data(), hy.data() + HL, nullptr, nullptr};
           run(b, (unsigned)((len + OUT - 1) / OUT));
         }
         ok = ok && same_bits(yn2, ref.y_new.components);

@@ -192,7 +192,9 @@ class GpuVector:
         return dict(shape=(self.local_len,), typestr="<f8", data=(self.data_ptr, False), version=3, stream=self.ctx.stream or None)
 
     def free(self):
-        if self._owned and self._h:
+        # a vector that outlives its (explicitly closed) context must not reach into it: b200rk_vec_free returns the
+        # buffer to the context's pool
+        if self._owned and self._h and self.ctx._h:
             capi.lib().b200rk_vec_free(self._h)
         self._h = C.c_void_p()
 
@@ -486,7 +488,7 @@ class JitRhs:
 
     def __del__(self):
         try:
-            if self.user:
+            if self.user and self.ctx._h:   # the free synchronises the context's stream
                 capi.lib().b200rk_jit_rhs_free(self.user)
         except Exception:
             pass
@@ -654,7 +656,8 @@ class Solver:
 
     def close(self):
         if self._h:
-            capi.lib().b200rk_solver_free(self._h)
+            if self.dctx._h:   # a solver that outlives its context has nothing left to release
+                capi.lib().b200rk_solver_free(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):

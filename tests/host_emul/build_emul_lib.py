@@ -87,5 +87,14 @@ def build(force: bool = False, sanitize: str = "") -> str:
     return OUT
 
 
+def build_fake_nccl() -> str:
+    """tests/host_emul/_build/libnccl_emul.so: in-process stand-in for NCCL (fake_nccl.cpp) — ranks are threads."""
+    src, out = os.path.join(HERE, "fake_nccl.cpp"), os.path.join(HERE, "_build", "libnccl_emul.so")
+    if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-pthread", "-Wall", src, "-o", out], check=True)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, sanitize="address" if "--asan" in sys.argv else ""))

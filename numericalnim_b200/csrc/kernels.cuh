@@ -347,6 +347,35 @@ __device__ __forceinline__ double block_sum(double v) {
   return r;  // valid in thread 0
 }
 
+#ifdef B200RK_EMULATE_SERIAL_SUM
+// Host emulation only (tests/host_emul): what peer_allreduce does, by one host thread — ranks are threads of one process
+// there, and the emulated device is handed to the other ranks' kernels while this one waits for their partials.
+#ifndef B200RK_EMUL_DEVICE_RELEASE
+#define B200RK_EMUL_DEVICE_RELEASE()
+#define B200RK_EMUL_DEVICE_ACQUIRE()
+#endif
+inline double emul_peer_exchange(double local, const ReduceScratch& rs) {
+  const int world = rs.mail.world, rank = rs.mail.rank;
+  const unsigned long long par = rs.seq & 1ull;
+  for (int q = 0; q < world; ++q) {
+    volatile unsigned long long* dst = rs.mail.box[q] + ((par * kMaxPeers + rank) << 1);
+    dst[1] = (unsigned long long)__double_as_longlong(local);
+    __threadfence_system();
+    dst[0] = rs.seq;
+  }
+  B200RK_EMUL_DEVICE_RELEASE();
+  double total = 0.0;
+  for (int q = 0; q < world; ++q) {
+    volatile unsigned long long* src = rs.mail.box[rank] + ((par * kMaxPeers + q) << 1);
+    while (src[0] != rs.seq) __threadfence_system();
+    __threadfence_system();
+    total = __dadd_rn(total, __longlong_as_double((long long)src[1]));   // rank order, as in peer_allreduce
+  }
+  B200RK_EMUL_DEVICE_ACQUIRE();
+  return total;
+}
+#endif
+
 template <int THREADS>
 __device__ __forceinline__ void grid_sum_finish(double thread_val, const ReduceScratch& rs) {
 #ifdef B200RK_EMULATE_SERIAL_SUM
@@ -355,6 +384,7 @@ __device__ __forceinline__ void grid_sum_finish(double thread_val, const ReduceS
   if (blockIdx.x == 0 && threadIdx.x == 0) *rs.result = 0.0;
   *rs.result = __dadd_rn(*rs.result, thread_val);
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x == THREADS - 1 && rs.result_host) {
+    if (rs.mail.world > 1) *rs.result = emul_peer_exchange(*rs.result, rs);
     *rs.result_host = *rs.result;
     *rs.seq_host = rs.seq;
   }

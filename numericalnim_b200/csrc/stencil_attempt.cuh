@@ -181,7 +181,11 @@ __global__ void __launch_bounds__(THREADS) l96_attempt_kernel(const L96AttemptAr
     double t = (blockIdx.x == 0) ? 0.0 : *a.f.rs.result;
     for (int i = 0; i < THREADS; ++i) t = __dadd_rn(t, red[i]);
     *a.f.rs.result = t;
-    if (blockIdx.x == gridDim.x - 1 && a.f.rs.result_host) { *a.f.rs.result_host = t; *a.f.rs.seq_host = a.f.rs.seq; }
+    if (blockIdx.x == gridDim.x - 1 && a.f.rs.result_host) {
+      if (a.f.rs.mail.world > 1) { t = emul_peer_exchange(t, a.f.rs); *a.f.rs.result = t; }
+      *a.f.rs.result_host = t;
+      *a.f.rs.seq_host = a.f.rs.seq;
+    }
   }
 #else
   grid_sum_finish<THREADS>(acc, a.f.rs);

@@ -29,8 +29,13 @@ struct EmulBlock {
 extern EmulBlock* g_emul_block;   // non-null only while a threaded launch is running (defined in emul_lib_support.cpp)
 // One emulated "device" per process: function-static __shared__ memory and g_emul_block are process-wide, so when several
 // ranks run as threads of one process (two_rank_emul.py) their kernels take turns.
-#include <mutex>
-extern std::mutex g_emul_device_mutex;
+// A semaphore, not a mutex: a kernel waiting for its peers' partial sums (kernels.cuh: emul_peer_exchange) hands the
+// device over from whichever emulated thread does the waiting.
+#include <semaphore>
+extern std::binary_semaphore g_emul_device;
+struct EmulDeviceTurn { EmulDeviceTurn() { g_emul_device.acquire(); } ~EmulDeviceTurn() { g_emul_device.release(); } };
+#define B200RK_EMUL_DEVICE_RELEASE() g_emul_device.release()
+#define B200RK_EMUL_DEVICE_ACQUIRE() g_emul_device.acquire()
 
 #define __device__
 #define __global__
@@ -72,7 +77,7 @@ inline double2 make_double2(double x, double y) { return double2{x, y}; }
 
 template <class F>
 inline void emul_launch_serial(unsigned grid, unsigned threads, F&& body) {
-  std::lock_guard<std::mutex> device(g_emul_device_mutex);
+  EmulDeviceTurn device;
   for (unsigned b = 0; b < grid; ++b)
     for (unsigned t = 0; t < threads; ++t) {
       gridDim.x = grid; blockDim.x = threads; blockIdx.x = b; threadIdx.x = t;
@@ -83,7 +88,7 @@ template <class F>
 inline void emul_launch_threaded(unsigned grid, unsigned threads, F&& body) {
   // one team of host threads per launch; it plays the CTAs one after another (function-static "shared memory" is one
   // copy), with a team-wide barrier between CTAs
-  std::lock_guard<std::mutex> device(g_emul_device_mutex);
+  EmulDeviceTurn device;
   EmulBlock blk(threads);
   g_emul_block = &blk;
   std::vector<std::thread> pool;

@@ -4,7 +4,7 @@
 #include "internal.hpp"
 
 EmulBlock* g_emul_block = nullptr;
-std::mutex g_emul_device_mutex;
+std::binary_semaphore g_emul_device{1};
 void emul_grid_sync() { if (g_emul_block) g_emul_block->block.arrive_and_wait(); }
 
 static int unavailable(const b200rk_ctx* c) { return fail(c, B200RK_ECUDA, "right-hand sides from source need NVRTC and a GPU: not available under host emulation"); }

@@ -49,6 +49,10 @@ def bits(a, b):
 
 def rank_main(rank, uid, refs):
     ctx = nn.Context(0, rank, WORLD, uid)
+    p2p = ctx.get("p2p")   # 1: peer mailboxes mapped (emulated CUDA IPC: a handle is the pointer) unless B200RK_P2P=0
+    if rank == 0:
+        print(f"info p2p={p2p}", flush=True)
+    ctx.set("device_loop", 0)   # the cooperative loop's own peer exchange spins inside a kernel team: not emulated across ranks
     try:
         # ---- element-local IVP, sharded: fused attempt + ncclAllReduce of the error norm ----
         n = 5003
@@ -71,15 +75,22 @@ def rank_main(rank, uid, refs):
             rc = rhs.fn(0.0, g._h, out._h, rhs.user)
             report(rank, f"lorenz96 rhs bitwise n={nl}", rc == 0 and bits(out.local_numpy(), O.rhs_eval(O.rhs_lorenz96(8.0), 0.0, yl)[lo:lo + ll]))
             ref = refs["l96", nl]
-            for knob, what in ((0, "3-element halo per evaluation"), (1, "one-kernel attempt, one halo exchange per call")):
+            modes = [(0, 1, "3-element halo per evaluation"), (1, 0, "one-kernel attempt, one halo exchange per call")]
+            if p2p:
+                modes.append((1, 1, "one-kernel attempt, halo read in place from the peer-mapped neighbour"))
+            for knob, peer_halo, what in modes:
                 ctx.set("fuse_stencil_attempt", knob)
+                ctx.set("l96_peer_halo", peer_halo)
                 c0 = ctx.stats()["collectives"]
                 t, ys = nn.solveODE(rhs, g, [0.0, 0.3], nn.newODEoptions(**KW), integrator="tsit54")
                 st = dict(nn.ode.last_stats)
                 ok = close(ys[-1].local_numpy(), ref.y[-1][lo:lo + ll]) and st["steps"] == ref.stats.steps and st["rejected"] == ref.stats.rejected
                 report(rank, f"lorenz96 tsit54 n={nl}: {what}", ok)
                 if rank == 0:
-                    print(f"info lorenz96 n={nl} fuse_stencil_attempt={knob}: steps={st['steps']} launches={st['launches']} collectives={ctx.stats()['collectives'] - c0}", flush=True)
+                    print(f"info lorenz96 n={nl} fuse_stencil_attempt={knob} peer_halo={peer_halo}: steps={st['steps']} attempts={st['attempts']} "
+                          f"launches={st['launches']} collectives={ctx.stats()['collectives'] - c0}", flush=True)
+            ctx.set("fuse_stencil_attempt", 1)
+            ctx.set("l96_peer_halo", 0)
             # one adaptive step, bit for bit against the oracle (same dt, no rejection)
             fs = O.rhs_eval(O.rhs_lorenz96(8.0), 0.0, yl)
             gf = nn.newVector(fs, ctx)

@@ -28,7 +28,7 @@ struct EmulBlock {
 };
 extern EmulBlock* g_emul_block;   // non-null only while a threaded launch is running (defined in emul_lib_support.cpp)
 // One emulated "device" per process: function-static __shared__ memory and g_emul_block are process-wide, so when several
-// ranks run as threads of one process (two_rank_emul.py) their kernels take turns.
+// ranks run as threads of one process (multi_rank_emul.py) their kernels take turns.
 // A semaphore, not a mutex: a kernel waiting for its peers' partial sums (kernels.cuh: emul_peer_exchange) hands the
 // device over from whichever emulated thread does the waiting.
 #include <semaphore>

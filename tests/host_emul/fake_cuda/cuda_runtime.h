@@ -60,7 +60,7 @@ inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t* p, int) { *p = nul
 inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, cudaMemPoolAttr, void*) { return cudaSuccess; }
 
 struct cudaIpcMemHandle_t { char reserved[64]; };
-// ranks are threads of one process (two_rank_emul.py): a handle is the pointer itself
+// ranks are threads of one process (multi_rank_emul.py): a handle is the pointer itself
 inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { std::memset(h, 0, sizeof(*h)); std::memcpy(h->reserved, &p, sizeof(p)); return cudaSuccess; }
 inline cudaError_t cudaIpcOpenMemHandle(void** out, cudaIpcMemHandle_t h, unsigned) { std::memcpy(out, h.reserved, sizeof(void*)); return *out ? cudaSuccess : cudaErrorNotSupported; }
 inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }

@@ -2,7 +2,7 @@
 // An in-process stand-in for the handful of NCCL entry points libb200rk binds with dlopen (runtime.cu: nccl_bind), so
 // that the host-emulated library can run with world > 1 on the CPU: every rank is a THREAD of one process holding its
 // own b200rk context; "device" memory is host memory and the emulated streams are synchronous, so a collective is a
-// blocking rendezvous of the rank threads. Selected with B200RK_NCCL_LIB by tests/host_emul/two_rank_emul.py.
+// blocking rendezvous of the rank threads. Selected with B200RK_NCCL_LIB by tests/host_emul/multi_rank_emul.py.
 // Semantics kept from NCCL: collectives match by call order per communicator; ncclSend / ncclRecv between one pair of
 // ranks match in order; inside ncclGroupStart/End nothing blocks until the group ends (sends are buffered).
 #include <condition_variable>

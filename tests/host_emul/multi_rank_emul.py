@@ -4,7 +4,7 @@ its own b200rk context, meeting in an in-process stand-in for NCCL (fake_nccl.cp
 the host code no single-rank run reaches: sharding, the ncclAllReduce form of the error norm, the 3-element Lorenz-96 halo
 per right-hand-side evaluation, and the one-kernel Lorenz-96 attempt / RK4 step with ONE halo exchange per call
 (executor.cu: exchange_attempt_halo) — every shard against the unsharded CPU oracle. CUDA IPC is not emulated, so the
-peer-mailbox all-reduce and the peer-mapped halo stay GPU-only. Run as a script (tests/test_two_rank_emulation.py):
+peer-mailbox all-reduce and the peer-mapped halo stay GPU-only. Run as a script (tests/test_multi_rank_emulation.py):
 prints one `case <name> ok=<0|1>` line per check."""
 import os
 import sys
@@ -27,7 +27,7 @@ _capi.LIB_PATH = build_emul_lib.build()
 import numericalnim_b200 as nn
 import oracle as O
 
-WORLD = 2
+WORLD = int(os.environ.get("B200RK_TEST_EMUL_WORLD", "2"))   # 3: the ring neighbours are two different peers
 KW = dict(absTol=1e-6, relTol=1e-6, dtMax=1.0, dtMin=1e-8)
 results = {}
 lock = threading.Lock()
@@ -65,6 +65,24 @@ def rank_main(rank, uid, refs):
             t, ys = nn.solveODE(nn.rhsDiagLinear(gl), gy, [0.0, 2.0], nn.newODEoptions(**KW), integrator="dopri54")
             report(rank, f"diag dopri54 sharded fuse_pointwise={fuse}", close(ys[-1].local_numpy(), refs["diag"].y[-1][lo:lo + ll], 1e-9))
         ctx.set("fuse_pointwise", 1)
+        # ---- sum(v) and the trajectory consumers, sharded (the duplicate check is the one collective of that path) ----
+        s_glob = gy.sum()
+        report(rank, "sum(v) sharded", abs(s_glob - O.vector_sum(y0)) <= 1e-12 * float(np.abs(y0).sum()))
+        rngq = np.random.default_rng(11)
+        Xq = np.array([0.0, 1.0, 0.5, 1.0, 2.0, 1.5, 3.0])
+        base = rngq.uniform(-1.0, 1.0, (6, n))
+        Yq = np.stack([base[0], base[1], base[2], base[1], base[3], base[4], base[5]])
+        dv = [nn.newVector(r, ctx) for r in Yq]
+        for name, ofn in (("cumtrapz", O.cumtrapz), ("cumsimpson", O.cumsimpson)):
+            got = np.array([v.local_numpy() for v in getattr(nn, name)(dv, Xq)])
+            report(rank, f"{name} sharded bitwise", bits(got, ofn(Yq, Xq)[:, lo:lo + ll]))
+        Ybad = Yq.copy()
+        Ybad[3, n - 1] += 1.0   # lives on the LAST rank only: every rank must still see the impure duplicate
+        try:
+            nn.cumtrapz([nn.newVector(r, ctx) for r in Ybad], Xq)
+            report(rank, "impure duplicate on one rank raises on every rank", False)
+        except ValueError:
+            report(rank, "impure duplicate on one rank raises on every rank", True)
         # ---- Lorenz-96, sharded ----
         for nl in (1000, 2600):
             yl = 8.0 + 0.5 * np.sin(2 * np.pi * 37 * np.arange(nl) / nl)

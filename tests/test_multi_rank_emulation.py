@@ -16,17 +16,17 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("p2p", [1, 0])
-def test_two_ranks_against_the_unsharded_oracle(p2p):
-    env = dict(os.environ)
+@pytest.mark.parametrize("world,p2p", [(2, 1), (2, 0), (3, 1), (4, 0)])   # 3+: the ring neighbours are two different peers
+def test_rank_threads_against_the_unsharded_oracle(world, p2p):
+    env = dict(os.environ, B200RK_TEST_EMUL_WORLD=str(world))
     env.pop("B200RK_P2P", None)
     if not p2p:
         env["B200RK_P2P"] = "0"
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "host_emul", "two_rank_emul.py")], capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "host_emul", "multi_rank_emul.py")], capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
     cases = dict(re.findall(r"^case (.+) ok=(\d)$", r.stdout, flags=re.M))
-    assert r.returncode == 0 and len(cases) >= 16 and all(v == "1" for v in cases.values()), r.stdout[-3000:] + r.stderr[-2000:]
+    assert r.returncode == 0 and len(cases) >= 20 and all(v == "1" for v in cases.values()), r.stdout[-3000:] + r.stderr[-2000:]
     assert f"info p2p={p2p}" in r.stdout
-    families = ["diag dopri54 sharded", "3-element halo per evaluation", "one halo exchange per call", "one-kernel step bitwise", "rk4 one-kernel step"]
+    families = ["diag dopri54 sharded", "sum(v) sharded", "cumsimpson sharded bitwise", "impure duplicate", "3-element halo per evaluation", "one halo exchange per call", "one-kernel step bitwise", "rk4 one-kernel step"]
     if p2p:
         families.append("halo read in place from the peer-mapped neighbour")
     for family in families:

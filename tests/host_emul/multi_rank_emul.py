@@ -109,6 +109,21 @@ def rank_main(rank, uid, refs):
                           f"launches={st['launches']} collectives={ctx.stats()['collectives'] - c0}", flush=True)
             ctx.set("fuse_stencil_attempt", 1)
             ctx.set("l96_peer_halo", 0)
+            # the resumable solver (b200rk_solver_new / advance / free): the peer mapping lives as long as the solver, across
+            # several advance calls, and is closed collectively by close(); same final state as the one-call solve
+            for peer_halo in ((1, 0) if p2p else (0,)):
+                ctx.set("l96_peer_halo", peer_halo)
+                sol = nn.Solver("tsit54", rhs, g, 0.3, nn.newODEoptions(**KW))
+                steps = 0
+                while True:
+                    done, fin = sol.advance(2)
+                    steps += done
+                    if fin:
+                        break
+                yend = sol.state()[3].local_numpy().copy()
+                sol.close()
+                report(rank, f"lorenz96 tsit54 n={nl}: resumable solver, peer_halo={peer_halo}", steps == ref.stats.steps and close(yend, ref.y[-1][lo:lo + ll]))
+            ctx.set("l96_peer_halo", 0)
             # one adaptive step, bit for bit against the oracle (same dt, no rejection)
             fs = O.rhs_eval(O.rhs_lorenz96(8.0), 0.0, yl)
             gf = nn.newVector(fs, ctx)

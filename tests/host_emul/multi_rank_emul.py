@@ -23,7 +23,7 @@ os.environ["B200RK_NCCL_LIB"] = build_emul_lib.build_fake_nccl()
 os.environ["B200RK_TEST_HOST_EMULATION"] = "1"
 from numericalnim_b200 import _capi
 
-_capi.LIB_PATH = build_emul_lib.build()
+_capi.LIB_PATH = build_emul_lib.build(sanitize=os.environ.get("B200RK_TEST_EMULATION_SANITIZE", ""))
 import numericalnim_b200 as nn
 import oracle as O
 

@@ -38,3 +38,25 @@ def test_rank_threads_against_the_unsharded_oracle(world, p2p):
     assert info[(1, 0)] < info[(0, 1)] / 2, info
     if p2p:
         assert info[(1, 1)] < info[(1, 0)], info
+
+
+def test_three_ranks_under_address_sanitizer(tmp_path):
+    """The same run on the AddressSanitizer build of the emulated library: the halo staging buffer, the handle tables of
+    peer_view_open and the shard-edge indexing are host code no single-rank run touches."""
+    def gcc_file(name):
+        p = subprocess.run(["gcc", "-print-file-name=" + name], capture_output=True, text=True).stdout.strip()
+        return p if os.path.isabs(p) and os.path.exists(p) else ""
+    asan, stdcpp = gcc_file("libasan.so"), gcc_file("libstdc++.so.6")
+    if not asan or not stdcpp:
+        pytest.skip("AddressSanitizer runtime not available")
+    log = str(tmp_path / "asan")
+    env = dict(os.environ, LD_PRELOAD=f"{asan} {stdcpp}", ASAN_OPTIONS=f"detect_leaks=0:log_path={log}", B200RK_TEST_EMULATION_SANITIZE="address",
+               B200RK_TEST_EMUL_WORLD="3")
+    env.pop("B200RK_P2P", None)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "host_emul", "multi_rank_emul.py")], capture_output=True, text=True, timeout=1500, cwd=ROOT, env=env)
+    reports = [f for f in os.listdir(tmp_path) if f.startswith("asan")]
+    detail = "".join(open(os.path.join(tmp_path, f)).read()[:3000] for f in reports[:2])
+    if "Shadow memory range interleaves" in detail or "ASan runtime does not come first" in r.stderr + detail:
+        pytest.skip("AddressSanitizer cannot be preloaded into this interpreter")
+    assert not reports, detail
+    assert r.returncode == 0 and "failures=0 hung=0" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]

@@ -28,6 +28,7 @@ import numericalnim_b200 as nn
 import oracle as O
 
 WORLD = int(os.environ.get("B200RK_TEST_EMUL_WORLD", "2"))   # 3: the ring neighbours are two different peers
+SIZES = (1000,) if os.environ.get("B200RK_TEST_EMULATION_SANITIZE") else (1000, 2600)   # the sanitizer pass: one size (several tiles per shard at 2 ranks)
 KW = dict(absTol=1e-6, relTol=1e-6, dtMax=1.0, dtMin=1e-8)
 results = {}
 lock = threading.Lock()
@@ -84,7 +85,7 @@ def rank_main(rank, uid, refs):
         except ValueError:
             report(rank, "impure duplicate on one rank raises on every rank", True)
         # ---- Lorenz-96, sharded ----
-        for nl in (1000, 2600):
+        for nl in SIZES:
             yl = 8.0 + 0.5 * np.sin(2 * np.pi * 37 * np.arange(nl) / nl)
             g = nn.newVector(yl, ctx)
             lo, ll = g.local_offset, g.local_len
@@ -150,7 +151,7 @@ def main():
     lam = 0.1 + 9.9 * np.arange(n) / (n - 1)
     y0 = 1.0 + 0.5 * np.sin(2 * np.pi * np.arange(n) / n)
     refs["diag"] = O.solve_vector("dopri54", O.rhs_diag_linear(lam), y0, [0.0, 2.0], O.new_options(**KW))
-    for nl in (1000, 2600):
+    for nl in SIZES:
         yl = 8.0 + 0.5 * np.sin(2 * np.pi * 37 * np.arange(nl) / nl)
         refs["l96", nl] = O.solve_vector("tsit54", O.rhs_lorenz96(8.0), yl, [0.0, 0.3], O.new_options(**KW))
         refs["rk4", nl] = O.solve_vector("rk4", O.rhs_lorenz96(8.0), yl, [0.0, 0.02], O.new_options(dt=2e-3))

@@ -28,7 +28,8 @@ import numericalnim_b200 as nn
 import oracle as O
 
 WORLD = int(os.environ.get("B200RK_TEST_EMUL_WORLD", "2"))   # 3: the ring neighbours are two different peers
-SIZES = (1000,) if os.environ.get("B200RK_TEST_EMULATION_SANITIZE") else (1000, 2600)   # the sanitizer pass: one size (several tiles per shard at 2 ranks)
+SIZES = tuple(int(x) for x in os.environ["B200RK_TEST_EMUL_SIZES"].split(",")) if os.environ.get("B200RK_TEST_EMUL_SIZES") else \
+    (1000,) if os.environ.get("B200RK_TEST_EMULATION_SANITIZE") else (1000, 2600)   # the sanitizer pass: one size (several tiles per shard at 2 ranks)
 KW = dict(absTol=1e-6, relTol=1e-6, dtMax=1.0, dtMin=1e-8)
 results = {}
 lock = threading.Lock()

@@ -225,12 +225,15 @@ static uint32_t row_mask(const b200rk_ctx* c, const Row& row, double* w_dense, i
   return mask;
 }
 
+// The reduction scratch is taken AFTER ensure_partials: growing the partials array reallocates it, and a scratch
+// block captured earlier would hand the kernel the freed pointer.
 template <int PAT, int KIND>
-static int launch_fused_cfg(b200rk_ctx* c, const FusedArgs<Pattern<PAT>::S>& a) {
+static int launch_fused_cfg(b200rk_ctx* c, FusedArgs<Pattern<PAT>::S>& a) {
   const size_t n = a.n;
   if (c->vec_width == 4) {
     unsigned grid = grid_for(c, n / 4, kThreads, c->fused_ctas_per_sm);
     TRY(ensure_partials(c, grid));
+    a.rs = reduce_scratch(c);
     // L2-resident lambda / yNew: measured neutral at 2^23 (64.8 vs 65.8 us; the kernel is co-limited by the fp64
     // pipe) and +3 % at 2^22, so only on explicit request, not under the auto policy
     if (c->l2_hints == 1) fused_attempt_kernel<PAT, KIND, 4, kThreads, 1><<<grid, kThreads, 0, c->stream>>>(a);
@@ -238,6 +241,7 @@ static int launch_fused_cfg(b200rk_ctx* c, const FusedArgs<Pattern<PAT>::S>& a) 
   } else {
     unsigned grid = grid_for(c, n / 2, kThreads, c->fused_ctas_per_sm);
     TRY(ensure_partials(c, grid));
+    a.rs = reduce_scratch(c);
     fused_attempt_kernel<PAT, KIND, 2, kThreads><<<grid, kThreads, 0, c->stream>>>(a);
   }
   CUDA_TRY(c, cudaGetLastError());
@@ -283,13 +287,13 @@ static int launch_fused_pair(b200rk_ctx* c, const MethodDef& md, const PwSpec& p
   row_mask(c, md.bhat, a.bh, S);
   a.dt = dt; a.cb = dt; a.cbh = dt; a.absTol = o.absTol; a.relTol = o.relTol;
   a.ynew = y_new->d; a.ks_out = fsal_new->d; a.n = y->n_local;
-  a.rs = reduce_scratch(c);
   const int streams = 4 + pw.np;  // y, k1 (+ parameters) read; yNew, k_S written
   ProfScope ps(c, B200RK_K_FUSED, 8.0 * double(y->n_local) * streams);
   if (pw.kind == PW_USER) {  // the same kernel, compiled at run time around the caller's expression (jit.cu)
     const int W = (c->vec_width == 4) ? 4 : 2;
     const unsigned grid = grid_for(c, a.n / W, kThreads, c->fused_ctas_per_sm);
     TRY(ensure_partials(c, grid));
+    a.rs = reduce_scratch(c);
     return jit_launch(c, pw.jit, PAT, jit_slot_attempt(W), grid, &a, false);
   }
   if (pw.kind == PW_SCALE) return launch_fused_cfg<PAT, PW_SCALE>(c, a);

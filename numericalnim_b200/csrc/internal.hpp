@@ -80,12 +80,12 @@ struct b200rk_ctx {
   int fused_ctas_per_sm = 4;   // fused pointwise attempt kernel: persistent grid of 4 CTAs per SM (~100 registers: 2 resident, 2 waves; measured best, profiles/r01_tune_*)
   bool fuse_pointwise = true;  // element-local built-in RHS: whole attempt in one kernel
   bool fuse_stencil = true;    // built-in Lorenz-96 (single GPU): stage accumulate + stencil RHS in one kernel
-  bool fuse_stencil_attempt = false;  // built-in Lorenz-96: a whole attempt in one kernel, overlapped tiles (experimental: verified by host emulation, not yet run on the GPU)
+  bool fuse_stencil_attempt = true;  // built-in Lorenz-96: a whole attempt in one kernel over overlapped tiles (default since round 2: 914 -> 3939 steps/s on config 3, profiles/r02_*)
   bool l96_peer_halo = true;   // sharded one-kernel Lorenz-96 attempt inside a solver: read the halo in place from the peer-mapped neighbours (false: ncclSend/ncclRecv)
   int l96_attempt_pairs = 2;   // l96_attempt_kernel: 128-bit pairs per thread (tile = 512 * pairs positions); 1 or 2
-  bool finish_prefetch = false; // software-pipelined finish kernel (experimental: verified by host emulation, not yet measured on the GPU)
+  bool finish_prefetch = false; // register-prefetching finish kernel: measured on the B200 in round 2 — no gain (88.5 vs 90.1-91.8 us), stays off
   int stream_simpson = -1;     // cumsimpson(f, X, dx): -1 = stream the grid only when the composed form would not fit, 0 never, 1 always
-  bool fuse_simpson = false;   // cumsimpson as one kernel (experimental: verified by host emulation, not yet measured on the GPU)
+  bool fuse_simpson = true;    // cumsimpson as one kernel (default since round 2: 1.166 -> 0.674 ms at 2^23 x 33 points, profiles/r02_quadrature_*)
   int l2_hints = -1;           // producer stores evict_last / streams evict_first: -1 auto (vector <= 0.65 L2), 0 off, 1 on
   size_t l2_bytes = 126u << 20;
   bool strict_zeros = false;

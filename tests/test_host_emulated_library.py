@@ -4,7 +4,7 @@ product's own host sources (drivers, planners, launch code) and kernels compiled
 the shared-memory Lorenz-96 kernel and the cooperative device loop); CUDA runtime calls resolve to a fake runtime whose
 "device" memory is host memory. It is what lets a change to host logic or kernel arithmetic be checked end to end
 against the oracle before any GPU time is spent — and what verified, this round, everything written after the GPU budget
-ran out (including the experimental default-off paths, which XPASS here).
+ran out.
 
 TEST INFRASTRUCTURE ONLY: the library is built under tests/, selected by a pytest option, and the product package has no
 way to load it (numericalnim_b200 still raises without a CUDA device; tests/test_capi_host.py checks that). What it
@@ -17,7 +17,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SUITES = ["tests/test_gpu_parity.py", "tests/test_gpu_fuzz.py", "tests/test_gpu_quadrature.py", "tests/test_gpu_device_loop.py",
-          "tests/test_zz_experimental_gpu.py"]
+          "tests/test_gpu_fused_paths.py"]
 
 
 def test_gpu_suites_pass_under_host_emulation():
@@ -29,9 +29,8 @@ def test_gpu_suites_pass_under_host_emulation():
     counts = {k: int(v) for v, k in re.findall(r"(\d+) (passed|failed|error|errors|xpassed|xfailed|skipped)", tail)}
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
     assert counts.get("failed", 0) == 0 and counts.get("error", 0) == 0 and counts.get("errors", 0) == 0, tail
-    assert counts.get("passed", 0) >= 199, tail            # parity 147 + fuzz 3 + quadrature 40 + device loop 9
-    assert counts.get("xpassed", 0) + counts.get("xfailed", 0) == 22, tail
-    assert counts.get("xpassed", 0) == 22, "an experimental (default-off) path fails under host emulation: " + tail
+    assert counts.get("passed", 0) >= 221, tail            # parity 147 + fuzz 3 + quadrature 40 + device loop 9 + fused paths 22
+    assert counts.get("xpassed", 0) + counts.get("xfailed", 0) == 0, tail
 
 
 def test_emulated_library_is_not_reachable_from_the_product():
@@ -84,7 +83,7 @@ def test_memory_errors_under_address_sanitizer(tmp_path):
     asan, stdcpp = _gcc_file("libasan.so"), _gcc_file("libstdc++.so.6")
     if not asan or not stdcpp:
         pytest.skip("AddressSanitizer runtime not available")
-    suites = SUITES if os.environ.get("B200RK_TEST_ASAN") == "full" else ["tests/test_gpu_quadrature.py", "tests/test_zz_experimental_gpu.py", "tests/test_gpu_fuzz.py"]
+    suites = SUITES if os.environ.get("B200RK_TEST_ASAN") == "full" else ["tests/test_gpu_quadrature.py", "tests/test_gpu_fused_paths.py", "tests/test_gpu_fuzz.py"]
     log = str(tmp_path / "asan")
     env = dict(os.environ, LD_PRELOAD=f"{asan} {stdcpp}", ASAN_OPTIONS=f"detect_leaks=0:log_path={log}", B200RK_TEST_EMULATION_SANITIZE="address")
     cmd = [sys.executable, "-m", "pytest", *suites, "-q", "-m", "gpu", "--host-emulation", "-p", "no:cacheprovider"]

@@ -121,6 +121,100 @@ def dist_env():
 # ======================================================================================================
 # our arm
 # ======================================================================================================
+UNIT = "RK steps/s"   # the same string in both arms and in `e2e`, so that the driver can divide them
+REPEATS = 5           # the timed region (exactly K accepted steps) is measured this many times: median + min / max
+
+
+def base_config(workload: str, lg: int) -> dict:
+    """`config` of the JSON line: the workload only, byte-identical between `--impl ours` and `--impl reference`
+    (library knobs and notes live in the top-level `knobs` / `notes` objects of our arm)."""
+    integrator, rhs_kind, _ = WORKLOADS[workload]
+    return {"workload": workload, "integrator": integrator, "rhs": rhs_kind, "elems_per_gpu": 1 << lg, "options": OPTS}
+
+
+def pin_to_gpu_numa_node(local_rank: int):
+    """Bind this rank to the host NUMA node its GPU hangs off BEFORE any pinned buffer is allocated (first touch then
+    places the staging buffers next to the GPU's PCIe root): at 8 ranks the end-to-end solves otherwise push 8 x 3 x 64 MiB
+    per solve through whichever socket the processes happen to start on. Returns a note for the JSON line."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return {"numa_node": None, "note": "single NUMA node / not reported"}
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed)}
+    except Exception as e:  # noqa: BLE001 — best effort: containers may hide sysfs
+        return {"numa_node": None, "note": str(e)[:120]}
+
+
+def parity_check(nn, ctx, dist, rank: int, world: int) -> dict:
+    """Sharded (or single-GPU) results against the CPU oracle BEFORE anything is timed, so that the scaling record carries
+    parity next to throughput: the three adaptive pairs + RK4 on the diag-linear IVP and Tsit54 / Vern65 / RK4 on the
+    Lorenz-96 ring (one-kernel attempt; N > 1: halo read in place from the ring neighbours over NVLink), n = 100 003
+    global. The oracle (oracle/, test infrastructure) is used as the CHECKER only and is outside every timed region.
+    Pass = step / rejection counts equal, states within the tolerances of DESIGN.md 5 (RK4: bit-identical)."""
+    import oracle as O
+
+    n = 100003
+    kw = dict(absTol=1e-6, relTol=1e-6, dtMax=1.0, dtMin=1e-8)
+    lam = 0.1 + 9.9 * np.arange(n) / (n - 1)
+    y0 = 1.0 + 0.5 * np.sin(2 * np.pi * np.arange(n) / n)
+    yl = 8.0 + 0.01 * np.sin(2 * np.pi * 37 * np.arange(n) / n)
+    glam, gy0, gl = nn.newVector(lam, ctx), nn.newVector(y0, ctx), nn.newVector(yl, ctx)
+    off, ln = gy0.local_offset, gy0.local_len
+    cases, max_rel, bad = [], 0.0, []
+
+    def one(name, method, rhs, orhs, g0, h0, ts, rtol, bitwise=False, **okw):
+        nonlocal max_rel
+        o = dict(kw, **okw)
+        ref = O.solve_vector(method, orhs, h0, ts, O.new_options(**o))
+        _, ys = nn.solveODE(rhs, g0, ts, nn.newODEoptions(**o), integrator=method)
+        st = dict(nn.ode.last_stats)
+        got, exp = ys[-1].local_numpy(), np.asarray(ref.y[-1])[off:off + ln]
+        scale = float(np.max(np.abs(ref.y[-1])))
+        rel = float(np.max(np.abs(got - exp) / (np.abs(exp) + 1e-4 * scale))) if ln else 0.0
+        if bitwise:
+            ok = np.array_equal(got.view(np.uint64), exp.view(np.uint64))
+        else:
+            ok = bool(np.all(np.abs(got - exp) <= rtol * np.abs(exp) + 1e-13 * scale))
+        ok = ok and st["steps"] == ref.stats.steps and st["rejected"] == ref.stats.rejected
+        max_rel = max(max_rel, rel)
+        cases.append(name)
+        if not ok:
+            bad.append({"case": name, "rank": rank, "steps": [st["steps"], ref.stats.steps], "rejected": [st["rejected"], ref.stats.rejected], "max_rel": rel})
+
+    d_rhs, d_or = nn.rhsDiagLinear(glam), O.rhs_diag_linear(lam)
+    for m in ("dopri54", "tsit54", "vern65"):
+        one("diag_linear/" + m, m, d_rhs, d_or, gy0, y0, [0.0, 2.0], 1e-9)
+    one("diag_linear/rk4", "rk4", d_rhs, d_or, gy0, y0, [0.0, 0.5], 0.0, bitwise=True, dt=5e-3)
+    l_rhs, l_or = nn.rhsLorenz96(8.0, ctx), O.rhs_lorenz96(8.0)
+    one("lorenz96/tsit54", "tsit54", l_rhs, l_or, gl, yl, [0.0, 0.5], 1e-7)
+    one("lorenz96/vern65", "vern65", l_rhs, l_or, gl, yl, [0.0, 0.5], 1e-7)
+    one("lorenz96/rk4", "rk4", l_rhs, l_or, gl, yl, [0.0, 0.05], 0.0, bitwise=True, dt=2e-3)
+    for v in (glam, gy0, gl):
+        v.free()
+    n_bad, worst = len(bad), max_rel
+    if dist is not None:
+        import torch
+        t = torch.tensor([float(n_bad), worst], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        n_bad, worst = int(t[0].item()), float(t[1].item())
+    return {"ok": n_bad == 0, "cases": len(cases), "max_rel": worst, "n_global": n, "ranks": world, "names": cases,
+            "failed_on_rank0": bad or None,
+            "how": "every rank compares its shard with the unsharded CPU oracle (checker only, outside the timed regions): "
+                   "step and rejection counts equal; states within 1e-9 (diag-linear) / 1e-7 (Lorenz-96) relative; RK4 bit-identical"}
+
+
 def run_ours(args):
     import torch
 
@@ -132,6 +226,7 @@ def run_ours(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch N>1 with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N bench.py --gpus N ...")
     torch.cuda.set_device(local_rank)
+    numa = pin_to_gpu_numa_node(local_rank)
     dist = None
     nccl_id = None
     if world > 1:
@@ -142,25 +237,13 @@ def run_ours(args):
         nccl_id = box[0]
     ctx = nn.Context(local_rank, rank, world, nccl_id)
     nn.set_default_context(ctx)
-    integrator, rhs_kind, lg = WORKLOADS[args.workload]
-    if args.log2n:
-        lg = args.log2n
-    n_shard = 1 << lg
-    n_global = n_shard * world
-    probe = nn.GpuVector.empty(n_global, ctx)
-    off, ln = probe.local_offset, probe.local_len
-    probe.free()
-    opts = nn.newODEoptions(**OPTS)
-    if rhs_kind == "diag":
-        lam_h, y0_h = problem_arrays(n_global, off, ln)
-        glam = nn.GpuVector.from_local(n_global, lam_h, ctx)
-        rhs = nn.rhsDiagLinear(glam)
-    else:
-        y0_h = l96_y0(n_global, off, ln)  # sharded: 3-element ring halo per RHS evaluation (ncclSend/Recv)
-        lam_h = None
-        rhs = nn.rhsLorenz96(8.0, ctx)
-    gy0 = nn.GpuVector.from_local(n_global, y0_h, ctx)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+    peak, peak_src = peaks()
+    traffic_db = {}
+    tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as fh:
+            traffic_db = json.load(fh)
 
     def barrier():
         torch.cuda.synchronize()
@@ -168,34 +251,80 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timed region: exactly K accepted steps of the driver loop --------------------
+    def allmax(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    parity = None if args.no_parity else parity_check(nn, ctx, dist, rank, world)
+
     clocks = ClockSampler(local_rank)
     clocks.__enter__()  # sampled from the warm-up through the timed regions and the end-to-end solves
 
-    def timed_steps(fuse: int, rhs=rhs) -> dict:
-        """W untimed + K timed accepted steps with the given fuse_pointwise setting; device time (CUDA events on
-        the library stream), max over ranks; per-kernel-class event times from the library's profiler."""
-        ctx.set("fuse_pointwise", fuse)
-        ctx.set("fuse_stencil", fuse)
+    def gbs(p):
+        return p["bytes"] / (p["ms"] * 1e-3) / 1e9 if p["ms"] > 0 else 0.0
+
+    class Problem:
+        """One workload's device-resident inputs (this rank's shard)."""
+
+        def __init__(self, workload: str, log2n: int = 0):
+            self.workload = workload
+            self.integrator, self.rhs_kind, lg = WORKLOADS[workload]
+            self.lg = log2n or lg
+            self.n_shard = 1 << self.lg
+            self.n_global = self.n_shard * world
+            probe = nn.GpuVector.empty(self.n_global, ctx)
+            self.off, self.ln = probe.local_offset, probe.local_len
+            probe.free()
+            self.opts = nn.newODEoptions(**OPTS)
+            self.glam, self.lam_h = None, None
+            if self.rhs_kind == "diag":
+                self.lam_h, self.y0_h = problem_arrays(self.n_global, self.off, self.ln)
+                self.glam = nn.GpuVector.from_local(self.n_global, self.lam_h, ctx)
+                self.rhs = nn.rhsDiagLinear(self.glam)
+            else:
+                self.y0_h = l96_y0(self.n_global, self.off, self.ln)
+                self.rhs = nn.rhsLorenz96(8.0, ctx)
+            self.gy0 = nn.GpuVector.from_local(self.n_global, self.y0_h, ctx)
+
+        def free(self):
+            for v in (self.glam, self.gy0):
+                if v is not None:
+                    v.free()
+
+    def timed_steps(pb: Problem, fuse: int, rhs=None, repeats: int = 1) -> dict:
+        """`repeats` x (fresh solver, W untimed + K timed accepted steps) with the fused paths on / off; device time (CUDA
+        events on the library's stream), max over ranks per repeat; then K more steps with one event pair around every
+        launch (the library's profiler) for the per-kernel roofline."""
+        rhs = rhs or pb.rhs
+        for k in ("fuse_pointwise", "fuse_stencil", "fuse_stencil_attempt"):
+            ctx.set(k, fuse)
         ctx.set("profile", 0)
-        solver = nn.Solver(integrator, rhs, gy0, 1e12, opts)
-        solver.advance(args.warmup)
-        st0, cs0 = solver.stats(), ctx.stats()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        with torch.cuda.stream(stream):
-            e0.record()
-        done, _ = solver.advance(args.steps)
-        with torch.cuda.stream(stream):
-            e1.record()
-        barrier()
-        ms_loc = e0.elapsed_time(e1)
-        st1, cs1 = solver.stats(), ctx.stats()
+        ms_all, last = [], None
+        for _ in range(repeats):
+            if last is not None:
+                last[0].close()
+            solver = nn.Solver(pb.integrator, rhs, pb.gy0, 1e12, pb.opts)
+            solver.advance(args.warmup)
+            st0, cs0 = solver.stats(), ctx.stats()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            with torch.cuda.stream(stream):
+                e0.record()
+            done, _ = solver.advance(args.steps)
+            with torch.cuda.stream(stream):
+                e1.record()
+            barrier()
+            assert done == args.steps, (done, args.steps)
+            ms_all.append(allmax(e0.elapsed_time(e1)))
+            last = (solver, st0, cs0, solver.stats(), ctx.stats())
+        solver, st0, cs0, st1, cs1 = last
         t_now_, dt_next_, _, _ = solver.state()
-        assert done == args.steps, (done, args.steps)
-        # The same solver continues for K more steps with one CUDA-event pair around EVERY kernel launch (the
-        # library's profiler, on the launching stream): per-kernel durations for the roofline. Kept out of the
-        # region above because 2 event records per launch cost a few percent of a ~80 us fused step.
+        # The same solver continues for K more steps with one CUDA-event pair around EVERY kernel launch (on the
+        # launching stream): per-kernel durations for the roofline. Kept out of the timed region above because 2 event
+        # records per launch cost a few percent of a ~60 us fused step.
         ctx.set("profile", 1)
         ctx.profile_reset()
         i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -209,37 +338,103 @@ def run_ours(args):
         prof_["instrumented_ms"] = i0.elapsed_time(i1)
         ctx.set("profile", 0)
         solver.close()
-        ms_t = torch.tensor([ms_loc], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-        return dict(ms=ms_loc, ms_max=float(ms_t.item()), prof=prof_, attempts=st1["attempts"] - st0["attempts"],
+        med = statistics.median(ms_all)
+        return dict(ms_max=med, ms_all=ms_all, prof=prof_, attempts=st1["attempts"] - st0["attempts"],
                     rejected=st1["rejected"] - st0["rejected"], launches=cs1["launches"] - cs0["launches"],
                     collectives=cs1["collectives"] - cs0["collectives"], t=t_now_, dt_next=dt_next_)
 
-    # fused paths for built-in right-hand sides: diag-linear (element-local) -> whole attempt in one kernel;
-    # Lorenz-96 on one GPU -> stage accumulate + stencil in one kernel (shared-memory tile)
-    fusable = not args.no_fuse and (rhs_kind == "diag" or world == 1)
-    pipe = timed_steps(0)                       # stage / RHS / finish pipeline (what any user closure gets)
-    head = timed_steps(1) if fusable else pipe  # headline: the library's default path for this workload
-    # experimental (knob fuse_stencil_attempt, off by default): the whole Lorenz-96 attempt in ONE kernel — reported as
-    # an extra object next to the default path, on request
-    l96_attempt = None
-    if args.l96_attempt and rhs_kind != "diag" and not args.no_fuse:   # sharded too: one 12 + 8 element halo exchange per step
-        try:
-            ctx.set("fuse_stencil_attempt", 1)
-            l96_attempt = timed_steps(1)
-        except Exception as e:  # noqa: BLE001 — the headline must survive an experimental path
-            l96_attempt = {"error": str(e)[:400]}
-        finally:
-            ctx.set("fuse_stencil_attempt", 0)
-            ctx.set("profile", 0)
-    ctx.set("fuse_pointwise", 1 if fusable else 0)
-    ctx.set("fuse_stencil", 1 if fusable else 0)
-    ms, ms_max, prof = head["ms"], head["ms_max"], head["prof"]
-    attempts, launches, t_now, dt_next = head["attempts"], head["launches"], head["t"], head["dt_next"]
+    def stage_roofline(pb: Problem, r: dict) -> dict:
+        """Roofline object of the stage / RHS / finish pipeline: the dominant kernel family is stage_kernel."""
+        st, fn_, rh = r["prof"]["stage"], r["prof"]["finish"], r["prof"]["rhs"]
+        kms = st["ms"] + fn_["ms"] + rh["ms"] + r["prof"]["other"]["ms"]
+        a = gbs(st)
+        return {"bound": "hbm", "kernel": "stage_kernel<M,W,U> (fused stage accumulate y + dt*sum(a_sj k_j); all %d launches of the timed region)" % st["launches"],
+                "achieved": a, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": a / peak, "frac_of_nominal_8000": a / 8000.0,
+                "traffic": traffic_db.get("stage_kernel_%s_2p%d" % (pb.integrator, pb.lg)), "launches": st["launches"],
+                "avg_launch_us": 1e3 * st["ms"] / max(1, st["launches"]), "algorithmic_bytes_per_launch": st["bytes"] / max(1, st["launches"]),
+                "finish_kernel": {"achieved": gbs(fn_), "frac": gbs(fn_) / peak, "launches": fn_["launches"], "avg_launch_us": 1e3 * fn_["ms"] / max(1, fn_["launches"])},
+                "rhs_kernel": {"achieved": gbs(rh), "launches": rh["launches"]},
+                "instrumented_ms_per_step": r["prof"]["instrumented_ms"] / args.steps,
+                "kernel_time_share_of_step": kms / r["prof"]["instrumented_ms"] if r["prof"]["instrumented_ms"] > 0 else None}
 
-    # ---- end to end: solveODE over [0, 2] from pinned HOST buffers (H2D y0 + lambda, solve, D2H states) ----
+    def fused_roofline(pb: Problem, r: dict) -> tuple:
+        """Roofline of the library's default (fused) path of a workload: (path description, roofline object)."""
+        fu = r["prof"]["fused"]
+        a = gbs(fu)
+        common = {"bound": "hbm", "achieved": a, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": a / peak,
+                  "frac_of_nominal_8000": a / 8000.0, "launches": fu["launches"], "avg_launch_us": 1e3 * fu["ms"] / max(1, fu["launches"]),
+                  "algorithmic_bytes_per_launch": fu["bytes"] / max(1, fu["launches"]),
+                  "instrumented_ms_per_step": r["prof"]["instrumented_ms"] / args.steps,
+                  "kernel_time_share_of_step": fu["ms"] / r["prof"]["instrumented_ms"] if r["prof"]["instrumented_ms"] > 0 else None}
+        if pb.rhs_kind != "diag":
+            path = "l96_attempt (built-in Lorenz-96: every attempt = ONE kernel over overlapped tiles; sharded: halo read in place from the ring neighbours)"
+            common.update({"kernel": "l96_attempt_kernel<PAT,J> (whole attempt: all stages, Lorenz-96 stencil, yNew, error norm; 4 vector passes of algorithmic traffic)",
+                           "traffic": traffic_db.get("l96_attempt_kernel_%s_2p%d" % (pb.integrator, pb.lg))})
+            return path, common
+        passes = 5
+        attempts_instr = fu["bytes"] / (8.0 * pb.n_shard * passes) if pb.n_shard else 0.0
+        devloop = ctx.get("device_loop") != 0 and (world == 1 or bool(ctx.get("p2p")))
+        if devloop:
+            path = "fused_run (element-local built-in RHS: all K steps in one persistent cooperative kernel, controller on the device)"
+            kname = ("fused_run_kernel<PAT,RHS> (persistent cooperative kernel: every attempt = all stages, RHS, yNew, error norm, "
+                     "grid-wide exchange of the norm, device-side controller; one launch runs the K steps)")
+            per_attempt = traffic_db.get("fused_run_kernel_per_attempt_%s_2p%d" % (pb.integrator, pb.lg))
+            traffic = per_attempt * attempts_instr / max(1, fu["launches"]) if per_attempt else None
+        else:
+            path = "fused_attempt (element-local built-in RHS)"
+            kname = "fused_attempt_kernel<PAT,RHS> (whole attempt of an element-local IVP in one kernel: all stages, RHS, yNew, error norm)"
+            traffic = traffic_db.get("fused_attempt_kernel_%s_2p%d" % (pb.integrator, pb.lg))
+        common.update({"kernel": kname, "traffic": traffic, "attempts_in_launches": attempts_instr,
+                       "us_per_attempt": 1e3 * fu["ms"] / max(1.0, attempts_instr)})
+        return path, common
+
+    def summarize(pb: Problem, r: dict, roofline: dict, path: str) -> dict:
+        return {"workload": pb.workload, "value": args.steps * world / (r["ms_max"] * 1e-3), "unit": UNIT, "ms_per_step": r["ms_max"] / args.steps,
+                "attempts": r["attempts"], "rejected": r["rejected"], "attempts_per_sec": r["attempts"] * world / (r["ms_max"] * 1e-3),
+                "gpu_launches": r["launches"], "collectives": r["collectives"], "t_reached": r["t"], "path": path, "roofline": roofline,
+                "config": base_config(pb.workload, pb.lg)}
+
+    # ---- headline workload: the general pipeline (what any user closure gets), then the library's default path ----------
+    pb = Problem(args.workload, args.log2n)
+    integrator, rhs_kind, lg, n_shard, n_global = pb.integrator, pb.rhs_kind, pb.lg, pb.n_shard, pb.n_global
+    fusable = not args.no_fuse
+    pipe = timed_steps(pb, 0)
+    head = timed_steps(pb, 1, repeats=REPEATS) if fusable else timed_steps(pb, 0, repeats=REPEATS)
+    for k in ("fuse_pointwise", "fuse_stencil", "fuse_stencil_attempt"):
+        ctx.set(k, 1 if fusable else 0)
+    if fusable:
+        path, roofline = fused_roofline(pb, head)
+    else:
+        path, roofline = "stage/RHS/finish pipeline", stage_roofline(pb, head)
+    ms_max, attempts, launches, t_now, dt_next = head["ms_max"], head["attempts"], head["launches"], head["t"], head["dt_next"]
+    pipeline_obj = None
+    if fusable:
+        pipeline_obj = {"note": "same K steps with the fused paths off: the stage / RHS / finish pipeline every user-supplied right-hand side runs through",
+                        "value": args.steps * world / (pipe["ms_max"] * 1e-3), "ms_per_step": pipe["ms_max"] / args.steps, "attempts": pipe["attempts"],
+                        "gpu_launches": pipe["launches"],
+                        "hbm_gbs_step": ALG_BYTES_PER_ELEM.get(integrator, 0) * n_shard * pipe["attempts"] / (pipe["ms_max"] * 1e-3) / 1e9,
+                        "roofline": stage_roofline(pb, pipe)}
+
+    # ---- the other single-/multi-GPU configurations of BASELINE.json on the same line: config 3 (N = 1) and config 4 (every N)
+    extra = {}
+    if not args.no_extra_configs and fusable:
+        for key, wl, cond in (("cfg3", "cfg3_tsit54_lorenz96_16M", world == 1), ("cfg4", "cfg4_vern65_diag_16M_per_gpu", True)):
+            if not cond or wl == args.workload:
+                continue
+            try:
+                pbx = Problem(wl)
+                rx = timed_steps(pbx, 1, repeats=3)
+                px, rfx = fused_roofline(pbx, rx)
+                extra[key] = summarize(pbx, rx, rfx, px)
+                extra[key]["repeats"] = {"n": len(rx["ms_all"]), "ms": rx["ms_all"]}
+                pbx.free()
+            except Exception as e:  # noqa: BLE001 — the headline must survive
+                extra[key] = {"error": str(e)[:400]}
+                ctx.set("profile", 0)
+
+    # ---- end to end: solveODE over [0, 2] from pinned HOST buffers (H2D y0 [+ lambda], solve, D2H states) ----------------
     L = _capi.lib()
+    y0_h, lam_h, ln, rhs, glam, opts = pb.y0_h, pb.lam_h, pb.ln, pb.rhs, pb.glam, pb.opts
     y0_pin = torch.from_numpy(y0_h).pin_memory()
     lam_pin = torch.from_numpy(lam_h).pin_memory() if lam_h is not None else None
     out_pin = torch.empty((2, ln), dtype=torch.float64).pin_memory()
@@ -247,32 +442,61 @@ def run_ours(args):
     t_out = np.empty(2)
     n_out = C.c_size_t(0)
     method = nn.ode.method_id(integrator)
-    e2e_steps, e2e_ms, h2d, d2h = 0, 0.0, 0, 0
     reps = max(1, args.e2e_reps)
-    for rep in range(reps + 1):  # first repetition is warm-up
-        st = _capi.Stats()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        with torch.cuda.stream(stream):
-            a0.record()
-        if lam_pin is not None:
-            _capi.check(L.b200rk_vec_upload_local(glam._h, lam_pin.data_ptr()), ctx.handle)
-        _capi.check(L.b200rk_solve_host(ctx.handle, method, rhs.fn, rhs.user, n_global, y0_pin.data_ptr(), ts.ctypes.data, 2,
-                                        C.byref(opts), t_out.ctypes.data, out_pin.data_ptr(), C.byref(n_out), C.byref(st)), ctx.handle)
-        with torch.cuda.stream(stream):
-            a1.record()
-        barrier()
-        if rep == 0:
-            continue
-        e2e_ms += a0.elapsed_time(a1)
-        e2e_steps += st.steps
-        h2d += y0_pin.numel() * 8 + (lam_pin.numel() * 8 if lam_pin is not None else 0)
-        d2h += int(n_out.value) * ln * 8
+
+    def e2e_variant(upload_params: bool) -> dict:
+        steps_, ms_, h2d_, d2h_ = 0, [], 0, 0
+        for rep in range(reps + 1):  # first repetition is warm-up
+            st = _capi.Stats()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            with torch.cuda.stream(stream):
+                a0.record()
+            if upload_params and lam_pin is not None:
+                _capi.check(L.b200rk_vec_upload_local_async(glam._h, lam_pin.data_ptr()), ctx.handle)
+            _capi.check(L.b200rk_solve_host(ctx.handle, method, rhs.fn, rhs.user, n_global, y0_pin.data_ptr(), ts.ctypes.data, 2,
+                                            C.byref(opts), t_out.ctypes.data, out_pin.data_ptr(), C.byref(n_out), C.byref(st)), ctx.handle)
+            with torch.cuda.stream(stream):
+                a1.record()
+            barrier()
+            if rep == 0:
+                continue
+            ms_.append(allmax(a0.elapsed_time(a1)))
+            steps_ += st.steps
+            h2d_ += y0_pin.numel() * 8 + (lam_pin.numel() * 8 if (upload_params and lam_pin is not None) else 0)
+            d2h_ += int(n_out.value) * ln * 8
+        tot = sum(ms_)
+        return {"value": steps_ * world / (tot * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_ / max(1, steps_), "d2h_bytes_per_step": d2h_ / max(1, steps_),
+                "steps_per_solve": steps_ / reps, "ms_per_solve": tot / reps, "ms_per_solve_all": ms_,
+                "h2d_bytes_per_solve": h2d_ / reps, "d2h_bytes_per_solve": d2h_ / reps}
+
+    e2e_full = e2e_variant(True)
+    e2e_res = e2e_variant(False) if lam_pin is not None else None
+    # PCIe roofline of the end-to-end number: the same pinned buffers copied alone, both directions
+    pcie = {}
+    try:
+        dbuf = torch.empty(ln, dtype=torch.float64, device="cuda")
+        for name, dst, src in (("h2d", dbuf, y0_pin), ("d2h", out_pin[0], dbuf)):
+            best = 1e30
+            for _ in range(4):
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                barrier()
+                c0.record()
+                dst.copy_(src, non_blocking=True)
+                c1.record()
+                torch.cuda.synchronize()
+                best = min(best, allmax(c0.elapsed_time(c1)))
+            pcie[name + "_gbs_per_gpu"] = ln * 8 / (best * 1e-3) / 1e9
+        del dbuf
+        for v, key in ((e2e_full, "value"), (e2e_res, "rhs_resident")):
+            if v is None:
+                continue
+            floor_ms = 1e3 * (v["h2d_bytes_per_solve"] / (pcie["h2d_gbs_per_gpu"] * 1e9) + v["d2h_bytes_per_solve"] / (pcie["d2h_gbs_per_gpu"] * 1e9))
+            v["pcie_floor_ms_per_solve"] = floor_ms
+            v["pcie_share_of_solve"] = floor_ms / v["ms_per_solve"]
+    except Exception as e:  # noqa: BLE001
+        pcie = {"error": str(e)[:200]}
     clocks.__exit__(None, None, None)
-    e2e_t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_ms_max = float(e2e_t.item())
 
     # ---- the same IVP with the right-hand side handed over as SOURCE ("-(p0*y)"): NVRTC compiles it into the fused
     # kernels at run time (csrc/jit.cu) — what a user-defined element-local closure gets instead of the built-in.
@@ -282,7 +506,7 @@ def run_ours(args):
         try:
             t0 = time.time()
             jrhs = nn.rhsJit("-(p0*y)", [glam])
-            jr = timed_steps(1, jrhs)
+            jr = timed_steps(pb, 1, jrhs)
             fu = jr["prof"]["fused"]
             jit_obj = {"note": "right-hand side given as the source expression -(p0*y), compiled at run time (NVRTC) into the same fused kernels",
                        "value": args.steps * world / (jr["ms_max"] * 1e-3), "ms_per_step": jr["ms_max"] / args.steps, "attempts": jr["attempts"],
@@ -312,105 +536,48 @@ def run_ours(args):
             quad_obj = {"error": str(e)[:400]}
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on a bounded sample -----------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and rhs_kind == "diag":
-        cpu = cpu_baseline_sample(integrator, n_shard, steps=2)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_sample(integrator, rhs_kind, n_shard, steps=2)
 
     if rank == 0:
-        peak, peak_src = peaks()
-        traffic_db = {}
-        tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
-        if os.path.exists(tp):
-            with open(tp) as fh:
-                traffic_db = json.load(fh)
-
-        def gbs(p):
-            return p["bytes"] / (p["ms"] * 1e-3) / 1e9 if p["ms"] > 0 else 0.0
-
-        def stage_roofline(r):
-            """Roofline object of the stage / RHS / finish pipeline: the dominant kernel family is stage_kernel."""
-            st, fn_, rh = r["prof"]["stage"], r["prof"]["finish"], r["prof"]["rhs"]
-            kms = st["ms"] + fn_["ms"] + rh["ms"] + r["prof"]["other"]["ms"]
-            a = gbs(st)
-            return {"bound": "hbm", "kernel": "stage_kernel<M,W,U> (fused stage accumulate y + dt*sum(a_sj k_j); all %d launches of the timed region)" % st["launches"],
-                    "achieved": a, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": a / peak, "frac_of_nominal_8000": a / 8000.0,
-                    "traffic": traffic_db.get("stage_kernel_%s_2p%d" % (integrator, lg)), "launches": st["launches"],
-                    "avg_launch_us": 1e3 * st["ms"] / max(1, st["launches"]), "algorithmic_bytes_per_launch": st["bytes"] / max(1, st["launches"]),
-                    "finish_kernel": {"achieved": gbs(fn_), "frac": gbs(fn_) / peak, "launches": fn_["launches"], "avg_launch_us": 1e3 * fn_["ms"] / max(1, fn_["launches"])},
-                    "rhs_kernel": {"achieved": gbs(rh), "launches": rh["launches"]},
-                    "instrumented_ms_per_step": r["prof"]["instrumented_ms"] / args.steps,
-                    "kernel_time_share_of_step": kms / r["prof"]["instrumented_ms"] if r["prof"]["instrumented_ms"] > 0 else None}
-
-        pipeline_obj = None
-        if head is not pipe:
-            pipeline_obj = {"note": "same K steps with the fused paths off: the stage / RHS / finish pipeline every user-supplied right-hand side runs through",
-                            "value": args.steps * world / (pipe["ms_max"] * 1e-3), "ms_per_step": pipe["ms_max"] / args.steps, "attempts": pipe["attempts"],
-                            "gpu_launches": pipe["launches"],
-                            "hbm_gbs_step": ALG_BYTES_PER_ELEM.get(integrator, 0) * n_shard * pipe["attempts"] / (pipe["ms"] * 1e-3) / 1e9,
-                            "roofline": stage_roofline(pipe)}
-        if head is pipe:
-            roofline = stage_roofline(pipe)
-            path = "stage/RHS/finish pipeline"
-        elif rhs_kind != "diag":
-            roofline = stage_roofline(head)
-            roofline["kernel"] = "stage_l96_kernel<M> (stage accumulate fused with the Lorenz-96 stencil through a shared-memory tile; all %d launches)" % head["prof"]["stage"]["launches"]
-            roofline["traffic"] = traffic_db.get("stage_l96_kernel_%s_2p%d" % (integrator, lg))
-            path = "stage+stencil fused (built-in Lorenz-96), finish kernel"
-        else:
-            devloop = ctx.get("device_loop") != 0 and (world == 1 or bool(ctx.get("p2p")))
-            fu = prof["fused"]
-            a = gbs(fu)
-            attempts_instr = fu["bytes"] / (8.0 * n_shard * 5) if n_shard else 0.0  # 5 vector passes per attempt
-            if devloop:
-                path = "fused_run (element-local built-in RHS: all K steps in one persistent cooperative kernel, controller on the device)"
-                kname = ("fused_run_kernel<PAT,RHS> (persistent cooperative kernel: every attempt = all stages, RHS, yNew, error norm, "
-                         "grid barrier, device-side controller; one launch runs the K steps)")
-            else:
-                path = "fused_attempt (element-local built-in RHS)"
-                kname = "fused_attempt_kernel<PAT,RHS> (whole attempt of an element-local IVP in one kernel: all stages, RHS, yNew, error norm)"
-            roofline = {"bound": "hbm", "kernel": kname,
-                        "achieved": a, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": a / peak, "frac_of_nominal_8000": a / 8000.0,
-                        "traffic": (traffic_db.get("fused_run_kernel_per_attempt_%s_2p%d" % (integrator, lg), 0.0) * attempts_instr / max(1, fu["launches"]) or None)
-                        if devloop else traffic_db.get("fused_attempt_kernel_%s_2p%d" % (integrator, lg)),
-                        "launches": fu["launches"], "attempts_in_launches": attempts_instr, "us_per_attempt": 1e3 * fu["ms"] / max(1.0, attempts_instr),
-                        "avg_launch_us": 1e3 * fu["ms"] / max(1, fu["launches"]), "algorithmic_bytes_per_launch": fu["bytes"] / max(1, fu["launches"]),
-                        "instrumented_ms_per_step": prof["instrumented_ms"] / args.steps,
-                        "kernel_time_share_of_step": fu["ms"] / prof["instrumented_ms"] if prof["instrumented_ms"] > 0 else None}
-        l96_obj = None
-        if l96_attempt is not None:
-            if "error" in l96_attempt:
-                l96_obj = l96_attempt
-            else:
-                fu = l96_attempt["prof"]["fused"]
-                l96_obj = {"note": "experimental knob fuse_stencil_attempt=1: the whole attempt (all stages, Lorenz-96 stencil, yNew, error norm) in one "
-                                   "kernel over overlapped tiles (csrc/stencil_attempt.cuh); algorithmic bytes = 4 vector passes per attempt",
-                           "value": args.steps * world / (l96_attempt["ms_max"] * 1e-3), "ms_per_step": l96_attempt["ms_max"] / args.steps,
-                           "attempts": l96_attempt["attempts"], "rejected": l96_attempt["rejected"], "gpu_launches": l96_attempt["launches"],
-                           "t_reached": l96_attempt["t"], "hbm_gbs": gbs(fu), "frac_of_peak": gbs(fu) / peak, "launches": fu["launches"],
-                           "avg_launch_us": 1e3 * fu["ms"] / max(1, fu["launches"])}
+        e2e = dict(e2e_full)
+        e2e["note"] = ("complete solveODE calls through b200rk_solve_host on pinned HOST buffers, inside the timed region every solve: H2D y0 and lambda "
+                       "(the right-hand side's parameter vector), the solve, D2H of the returned states; accepted steps / device time (max over ranks)")
+        if e2e_res is not None:
+            e2e["rhs_resident"] = dict(e2e_res, note="same, with lambda left on the device between solves (it belongs to the right-hand-side object, "
+                                                     "like the data a reference ODEProc closure captures): only y0 goes up, the states come down")
+        e2e["pcie"] = pcie
+        e2e["host_numa"] = numa
+        ms_all = head["ms_all"]
         line = {
-            "metric": "rk_steps_per_sec", "value": args.steps * world / (ms_max * 1e-3), "unit": "RK steps/s (x 2^%d-element shard, summed over GPUs)" % lg,
+            "metric": "rk_steps_per_sec", "value": args.steps * world / (ms_max * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "integrator": integrator, "rhs": rhs_kind, "elems_per_gpu": n_shard, "elems_global": n_global,
-                       "options": OPTS, "l2": "working set (>= 10 vectors x %d MiB per GPU) exceeds the 126 MB L2; no flush" % (n_shard * 8 >> 20),
-                       "sharding": "contiguous shards, 1 all-reduce(sum, 1 x f64) of the error norm per attempt" if world > 1 else "single GPU, no collective",
-                       "vec_width": ctx.get("vec_width"), "ctas_per_sm": ctx.get("ctas_per_sm"), "finish_ctas_per_sm": ctx.get("finish_ctas_per_sm"),
-                       "fuse_pointwise": ctx.get("fuse_pointwise"), "fused_ctas_per_sm": ctx.get("fused_ctas_per_sm"),
-                       "spin_readback": ctx.get("spin_readback"), "l2_hints": ctx.get("l2_hints"), "device_loop": ctx.get("device_loop"),
-                       "error_norm_allreduce": ("in-kernel peer mailboxes over NVLink (CUDA IPC)" if ctx.get("p2p") else "ncclAllReduce") if world > 1 else None},
+            "config": base_config(args.workload, lg),
+            "repeats": {"n": len(ms_all), "ms_per_K_steps": ms_all, "median_ms": ms_max, "min_ms": min(ms_all), "max_ms": max(ms_all),
+                        "value_from": "median", "value_at_min": args.steps * world / (min(ms_all) * 1e-3), "value_at_max": args.steps * world / (max(ms_all) * 1e-3)},
+            "notes": {"value": "accepted RK steps of one 2^%d-element shard per second, summed over the %d GPU(s) (weak scaling: every rank advances its own shard "
+                               "of one N_global = %d system in lockstep)" % (lg, world, n_global),
+                      "elems_global": n_global,
+                      "l2": "working set (>= 5 vectors x %d MiB per GPU) exceeds the 126 MB L2; no flush" % (n_shard * 8 >> 20),
+                      "sharding": "contiguous shards, 1 all-reduce(sum, 1 x f64) of the error norm per attempt" if world > 1 else "single GPU, no collective",
+                      "error_norm_allreduce": ("in-kernel peer mailboxes over NVLink (CUDA IPC)" if ctx.get("p2p") else "ncclAllReduce") if world > 1 else None,
+                      "butcher_row": "kernel parameters / constant bank (uniform broadcast) instead of shared-memory staging (DESIGN.md 4)"},
+            "knobs": {k: ctx.get(k) for k in ("vec_width", "ctas_per_sm", "finish_ctas_per_sm", "fuse_pointwise", "fuse_stencil", "fuse_stencil_attempt",
+                                              "fused_ctas_per_sm", "spin_readback", "l2_hints", "device_loop")},
             "attempts": attempts, "attempts_per_sec": attempts * world / (ms_max * 1e-3), "rejected": head["rejected"],
             "t_reached": t_now, "dt_next": dt_next,
             "gpu_launches": launches, "collectives": head["collectives"],
             "path": path,
             "roofline": roofline,
+            "parity_check": parity,
             "pipeline": pipeline_obj,
+            "cfg3": extra.get("cfg3"),
+            "cfg4": extra.get("cfg4"),
             "jit_rhs": jit_obj,
-            "l96_attempt": l96_obj,
             "trajectory_consumers": quad_obj,
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_steps * world / (e2e_ms_max * 1e-3), "unit": "RK steps/s (solveODE on host buffers: H2D y0+lambda, solve, D2H states)",
-                    "h2d_bytes_per_step": h2d / max(1, e2e_steps), "d2h_bytes_per_step": d2h / max(1, e2e_steps), "steps_per_solve": e2e_steps / reps,
-                    "ms_per_solve": e2e_ms_max / reps},
+            "e2e": e2e,
             "clocks": clocks.summary(),
         }
         print(json.dumps(line), flush=True)
@@ -422,65 +589,78 @@ def run_ours(args):
 # ======================================================================================================
 # CPU: oracle port (the reference cannot be built: Nim, no toolchain) — bench.py's only use of oracle/
 # ======================================================================================================
-def cpu_baseline_sample(integrator: str, n: int, steps: int):
+def oracle_problem(O, rhs_kind: str, n: int):
+    if rhs_kind == "diag":
+        lam, y0 = problem_arrays(n, 0, n)
+        return O.rhs_diag_linear(lam), y0, lam
+    return O.rhs_lorenz96(8.0), l96_y0(n, 0, n), None
+
+
+def cpu_baseline_sample(integrator: str, rhs_kind: str, n: int, steps: int):
     import oracle as O
 
-    lam, y0 = problem_arrays(n, 0, n)
+    orhs, y0, lam = oracle_problem(O, rhs_kind, n)
     t0 = time.time()
-    s = O.solve_vector(integrator, O.rhs_diag_linear(lam), y0, [0.0, 1e12], O.new_options(**OPTS), max_steps=steps)
+    s = O.solve_vector(integrator, orhs, y0, [0.0, 1e12], O.new_options(**OPTS), max_steps=steps)
     wall = time.time() - t0
-    out = {"value": s.stats.steps / s.stats.seconds, "unit": "RK steps/s at 2^%d elements" % int(np.log2(n)), "cores": 1, "kind": "port",
-           "sample": "%d accepted %s steps (+2 start-up RHS evaluations) at N=2^%d on 1 of %d host cores; %.1f s" % (
+    out = {"value": s.stats.steps / s.stats.seconds, "unit": UNIT, "cores": 1, "kind": "port",
+           "sample": "%d accepted %s steps (+2 start-up RHS evaluations) at the full N=2^%d on 1 of %d host cores (numericalnim is single-threaded); %.1f s" % (
                s.stats.steps, integrator, int(np.log2(n)), os.cpu_count() or 0, wall)}
-    try:  # courtesy row: NOT the reference's behaviour — the attempt fused into one pass, all host cores
-        _, fs = O.fused_mt_solve_diag(integrator, lam, y0, 1e12, O.new_options(**OPTS), max_steps=10)
-        out["courtesy_fused_multithreaded"] = {"value": fs.steps / fs.seconds, "unit": out["unit"], "cores": int(fs.threads),
-                                               "note": "same IVP, whole attempt fused into one pass per element (5 vector passes), std::thread over all host cores, scalar -O2 code; "
-                                                       "element-wise results bit-identical to the port. numericalnim itself is single-threaded and allocates a Vector per operator."}
-    except Exception as e:  # noqa: BLE001
-        out["courtesy_fused_multithreaded"] = {"error": str(e)[:200]}
+    if lam is not None:
+        try:  # courtesy row: NOT the reference's behaviour — the attempt fused into one pass, all host cores
+            _, fs = O.fused_mt_solve_diag(integrator, lam, y0, 1e12, O.new_options(**OPTS), max_steps=10)
+            out["courtesy_fused_multithreaded"] = {"value": fs.steps / fs.seconds, "unit": UNIT, "cores": int(fs.threads),
+                                                   "note": "same IVP, whole attempt fused into one pass per element (5 vector passes), std::thread over all host cores, scalar -O2 code; "
+                                                           "element-wise results bit-identical to the port. numericalnim itself is single-threaded and allocates a Vector per operator."}
+        except Exception as e:  # noqa: BLE001
+            out["courtesy_fused_multithreaded"] = {"error": str(e)[:200]}
     return out
 
 
 def run_reference(args):
     """The reference's own CPU implementation of the path, as faithfully as it can be had here: the C++
     oracle port (allocating one-pass-per-operator Vectors, sequential sum, -O2, no FMA). Single thread because
-    numericalnim's ode.nim / utils.nim have no threading construct — that is every thread the reference uses."""
+    numericalnim's ode.nim / utils.nim have no threading construct — that is every thread the reference uses.
+    Runs the FULL workload size (2^23 elements: ~6.5 s per step); only when W + K steps would not fit --cpu-budget-s does
+    it fall back to a power-of-two sample, scaling the time linearly in N (which favours the CPU) and saying so."""
     rank, _, world = dist_env()
     if rank != 0:
         return
     import oracle as O
 
     integrator, rhs_kind, lg = WORKLOADS[args.workload]
-    if rhs_kind != "diag":
-        raise SystemExit("reference arm implements the diag-linear workloads")
-    n_full = 1 << (args.log2n or lg)
-    # calibrate on a small sample, then pick the largest power-of-two N_s whose K+W steps fit the budget
-    lam, y0 = problem_arrays(1 << 18, 0, 1 << 18)
-    c = O.solve_vector(integrator, O.rhs_diag_linear(lam), y0, [0.0, 1e12], O.new_options(**OPTS), max_steps=2)
-    per_elem_step = c.stats.seconds / 2 / (1 << 18) * 3.0  # large vectors are ~3x slower per element (page faults)
-    budget = args.cpu_budget_s
+    lg = args.log2n or lg
+    n_full = 1 << lg
+    warm = min(args.warmup, 1)   # a CPU has no clocks to ramp or JIT to warm: one untimed step pages the buffers in
+    # calibrate on ONE step at the full size (page faults and all), then pick the largest power-of-two N_s that fits
+    orhs, y0, _ = oracle_problem(O, rhs_kind, n_full)
+    c = O.solve_vector(integrator, orhs, y0, [0.0, 1e12], O.new_options(**OPTS), max_steps=1)
+    per_step_full = c.stats.seconds
     n_s = n_full
-    while n_s > (1 << 16) and per_elem_step * n_s * (args.steps + args.warmup) > budget:
+    while n_s > (1 << 16) and per_step_full * (n_s / n_full) * (args.steps + warm) > args.cpu_budget_s:
         n_s >>= 1
-    lam, y0 = problem_arrays(n_s, 0, n_s)
-    O.solve_vector(integrator, O.rhs_diag_linear(lam), y0, [0.0, 1e12], O.new_options(**OPTS), max_steps=max(1, args.warmup))
+    if n_s != n_full:
+        orhs, y0, _ = oracle_problem(O, rhs_kind, n_s)
+    if warm and n_s != n_full:
+        O.solve_vector(integrator, orhs, y0, [0.0, 1e12], O.new_options(**OPTS), max_steps=warm)
     t0 = time.time()
-    s = O.solve_vector(integrator, O.rhs_diag_linear(lam), y0, [0.0, 1e12], O.new_options(**OPTS), max_steps=args.steps)
+    s = O.solve_vector(integrator, orhs, y0, [0.0, 1e12], O.new_options(**OPTS), max_steps=args.steps)
     wall = time.time() - t0
-    scale = n_full / n_s  # time assumed linear in N (bandwidth-bound) — favours the CPU, see DESIGN.md §6
+    scale = n_full / n_s  # time assumed linear in N (bandwidth-bound) — favours the CPU, see DESIGN.md 6
     secs = s.stats.seconds * scale
     value = s.stats.steps / secs
-    sample = "%d accepted %s steps at N_s=2^%d (%s of the 2^%d workload, time scaled x%g), 1 of %d host cores, %.1f s wall" % (
-        s.stats.steps, integrator, int(np.log2(n_s)), "all" if n_s == n_full else "1/%d" % int(scale), int(np.log2(n_full)), scale, os.cpu_count() or 0, wall)
-    line = {"impl": "reference", "metric": "rk_steps_per_sec", "value": value,
-            "unit": "RK steps/s (x 2^%d-element shard, summed over GPUs)" % int(np.log2(n_full)), "n_gpus": world, "steps": args.steps,
+    sample = "%d accepted %s steps at N_s=2^%d (%s of the 2^%d workload%s), 1 of %d host cores (the reference is single-threaded), %.1f s wall" % (
+        s.stats.steps, integrator, int(np.log2(n_s)), "all" if n_s == n_full else "1/%d" % int(scale), lg,
+        "" if n_s == n_full else ", time scaled x%g" % scale, os.cpu_count() or 0, wall)
+    line = {"impl": "reference", "metric": "rk_steps_per_sec", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, s.stats.steps), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "integrator": integrator, "rhs": rhs_kind, "elems_per_gpu": n_full, "options": OPTS,
-                       "note": "CPU arm: one shard on one host thread (the reference is single-threaded); not multiplied by n_gpus"},
-            "cpu_baseline": {"value": value, "unit": "RK steps/s", "cores": 1, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": "RK steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "config": base_config(args.workload, lg),
+            "notes": {"value": "CPU arm: one 2^%d-element shard on one host thread (the reference is single-threaded); not multiplied by n_gpus" % lg,
+                      "warmup": "%d untimed step(s) at the full size (the calibration step), then exactly K timed steps" % 1},
+            "knobs": {},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -740,9 +920,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-quad", action="store_true", help="skip the trajectory-consumer bandwidth leg")
     ap.add_argument("--no-jit", action="store_true", help="skip the run-time compiled right-hand-side leg")
-    ap.add_argument("--l96-attempt", action="store_true", help="Lorenz-96 workloads: also time the experimental one-kernel attempt (knob fuse_stencil_attempt)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sharded parity check against the oracle that precedes the timing")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the cfg3 / cfg4 objects of the default line")
     ap.add_argument("--no-fuse", action="store_true", help="headline = the stage/RHS/finish pipeline even for element-local built-in RHS")
-    ap.add_argument("--cpu-budget-s", type=float, default=120.0)
+    ap.add_argument("--cpu-budget-s", type=float, default=280.0)
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--quad", action="store_true", help="trajectory consumers: cumtrapz / cumsimpson / hermiteInterpolate bandwidth")
     ap.add_argument("--quad-points", type=int, default=33)

@@ -138,6 +138,9 @@ B200RK_API int b200rk_vec_download(const b200rk_vec* v, double* host_global);
 /* host arrays of LOCAL length */
 B200RK_API int b200rk_vec_upload_local(b200rk_vec* v, const double* host_local);
 B200RK_API int b200rk_vec_download_local(const b200rk_vec* v, double* host_local);
+/* same as upload_local without the trailing stream synchronisation: the copy is ordered on the context stream in front of
+ * whatever is enqueued next (host_local must be pinned and stay untouched until b200rk_synchronize or a solve returns) */
+B200RK_API int b200rk_vec_upload_local_async(b200rk_vec* v, const double* host_local);
 B200RK_API int b200rk_vec_copy(b200rk_vec* dst, const b200rk_vec* src);          /* clone, utils.nim:269 */
 B200RK_API int b200rk_vec_fill(b200rk_vec* v, double value);
 /* element-wise operators; size mismatch -> B200RK_EINVAL (utils.nim:22-26). out may alias an input. */

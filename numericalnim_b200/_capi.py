@@ -73,6 +73,7 @@ _DECLS = {
     "b200rk_vec_download": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200rk_vec_upload_local": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200rk_vec_download_local": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200rk_vec_upload_local_async": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200rk_vec_copy": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200rk_vec_fill": (C.c_int, [C.c_void_p, C.c_double]),
     "b200rk_vec_add": (C.c_int, [C.c_void_p] * 3),

@@ -212,6 +212,12 @@ static int solver_create(b200rk_ctx* c, int method, b200rk_rhs_fn f, void* user,
   s->adaptive = s->md->adaptive;
   s->dtInit = s->adaptive ? std::sqrt(s->o.dtMax * s->o.dtMin) : s->o.dt;       // ode.nim:491-496
   int rc = solver_alloc(s, N);
+  if (rc == B200RK_OK && f == &jit_rhs_fn) {
+    // right-hand side from source: every rank compiles and loads its units now, then the ranks meet on the stream, so the
+    // first attempt's in-kernel all-reduce does not have to absorb a multi-second NVRTC compile on one of them
+    rc = jit_prepare(c, static_cast<JitRhs*>(user), c->fuse_pointwise ? fused_pattern_for(c, *s->md) : -1);
+    if (rc == B200RK_OK && c->world > 1) { rc = stream_barrier(c); c->collectives--; }   // set-up, not a data-path collective: not counted
+  }
   if (rc == B200RK_OK && l96_peer_halo_possible(c, *s->md, s->rhs, N)) {
     b200rk_vec* const vecs[4] = {s->Y[0], s->Y[1], s->F[0], s->F[1]};
     rc = peer_view_open(c, vecs, 4, &s->peers);   // peers.count stays 0 when the mapping is not available: ncclSend/ncclRecv halo

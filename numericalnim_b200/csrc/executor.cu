@@ -21,7 +21,13 @@ int builtin_rhs_fn(double /*t*/, const b200rk_vec* y, b200rk_vec* dydt, void* us
         // Sharded stencil: 3-element halo per evaluation over NVLink. Each rank sends its
         // first element to the left neighbour and its last two to the right neighbour (ring), on the
         // context stream, so the exchange is ordered with the producing and consuming kernels.
-        if (n < 2) return fail(c, B200RK_EINVAL, "lorenz96: every shard needs at least 2 elements");
+        // the same verdict on every rank (shard_range is a pure function): a rank that bailed out alone would leave
+        // its neighbours waiting in ncclSend/ncclRecv forever
+        for (int r = 0; r < c->world; ++r) {
+          size_t o_ = 0, l_ = 0;
+          shard_range(y->n_global, r, c->world, &o_, &l_);
+          if (l_ < 2) return fail(c, B200RK_EINVAL, "lorenz96: every shard needs at least 2 elements (rank " + std::to_string(r) + " would hold " + std::to_string(l_) + ")");
+        }
         const int left = (c->rank + c->world - 1) % c->world, right = (c->rank + 1) % c->world;
         NCCL_TRY(c, g_nccl.GroupStart());
         NCCL_TRY(c, g_nccl.Send(y->d, 1, ncclDouble, left, c->comm, c->stream));
@@ -271,6 +277,10 @@ static int fused_pattern_of(const b200rk_ctx* c, const MethodDef& md) {
   if (pattern_matches<PAT_VERN65>(c, md)) return PAT_VERN65;
   if (pattern_matches<PAT_VERN65_STRICT>(c, md)) return PAT_VERN65_STRICT;
   return -1;
+}
+
+int fused_pattern_for(const b200rk_ctx* c, const MethodDef& md) {
+  return (!md.rk4_final && method_fusable(md)) ? fused_pattern_of(c, md) : -1;
 }
 
 template <int PAT>
@@ -630,7 +640,7 @@ static int run_device_loop_pat(b200rk_ctx* c, const MethodDef& md, const PwSpec&
   a.n_global = double(io->Y[0]->n_global);
   a.max_steps = max_steps < 0 ? (long long)1 << 62 : (long long)max_steps;
   if (!c->d_run_state) {
-    CUDA_TRY(c, cudaMalloc(&c->d_run_state, sizeof(RunState) + 64));   // + [2][2] words: global-sum hand-off between CTAs
+    CUDA_TRY(c, cudaMalloc(&c->d_run_state, sizeof(RunState) + 64));   // + the CTA arrival counter of the in-kernel sum exchange
     CUDA_TRY(c, cudaMemset(c->d_run_state, 0, sizeof(RunState) + 64));
     CUDA_TRY(c, cudaHostAlloc(&c->h_run_state, sizeof(RunState), cudaHostAllocMapped));
     CUDA_TRY(c, cudaHostGetDevicePointer(&c->h_run_state_dev, c->h_run_state, 0));
@@ -642,10 +652,16 @@ static int run_device_loop_pat(b200rk_ctx* c, const MethodDef& md, const PwSpec&
   a.state_host = c->h_run_state_dev;
   a.seq_host = c->h_seq_dev;
   a.seq = c->seq + 1;  // attempt i of this launch uses sequence number seq + i (same on every rank: lockstep)
+  // The attempt's sum travels through mailboxes (kernels.cuh: mail_put / mail_wait): the peers' when sharded, this GPU's
+  // own single slot otherwise — the same code path, and no grid barrier in either case.
+  TRY(ensure_local_mailbox(c));
   a.mail.world = (c->world > 1 && c->p2p) ? c->world : 1;
-  a.mail.rank = c->rank;
+  a.mail.rank = a.mail.world > 1 ? c->rank : 0;
+  a.mail.timeout_cycles = c->peer_timeout_cycles;
   for (int p = 0; p < kMaxPeers; ++p) a.mail.box[p] = (a.mail.world > 1 && p < c->world) ? c->peer_mail[p] : nullptr;
-  a.bcast = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(c->d_run_state) + ((sizeof(RunState) + 31) / 32) * 32);
+  if (a.mail.world == 1) a.mail.box[0] = c->d_mail;
+  a.arrive = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(c->d_run_state) + ((sizeof(RunState) + 31) / 32) * 32);
+  CUDA_TRY(c, cudaMemsetAsync(a.arrive, 0, sizeof(unsigned long long), c->stream));
   const size_t prof_slot = c->prof.size();
   {
     ProfScope ps(c, B200RK_K_FUSED, 0.0);  // bytes patched below: the number of attempts is data-dependent

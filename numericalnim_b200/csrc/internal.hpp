@@ -70,6 +70,12 @@ struct b200rk_ctx {
   bool peer_opened[kMaxPeers] = {false};
   bool p2p = false;
   std::string p2p_note;
+  // How long a kernel waits for a peer's partial sum before it reports B200RK_ENCCL instead of hanging. Generous on
+  // purpose: ranks can be seconds apart on the host (first-use NVRTC compile, a slow user callback, a large allocation),
+  // and NCCL's own collectives have no such limit. Knob "peer_timeout_s" / env B200RK_PEER_TIMEOUT_S.
+  int peer_timeout_s = 120;
+  int clock_khz = 1965000;
+  long long peer_timeout_cycles = 120ll * 1965000ll * 1000ll;
   // workspace pool (free vectors by global length)
   std::vector<b200rk_vec*> pool;
   size_t pool_budget_bytes = (size_t)48 << 30;
@@ -243,6 +249,7 @@ struct RhsCall {
 
 // ---- runtime.cu -------------------------------------------------------------------------------------
 int ensure_partials(b200rk_ctx* c, size_t blocks);
+int ensure_local_mailbox(b200rk_ctx* c);
 ReduceScratch reduce_scratch(b200rk_ctx* c);                 // hands out the next reduction sequence number
 int setup_p2p(b200rk_ctx* c);
 // The same-role vectors of the two ring neighbours, peer-mapped (CUDA IPC over NVLink): the one-kernel Lorenz-96 attempt
@@ -254,6 +261,8 @@ int stream_barrier(b200rk_ctx* c);   // every rank's stream has reached this poi
 void shard_range(size_t n, int rank, int world, size_t* off, size_t* len);
 int vec_alloc(b200rk_ctx* c, size_t n_global, b200rk_vec** out);
 void vec_release(b200rk_vec* v);
+void pool_trim(b200rk_ctx* c, size_t keep_bytes);            // free pooled vectors down to keep_bytes
+bool pool_put(b200rk_vec* v);                                 // false: the pool is full (count or byte budget)
 int check_same(const b200rk_ctx* c, const b200rk_vec* a, const b200rk_vec* b);
 int vec_copy_raw(b200rk_ctx* c, b200rk_vec* dst, const b200rk_vec* src);
 
@@ -321,5 +330,7 @@ void jit_describe(const JitRhs* j, int* np, const b200rk_vec* const** vecs, cons
 int jit_slot_attempt(int w);
 int jit_slot_run(int w);
 int jit_launch(b200rk_ctx* c, JitRhs* j, int pattern, int slot, unsigned grid, void* arg_block, bool cooperative);
+int jit_prepare(b200rk_ctx* c, JitRhs* j, int pattern);      // compile + load the base unit and (pattern >= 0) the fused unit now
+int fused_pattern_for(const b200rk_ctx* c, const MethodDef& md);   // sparsity pattern of the method's fused kernels, -1: none
 int jit_max_blocks_per_sm(b200rk_ctx* c, JitRhs* j, int pattern, int slot, int* per_sm);
 int jit_launch_rk4(b200rk_ctx* c, JitRhs* j, bool negate, double t, double dt, const b200rk_vec* y, b200rk_vec* y_new);

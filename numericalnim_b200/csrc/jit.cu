@@ -382,6 +382,17 @@ int jit_launch(b200rk_ctx* c, JitRhs* j, int pattern, int slot, unsigned grid, v
   return B200RK_OK;
 }
 
+// Compile (or fetch from the caches) and load everything a solver over this right-hand side will launch — the plain
+// dy = f(t, y) unit and, when the method has a fused form, its pattern unit — BEFORE the first reducing launch: a first-use
+// NVRTC compile takes seconds, and a rank that compiles lazily inside its first attempt keeps its peers' kernels spinning
+// on the mailbox for that long.
+int jit_prepare(b200rk_ctx* c, JitRhs* j, int pattern) {
+  JitModule* m = nullptr;
+  TRY(ensure_module(c, j, -1, &m));
+  if (pattern >= 0) TRY(ensure_module(c, j, pattern, &m));
+  return B200RK_OK;
+}
+
 int jit_max_blocks_per_sm(b200rk_ctx* c, JitRhs* j, int pattern, int slot, int* per_sm) {
   JitModule* m = nullptr;
   TRY(ensure_module(c, j, pattern, &m));

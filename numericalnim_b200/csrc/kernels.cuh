@@ -30,7 +30,6 @@
 #else
 typedef unsigned int uint32_t;  // NVRTC: no host headers
 #endif
-#include <cooperative_groups.h>
 
 namespace b200rk {
 
@@ -279,9 +278,57 @@ constexpr int kMaxPeers = 16;
 struct PeerMail {
   int world;   // <= 1: no exchange
   int rank;
+  long long timeout_cycles;            // give up waiting for a peer after this many SM clocks (context knob "peer_timeout_s")
   unsigned long long* box[kMaxPeers];  // box[p] = base of rank p's mailbox: [2 parities][kMaxPeers][2] words
 };
 constexpr unsigned long long kPeerTimeoutFlag = 1ull << 63;
+
+// A mailbox slot is two 8-byte words; each carries 32 bits of the fp64 payload under a 32-bit tag derived from the
+// attempt's sequence number: word_h = (tag << 32) | half_h. An aligned 8-byte store is single-copy atomic, so a reader
+// that finds the current tag in BOTH words holds the complete value whatever order the two stores arrive in — there is no
+// separate flag and therefore no fence between payload and flag: one 16-byte store per peer, one NVLink traversal per
+// exchange (the previous protocol — value, system fence, flag — paid a store round trip before the flag could leave).
+// A slot is reused two attempts later (parity double buffer), when its old tag (seq - 2) can no longer match.
+__device__ __forceinline__ unsigned int mail_tag(unsigned long long seq) { return (unsigned int)(seq & 0x7fffffffull) | 0x80000000u; }
+__device__ __forceinline__ unsigned long long* mail_slot(unsigned long long* box, unsigned long long seq, int src_rank) {
+  return box + ((((seq & 1ull) * kMaxPeers) + (unsigned)src_rank) << 1);
+}
+#ifndef B200RK_HOST_EMULATION
+__device__ __forceinline__ void mail_put(unsigned long long* slot, double v, unsigned int tag) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v), t = (unsigned long long)tag << 32;
+  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1,%2};" ::"l"(slot), "l"(t | (b & 0xffffffffull)), "l"(t | (b >> 32)) : "memory");
+}
+__device__ __forceinline__ bool mail_try_get(const unsigned long long* slot, unsigned int tag, double* v) {
+  unsigned long long w0, w1;
+  asm volatile("ld.relaxed.sys.global.v2.u64 {%0,%1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+  if ((unsigned int)(w0 >> 32) != tag || (unsigned int)(w1 >> 32) != tag) return false;
+  *v = __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
+  return true;
+}
+#else
+inline void mail_put(unsigned long long* slot, double v, unsigned int tag) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v), t = (unsigned long long)tag << 32;
+  __atomic_store_n(slot, t | (b & 0xffffffffull), __ATOMIC_RELAXED);
+  __atomic_store_n(slot + 1, t | (b >> 32), __ATOMIC_RELAXED);
+}
+inline bool mail_try_get(const unsigned long long* slot, unsigned int tag, double* v) {
+  const unsigned long long w0 = __atomic_load_n(slot, __ATOMIC_RELAXED), w1 = __atomic_load_n(slot + 1, __ATOMIC_RELAXED);
+  if ((unsigned int)(w0 >> 32) != tag || (unsigned int)(w1 >> 32) != tag) return false;
+  *v = __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
+  return true;
+}
+#endif
+// threads q < world of a CTA: wait for rank q's slot of the LOCAL mailbox; false on timeout
+__device__ __forceinline__ bool mail_wait(const PeerMail& mail, unsigned long long seq, int q, double* v) {
+  const unsigned long long* src = mail_slot(mail.box[mail.rank], seq, q);
+  const unsigned int tag = mail_tag(seq);
+  if (mail_try_get(src, tag, v)) return true;
+  const long long t0 = clock64();
+  while (!mail_try_get(src, tag, v)) {
+    if (clock64() - t0 > mail.timeout_cycles) return false;   // a peer died or never launched: report instead of hanging
+  }
+  return true;
+}
 
 struct ReduceScratch {
   double* partials;        // gridDim.x doubles
@@ -299,25 +346,17 @@ __device__ __forceinline__ double peer_allreduce(double local, const ReduceScrat
   __shared__ double peer_vals[kMaxPeers];
   __shared__ int peer_bad;
   const int q = threadIdx.x;
-  const int world = rs.mail.world, rank = rs.mail.rank;
-  const unsigned long long par = rs.seq & 1ull;
+  const int world = rs.mail.world;
   if (q == 0) peer_bad = 0;
   __syncthreads();
   if (q < world) {
-    // publish into peer q's mailbox (for q == rank this is a local store)
-    volatile unsigned long long* dst = rs.mail.box[q] + ((par * kMaxPeers + rank) << 1);
-    dst[1] = (unsigned long long)__double_as_longlong(local);
+    // Everything this rank's kernel stored (a ring neighbour may read yNew / k_S in place in its next attempt) is
+    // visible system-wide before a peer can learn the sum: one fence, in front of the publication.
     __threadfence_system();
-    dst[0] = rs.seq;
-    // gather slot q of my own mailbox
-    volatile unsigned long long* src = rs.mail.box[rank] + ((par * kMaxPeers + q) << 1);
-    const long long t0 = clock64();
-    bool ok = true;
-    while (src[0] != rs.seq) {
-      if (clock64() - t0 > (2ll << 30)) { ok = false; break; }  // ~1 s: a peer died; report instead of hanging
-    }
-    __threadfence_system();
-    peer_vals[q] = ok ? __longlong_as_double((long long)src[1]) : 0.0;
+    mail_put(mail_slot(rs.mail.box[q], rs.seq, rs.mail.rank), local, mail_tag(rs.seq));   // q == rank: a local store
+    double v = 0.0;
+    const bool ok = mail_wait(rs.mail, rs.seq, q, &v);
+    peer_vals[q] = ok ? v : 0.0;
     if (!ok) atomicExch(&peer_bad, 1);
   }
   __syncthreads();
@@ -356,21 +395,16 @@ __device__ __forceinline__ double block_sum(double v) {
 #endif
 inline double emul_peer_exchange(double local, const ReduceScratch& rs) {
   const int world = rs.mail.world, rank = rs.mail.rank;
-  const unsigned long long par = rs.seq & 1ull;
-  for (int q = 0; q < world; ++q) {
-    volatile unsigned long long* dst = rs.mail.box[q] + ((par * kMaxPeers + rank) << 1);
-    dst[1] = (unsigned long long)__double_as_longlong(local);
-    __threadfence_system();
-    dst[0] = rs.seq;
-  }
+  __threadfence_system();
+  for (int q = 0; q < world; ++q) mail_put(mail_slot(rs.mail.box[q], rs.seq, rank), local, mail_tag(rs.seq));
   B200RK_EMUL_DEVICE_RELEASE();
   double total = 0.0;
   for (int q = 0; q < world; ++q) {
-    volatile unsigned long long* src = rs.mail.box[rank] + ((par * kMaxPeers + q) << 1);
-    while (src[0] != rs.seq) __threadfence_system();
-    __threadfence_system();
-    total = __dadd_rn(total, __longlong_as_double((long long)src[1]));   // rank order, as in peer_allreduce
+    double v = 0.0;
+    while (!mail_try_get(mail_slot(rs.mail.box[rank], rs.seq, q), mail_tag(rs.seq), &v)) __threadfence_system();
+    total = __dadd_rn(total, v);   // rank order, as in peer_allreduce
   }
+  __threadfence_system();
   B200RK_EMUL_DEVICE_ACQUIRE();
   return total;
 }
@@ -780,8 +814,9 @@ struct RunArgs {
   RunState* state_host;   // mapped pinned mirror, written once at exit
   unsigned long long* seq_host;
   unsigned long long seq;        // sequence number of attempt 0 of this launch (attempt i uses seq + i)
-  PeerMail mail;                 // world > 1: the error norm is all-reduced over the peer mailboxes every attempt
-  unsigned long long* bcast;     // world > 1: [2][2] device words, CTA 0 -> all CTAs hand-off of the global sum
+  PeerMail mail;                 // the error norm travels through mailboxes every attempt: the peers' (world > 1, NVLink) or
+                                 // a local one (world == 1: box[0] is this GPU's own, the same code path)
+  unsigned long long* arrive;    // device counter, zero at launch: CTA arrivals (attempt i of the launch is complete at (i+1)*gridDim.x)
 };
 
 __device__ __forceinline__ double dev_nim_min(double x, double y) { return (x <= y) ? x : y; }
@@ -789,7 +824,7 @@ __device__ __forceinline__ double dev_nim_max(double x, double y) { return (y <=
 
 template <int PAT, int KIND, int W, int THREADS>
 __global__ void __launch_bounds__(THREADS, 2) fused_run_kernel(const RunArgs<Pattern<PAT>::S> a) {
-  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  // launched cooperatively for the co-residency guarantee only (CTAs wait for each other's tickets): no grid.sync()
   __shared__ double bcast;
   RunState st = *a.state;
   FusedArgs<Pattern<PAT>::S> f = a.f;
@@ -797,7 +832,7 @@ __global__ void __launch_bounds__(THREADS, 2) fused_run_kernel(const RunArgs<Pat
   const size_t stride = (size_t)gridDim.x * THREADS;
   constexpr int NP = PwTraits<KIND>::NP, NPX = PwTraits<KIND>::NPX;
   int parity = 0;
-  long long done = 0;
+  long long done = 0, launch_attempts = 0;   // launch_attempts: attempts made by THIS launch (the arrival counter starts at 0)
   while (st.t < st.t_end && done < a.max_steps && st.status == 0) {
     double dt = dev_nim_min(st.dt, st.t_end - st.t);                      // ode.nim:525
     f.t = st.t;                                                           // PW_USER: stage times t + dt*c_s
@@ -855,73 +890,49 @@ __global__ void __launch_bounds__(THREADS, 2) fused_run_kernel(const RunArgs<Pat
           ks[i] = k1o;
         }
       }
+      // ---- grid-wide (and, sharded, machine-wide) sum of the attempt's r*r terms: ticket + mailbox, no grid barrier ----
+      // Every CTA deposits its partial and takes a ticket; the LAST CTA to arrive adds the partials in index order (same
+      // bits every run) and publishes the shard's sum into slot [rank] of every rank's mailbox — its own included — with one
+      // 16-byte store each (mail_put). EVERY CTA of every rank then waits for the `world` slots of its local mailbox and adds
+      // them in rank order: all CTAs of all ranks obtain identical bits and take the identical accept / reject branch.
+      // There is no grid barrier, no second hop from a leader CTA to the others and no fence on the critical path: nothing
+      // but the sum crosses CTAs in this kernel (a thread re-reads only the elements of yNew / k_S it wrote itself).
       const double bsum = block_sum<THREADS>(acc);
+      const unsigned long long seq = a.seq + (unsigned long long)st.attempts;
       double* part = a.partials + (size_t)parity * gridDim.x;
-      if (threadIdx.x == 0) part[blockIdx.x] = bsum;
-      __threadfence();
-      grid.sync();
-      double p = 0.0;
-      for (unsigned int i = threadIdx.x; i < gridDim.x; i += THREADS) p = __dadd_rn(p, __ldcg(part + i));
-      const double total = block_sum<THREADS>(p);
-      if (threadIdx.x == 0) bcast = total;
-      __syncthreads();
-      double S2 = bcast;
-      __syncthreads();
-      if (a.mail.world > 1) {
-        // Sharded: only CTA 0 talks to the peers — it stores this shard's partial into every peer's mailbox,
-        // waits for the `world` slots of the local mailbox, adds them in rank order and hands the global sum to the
-        // other CTAs through a local (value, sequence) pair they poll in L2. Peer-written memory is thus polled by
-        // `world` threads instead of by every CTA, and there is still no second grid barrier.
-        __shared__ double peer_vals[kMaxPeers];
-        __shared__ int peer_bad;
-        const unsigned long long seq = a.seq + (unsigned long long)st.attempts;
-        const unsigned long long par = seq & 1ull;
-        volatile unsigned long long* gflag = a.bcast + (par << 1);      // [par][0] = sequence, [par][1] = value bits
-        if (blockIdx.x == 0) {
-          const int q = threadIdx.x;
-          if (q == 0) peer_bad = 0;
-          __syncthreads();
-          if (q < a.mail.world) {
-            volatile unsigned long long* dst = a.mail.box[q] + ((par * kMaxPeers + a.mail.rank) << 1);
-            dst[1] = (unsigned long long)__double_as_longlong(S2);
-            __threadfence_system();
-            dst[0] = seq;
-            volatile unsigned long long* src = a.mail.box[a.mail.rank] + ((par * kMaxPeers + q) << 1);
-            const long long t0 = clock64();
-            bool ok = true;
-            while (src[0] != seq) {
-              if (clock64() - t0 > (2ll << 30)) { ok = false; break; }
-            }
-            __threadfence_system();
-            peer_vals[q] = ok ? __longlong_as_double((long long)src[1]) : 0.0;
-            if (!ok) atomicExch(&peer_bad, 1);
-          }
-          __syncthreads();
-          if (q == 0) {
-            double g = 0.0;
-            for (int p2 = 0; p2 < a.mail.world; ++p2) g = __dadd_rn(g, peer_vals[p2]);
-            gflag[1] = (unsigned long long)__double_as_longlong(g);
-            __threadfence();
-            gflag[0] = peer_bad ? (seq | kPeerTimeoutFlag) : seq;
-          }
-        }
-        if (threadIdx.x == 0) {
-          const long long t0 = clock64();
-          unsigned long long f = gflag[0];
-          while ((f & ~kPeerTimeoutFlag) != seq) {
-            if (clock64() - t0 > (4ll << 30)) { f = seq | kPeerTimeoutFlag; break; }
-            f = gflag[0];
-          }
-          __threadfence();
-          bcast = __longlong_as_double((long long)gflag[1]);
-          peer_bad = (f & kPeerTimeoutFlag) ? 1 : 0;
-        }
-        __syncthreads();
-        S2 = bcast;
-        const int bad = peer_bad;
-        __syncthreads();
-        if (bad) { st.status = 2; st.attempts++; break; }
+      __shared__ bool is_last;
+      __shared__ double peer_vals[kMaxPeers];
+      __shared__ int peer_bad;
+      if (threadIdx.x == 0) {
+        part[blockIdx.x] = bsum;
+        peer_bad = 0;
+        __threadfence();
+        const unsigned long long ticket = atomicAdd(a.arrive, 1ull);
+        is_last = (ticket == (unsigned long long)(launch_attempts + 1) * gridDim.x - 1ull);
       }
+      __syncthreads();
+      if (is_last) {
+        __threadfence();
+        double p = 0.0;
+        for (unsigned int i = threadIdx.x; i < gridDim.x; i += THREADS) p = __dadd_rn(p, __ldcg(part + i));
+        const double total = block_sum<THREADS>(p);
+        if (threadIdx.x == 0) bcast = total;
+        __syncthreads();
+        if ((int)threadIdx.x < a.mail.world) mail_put(mail_slot(a.mail.box[threadIdx.x], seq, a.mail.rank), bcast, mail_tag(seq));
+      }
+      if ((int)threadIdx.x < a.mail.world) {
+        double v = 0.0;
+        const bool ok = mail_wait(a.mail, seq, (int)threadIdx.x, &v);
+        peer_vals[threadIdx.x] = ok ? v : 0.0;
+        if (!ok) atomicExch(&peer_bad, 1);
+      }
+      __syncthreads();
+      double S2 = 0.0;
+      for (int p2 = 0; p2 < a.mail.world; ++p2) S2 = __dadd_rn(S2, peer_vals[p2]);   // rank order: identical everywhere
+      const int bad = peer_bad;
+      __syncthreads();   // peer_vals / peer_bad / is_last are rewritten by the next attempt
+      ++launch_attempts;
+      if (bad) { st.status = 2; st.attempts++; break; }
       parity ^= 1;
       st.attempts++;
       error = sqrt(1.0 / a.n_global * S2);                                // ode.nim:64-65
@@ -945,8 +956,7 @@ __global__ void __launch_bounds__(THREADS, 2) fused_run_kernel(const RunArgs<Pat
     else if (a.dtMax < dt) dt = a.dtMax;
     st.dt = dt;
   }
-  grid.sync();  // every store of the last attempt is done before the host is told
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {   // identical in every CTA; kernel completion orders all stores before the host's read
     *a.state = st;
     *a.state_host = st;  // the host waits for the launch with a stream synchronisation (once per many steps)
     __threadfence_system();

@@ -61,6 +61,7 @@ ReduceScratch reduce_scratch(b200rk_ctx* c) {
   rs.seq = ++c->seq;
   rs.mail.world = in_kernel_collective ? c->world : 1;
   rs.mail.rank = c->rank;
+  rs.mail.timeout_cycles = c->peer_timeout_cycles;
   for (int p = 0; p < kMaxPeers; ++p) rs.mail.box[p] = (in_kernel_collective && p < c->world) ? c->peer_mail[p] : nullptr;
   if (in_kernel_collective) c->collectives++;
   return rs;
@@ -112,6 +113,16 @@ int setup_p2p(b200rk_ctx* c) {
   c->p2p = agreed != 0;
   if (c->p2p) c->p2p_note = "peer mailboxes mapped over CUDA IPC";
   else if (c->p2p_note.empty()) c->p2p_note = "a peer could not map the mailboxes";
+  return B200RK_OK;
+}
+
+// This GPU's own mailbox (setup_p2p allocates it for sharded contexts; a single-GPU context gets it on first use by the
+// device-resident loop, which sends its grid-wide sum through it).
+int ensure_local_mailbox(b200rk_ctx* c) {
+  if (c->d_mail) return B200RK_OK;
+  const size_t mail_bytes = 2 * kMaxPeers * 2 * sizeof(unsigned long long);
+  CUDA_TRY(c, cudaMalloc(&c->d_mail, mail_bytes));
+  CUDA_TRY(c, cudaMemset(c->d_mail, 0, mail_bytes));
   return B200RK_OK;
 }
 
@@ -217,6 +228,12 @@ int vec_alloc(b200rk_ctx* c, size_t n_global, b200rk_vec** out) {
   b200rk_vec* v = new b200rk_vec{c, n_global, 0, 0, nullptr};
   shard_range(n_global, c->rank, c->world, &v->offset, &v->n_local);
   cudaError_t e = cudaMalloc(&v->d, std::max<size_t>(v->n_local, 4) * sizeof(double));
+  if (e == cudaErrorMemoryAllocation && !c->pool.empty()) {
+    // cached vectors of other lengths are holding the memory: give them back to the driver and try once more
+    cudaGetLastError();
+    pool_trim(c, 0);
+    e = cudaMalloc(&v->d, std::max<size_t>(v->n_local, 4) * sizeof(double));
+  }
   if (e != cudaSuccess) {
     delete v;
     return fail(c, e == cudaErrorMemoryAllocation ? B200RK_ENOMEM : B200RK_ECUDA,
@@ -225,11 +242,34 @@ int vec_alloc(b200rk_ctx* c, size_t n_global, b200rk_vec** out) {
   *out = v;
   return B200RK_OK;
 }
-void vec_release(b200rk_vec* v) {  // back to the pool (bounded: a call that held 10^5 vectors must not leave them all cached)
-  if (!v) return;
+// Free pooled vectors until at most `keep_bytes` stay cached (0: empty the pool).
+void pool_trim(b200rk_ctx* c, size_t keep_bytes) {
+  size_t held = 0;
+  for (auto* p : c->pool) held += p->n_local * sizeof(double);
+  if (held <= keep_bytes) return;
+  cudaStreamSynchronize(c->stream);  // enqueued work may still use them
+  while (!c->pool.empty() && held > keep_bytes) {
+    b200rk_vec* p = c->pool.back();
+    c->pool.pop_back();
+    held -= p->n_local * sizeof(double);
+    cudaFree(p->d);
+    delete p;
+  }
+}
+// Back to the pool (stream-ordered reuse is safe: one stream per context), bounded by count AND by the byte budget — the
+// same rule for the library's internal releases (solver work vectors, solve_host / quadrature outputs) and the public
+// b200rk_vec_free: a call that held 10^5 vectors, or 512 x 64 MiB, must not leave them all cached.
+bool pool_put(b200rk_vec* v) {
   b200rk_ctx* c = v->ctx;
-  if (c->pool.size() < 512) { c->pool.push_back(v); return; }
-  cudaStreamSynchronize(c->stream);  // enqueued work may still use it
+  size_t held = 0;
+  for (auto* p : c->pool) held += p->n_local * sizeof(double);
+  if (c->pool.size() < 512 && held + v->n_local * sizeof(double) <= c->pool_budget_bytes) { c->pool.push_back(v); return true; }
+  return false;
+}
+void vec_release(b200rk_vec* v) {
+  if (!v) return;
+  if (pool_put(v)) return;
+  cudaStreamSynchronize(v->ctx->stream);  // enqueued work may still use it
   cudaFree(v->d);
   delete v;
 }
@@ -254,6 +294,9 @@ static int ctx_common_init(b200rk_ctx* c) {
   cudaDeviceProp prop;
   CUDA_TRY(c, cudaGetDeviceProperties(&prop, c->device));
   c->sm_count = prop.multiProcessorCount;
+  c->clock_khz = prop.clockRate > 0 ? prop.clockRate : 1965000;
+  if (const char* e = getenv("B200RK_PEER_TIMEOUT_S")) c->peer_timeout_s = std::max(1, atoi(e));
+  c->peer_timeout_cycles = (long long)c->peer_timeout_s * (long long)c->clock_khz * 1000ll;
   if (prop.l2CacheSize > 0) c->l2_bytes = (size_t)prop.l2CacheSize;
   CUDA_TRY(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   {  // stream-ordered scratch (quadrature.cu's per-call tables): keep freed blocks cached instead of returning them to the OS at every sync
@@ -381,6 +424,11 @@ int b200rk_set(b200rk_ctx* c, const char* key, int64_t v) {
   else if (k == "stream_simpson") c->stream_simpson = v < 0 ? -1 : (v != 0);
   else if (k == "l2_hints") c->l2_hints = v < 0 ? -1 : (v != 0);
   else if (k == "fused_ctas_per_sm") { if (v < 0) return fail(c, B200RK_EINVAL, "fused_ctas_per_sm must be >= 0"); c->fused_ctas_per_sm = (int)v; }
+  else if (k == "peer_timeout_s") {
+    if (v < 1) return fail(c, B200RK_EINVAL, "peer_timeout_s must be >= 1");
+    c->peer_timeout_s = (int)std::min<int64_t>(v, 86400);
+    c->peer_timeout_cycles = (long long)c->peer_timeout_s * (long long)c->clock_khz * 1000ll;
+  }
   else if (k == "pool_budget_mb") {
     c->pool_budget_bytes = (size_t)std::max<int64_t>(0, v) << 20;
     if (v == 0) {  // trim now
@@ -415,6 +463,7 @@ int b200rk_get(const b200rk_ctx* c, const char* key, int64_t* v) {
   else if (k == "profile") *v = c->profile;
   else if (k == "sm_count") *v = c->sm_count;
   else if (k == "pool_budget_mb") *v = (int64_t)(c->pool_budget_bytes >> 20);
+  else if (k == "peer_timeout_s") *v = c->peer_timeout_s;
   else return fail(c, B200RK_EINVAL, "unknown knob " + k);
   return B200RK_OK;
 }
@@ -457,12 +506,7 @@ int b200rk_vec_free(b200rk_vec* v) {
   // beyond the pool budget they are released to the driver.
   if (!v) return B200RK_OK;
   b200rk_ctx* c = v->ctx;
-  size_t held = 0;
-  for (auto* p : c->pool) held += p->n_local * sizeof(double);
-  if (c->pool.size() < 512 && held + v->n_local * sizeof(double) <= c->pool_budget_bytes) {
-    c->pool.push_back(v);
-    return B200RK_OK;
-  }
+  if (pool_put(v)) return B200RK_OK;
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   CUDA_TRY(c, cudaFree(v->d));
   delete v;
@@ -478,6 +522,12 @@ int b200rk_vec_upload_local(b200rk_vec* v, const double* h) {
   b200rk_ctx* c = v->ctx;
   CUDA_TRY(c, cudaMemcpyAsync(v->d, h, v->n_local * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return B200RK_OK;
+}
+int b200rk_vec_upload_local_async(b200rk_vec* v, const double* h) {
+  if (!v || (!h && v->n_local)) return fail(v ? v->ctx : nullptr, B200RK_EINVAL, "null argument");
+  b200rk_ctx* c = v->ctx;
+  CUDA_TRY(c, cudaMemcpyAsync(v->d, h, v->n_local * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   return B200RK_OK;
 }
 int b200rk_vec_download_local(const b200rk_vec* v, double* h) {

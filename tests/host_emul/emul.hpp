@@ -52,6 +52,7 @@ inline T __shfl_down_sync(unsigned, T v, int off) {
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 #else
 static EmulDim3 threadIdx, blockIdx, gridDim, blockDim;
@@ -61,6 +62,7 @@ inline void __syncthreads() {}
 inline void __threadfence() {}
 inline void __threadfence_system() {}
 inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned o = *p; *p += v; return o; }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p += v; return o; }
 inline int atomicExch(int* p, int v) { const int o = *p; *p = v; return o; }
 #define B200RK_EMULATE_SERIAL_SUM 1   // kernels.cuh: grid_sum_finish becomes a running sum
 #endif

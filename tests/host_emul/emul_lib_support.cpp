@@ -15,6 +15,7 @@ int jit_slot_attempt(int) { return 0; }
 int jit_slot_run(int) { return 0; }
 int jit_launch(b200rk_ctx* c, JitRhs*, int, int, unsigned, void*, bool) { return unavailable(c); }
 int jit_max_blocks_per_sm(b200rk_ctx* c, JitRhs*, int, int, int*) { return unavailable(c); }
+int jit_prepare(b200rk_ctx* c, JitRhs*, int) { return unavailable(c); }
 int jit_launch_rk4(b200rk_ctx* c, JitRhs*, bool, double, double, const b200rk_vec*, b200rk_vec*) { return unavailable(c); }
 
 extern "C" {

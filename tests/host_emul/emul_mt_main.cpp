@@ -148,7 +148,9 @@ static void test_device_loop(const char* name, const rk_oracle::Pair& p, rk_orac
     a.dtMin = o.dtMin; a.dtMax = o.dtMax; a.inv_order_inner = 1.0 / double(p.order); a.inv_order_outer = 1.0 / double(p.order);
     a.n_global = double(n); a.max_steps = 1ll << 40;
     a.partials = partials.data(); a.state = &st; a.state_host = &st_host; a.seq_host = &seq_host; a.seq = 1;
-    a.mail.world = 1;
+    std::vector<unsigned long long> mailbox(2 * kMaxPeers * 2, 0ull);   // world == 1: this "GPU's" own mailbox carries the grid-wide sum
+    unsigned long long arrive = 0;
+    a.mail.world = 1; a.mail.rank = 0; a.mail.box[0] = mailbox.data(); a.arrive = &arrive;
     emul_launch(1, T, [&] { fused_run_kernel<PAT, KIND, W, T>(a); });
     const auto& yend = Y[st_host.cur];
     bool states = yend.size() == ref.y.back().components.size();

@@ -25,8 +25,8 @@ enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cuda
 
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
-struct cudaDeviceProp { int multiProcessorCount; int l2CacheSize; };
-inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->multiProcessorCount = 1; p->l2CacheSize = 126 << 20; return cudaSuccess; }  // one SM: cooperative grids are one CTA
+struct cudaDeviceProp { int multiProcessorCount; int l2CacheSize; int clockRate; };
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->multiProcessorCount = 1; p->l2CacheSize = 126 << 20; p->clockRate = 1965000; return cudaSuccess; }  // one SM: cooperative grids are one CTA
 inline cudaError_t cudaMemGetInfo(size_t* f, size_t* t) { *f = *t = (size_t)8 << 30; return cudaSuccess; }
 
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = new EmulStreamObj{1}; return cudaSuccess; }
@@ -53,6 +53,7 @@ inline cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
 template <class T> inline cudaError_t cudaHostGetDevicePointer(T** dev, T* host, unsigned) { *dev = host; return cudaSuccess; }  // mapped memory: same address
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { if (n) std::memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemset(void* p, int v, size_t n) { std::memset(p, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return cudaSuccess; }
 
 typedef void* cudaMemPool_t;
 enum cudaMemPoolAttr { cudaMemPoolAttrReleaseThreshold = 4 };

@@ -24,6 +24,15 @@ def test_reference_arm_line():
     assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] == d["value"] and "sample" in cb
     assert d["e2e"] == {"value": d["value"], "unit": "RK steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["value"] > 0 and d["gpu_launches"] == 0
+    # both arms print the same `unit` and a `config` with identical keys AND values (the driver divides the two lines and
+    # compares their configs): the workload only — library knobs and notes live outside `config`
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["unit"] == bench.UNIT == "RK steps/s"
+    assert d["config"] == bench.base_config("cfg2_dopri54_diag_8M", 23)
+    assert set(d["config"]) == {"workload", "integrator", "rhs", "elems_per_gpu", "options"} and d["knobs"] == {}
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count('"config": base_config(') == 3   # our line, the cfg3 / cfg4 objects, the reference line
 
 
 def test_non_zero_ranks_of_the_reference_arm_exit_quietly():

@@ -59,9 +59,11 @@ def fuse_mode(nn, request):
     ctx = nn.default_context()
     ctx.set("fuse_pointwise", request.param)
     ctx.set("fuse_stencil", request.param)  # built-in Lorenz-96: stage accumulate + stencil RHS in one kernel
+    ctx.set("fuse_stencil_attempt", request.param)  # built-in Lorenz-96: the whole attempt in one kernel (default)
     yield request.param
     ctx.set("fuse_pointwise", 1)
     ctx.set("fuse_stencil", 1)
+    ctx.set("fuse_stencil_attempt", 1)
 
 
 def rng_vec(rng, n, scale=1.0):
@@ -588,6 +590,7 @@ def test_stencil_fused_stage_bitwise_equals_pipeline(nn, method):
     rhs = nn.rhsLorenz96(8.0)
     o = nn.newODEoptions(absTol=1e-2, relTol=1e-2, dtMax=1.0, dtMin=1e-8, dt=0.005)
     try:
+        ctx.set("fuse_stencil_attempt", 0)   # this test is about stage_l96_kernel (the per-stage fusion below the one-kernel attempt)
         for n in [4, 5, 6, 7, 9, 1022, 1023, 1024, 1025, 1027, 2048, 4099, 65536 + 3]:
             y = 8.0 + rng_vec(rng, n)
             gy = nn.newVector(y)
@@ -608,6 +611,7 @@ def test_stencil_fused_stage_bitwise_equals_pipeline(nn, method):
             assert_bitwise_equal(out[1][1], fn_ref, f"{method} FSAL vs oracle n={n}")
     finally:
         ctx.set("fuse_stencil", 1)
+        ctx.set("fuse_stencil_attempt", 1)
 
 
 def test_stencil_fused_backward_and_dense(nn):
@@ -619,12 +623,15 @@ def test_stencil_fused_backward_and_dense(nn):
     ts = nn.linspace(-0.05, 0.1, 7)
     res = {}
     try:
-        for fuse in (1, 0):
-            ctx.set("fuse_stencil", fuse)
+        for fuse in (2, 1, 0):   # 2: one-kernel RK4 step (default), 1: stage + stencil per stage, 0: stage / RHS pipeline
+            ctx.set("fuse_stencil", 1 if fuse else 0)
+            ctx.set("fuse_stencil_attempt", 1 if fuse == 2 else 0)
             t, ys = nn.solveODE(nn.rhsLorenz96(8.0), nn.newVector(y0), ts, nn.newODEoptions(dt=2e-3), integrator="rk4")
             res[fuse] = np.array([v.to_numpy() for v in ys])
         assert_bitwise_equal(res[1], res[0], "l96 rk4 fused-stencil vs pipeline")
+        assert_bitwise_equal(res[2], res[0], "l96 rk4 one-kernel step vs pipeline")
         ref = O.solve_vector("rk4", O.rhs_lorenz96(8.0), y0, ts, O.new_options(dt=2e-3))
         assert_bitwise_equal(res[1], ref.y, "l96 rk4 vs oracle")
     finally:
         ctx.set("fuse_stencil", 1)
+        ctx.set("fuse_stencil_attempt", 1)

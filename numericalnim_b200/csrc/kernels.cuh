@@ -481,6 +481,36 @@ struct FinishArgs {
   ReduceScratch rs;
 };
 
+// r = e / tol of the scaled error norm (ode.nim:62-63). r feeds ONLY the sum of squares, which is compared with the
+// reference at a stated tolerance (its summation order differs anyway) — never bit for bit; yNew, error_y and k_S do not
+// pass through here. The IEEE division costs ~14 fp64-pipe issue slots per element in kernels that are fp64-issue bound
+// (no FMA allowed elsewhere), so r is formed as e * (1/tol) with the reciprocal from MUFU.RCP64H refined by two Newton
+// steps (error 2^-20 -> 2^-40 -> below 2^-53): 6 slots, |relative error| <= ~2 ulp. tol = absTol + relTol*|yNew| is a
+// positive normal number in any sane configuration; everything else (zero tolerances, overflow, NaN) takes the exact
+// division so that inf / NaN outcomes are those of the reference expression.
+__device__ __forceinline__ double err_ratio(double e, double tol) {
+#ifdef B200RK_HOST_EMULATION
+  return __ddiv_rn(e, tol);
+#else
+  const unsigned int hi = (unsigned int)__double2hiint(tol);
+  if ((hi - 0x00300000u) < 0x7fa00000u) {   // 2^-1020 <= tol < 2^1021 and the sign bit clear: 1/tol is normal too
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(tol));
+    double t = __fma_rn(-tol, x, 1.0);
+    x = __fma_rn(x, t, x);
+    t = __fma_rn(-tol, x, 1.0);
+    x = __fma_rn(x, t, x);
+    return __dmul_rn(e, x);
+  }
+  return __ddiv_rn(e, tol);
+#endif
+}
+
+// v with its sign flipped when sgn is negative (sgn = +-1): an integer XOR on the high word, no fp64 issue slot.
+__device__ __forceinline__ double flip_sign_by(double v, double sgn) {
+  return __longlong_as_double(__double_as_longlong(v) ^ (__double_as_longlong(sgn) & (long long)0x8000000000000000ull));
+}
+
 template <int NK>
 __device__ __forceinline__ double masked_wsum(const double (&k)[NK], const double (&w)[NK], uint32_t mask) {
   double acc = 0.0;
@@ -505,7 +535,7 @@ __device__ __forceinline__ double finish_elem(double y, const double (&k)[NK], c
   if (DIRECT) e = lo;
   else e = __dadd_rn(ynew, -__dadd_rn(y, lo));  // a - b == a + (-b) exactly
   const double tol = __dadd_rn(a.absTol, __dmul_rn(fabs(ynew), a.relTol));
-  const double r = __ddiv_rn(e, tol);
+  const double r = err_ratio(e, tol);
   return __dmul_rn(r, r);
 }
 
@@ -581,13 +611,20 @@ struct PwTraits {  // per-element parameter streams the right-hand side reads ne
   static constexpr int NPX = NP > 0 ? NP : 1;  // array extent (no zero-length arrays)
 };
 
-// `sgn`: PW_SCALE folds the backward-pass negation (g = -f(-t, y), ode.nim:545) into the scalar on the
-// host (-(y*c) == y*(-c) exactly); PW_DIAG multiplies by -1 (forward: -(lam*y)) or +1 (backward), also
-// exact. No select instructions on the fp64 path.
+// Signs: PW_SCALE folds the backward-pass negation (g = -f(-t, y), ode.nim:545) into the scalar on the host
+// (-(y*c) == y*(-c) exactly). PW_DIAG: k = -(lam*y) forward, +(lam*y) backward; since -(lam*y) == (-lam)*y exactly under
+// round-to-nearest, the sign goes onto lambda ONCE per element when it is loaded (pw_param: an integer XOR) instead of
+// costing a multiplication by -1 in every one of the S-1 evaluations. No select instructions on the fp64 path.
 template <int KIND>
-__device__ __forceinline__ double pointwise_rhs(double y, double lam, double c, double sgn) {
+__device__ __forceinline__ double pointwise_rhs(double y, double lam_signed, double c) {
   if (KIND == PW_SCALE) return __dmul_rn(y, c);           // EW_SCALE
-  return __dmul_rn(__dmul_rn(lam, y), sgn);               // EW_NEG_HMUL (sgn = -1)
+  return __dmul_rn(lam_signed, y);                        // EW_NEG_HMUL with the sign already on lambda
+}
+// parameter j of an element as the right-hand side wants it (PW_DIAG: lambda carrying the sign of `sgn`)
+template <int KIND>
+__device__ __forceinline__ double pw_param(double p, double sgn) {
+  if (KIND == PW_DIAG) return flip_sign_by(p, sgn);
+  return p;
 }
 
 // Sparsity patterns of the three FSAL pairs, as COMPILE-TIME constants: which terms of each row are kept
@@ -683,10 +720,10 @@ __device__ __forceinline__ double pw_eval(double in, const double (&pe)[PwTraits
 #ifdef B200RK_JIT
   if constexpr (KIND == PW_USER) {
     const double ts = __dadd_rn(a.t, __dmul_rn(a.dt, a.cnode[s - 1]));   // same rounding as the host's t + dt*c[s]
-    return __dmul_rn(user_rhs(__dmul_rn(ts, a.tsign), in, pe, a.cs), a.rhs_sign);
+    return flip_sign_by(user_rhs(flip_sign_by(ts, a.tsign), in, pe, a.cs), a.rhs_sign);   // x * (+-1) == x with the sign flipped, exactly
   }
 #endif
-  return pointwise_rhs<KIND>(in, pe[0], a.rhs_scalar, a.rhs_sign);
+  return pointwise_rhs<KIND>(in, pe[0], a.rhs_scalar);
 }
 
 template <int PAT, int KIND, int s>
@@ -719,7 +756,7 @@ __device__ __forceinline__ double fused_elem(double y, double k1, const double (
   if (Pattern<PAT>::direct) e = lo;
   else e = __dadd_rn(ynew, -__dadd_rn(y, lo));
   const double tol = __dadd_rn(a.absTol, __dmul_rn(fabs(ynew), a.relTol));
-  const double r = __ddiv_rn(e, tol);
+  const double r = err_ratio(e, tol);
   return __dmul_rn(r, r);
 }
 
@@ -760,7 +797,7 @@ __global__ void __launch_bounds__(THREADS) fused_attempt_kernel(const FusedArgs<
     for (int e = 0; e < W; ++e) {
       double pe[NPX] = {};
 #pragma unroll
-      for (int j = 0; j < NP; ++j) pe[j] = pv[j].v[e];
+      for (int j = 0; j < NP; ++j) pe[j] = pw_param<KIND>(pv[j].v[e], a.rhs_sign);
       acc = __dadd_rn(acc, fused_elem<PAT, KIND>(yv.v[e], kv.v[e], pe, a, yo.v[e], ko.v[e]));
     }
     st_pol<W, YSTP>(a.ynew + v * W, yo);
@@ -775,7 +812,7 @@ __global__ void __launch_bounds__(THREADS) fused_attempt_kernel(const FusedArgs<
     if (i < a.n) {
       double yn, ks, pe[NPX] = {};
 #pragma unroll
-      for (int j = 0; j < NP; ++j) pe[j] = a.p[j][i];
+      for (int j = 0; j < NP; ++j) pe[j] = pw_param<KIND>(a.p[j][i], a.rhs_sign);
       acc = __dadd_rn(acc, fused_elem<PAT, KIND>(a.y[i], a.k1[i], pe, a, yn, ks));
       a.ynew[i] = yn;
       a.ks_out[i] = ks;
@@ -868,7 +905,7 @@ __global__ void __launch_bounds__(THREADS, 2) fused_run_kernel(const RunArgs<Pat
           for (int e = 0; e < W; ++e) {
             double pe[NPX] = {};
 #pragma unroll
-            for (int j = 0; j < NP; ++j) pe[j] = pv[j].v[e];
+            for (int j = 0; j < NP; ++j) pe[j] = pw_param<KIND>(pv[j].v[e], f.rhs_sign);
             acc = __dadd_rn(acc, fused_elem<PAT, KIND>(yv.v[e], kv.v[e], pe, f, yo.v[e], ko.v[e]));
           }
           st_stream<W>(yn + v * W, yo);
@@ -884,7 +921,7 @@ __global__ void __launch_bounds__(THREADS, 2) fused_run_kernel(const RunArgs<Pat
         if (i < f.n) {
           double y1, k1o, pe[NPX] = {};
 #pragma unroll
-          for (int j = 0; j < NP; ++j) pe[j] = f.p[j][i];
+          for (int j = 0; j < NP; ++j) pe[j] = pw_param<KIND>(f.p[j][i], f.rhs_sign);
           acc = __dadd_rn(acc, fused_elem<PAT, KIND>(y[i], k1[i], pe, f, y1, k1o));
           yn[i] = y1;
           ks[i] = k1o;
@@ -965,11 +1002,12 @@ __global__ void __launch_bounds__(THREADS, 2) fused_run_kernel(const RunArgs<Pat
 
 // Fused RK4 step for element-local right-hand sides (ode.nim:180-189): reads y (+ lambda), writes yNew.
 template <int KIND>
-__device__ __forceinline__ double fused_rk4_elem(double y, double lam, double c, double neg, double hdt, double dt, double c6) {
-  const double k1 = pointwise_rhs<KIND>(y, lam, c, neg);
-  const double k2 = pointwise_rhs<KIND>(__dadd_rn(y, __dmul_rn(k1, hdt)), lam, c, neg);
-  const double k3 = pointwise_rhs<KIND>(__dadd_rn(y, __dmul_rn(k2, hdt)), lam, c, neg);
-  const double k4 = pointwise_rhs<KIND>(__dadd_rn(y, __dmul_rn(k3, dt)), lam, c, neg);
+__device__ __forceinline__ double fused_rk4_elem(double y, double lam_raw, double c, double neg, double hdt, double dt, double c6) {
+  const double lam = pw_param<KIND>(lam_raw, neg);
+  const double k1 = pointwise_rhs<KIND>(y, lam, c);
+  const double k2 = pointwise_rhs<KIND>(__dadd_rn(y, __dmul_rn(k1, hdt)), lam, c);
+  const double k3 = pointwise_rhs<KIND>(__dadd_rn(y, __dmul_rn(k2, hdt)), lam, c);
+  const double k4 = pointwise_rhs<KIND>(__dadd_rn(y, __dmul_rn(k3, dt)), lam, c);
   return rk4_elem(y, k1, k2, k3, k4, c6);
 }
 template <int KIND, int W, int THREADS>
@@ -1055,10 +1093,10 @@ __global__ void __launch_bounds__(THREADS) user_rhs_kernel(const UserRhsArgs a) 
 // k_s = g(t_s, in) with g = f forward and g(t, y) = -f(-t, y) backward; t_s = t + dt*c_s rounded like the host's
 __device__ __forceinline__ double user_rk4_elem(double y, const double (&pe)[PwTraits<PW_USER>::NPX], const UserRhsArgs& a) {
   const double tm = __dadd_rn(a.t, __dmul_rn(a.dt, 0.5)), te = __dadd_rn(a.t, __dmul_rn(a.dt, 1.0));   // ode.nim:185-187
-  const double k1 = __dmul_rn(user_rhs(__dmul_rn(a.t, a.tsign), y, pe, a.cs), a.rsign);
-  const double k2 = __dmul_rn(user_rhs(__dmul_rn(tm, a.tsign), __dadd_rn(y, __dmul_rn(k1, a.hdt)), pe, a.cs), a.rsign);
-  const double k3 = __dmul_rn(user_rhs(__dmul_rn(tm, a.tsign), __dadd_rn(y, __dmul_rn(k2, a.hdt)), pe, a.cs), a.rsign);
-  const double k4 = __dmul_rn(user_rhs(__dmul_rn(te, a.tsign), __dadd_rn(y, __dmul_rn(k3, a.dt)), pe, a.cs), a.rsign);
+  const double k1 = flip_sign_by(user_rhs(flip_sign_by(a.t, a.tsign), y, pe, a.cs), a.rsign);
+  const double k2 = flip_sign_by(user_rhs(flip_sign_by(tm, a.tsign), __dadd_rn(y, __dmul_rn(k1, a.hdt)), pe, a.cs), a.rsign);
+  const double k3 = flip_sign_by(user_rhs(flip_sign_by(tm, a.tsign), __dadd_rn(y, __dmul_rn(k2, a.hdt)), pe, a.cs), a.rsign);
+  const double k4 = flip_sign_by(user_rhs(flip_sign_by(te, a.tsign), __dadd_rn(y, __dmul_rn(k3, a.dt)), pe, a.cs), a.rsign);
   return rk4_elem(y, k1, k2, k3, k4, a.c6);
 }
 template <int W, int THREADS>

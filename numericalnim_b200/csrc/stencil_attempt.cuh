@@ -19,7 +19,7 @@
 // Within the CTA the stage input travels through shared memory (two buffers, so one barrier per stage): a thread
 // computes the stage input at its own E = 2*J positions from registers, publishes it, and after the barrier applies the
 // stencil to its positions. Per element the operations are exactly those of stage_elem / stage_l96_kernel /
-// finish_elem in the same order (__dmul_rn / __dadd_rn / __ddiv_rn), so yNew, k_S and every r*r term are bit-identical
+// finish_elem in the same order (__dmul_rn / __dadd_rn; err_ratio for r), so yNew, k_S and every r*r term are bit-identical
 // to the unfused pipeline; the sum of the r*r terms is taken in a different order (tile by tile), like every other
 // grid geometry of the reducing kernels.
 #pragma once
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(THREADS) l96_attempt_kernel(const L96AttemptAr
       if (Pattern<PAT>::direct) err = lo;
       else err = __dadd_rn(yn[h], -__dadd_rn(y[e], lo));
       const double tol = __dadd_rn(a.f.absTol, __dmul_rn(fabs(yn[h]), a.f.relTol));
-      const double r = __ddiv_rn(err, tol);
+      const double r = err_ratio(err, tol);
       if (stored && g + h < n) acc = __dadd_rn(acc, __dmul_rn(r, r));
     }
     if (stored) {

@@ -407,7 +407,16 @@ static int launch_l96_attempt_j(b200rk_ctx* c, const MethodDef& md, double F, bo
   a.f.ynew = y_new->d; a.f.ks_out = fsal_new->d; a.f.n = y->n_local;
   a.F = F;
   a.halo = halo;
-  const unsigned grid = (unsigned)((a.f.n + OUT - 1) / OUT);
+  // persistent grid: as many CTAs as fit on the device at once (3 per SM at 78-80 registers, 2 for Vern65), each walking
+  // its share of the tiles with the next tile's bulk copies in flight
+  static int per_sm = 0;   // per instantiation
+  if (per_sm == 0) {
+    CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l96_attempt_kernel<PAT, J, kThreads, false>, kThreads, 0));
+    if (per_sm < 1) per_sm = 1;
+  }
+  const size_t n_tiles = (a.f.n + OUT - 1) / OUT;
+  const int want = c->l96_ctas_per_sm > 0 ? c->l96_ctas_per_sm : per_sm;
+  const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>(n_tiles, (size_t)want * c->sm_count));
   TRY(ensure_partials(c, grid));
   a.f.rs = reduce_scratch(c);
   ProfScope ps(c, B200RK_K_FUSED, 8.0 * double(a.f.n) * 4);  // y, k1 read; yNew, k_S written
@@ -417,11 +426,45 @@ static int launch_l96_attempt_j(b200rk_ctx* c, const MethodDef& md, double F, bo
   return B200RK_OK;
 }
 
+// Warp-sized tiles (stencil_attempt.cuh: l96_warp_attempt_kernel): same argument block, persistent grid of warps.
+template <int PAT>
+static int launch_l96_warp(b200rk_ctx* c, const MethodDef& md, double F, bool negate, double dt, const b200rk_options& o,
+                           const L96Halo& halo, const b200rk_vec* y, const b200rk_vec* fsal, b200rk_vec* y_new, b200rk_vec* fsal_new) {
+  constexpr int S = Pattern<PAT>::S;
+  constexpr int OUT = WarpTile<S>::OUT, WPB = kThreads / 32;
+  L96AttemptArgs<S> a;
+  std::memset(&a, 0, sizeof(a));
+  a.f.y = y->d; a.f.k1 = fsal->d;
+  for (int s = 2; s <= S; ++s) row_mask(c, md.a[s], a.f.a[s - 2], S - 1);
+  row_mask(c, md.b, a.f.b, S);
+  row_mask(c, md.bhat, a.f.bh, S);
+  a.f.dt = dt; a.f.cb = dt; a.f.cbh = dt; a.f.absTol = o.absTol; a.f.relTol = o.relTol;
+  a.f.ynew = y_new->d; a.f.ks_out = fsal_new->d; a.f.n = y->n_local;
+  a.F = F;
+  a.halo = halo;
+  static int per_sm = 0;   // per instantiation
+  if (per_sm == 0) {
+    CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l96_warp_attempt_kernel<PAT, kThreads, false>, kThreads, 0));
+    if (per_sm < 1) per_sm = 1;
+  }
+  const size_t n_tiles = (a.f.n + OUT - 1) / OUT;
+  const int want = c->l96_ctas_per_sm > 0 ? c->l96_ctas_per_sm : per_sm;
+  const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((n_tiles + WPB - 1) / WPB, (size_t)want * c->sm_count));
+  TRY(ensure_partials(c, grid));
+  a.f.rs = reduce_scratch(c);
+  ProfScope ps(c, B200RK_K_FUSED, 8.0 * double(a.f.n) * 4);  // y, k1 read; yNew, k_S written
+  if (negate) l96_warp_attempt_kernel<PAT, kThreads, true><<<grid, kThreads, 0, c->stream>>>(a);
+  else l96_warp_attempt_kernel<PAT, kThreads, false><<<grid, kThreads, 0, c->stream>>>(a);
+  CUDA_TRY(c, cudaGetLastError());
+  return B200RK_OK;
+}
+
 // Tile width = 512 * J positions (knob "l96_attempt_pairs": 2 = 1024-wide tiles, 2 % overlap, 80-98 registers; 1 = 512-wide,
 // 4 % overlap, fewer registers and more resident CTAs) — to be settled by measurement.
 template <int PAT>
 static int launch_l96_attempt(b200rk_ctx* c, const MethodDef& md, double F, bool negate, double dt, const b200rk_options& o,
                               const L96Halo& halo, const b200rk_vec* y, const b200rk_vec* fsal, b200rk_vec* y_new, b200rk_vec* fsal_new) {
+  if (c->l96_warp_tiles) return launch_l96_warp<PAT>(c, md, F, negate, dt, o, halo, y, fsal, y_new, fsal_new);
   if (c->l96_attempt_pairs == 1) return launch_l96_attempt_j<PAT, 1>(c, md, F, negate, dt, o, halo, y, fsal, y_new, fsal_new);
   return launch_l96_attempt_j<PAT, 2>(c, md, F, negate, dt, o, halo, y, fsal, y_new, fsal_new);
 }

@@ -51,37 +51,70 @@ struct L96AttemptArgs {
 };
 
 // lorenz96_kernel's ((y[i+1] - y[i-2]) * y[i-1] - y[i]) + F at the two adjacent positions p, p+1 a thread owns: c0, c1 are
-// its own stage inputs (registers), sh[p-2], sh[p-1] (one 128-bit shared-memory load) and sh[p+2] its neighbours'.
+// its own stage inputs (registers); m2 = in[p-2], m1 = in[p-1] (one 128-bit shared-memory load) and p2 = in[p+2] its neighbours'.
 // NEG: the backward pass g = -f(-t, y) (ode.nim:545). v * (+1.0) == v and v * (-1.0) == -v exactly, so instead of
 // stage_l96_kernel's multiplication by sgn the sign is a compile-time negation (an operand modifier, no fp64 issue).
 template <bool NEG>
-__device__ __forceinline__ void l96_pair(const double* sh, int p, double c0, double c1, double F, double& k0, double& k1) {
-  const double m2 = sh[p - 2], m1 = sh[p - 1], p2 = sh[p + 2];
+__device__ __forceinline__ void l96_pair(double m2, double m1, double p2, double c0, double c1, double F, double& k0, double& k1) {
   const double v0 = __dadd_rn(__dadd_rn(__dmul_rn(__dadd_rn(c1, -m2), m1), -c0), F);
   const double v1 = __dadd_rn(__dadd_rn(__dmul_rn(__dadd_rn(p2, -m1), c0), -c1), F);
   k0 = NEG ? -v0 : v0;
   k1 = NEG ? -v1 : v1;
 }
 
+// const_wsum's left-associated chain split at term NT: the prefix over the kept terms j < NT, and its continuation with
+// term NT. prefix followed by finish performs exactly const_wsum's operations in const_wsum's order (bit-identical); the
+// split exists so that the prefix — which needs only k_1..k_NT — can be evaluated while the operands of k_{NT+1} (the
+// neighbours' stage inputs) are still on their way from shared memory.
+template <int NK, uint32_t MASK, int NT>
+__device__ __forceinline__ double const_wsum_prefix(const double (&k)[NK], const double* w) {
+  return const_wsum<NK, (MASK & ((1u << NT) - 1u))>(k, w);
+}
+template <int NK, uint32_t MASK, int NT>
+__device__ __forceinline__ double const_wsum_finish(double prefix, const double (&k)[NK], const double* w) {
+  if constexpr (((MASK >> NT) & 1u) == 0u) return prefix;
+  else {
+    const double p = __dmul_rn(k[NT], w[NT]);
+    if constexpr ((MASK & ((1u << NT) - 1u)) != 0u) return __dadd_rn(prefix, p);
+    else return p;
+  }
+}
+
 // stage s (compile-time) of every element the thread owns; recursion keeps the row masks template constants.
 // A thread owns J pairs of adjacent positions (p, p+1).
+// Software pipelining across stages: on entry part[e] holds row s's sum over k_1..k_{s-2}; the stage adds the k_{s-1} term,
+// publishes its stage input, and — between issuing the shared-memory loads of the neighbours' inputs and consuming them in
+// the stencil — evaluates the NEXT row's prefix over k_1..k_{s-1} (after the last stage: the prefixes of the b and bHat
+// rows), so the ~30-cycle shared-memory latency right after the barrier hides under independent fp64 work instead of
+// stalling the warp (first persistent form: 17 % of all stall samples sat on the stencil's first DADD).
 template <int PAT, int s, int J, int TW, bool NEG>
 struct L96Stages {
   template <int S>
-  __device__ __forceinline__ static void run(const double (&y)[2 * J], double (&k)[2 * J][S], double (&in)[2 * J], const int (&pos)[J],
-                                             double (*buf)[TW + 4], const L96AttemptArgs<S>& a) {
-    if constexpr (s > 2) L96Stages<PAT, s - 1, J, TW, NEG>::run(y, k, in, pos, buf, a);
+  __device__ __forceinline__ static void run(const double (&y)[2 * J], double (&k)[2 * J][S], double (&in)[2 * J], double (&part)[2 * J],
+                                             double (&part_bh)[2 * J], const int (&pos)[J], double (*buf)[TW + 4], const L96AttemptArgs<S>& a) {
+    if constexpr (s > 2) L96Stages<PAT, s - 1, J, TW, NEG>::run(y, k, in, part, part_bh, pos, buf, a);
     double* sh = buf[s & 1] + 2;   // sh[-2], sh[-1] and sh[TW] are zero pads (their consumers are outside the stored range)
 #pragma unroll
     for (int e = 0; e < 2 * J; ++e) {
-      const double acc = const_wsum<S, Pattern<PAT>::a(s - 2)>(k[e], a.f.a[s - 2]);
+      const double acc = const_wsum_finish<S, Pattern<PAT>::a(s - 2), s - 2>(part[e], k[e], a.f.a[s - 2]);
       in[e] = __dadd_rn(y[e], __dmul_rn(acc, a.f.dt));                                   // stage_elem
     }
 #pragma unroll
     for (int j = 0; j < J; ++j) { sh[pos[j]] = in[2 * j]; sh[pos[j] + 1] = in[2 * j + 1]; }
     __syncthreads();   // the other buffer was last read before the previous stage's barrier: one barrier per stage
+    double m2[J], m1[J], p2[J];
 #pragma unroll
-    for (int j = 0; j < J; ++j) l96_pair<NEG>(sh, pos[j], in[2 * j], in[2 * j + 1], a.F, k[2 * j][s - 1], k[2 * j + 1][s - 1]);
+    for (int j = 0; j < J; ++j) { m2[j] = sh[pos[j] - 2]; m1[j] = sh[pos[j] - 1]; p2[j] = sh[pos[j] + 2]; }
+#pragma unroll
+    for (int e = 0; e < 2 * J; ++e) {
+      if constexpr (s < S) part[e] = const_wsum_prefix<S, Pattern<PAT>::a(s - 1), s - 1>(k[e], a.f.a[s - 1]);
+      else {
+        if constexpr (!Pattern<PAT>::last) part[e] = const_wsum_prefix<S, Pattern<PAT>::b(), S - 1>(k[e], a.f.b);
+        part_bh[e] = const_wsum_prefix<S, Pattern<PAT>::bh(), S - 1>(k[e], a.f.bh);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j) l96_pair<NEG>(m2[j], m1[j], p2[j], in[2 * j], in[2 * j + 1], a.F, k[2 * j][s - 1], k[2 * j + 1][s - 1]);
   }
 };
 
@@ -99,30 +132,90 @@ __device__ __forceinline__ double l96_edge_load(const double* v, const double* l
   return v[(tile0 + (size_t)p + (n - (size_t)HL % n)) % n];
 }
 
+// ---- tile prefetch: TMA 1-D bulk copies into shared memory, completion on an mbarrier ---------------------------------
+// One elected thread arms the barrier with the byte count and issues two cp.async.bulk copies (the tile's y and k1, 8 KB
+// each); the copies run in the async proxy while the CTA computes the previous tile, cost no registers, and every thread
+// picks its four elements up from shared memory with two conflict-free 128-bit loads once the barrier's phase flips.
+#ifndef B200RK_HOST_EMULATION
+__device__ __forceinline__ unsigned int smem_addr(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tile_barrier_init(unsigned long long* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tile_prefetch(double* dst_y, const double* src_y, double* dst_k, const double* src_k, unsigned int bytes_each,
+                                              unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(2u * bytes_each) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_y)), "l"(src_y),
+               "r"(bytes_each), "r"(smem_addr(bar))
+               : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_k)), "l"(src_k),
+               "r"(bytes_each), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tile_wait(unsigned long long* bar, unsigned int parity) {
+  unsigned int done;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done)
+                 : "r"(smem_addr(bar)), "r"(parity)
+                 : "memory");
+  } while (!done);
+}
+#else
+// host emulation: the elected thread copies synchronously; the stage barriers that follow order it before the readers
+inline void tile_barrier_init(unsigned long long*) {}
+inline void tile_prefetch(double* dst_y, const double* src_y, double* dst_k, const double* src_k, unsigned int bytes_each, unsigned long long*) {
+  for (unsigned int i = 0; i < bytes_each / 8; ++i) { dst_y[i] = src_y[i]; dst_k[i] = src_k[i]; }
+}
+inline void tile_wait(unsigned long long*, unsigned int) {}
+#endif
+
+// Persistent grid: a CTA walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ...; while it evaluates the S - 1 stages of
+// one tile the next tile's y and k1 are already on their way into shared memory (tile_prefetch), so the HBM latency of a
+// tile hides under the ~500 fp64 instructions per warp of the previous one instead of idling the CTA (first measured form,
+// one tile per CTA and register loads: 188 us per attempt at 2^24 with the fp64 pipe 55 % busy and 17 % of the warp
+// stalls on the tile's loads).
 template <int PAT, int J, int THREADS, bool NEG>
-__global__ void __launch_bounds__(THREADS) l96_attempt_kernel(const L96AttemptArgs<Pattern<PAT>::S> a) {
+__global__ void __launch_bounds__(THREADS, (Pattern<PAT>::S > 7 || J > 2) ? 2 : 3) l96_attempt_kernel(const L96AttemptArgs<Pattern<PAT>::S> a) {
   constexpr int S = Pattern<PAT>::S;
   constexpr int E = 2 * J, TW = E * THREADS;
   constexpr int HL = StencilTile<S>::HL, HR = StencilTile<S>::HR, OUT = TW - HL - HR;
   __shared__ double buf[2][TW + 4];
+  alignas(128) __shared__ double staged[2][TW];   // [0]: the tile's y, [1]: its k1 (FSAL) — written by the bulk copies
+  alignas(8) __shared__ unsigned long long tile_bar;
   const size_t n = a.f.n;
-  const size_t tile0 = (size_t)blockIdx.x * OUT;          // first stored element of this tile
+  const size_t n_tiles = (n + OUT - 1) / OUT;
   if (threadIdx.x < 3) {
     const int q = threadIdx.x < 2 ? (int)threadIdx.x : TW + 2;
     buf[0][q] = 0.0; buf[1][q] = 0.0;
   }
-  double y[E], k[E][S], in[E];
+  // a tile whose TW positions all lie inside the block is read with the bulk copies; the first and last tile(s) reach
+  // around the ring (or into the neighbouring shards) and take the element-wise path
+  auto interior_tile = [&](size_t t) { const size_t t0 = t * (size_t)OUT; return t0 >= (size_t)HL && t0 - HL + TW <= n; };
+  size_t tile = blockIdx.x;
+  if (threadIdx.x == 0) {
+    tile_barrier_init(&tile_bar);
+    if (tile < n_tiles && interior_tile(tile))
+      tile_prefetch(staged[0], a.f.y + (tile * OUT - HL), staged[1], a.f.k1 + (tile * OUT - HL), TW * 8u, &tile_bar);
+  }
+  __syncthreads();
+  unsigned int phase = 0;
+  double acc = 0.0;
   int pos[J];   // first position of each pair the thread owns
-  const bool interior = tile0 >= (size_t)HL && tile0 - HL + TW <= n;
+#pragma unroll
+  for (int j = 0; j < J; ++j) pos[j] = 2 * ((int)threadIdx.x + j * THREADS);
+  for (; tile < n_tiles; tile += gridDim.x) {
+  const size_t tile0 = tile * (size_t)OUT;          // first stored element of this tile
+  double y[E], k[E][S], in[E];
+  const bool interior = interior_tile(tile);
+  if (interior) { tile_wait(&tile_bar, phase); phase ^= 1u; }
 #pragma unroll
   for (int j = 0; j < J; ++j) {
-    const int p = 2 * ((int)threadIdx.x + j * THREADS);
-    pos[j] = p;
+    const int p = pos[j];
     if (interior) {
-      const size_t g = tile0 - HL + p;
-      const Pk<2> yv = ld_stream<2>(a.f.y + g), kv = ld_stream<2>(a.f.k1 + g);
-      y[2 * j] = yv.v[0]; y[2 * j + 1] = yv.v[1];
-      k[2 * j][0] = kv.v[0]; k[2 * j + 1][0] = kv.v[1];
+      const double2 yv = *reinterpret_cast<const double2*>(&staged[0][p]), kv = *reinterpret_cast<const double2*>(&staged[1][p]);   // LDS.128, conflict-free
+      y[2 * j] = yv.x; y[2 * j + 1] = yv.y;
+      k[2 * j][0] = kv.x; k[2 * j + 1][0] = kv.y;
     } else {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -131,13 +224,21 @@ __global__ void __launch_bounds__(THREADS) l96_attempt_kernel(const L96AttemptAr
       }
     }
   }
+  __syncthreads();   // every thread holds its part of the tile: the staging buffers (and the previous tile's last stage buffer) are free
+  {
+    const size_t nxt = tile + gridDim.x;
+    if (threadIdx.x == 0 && nxt < n_tiles && interior_tile(nxt))
+      tile_prefetch(staged[0], a.f.y + (nxt * OUT - HL), staged[1], a.f.k1 + (nxt * OUT - HL), TW * 8u, &tile_bar);
+  }
 #pragma unroll
   for (int e = 0; e < E; ++e)
 #pragma unroll
     for (int j = 1; j < S; ++j) k[e][j] = 0.0;
-  L96Stages<PAT, S, J, TW, NEG>::run(y, k, in, pos, buf, a);
+  double part[E], part_bh[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) { part[e] = 0.0; part_bh[e] = 0.0; }
+  L96Stages<PAT, S, J, TW, NEG>::run(y, k, in, part, part_bh, pos, buf, a);   // leaves the b / bHat rows' prefixes in part / part_bh
 
-  double acc = 0.0;
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     const int p = pos[j];
@@ -149,8 +250,8 @@ __global__ void __launch_bounds__(THREADS) l96_attempt_kernel(const L96AttemptAr
       const int e = 2 * j + h;
       ks[h] = k[e][S - 1];
       if (Pattern<PAT>::last) yn[h] = in[e];
-      else yn[h] = __dadd_rn(y[e], __dmul_rn(const_wsum<S, Pattern<PAT>::b()>(k[e], a.f.b), a.f.cb));
-      const double lo = __dmul_rn(const_wsum<S, Pattern<PAT>::bh()>(k[e], a.f.bh), a.f.cbh);
+      else yn[h] = __dadd_rn(y[e], __dmul_rn(const_wsum_finish<S, Pattern<PAT>::b(), S - 1>(part[e], k[e], a.f.b), a.f.cb));
+      const double lo = __dmul_rn(const_wsum_finish<S, Pattern<PAT>::bh(), S - 1>(part_bh[e], k[e], a.f.bh), a.f.cbh);
       double err;
       if (Pattern<PAT>::direct) err = lo;
       else err = __dadd_rn(yn[h], -__dadd_rn(y[e], lo));
@@ -171,9 +272,161 @@ __global__ void __launch_bounds__(THREADS) l96_attempt_kernel(const L96AttemptAr
       }
     }
   }
+  }  // tiles
 #ifdef B200RK_EMULATE_SERIAL_SUM
   // host emulation (threads of a CTA run concurrently, CTAs one after another): thread 0 adds the CTA's terms in thread
   // order to the running sum and the last CTA publishes it the way grid_sum_finish's last CTA does
+  __shared__ double red[THREADS];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = (blockIdx.x == 0) ? 0.0 : *a.f.rs.result;
+    for (int i = 0; i < THREADS; ++i) t = __dadd_rn(t, red[i]);
+    *a.f.rs.result = t;
+    if (blockIdx.x == gridDim.x - 1 && a.f.rs.result_host) {
+      if (a.f.rs.mail.world > 1) { t = emul_peer_exchange(t, a.f.rs); *a.f.rs.result = t; }
+      *a.f.rs.result_host = t;
+      *a.f.rs.seq_host = a.f.rs.seq;
+    }
+  }
+#else
+  grid_sum_finish<THREADS>(acc, a.f.rs);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The same attempt with WARP-sized overlapped tiles: no shared memory, no block barrier.
+// In the CTA-tile kernel above every stage is  publish -> __syncthreads -> shared-memory loads -> stencil, and the warps of a
+// CTA move through it in lockstep: measured on the B200 (profiles/r02_ncu_full_l96_attempt_*), the fp64 pipe stays 60 % busy
+// with a quarter of all warp stalls on the barrier and on the shared-memory latency right behind it. Here a tile is what ONE
+// warp holds: lane l owns the 4 adjacent positions 4l .. 4l+3 of a 128-position tile (one 256-bit load each of y and k1),
+// and the three neighbouring stage inputs an evaluation needs — in[-2], in[-1] from lane l-1, in[+4] from lane l+1 — travel
+// by warp shuffle. Warps never wait for each other, so the scheduler hides one warp's shuffle and dependency latency under
+// the arithmetic of the others, as in the element-local fused kernel. The price is a larger overlap: HL + HR of 128
+// positions (16 % for the 7-stage pairs, 19 % for Vern65) instead of 2 % of a 1024-wide tile. Per-element arithmetic is the
+// CTA-tile kernel's (const_wsum rows, l96_pair's operation order, err_ratio): yNew and k_S are bit-identical.
+// MEASURED (B200, Tsit54, 2^24; profiles/r02_l96_attempt_variants.md): 164 us per attempt with plain register loads (fp64 pipe
+// 68 % busy, a quarter of the stall samples on the tile's own loads), 182 us with the cp.async prefetch below at 80 registers
+// (88 bytes of spills), 185 us at 124 registers / 2 CTAs per SM — against 154 us for the CTA-tile kernel, whose 2 % overlap
+// outweighs its barriers. The kernel therefore stays behind knob "l96_warp_tiles" (default 0) as the measured alternative.
+// Positions whose neighbours lie outside the tile read another lane's value through the shuffle's clamping; they are
+// in the overlap and never stored (lane 0's left inputs and lane 31's right input go bad first: 2 resp. 1 position per stage).
+// ---------------------------------------------------------------------------------------------------
+template <int S>
+struct WarpTile {
+  static constexpr int E = 4, TW = 32 * E;
+  static constexpr int HL = StencilTile<S>::HL, HR = StencilTile<S>::HR, OUT = TW - HL - HR;
+};
+
+template <int PAT, int s, bool NEG>
+struct L96WarpStages {
+  template <int S>
+  __device__ __forceinline__ static void run(const double (&y)[4], double (&k)[4][S], double (&in)[4], const L96AttemptArgs<S>& a) {
+    if constexpr (s > 2) L96WarpStages<PAT, s - 1, NEG>::run(y, k, in, a);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const double acc = const_wsum<S, Pattern<PAT>::a(s - 2)>(k[e], a.f.a[s - 2]);
+      in[e] = __dadd_rn(y[e], __dmul_rn(acc, a.f.dt));                                   // stage_elem
+    }
+    const double m2 = __shfl_up_sync(0xffffffffu, in[2], 1), m1 = __shfl_up_sync(0xffffffffu, in[3], 1);   // positions -2, -1
+    const double p4 = __shfl_down_sync(0xffffffffu, in[0], 1);                                            // position +4
+    l96_pair<NEG>(m2, m1, in[2], in[0], in[1], a.F, k[0][s - 1], k[1][s - 1]);
+    l96_pair<NEG>(in[0], in[1], p4, in[2], in[3], a.F, k[2][s - 1], k[3][s - 1]);
+  }
+};
+
+// Register-free prefetch of a lane's own 2 x 32 bytes of the next tile: cp.async (LDGSTS) into a per-warp staging area.
+// A lane later reads back exactly the bytes it copied itself, so no warp- or block-level synchronisation is involved —
+// cp.async.wait_group on the issuing thread is all the ordering there is.
+#ifndef B200RK_HOST_EMULATION
+__device__ __forceinline__ void lane_prefetch32(double* dst_lo, double* dst_hi, const double* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned int)__cvta_generic_to_shared(dst_lo)), "l"(src) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned int)__cvta_generic_to_shared(dst_hi)), "l"(src + 2) : "memory");
+}
+__device__ __forceinline__ void lane_prefetch_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void lane_prefetch_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+#else
+inline void lane_prefetch32(double* dst_lo, double* dst_hi, const double* src) { dst_lo[0] = src[0]; dst_lo[1] = src[1]; dst_hi[0] = src[2]; dst_hi[1] = src[3]; }
+inline void lane_prefetch_commit() {}
+inline void lane_prefetch_wait() {}
+#endif
+
+template <int PAT, int THREADS, bool NEG>
+__global__ void __launch_bounds__(THREADS, Pattern<PAT>::S > 7 ? 2 : 3) l96_warp_attempt_kernel(const L96AttemptArgs<Pattern<PAT>::S> a) {
+  constexpr int S = Pattern<PAT>::S;
+  using T = WarpTile<S>;
+  constexpr int HL = T::HL, HR = T::HR, OUT = T::OUT, TW = T::TW;
+  const size_t n = a.f.n;
+  const size_t n_tiles = (n + OUT - 1) / OUT;
+  const int lane = threadIdx.x & 31;
+  const size_t warp = (size_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5), n_warps = (size_t)gridDim.x * (THREADS / 32);
+  const int p = 4 * lane;                                   // first of the lane's 4 positions
+  const bool lane_stores = p >= HL && p < HL + OUT;         // HL, OUT multiples of 4: a lane stores all 4 positions or none
+  double acc = 0.0;
+  alignas(16) __shared__ double staged[2][2][THREADS][2];   // [y | k1][low / high pair][thread][2]: each lane's own slots (16 bytes apart across lanes: conflict-free), written by cp.async
+  auto interior_tile = [&](size_t t) { const size_t t0 = t * (size_t)OUT; return t0 >= (size_t)HL && t0 - HL + TW <= n; };
+  if (warp < n_tiles && interior_tile(warp)) {
+    lane_prefetch32(staged[0][0][threadIdx.x], staged[0][1][threadIdx.x], a.f.y + (warp * OUT - HL + p));
+    lane_prefetch32(staged[1][0][threadIdx.x], staged[1][1][threadIdx.x], a.f.k1 + (warp * OUT - HL + p));
+  }
+  lane_prefetch_commit();
+  for (size_t tile = warp; tile < n_tiles; tile += n_warps) {
+    const size_t tile0 = tile * (size_t)OUT;                // first stored element of this tile
+    double y[4], k[4][S], in[4];
+    const bool interior = interior_tile(tile);
+    if (interior) {                                         // the lane's 2 x 32 bytes were prefetched while the previous tile was evaluated
+      lane_prefetch_wait();
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { y[e] = staged[0][e >> 1][threadIdx.x][e & 1]; k[e][0] = staged[1][e >> 1][threadIdx.x][e & 1]; }
+    }
+    {
+      const size_t nxt = tile + n_warps;
+      if (nxt < n_tiles && interior_tile(nxt)) {
+        lane_prefetch32(staged[0][0][threadIdx.x], staged[0][1][threadIdx.x], a.f.y + (nxt * OUT - HL + p));
+        lane_prefetch32(staged[1][0][threadIdx.x], staged[1][1][threadIdx.x], a.f.k1 + (nxt * OUT - HL + p));
+      }
+      lane_prefetch_commit();
+    }
+    if (!interior) {                                                // first / last tiles: around the ring, or into the neighbouring shards
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        y[e] = l96_edge_load<HL, HR>(a.f.y, a.halo.left_y, a.halo.right_y, n, tile0, p + e);
+        k[e][0] = l96_edge_load<HL, HR>(a.f.k1, a.halo.left_k, a.halo.right_k, n, tile0, p + e);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+      for (int j = 1; j < S; ++j) k[e][j] = 0.0;
+    L96WarpStages<PAT, S, NEG>::run(y, k, in, a);
+    const size_t g = tile0 + (size_t)(p - HL);              // meaningful when lane_stores
+    const bool stored = lane_stores && g < n;
+    Pk<4> yo, ko;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      ko.v[e] = k[e][S - 1];
+      if (Pattern<PAT>::last) yo.v[e] = in[e];
+      else yo.v[e] = __dadd_rn(y[e], __dmul_rn(const_wsum<S, Pattern<PAT>::b()>(k[e], a.f.b), a.f.cb));
+      const double lo = __dmul_rn(const_wsum<S, Pattern<PAT>::bh()>(k[e], a.f.bh), a.f.cbh);
+      double err;
+      if (Pattern<PAT>::direct) err = lo;
+      else err = __dadd_rn(yo.v[e], -__dadd_rn(y[e], lo));
+      const double tol = __dadd_rn(a.f.absTol, __dmul_rn(fabs(yo.v[e]), a.f.relTol));
+      const double r = err_ratio(err, tol);
+      if (stored && g + e < n) acc = __dadd_rn(acc, __dmul_rn(r, r));
+    }
+    if (stored) {
+      if (g + 4 <= n) {
+        st_stream<4>(a.f.ynew + g, yo);
+        st_stream<4>(a.f.ks_out + g, ko);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (g + e < n) { a.f.ynew[g + e] = yo.v[e]; a.f.ks_out[g + e] = ko.v[e]; }
+      }
+    }
+  }
+#ifdef B200RK_EMULATE_SERIAL_SUM
   __shared__ double red[THREADS];
   red[threadIdx.x] = acc;
   __syncthreads();
@@ -240,7 +493,7 @@ __global__ void __launch_bounds__(THREADS) l96_rk4_kernel(const L96Rk4Args a) {
     for (int j = 0; j < J; ++j) { sh[pos[j]] = in[2 * j]; sh[pos[j] + 1] = in[2 * j + 1]; }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < J; ++j) l96_pair<NEG>(sh, pos[j], in[2 * j], in[2 * j + 1], a.F, k[s][2 * j], k[s][2 * j + 1]);
+    for (int j = 0; j < J; ++j) l96_pair<NEG>(sh[pos[j] - 2], sh[pos[j] - 1], sh[pos[j] + 2], in[2 * j], in[2 * j + 1], a.F, k[s][2 * j], k[s][2 * j + 1]);
   }
 #pragma unroll
   for (int j = 0; j < J; ++j) {

@@ -20,7 +20,7 @@ CSRC = os.path.join(ROOT, "numericalnim_b200", "csrc")
 BUILD = os.path.join(HERE, "_build", "emul_lib")
 OUT = os.path.join(HERE, "_build", "libb200rk_emul.so")
 SOURCES = ["runtime.cu", "launch.cu", "executor.cu", "driver.cu", "capi.cu", "quadrature.cu"]
-THREADED = ("stage_l96_kernel", "l96_attempt_kernel", "l96_rk4_kernel")   # shared-memory tile + __syncthreads (the cooperative loop goes through cudaLaunchCooperativeKernel)
+THREADED = ("stage_l96_kernel", "l96_attempt_kernel", "l96_warp_attempt_kernel", "l96_rk4_kernel")   # shared-memory tile + __syncthreads (the cooperative loop goes through cudaLaunchCooperativeKernel)
 
 LAUNCH = re.compile(r"(?P<kernel>\b\w+<[^;<>]*(?:<[^;<>]*>[^;<>]*)*>)<<<(?P<grid>.+?), kThreads, 0, c->stream>>>\((?P<args>.*)\);(?P<tail>\s*(//.*)?)$")
 

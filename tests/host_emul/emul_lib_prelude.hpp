@@ -59,6 +59,17 @@ inline T __shfl_down_sync(unsigned, T v, int off) {
   g_emul_block->warp[w]->arrive_and_wait();
   return r;
 }
+template <class T>
+inline T __shfl_up_sync(unsigned, T v, int off) {
+  if (!g_emul_block) return v;
+  static T lanes_up[1024];
+  const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+  lanes_up[tid] = v;
+  g_emul_block->warp[w]->arrive_and_wait();
+  const T r = (lane >= (unsigned)off) ? lanes_up[tid - off] : v;
+  g_emul_block->warp[w]->arrive_and_wait();
+  return r;
+}
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }

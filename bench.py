@@ -472,6 +472,11 @@ def run_ours(args):
 
     e2e_full = e2e_variant(True)
     e2e_res = e2e_variant(False) if lam_pin is not None else None
+    # the tStart output slot (= y0): library default (auto: D2H on a second stream up to 3 ranks, host-side copy beyond) vs the other way
+    auto_host = world >= 4
+    ctx.set("tstart_copy", 0 if auto_host else 1)
+    e2e_alt = e2e_variant(True)
+    ctx.set("tstart_copy", -1)
     # PCIe roofline of the end-to-end number: the same pinned buffers copied alone, both directions
     pcie = {}
     try:
@@ -546,6 +551,9 @@ def run_ours(args):
         if e2e_res is not None:
             e2e["rhs_resident"] = dict(e2e_res, note="same, with lambda left on the device between solves (it belongs to the right-hand-side object, "
                                                      "like the data a reference ODEProc closure captures): only y0 goes up, the states come down")
+        e2e["tstart_slot"] = {"default": "host-side copy of y0 by helper threads" if auto_host else "device-to-host copy on a second stream while the solve runs",
+                              "alternative": "device-to-host copy on a second stream" if auto_host else "host-side copy of y0 by helper threads",
+                              "alternative_value": e2e_alt["value"], "alternative_ms_per_solve": e2e_alt["ms_per_solve"]}
         e2e["pcie"] = pcie
         e2e["host_numa"] = numa
         ms_all = head["ms_all"]
@@ -564,7 +572,7 @@ def run_ours(args):
                       "error_norm_allreduce": ("in-kernel peer mailboxes over NVLink (CUDA IPC)" if ctx.get("p2p") else "ncclAllReduce") if world > 1 else None,
                       "butcher_row": "kernel parameters / constant bank (uniform broadcast) instead of shared-memory staging (DESIGN.md 4)"},
             "knobs": {k: ctx.get(k) for k in ("vec_width", "ctas_per_sm", "finish_ctas_per_sm", "fuse_pointwise", "fuse_stencil", "fuse_stencil_attempt",
-                                              "fused_ctas_per_sm", "spin_readback", "l2_hints", "device_loop")},
+                                              "fused_ctas_per_sm", "spin_readback", "l2_hints", "device_loop", "tstart_copy", "peer_timeout_s")},
             "attempts": attempts, "attempts_per_sec": attempts * world / (ms_max * 1e-3), "rejected": head["rejected"],
             "t_reached": t_now, "dt_next": dt_next,
             "gpu_launches": launches, "collectives": head["collectives"],

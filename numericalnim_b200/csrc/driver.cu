@@ -2,6 +2,7 @@
 #include "internal.hpp"
 
 #include <limits>
+#include <thread>
 
 struct b200rk_solver {
   b200rk_ctx* c = nullptr;
@@ -323,7 +324,21 @@ int b200rk_solve_host(b200rk_ctx* c, int method, b200rk_rhs_fn f, void* user, si
   bool has_zero = false, has_neg = false;
   for (size_t i = 0; i < n_tspan; ++i) { has_zero |= (tspan[i] == t0); has_neg |= (tspan[i] < t0); }
   bool early = false;
-  if (rc == B200RK_OK && has_zero && !has_neg && bytes) {
+  // knob "tstart_copy" = 1: the host already holds those bytes — fill output slot 0 with a host-side copy of y0_local (a few
+  // helper threads, concurrent with the solve) instead of a second device-to-host transfer. Measured trade-off (profiles/):
+  // alone on its PCIe link the D2H rides the idle copy engine for free; with 8 ranks sharing one host fabric, D2H is the
+  // scarce direction (12 GB/s per GPU) and halving its volume is worth more than the host-memory traffic of a memcpy.
+  std::vector<std::thread> host_copy;
+  const bool host_side = c->tstart_copy == 1 || (c->tstart_copy < 0 && c->world >= 4);
+  if (rc == B200RK_OK && has_zero && !has_neg && bytes && host_side) {
+    const size_t nthreads = 4, n = y0->n_local, chunk = (n + nthreads - 1) / nthreads;
+    for (size_t i = 0; i < nthreads; ++i) {
+      const size_t lo = std::min(n, i * chunk), hi = std::min(n, lo + chunk);
+      if (hi > lo) host_copy.emplace_back([=] { std::memcpy(y_out_local + lo, y0_local + lo, (hi - lo) * sizeof(double)); });
+    }
+    early = true;
+  }
+  if (rc == B200RK_OK && has_zero && !has_neg && bytes && !host_side) {
     if (!c->copy_stream) {
       if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
           cudaEventCreateWithFlags(&c->copy_event, cudaEventDisableTiming) != cudaSuccess) {
@@ -351,7 +366,8 @@ int b200rk_solve_host(b200rk_ctx* c, int method, b200rk_rhs_fn f, void* user, si
     for (size_t i = 0; i < ny; ++i) vec_release(ys[i]);
     if (n_y_out) *n_y_out = ny;
   }
-  if (early) {  // y0 must stay untouched until its copy has left the device
+  for (auto& th : host_copy) th.join();
+  if (early && host_copy.empty()) {  // y0 must stay untouched until its copy has left the device
     e = cudaStreamSynchronize(c->copy_stream);
     if (e != cudaSuccess && rc == B200RK_OK) rc = fail(c, B200RK_ECUDA, cudaGetErrorString(e));
   }

@@ -2,8 +2,9 @@
 ## numericalnim's `solveODE` / `newODEoptions` / `IntegratorProc` for a device-resident vector type.
 ##
 ## STATUS: written against the C header, NOT compiled — this image has no Nim toolchain (nim, nimble and
-## choosenim are absent; see DESIGN.md §2). Every proc below is a 1:1 declaration of a symbol whose
-## behaviour is exercised through the same ABI by the pytest suite (ctypes). Usage from reference code:
+## choosenim are absent; see DESIGN.md §2). There is one `importc` declaration per B200RK_API symbol of the header
+## (69; tests/test_nim_shim.py parses both files and compares names and arities), and the behaviour of every symbol
+## is exercised through the same ABI by the pytest suite (ctypes). Usage from reference code:
 ##
 ##   import numericalnim            # for ODEoptions, NumContext, linspace, ...
 ##   import b200rk                  # adds the GpuVector overloads
@@ -82,6 +83,54 @@ proc b200rk_cumtrapz_fn(ctx: B200rkCtx, f: FnOfT, user: pointer, nGlobal: csize_
                         outVecs: ptr VecHandle, nOut: ptr csize_t): cint {.importc, cdecl, dynlib: lib.}
 proc b200rk_cumsimpson_fn(ctx: B200rkCtx, f: FnOfT, user: pointer, nGlobal: csize_t, X: ptr cdouble, m: csize_t, dx: cdouble,
                           outVecs: ptr VecHandle, nOut: ptr csize_t): cint {.importc, cdecl, dynlib: lib.}
+
+# the rest of the ABI, one declaration per B200RK_API symbol (tests/test_nim_shim.py compares this list with the header)
+type
+  SolverObj {.incompleteStruct.} = object
+  SolverHandle = ptr SolverObj
+  CProfile {.bycopy.} = object       ## b200rk_profile: per kernel class (stage, finish, rhs, other, fused, quad)
+    launches: array[6, int64]
+    ms: array[6, cdouble]
+    algorithmicBytes: array[6, cdouble]
+proc b200rk_synchronize(ctx: B200rkCtx): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_rank(ctx: B200rkCtx): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_world(ctx: B200rkCtx): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_set(ctx: B200rkCtx, key: cstring, value: int64): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_get(ctx: B200rkCtx, key: cstring, value: ptr int64): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_profile_reset(ctx: B200rkCtx): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_profile_read(ctx: B200rkCtx, outProfile: ptr CProfile): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_ctx_stats(ctx: B200rkCtx, outStats: ptr CStats): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_options_new(outOptions: ptr COptions, dt, absTol, relTol, dtMax, dtMin, scaleMax, scaleMin, tStart: cdouble): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_options_default(outOptions: ptr COptions) {.importc, cdecl, dynlib: lib.}
+proc b200rk_method_name(methodId: cint): cstring {.importc, cdecl, dynlib: lib.}
+proc b200rk_method_info(methodId: cint, stages, useFsal: ptr cint, order: ptr cdouble, adaptive: ptr cint): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_method_tableau(methodId: cint, c, a, b, bhat: ptr cdouble): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_shard_range(nGlobal: csize_t, rank, world: cint, offset, len: ptr csize_t): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_vec_local_len(v: VecHandle): csize_t {.importc, cdecl, dynlib: lib.}
+proc b200rk_vec_local_offset(v: VecHandle): csize_t {.importc, cdecl, dynlib: lib.}
+proc b200rk_vec_upload_local(v: VecHandle, hostLocal: ptr cdouble): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_vec_download_local(v: VecHandle, hostLocal: ptr cdouble): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_vec_upload_local_async(v: VecHandle, hostLocal: ptr cdouble): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_vec_fill(v: VecHandle, value: cdouble): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_builtin_rhs_new(ctx: B200rkCtx, kind: cint, scalar: cdouble, lambda: VecHandle, fn: ptr RhsFn, user: ptr pointer): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_builtin_rhs_free(user: pointer): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_jit_compile_only(expr: cstring, nVec, nScalar, pattern: cint, cubinOut: pointer, cubinCap: csize_t, cubinBytes: ptr csize_t,
+                             log: cstring, logCap: csize_t): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_hermite_plan(x: ptr cdouble, nx: csize_t, t: ptr cdouble, nt: csize_t, interval, isCopy: ptr cint, factors: ptr cdouble,
+                         nOut: ptr csize_t): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_simpson_weights(tail: cint, h1, h2: cdouble, alpha, beta, eta: ptr cdouble): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_solve_host(ctx: B200rkCtx, methodId: cint, f: RhsFn, user: pointer, nGlobal: csize_t, y0Local, tspan: ptr cdouble, nTspan: csize_t,
+                       options: ptr COptions, tOut, yOutLocal: ptr cdouble, nYOut: ptr csize_t, stats: ptr CStats): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_solver_new(ctx: B200rkCtx, methodId: cint, f: RhsFn, user: pointer, y0: VecHandle, tEnd: cdouble, options: ptr COptions,
+                       outSolver: ptr SolverHandle): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_solver_advance(s: SolverHandle, maxSteps: int64, stepsDone: ptr int64, finished: ptr cint): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_solver_state(s: SolverHandle, t, dtNext, lastError: ptr cdouble, y: ptr VecHandle): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_solver_stats(s: SolverHandle, outStats: ptr CStats): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_solver_free(s: SolverHandle): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_stage_accum(ctx: B200rkCtx, m: cint, w: ptr cdouble, c: cdouble, chain: cint, y: VecHandle, k: ptr VecHandle, outVec: VecHandle): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_combine_err(ctx: B200rkCtx, methodId: cint, dt, absTol, relTol: cdouble, y: VecHandle, k: ptr VecHandle, yNew, errY: VecHandle,
+                        sumsq, error: ptr cdouble): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_rk4_combine(ctx: B200rkCtx, dt: cdouble, y, k1, k2, k3, k4, outVec: VecHandle): cint {.importc, cdecl, dynlib: lib.}
 
 # ---- error convention: status code -> Nim exception (SURVEY.md §8b) ---------------------------------
 proc check(rc: cint, ctx: B200rkCtx = nil) =
@@ -304,3 +353,115 @@ proc cumtrapz*(f: NumContextProc[GpuVector, float], X: openArray[float], like: G
 proc cumsimpson*(f: NumContextProc[GpuVector, float], X: openArray[float], like: GpuVector,
                  ctx: NumContext[GpuVector, float] = nil, dx = 1e-5): seq[GpuVector] =    # integrate.nim:379-400
   cumulativeFn(b200rk_cumsimpson_fn, f, X, like, ctx, dx)
+
+# ---- solveODE on HOST sequences (b200rk_solve_host): seq[float] in, seq[seq[float]] out -----------------
+proc solveODEHost*(f: ODEProc[GpuVector], y0: openArray[float], tspan: openArray[float], options: ODEoptions = newODEoptions(),
+                   ctx: NumContext[GpuVector, float] = nil, integrator = "dopri54", dev: B200rkCtx = b200rkContext()): (seq[float], seq[seq[float]]) =
+  ## The call a maintainer makes when the state lives in host memory: y0 goes up, the states at `tspan` come down, the
+  ## right-hand side closure sees device vectors (its GpuVector operators enqueue kernels). ode.nim:589-591 for T = seq[float].
+  var nctx = ctx
+  if nctx.isNil: nctx = newNumContext[GpuVector, float]()
+  let mid = methodId(integrator.toLower())
+  var env = RhsEnv(f: f, ctx: nctx, dev: dev)
+  var co = toC(options)
+  var (ts, y0s) = (@tspan, @y0)
+  var tOut = newSeq[cdouble](ts.len)
+  var yOut = newSeq[cdouble](max(ts.len, 1) * y0s.len)
+  var nOut: csize_t
+  let rc = b200rk_solve_host(dev, mid, rhsTrampoline, addr env, y0s.len.csize_t, cast[ptr cdouble](addr y0s[0]), cast[ptr cdouble](addr ts[0]),
+                             ts.len.csize_t, addr co, cast[ptr cdouble](addr tOut[0]), cast[ptr cdouble](addr yOut[0]), addr nOut, nil)
+  if not env.err.isNil: raise env.err
+  check(rc, dev)
+  var ys = newSeq[seq[float]](nOut.int)
+  for i in 0 ..< nOut.int: ys[i] = yOut[i * y0s.len ..< (i + 1) * y0s.len]
+  while tOut.len > 0 and tOut[^1] != tOut[^1]: tOut.setLen(tOut.len - 1)
+  result = (@tOut, ys)
+
+# ---- built-in device right-hand sides (b200rk_builtin_rhs_new): c*y, -(lambda .* y), Lorenz-96 -------------
+type BuiltinRhs* = ref object
+  fn: RhsFn
+  user: pointer
+  lam: GpuVector        # kept alive
+proc newBuiltinRhs(kind: cint, scalar: float, lam: GpuVector, ctx: B200rkCtx): BuiltinRhs =
+  new(result, proc(r: BuiltinRhs) = (if not r.user.isNil: discard b200rk_builtin_rhs_free(r.user)))
+  result.lam = lam
+  check(b200rk_builtin_rhs_new(ctx, kind, scalar, lam.h, addr result.fn, addr result.user), ctx)
+proc rhsScale*(c: float, ctx: B200rkCtx = b200rkContext()): BuiltinRhs = newBuiltinRhs(0, c, GpuVector(), ctx)
+proc rhsDiagLinear*(lam: GpuVector): BuiltinRhs = newBuiltinRhs(1, 0.0, lam, lam.ctx)
+proc rhsLorenz96*(F = 8.0, ctx: B200rkCtx = b200rkContext()): BuiltinRhs = newBuiltinRhs(2, F, GpuVector(), ctx)
+
+proc solveODE*(f: BuiltinRhs, y0: GpuVector, tspan: openArray[float], options: ODEoptions = newODEoptions(),
+               integrator = "dopri54"): (seq[float], seq[GpuVector]) =
+  let mid = methodId(integrator.toLower())
+  var co = toC(options)
+  var ts = @tspan
+  var tOut = newSeq[cdouble](ts.len)
+  var slots = newSeq[VecHandle](max(ts.len, 1))
+  var nOut: csize_t
+  check(b200rk_solve(y0.ctx, mid, f.fn, f.user, y0.h, cast[ptr cdouble](addr ts[0]), ts.len.csize_t, addr co,
+                     cast[ptr cdouble](addr tOut[0]), addr slots[0], addr nOut, nil), y0.ctx)
+  var ys = newSeq[GpuVector](nOut.int)
+  for i in 0 ..< nOut.int: ys[i] = GpuVector(h: slots[i], ctx: y0.ctx, borrowed: false)
+  while tOut.len > 0 and tOut[^1] != tOut[^1]: tOut.setLen(tOut.len - 1)
+  result = (@tOut, ys)
+
+# ---- the ODESolver loop as a resumable object (b200rk_solver_*): advance K accepted steps at a time ---------
+type GpuSolver* = ref object
+  h: SolverHandle
+  ctx: B200rkCtx
+  env: ref RhsEnv       # kept alive: the library calls back into it
+proc newGpuSolver*(integrator: string, f: ODEProc[GpuVector], y0: GpuVector, tEnd: float, options: ODEoptions = newODEoptions(),
+                   ctx: NumContext[GpuVector, float] = nil): GpuSolver =
+  new(result, proc(s: GpuSolver) = (if not s.h.isNil: discard b200rk_solver_free(s.h)))
+  var nctx = ctx
+  if nctx.isNil: nctx = newNumContext[GpuVector, float]()
+  result.ctx = y0.ctx
+  new(result.env)
+  result.env[] = RhsEnv(f: f, ctx: nctx, dev: y0.ctx)
+  var co = toC(options)
+  check(b200rk_solver_new(y0.ctx, methodId(integrator.toLower()), rhsTrampoline, addr result.env[], y0.h, tEnd, addr co, addr result.h), y0.ctx)
+proc advance*(s: GpuSolver, maxSteps = -1): (int, bool) =
+  var done: int64
+  var fin: cint
+  let rc = b200rk_solver_advance(s.h, maxSteps.int64, addr done, addr fin)
+  if not s.env.err.isNil: raise s.env.err
+  check(rc, s.ctx)
+  (done.int, fin != 0)
+proc state*(s: GpuSolver): (float, float, float, GpuVector) =
+  var t, dtNext, err: cdouble
+  var y: VecHandle
+  check(b200rk_solver_state(s.h, addr t, addr dtNext, addr err, addr y), s.ctx)
+  (t.float, dtNext.float, err.float, GpuVector(h: y, ctx: s.ctx, borrowed: true))
+proc stats*(s: GpuSolver): tuple[steps, attempts, rejected, limiterHits, rhsEvals, launches, collectives: int] =
+  var st: CStats
+  check(b200rk_solver_stats(s.h, addr st), s.ctx)
+  (st.steps.int, st.attempts.int, st.rejected.int, st.limiterHits.int, st.rhsEvals.int, st.launches.int, st.collectives.int)
+
+# ---- IntegratorProc[GpuVector] values under the reference's step names (ode.nim:180, 237, 307, 377) -----------
+# (the reference keeps its *_step procs private and selects them by name in solveODE; here they can also be passed around)
+let
+  RK4_step* = gpuIntegrator("rk4")
+  DOPRI54_step* = gpuIntegrator("dopri54")
+  TSIT54_step* = gpuIntegrator("tsit54")
+  VERN65_step* = gpuIntegrator("vern65")
+
+# ---- context knobs, sharding, device synchronisation ----------------------------------------------------------------
+proc setKnob*(ctx: B200rkCtx, key: string, value: int) = check(b200rk_set(ctx, key.cstring, value.int64), ctx)
+proc getKnob*(ctx: B200rkCtx, key: string): int =
+  var v: int64
+  check(b200rk_get(ctx, key.cstring, addr v), ctx)
+  v.int
+proc synchronize*(ctx: B200rkCtx) = check(b200rk_synchronize(ctx), ctx)
+proc rank*(ctx: B200rkCtx): int = b200rk_rank(ctx).int
+proc world*(ctx: B200rkCtx): int = b200rk_world(ctx).int
+proc shardRange*(nGlobal, rank, world: int): (int, int) =
+  var off, ln: csize_t
+  check b200rk_shard_range(nGlobal.csize_t, rank.cint, world.cint, addr off, addr ln)
+  (off.int, ln.int)
+proc localLen*(v: GpuVector): int = b200rk_vec_local_len(v.h).int
+proc localOffset*(v: GpuVector): int = b200rk_vec_local_offset(v.h).int
+proc fill*(v: GpuVector, value: float) = check(b200rk_vec_fill(v.h, value), v.ctx)
+proc uploadLocal*(v: GpuVector, host: openArray[float]) = check(b200rk_vec_upload_local(v.h, cast[ptr cdouble](unsafeAddr host[0])), v.ctx)
+proc downloadLocal*(v: GpuVector): seq[float] =
+  result = newSeq[float](v.localLen)
+  if result.len > 0: check(b200rk_vec_download_local(v.h, cast[ptr cdouble](addr result[0])), v.ctx)

@@ -472,11 +472,11 @@ def run_ours(args):
 
     e2e_full = e2e_variant(True)
     e2e_res = e2e_variant(False) if lam_pin is not None else None
-    # the tStart output slot (= y0): library default (auto: D2H on a second stream up to 3 ranks, host-side copy beyond) vs the other way
-    auto_host = world >= 4
-    ctx.set("tstart_copy", 0 if auto_host else 1)
+    # the tStart output slot (= y0): library default (D2H on a second stream while the solve runs) vs a host-side copy of y0
+    auto_host = False
+    ctx.set("tstart_copy", 1)
     e2e_alt = e2e_variant(True)
-    ctx.set("tstart_copy", -1)
+    ctx.set("tstart_copy", 0)
     # PCIe roofline of the end-to-end number: the same pinned buffers copied alone, both directions
     pcie = {}
     try:

@@ -325,11 +325,12 @@ int b200rk_solve_host(b200rk_ctx* c, int method, b200rk_rhs_fn f, void* user, si
   for (size_t i = 0; i < n_tspan; ++i) { has_zero |= (tspan[i] == t0); has_neg |= (tspan[i] < t0); }
   bool early = false;
   // knob "tstart_copy" = 1: the host already holds those bytes — fill output slot 0 with a host-side copy of y0_local (a few
-  // helper threads, concurrent with the solve) instead of a second device-to-host transfer. Measured trade-off (profiles/):
-  // alone on its PCIe link the D2H rides the idle copy engine for free; with 8 ranks sharing one host fabric, D2H is the
-  // scarce direction (12 GB/s per GPU) and halving its volume is worth more than the host-memory traffic of a memcpy.
+  // helper threads, concurrent with the solve) instead of a second device-to-host transfer. MEASURED (profiles/r02_scale_cfg2_n*.json,
+  // e2e.tstart_slot): the device-to-host copy wins at every rank count — 5174 vs 5082 steps/s on 1 GPU, 11.7k vs 10.7k on 4,
+  // 14.0k vs 12.8k on 8 (host memory is the shared resource there, and a memcpy moves the bytes through it twice) — so the
+  // D2H on the second stream stays the default and the host-side copy is opt-in.
   std::vector<std::thread> host_copy;
-  const bool host_side = c->tstart_copy == 1 || (c->tstart_copy < 0 && c->world >= 4);
+  const bool host_side = c->tstart_copy == 1;
   if (rc == B200RK_OK && has_zero && !has_neg && bytes && host_side) {
     const size_t nthreads = 4, n = y0->n_local, chunk = (n + nthreads - 1) / nthreads;
     for (size_t i = 0; i < nthreads; ++i) {

@@ -94,7 +94,7 @@ struct b200rk_ctx {
   bool finish_prefetch = false; // register-prefetching finish kernel: measured on the B200 in round 2 — no gain (88.5 vs 90.1-91.8 us), stays off
   int stream_simpson = -1;     // cumsimpson(f, X, dx): -1 = stream the grid only when the composed form would not fit, 0 never, 1 always
   bool fuse_simpson = true;    // cumsimpson as one kernel (default since round 2: 1.166 -> 0.674 ms at 2^23 x 33 points, profiles/r02_quadrature_*)
-  int tstart_copy = -1;        // solve_host's tStart output (= y0): 0 D2H on a second stream, 1 host-side copy by helper threads, -1 auto (host-side from 4 ranks up)
+  int tstart_copy = 0;         // solve_host's tStart output (= y0): 0 D2H on a second stream while the solve runs (measured best at 1..8 ranks), 1 host-side copy by helper threads
   int l2_hints = -1;           // producer stores evict_last / streams evict_first: -1 auto (vector <= 0.65 L2), 0 off, 1 on
   size_t l2_bytes = 126u << 20;
   bool strict_zeros = false;

@@ -327,7 +327,7 @@ static int launch_fused_rk4(b200rk_ctx* c, const PwSpec& pw, bool negate, double
 }
 
 // Whole attempt of an FSAL pair with the built-in Lorenz-96 right-hand side in one kernel (stencil_attempt.cuh:
-// overlapped tiles, stage inputs through shared memory). Experimental, knob "fuse_stencil_attempt".
+// overlapped tiles, stage inputs through shared memory). Knob "fuse_stencil_attempt" (default on).
 // Sharded: every shard must hold at least the largest overlap, so that a halo comes from the immediate ring neighbour
 // only (same answer on every rank: shard_range is a pure function of n, rank, world).
 constexpr int kAttemptHaloMax = StencilTile<9>::HL + StencilTile<9>::HR;   // Vern65: 16 + 8
@@ -502,7 +502,7 @@ int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, double t, co
   if (fused && !md.rk4_final) { fused_pat = fused_pattern_of(c, md); fused = fused_pat >= 0; }
   const bool stencil_fused = !fused && c->fuse_stencil && c->world == 1 && rhs.f == &builtin_rhs_fn &&
                              static_cast<const BuiltinRhs*>(rhs.user)->kind == B200RK_RHS_LORENZ96 && y->n_global >= 4;
-  // experimental: the whole attempt of the stencil right-hand side in one kernel (overlapped tiles read y and FSAL far
+  // the whole attempt of the stencil right-hand side in one kernel (overlapped tiles read y and FSAL far
   // beyond a CTA's own outputs, so the outputs must not alias the inputs)
   const bool l96_builtin = !fused && rhs.f == &builtin_rhs_fn && static_cast<const BuiltinRhs*>(rhs.user)->kind == B200RK_RHS_LORENZ96 &&
                            y->n_global >= 4;

@@ -1,5 +1,5 @@
-// finish_pf.cuh — software-pipelined form of finish_kernel (kernels.cuh). EXPERIMENTAL: knob "finish_prefetch", off by
-// default until it has been measured on the GPU. finish_kernel is the one kernel of the general pipeline that sits
+// finish_pf.cuh — software-pipelined form of finish_kernel (kernels.cuh). Knob "finish_prefetch", OFF: measured on the B200 in
+// round 2 — 90.1-91.8 us against finish_kernel's 88.5 us inside a step (profiles/README.md) — and kept as the documented alternative. finish_kernel is the one kernel of the general pipeline that sits
 // below the HBM limit inside a step (profiles/r01_kernel_model.md: 28 us of fp64 pipe vs 73 us of HBM, 88 us measured):
 // its persistent loop loads a tile, then runs ~60 dependent fp64 issues per element (one IEEE division each) with no
 // load in flight. Here the next tile's NK+1 loads are issued before the current tile's arithmetic, as in

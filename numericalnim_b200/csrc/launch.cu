@@ -57,7 +57,7 @@ static int launch_finish_cfg(b200rk_ctx* c, const FinishPlan& p) {
   unsigned grid = grid_for(c, p.n / W, kThreads * U, c->finish_ctas_per_sm);
   TRY(ensure_partials(c, grid));
   a.rs = reduce_scratch(c);
-  if constexpr (NK >= 6 && U == 1) {  // experimental software-pipelined form (finish_pf.cuh), knob "finish_prefetch", default off
+  if constexpr (NK >= 6 && U == 1) {  // software-pipelined form (finish_pf.cuh), knob "finish_prefetch": measured, no gain, off
     if (c->finish_prefetch) {
       finish_pf_kernel<NK, W, DIRECT, MODE, kThreads><<<grid, kThreads, 0, c->stream>>>(a);
       CUDA_TRY(c, cudaGetLastError());

@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(THREADS) neq_count_kernel(const double* __rest
 }  // namespace b200rk
 
 // ---------------------------------------------------------------------------------------------------
-// cumsimpson(Y, X) in ONE pass (experimental, knob "fuse_simpson", off by default until measured on the GPU):
+// cumsimpson(Y, X) in ONE pass (knob "fuse_simpson", default since round 2: 1.166 -> 0.674 ms at 2^23 x 33 points):
 // the Simpson scan and the Hermite interpolation back onto X fused. While a thread walks the knot intervals it holds
 // exactly what every sample inside the current interval needs — the integrals at both knots (I_j, I_{j+1}) and the
 // data at both knots (the spline's slopes) — so the samples are emitted from registers and the knot integrals never

@@ -270,7 +270,7 @@ int cumsimpson_impl(b200rk_ctx* c, const b200rk_vec* const* Y, const double* X, 
   std::vector<HermiteOut> plan;
   TRY(hermite_plan(c, X, m, xs.data(), xs.size(), &plan));
   if (c->fuse_simpson && n) {
-    // experimental single-pass form (knob "fuse_simpson", off by default): scan + interpolation in one kernel, the knot
+    // single-pass form (knob "fuse_simpson", default): scan + interpolation in one kernel, the knot
     // integrals stay in registers — see simpson_fused_kernel
     std::vector<int> tail(steps.size(), 0), emit_begin, slot;
     if (evenN) tail.back() = 1;

@@ -1,6 +1,6 @@
 // stencil_attempt.cuh — a whole adaptive attempt of an FSAL pair for the built-in Lorenz-96 right-hand side in ONE
-// kernel (cyclic; one GPU, or one contiguous shard per GPU with a halo from the ring neighbours). EXPERIMENTAL: knob "fuse_stencil_attempt", off by default until it has been run and
-// measured on the GPU (bit-identical to the stage_l96_kernel / finish_kernel pipeline under host emulation).
+// kernel (cyclic; one GPU, or one contiguous shard per GPU with a halo from the ring neighbours). Knob "fuse_stencil_attempt", the default since its first
+// B200 runs in round 2 (bit-identical to the stage_l96_kernel / finish_kernel pipeline on the GPU and under host emulation).
 //
 // The element-local fused attempt (kernels.cuh: fused_attempt_kernel) keeps k_1..k_S of an element in registers because
 // nothing crosses elements. Lorenz-96 reads y[i-2], y[i-1], y[i+1] (ode.nim's ODEProc is the caller's; this one is

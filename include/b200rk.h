@@ -189,6 +189,19 @@ B200RK_API int b200rk_jit_rhs_free(void* user);
  * 0..4 = fused attempt + device-loop kernels (dopri54, dopri54 strict, tsit54, vern65, vern65 strict). */
 B200RK_API int b200rk_jit_compile_only(const char* expr, int n_vec, int n_scalar, int pattern, void* cubin_out,
                                        size_t cubin_cap, size_t* cubin_bytes, char* log, size_t log_cap);
+/* STENCIL right-hand sides from source: an ODEProc closure (ode.nim:36) whose dydt[i] reads a neighbourhood of y,
+ *     dydt[i] = expr(t, Y(-radius_left) .. Y(+radius_right), p0[i] .., c0 ..),     Y(d) = y[(i + d) mod N]   (cyclic),
+ * e.g. Lorenz-96 "((Y(1) - Y(-2)) * Y(-1) - Y(0)) + c0" with radii 2 / 1, diffusion "c0*((Y(-1) - 2.0*Y(0)) + Y(1))" with 1 / 1.
+ * Radii 0..8; a Y(d) outside them is a compile error. NVRTC compiles the expression into (i) a plain dydt = f(t, y) kernel
+ * every method calls through the stage / RHS / finish pipeline and (ii) — for DOPRI54 / Tsit54 / Vern65 — the ONE-KERNEL attempt
+ * over overlapped tiles (the built-in Lorenz-96's kernel with the overlap the radii ask for: 4 + n_vec vector passes per attempt
+ * instead of ~55). Sharded, the halo travels once per step (or is read in place from the peer-mapped ring neighbours inside a
+ * solver). Everything else as for b200rk_jit_rhs_new; freed with b200rk_jit_rhs_free. */
+B200RK_API int b200rk_jit_stencil_rhs_new(b200rk_ctx* ctx, const char* expr, int radius_left, int radius_right, int n_vec,
+                                          const b200rk_vec* const* vecs, int n_scalar, const double* scalars, b200rk_rhs_fn* fn, void** user);
+/* Host only: compile a stencil unit (pattern -1 = the dydt kernel, 0..4 = the whole-attempt kernel of that pair). */
+B200RK_API int b200rk_jit_stencil_compile_only(const char* expr, int radius_left, int radius_right, int n_vec, int n_scalar, int pattern,
+                                               size_t* cubin_bytes, char* log, size_t log_cap);
 
 /* ---- consumers of a trajectory: Hermite interpolation and cumulative quadrature -------- */
 /* A trajectory is a list of device vectors (what b200rk_solve returns) with its times. All results are newly

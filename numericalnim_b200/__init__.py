@@ -7,12 +7,12 @@ This package is the host-side mirror of the reference interface over that C-ABI;
 from ._capi import B200rkError, B200rkValueError, LIB_PATH, SYMBOLS  # noqa: F401
 from .ode import (  # noqa: F401
     Context, GpuVector, JitRhs, NumContext, ODEoptions, Solver, adaptiveODE, allODE, combineErr, default_context, fixedODE,
-    cumsimpson, cumtrapz, hermiteInterpolate, hermiteSpline, integratorStep, linspace, newNumContext, newODEoptions, newVector, rhsDiagLinear, rhsJit, rhsLorenz96,
+    cumsimpson, cumtrapz, hermiteInterpolate, hermiteSpline, integratorStep, linspace, newNumContext, newODEoptions, newVector, rhsDiagLinear, rhsJit, rhsJitStencil, JitStencilRhs, jitStencilCompileOnly, rhsLorenz96,
     rhsScale, jitCompileOnly, rk4Combine, set_default_context, solveODE, stageAccum,
 )
 
 __all__ = [
     "solveODE", "newODEoptions", "ODEoptions", "GpuVector", "newVector", "NumContext", "newNumContext", "fixedODE",
     "adaptiveODE", "allODE", "linspace", "hermiteSpline", "integratorStep", "Solver", "Context", "default_context",
-    "set_default_context", "rhsScale", "rhsDiagLinear", "rhsLorenz96", "rhsJit", "JitRhs", "jitCompileOnly", "hermiteInterpolate", "cumtrapz", "cumsimpson", "stageAccum", "combineErr", "rk4Combine",
+    "set_default_context", "rhsScale", "rhsDiagLinear", "rhsLorenz96", "rhsJit", "JitRhs", "jitCompileOnly", "rhsJitStencil", "JitStencilRhs", "jitStencilCompileOnly", "hermiteInterpolate", "cumtrapz", "cumsimpson", "stageAccum", "combineErr", "rk4Combine",
 ]

@@ -90,6 +90,8 @@ _DECLS = {
     "b200rk_builtin_rhs_new": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.POINTER(RHS_FN), C.POINTER(C.c_void_p)]),
     "b200rk_builtin_rhs_free": (C.c_int, [C.c_void_p]),
     "b200rk_jit_rhs_new": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.POINTER(RHS_FN), C.POINTER(C.c_void_p)]),
+    "b200rk_jit_stencil_rhs_new": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.POINTER(RHS_FN), C.POINTER(C.c_void_p)]),
+    "b200rk_jit_stencil_compile_only": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]),
     "b200rk_jit_rhs_set_scalars": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "b200rk_jit_rhs_free": (C.c_int, [C.c_void_p]),
     "b200rk_jit_compile_only": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]),

@@ -176,6 +176,7 @@ struct PwSpec {
 };
 static bool pointwise_spec(const RhsCall& rhs, PwSpec* pw) {
   if (rhs.f == &jit_rhs_fn) {
+    if (jit_is_stencil(static_cast<JitRhs*>(rhs.user), nullptr, nullptr)) return false;   // reads its neighbours: not element-local
     pw->kind = PW_USER;
     pw->jit = static_cast<JitRhs*>(rhs.user);
     const b200rk_vec* const* vecs = nullptr;
@@ -330,14 +331,21 @@ static int launch_fused_rk4(b200rk_ctx* c, const PwSpec& pw, bool negate, double
 // overlapped tiles, stage inputs through shared memory). Knob "fuse_stencil_attempt" (default on).
 // Sharded: every shard must hold at least the largest overlap, so that a halo comes from the immediate ring neighbour
 // only (same answer on every rank: shard_range is a pure function of n, rank, world).
-constexpr int kAttemptHaloMax = StencilTile<9>::HL + StencilTile<9>::HR;   // Vern65: 16 + 8
-static bool l96_attempt_shards_ok(const b200rk_ctx* c, size_t n_global) {
+constexpr int kAttemptHaloMax = 2 * stencil_halo(kMaxStencilRadius, 9);   // built-in Lorenz-96 / Vern65: 16 + 8; stencils from source: up to 64 + 64
+static bool stencil_shards_ok(const b200rk_ctx* c, size_t n_global, int need) {
   for (int r = 0; r < c->world; ++r) {
     size_t off = 0, len = 0;
     shard_range(n_global, r, c->world, &off, &len);
-    if (len < (size_t)StencilTile<9>::HL) return false;
+    if (len < (size_t)need) return false;
   }
   return true;
+}
+static bool l96_attempt_shards_ok(const b200rk_ctx* c, size_t n_global) { return stencil_shards_ok(c, n_global, StencilTile<9>::HL); }
+// a stencil right-hand side given as source (jit.cu) and its radii
+static JitRhs* jit_stencil_of(const RhsCall& rhs, int* rl, int* rr) {
+  if (rhs.f != &jit_rhs_fn) return nullptr;
+  JitRhs* j = static_cast<JitRhs*>(rhs.user);
+  return jit_is_stencil(j, rl, rr) ? j : nullptr;
 }
 // The HL elements before this shard and the HR after it, of y and of k1 (FSAL): one grouped exchange with the ring
 // neighbours on the context stream per IntegratorProc call — y and k1 do not change between the retries of an attempt.
@@ -348,17 +356,17 @@ static int exchange_attempt_halo(b200rk_ctx* c, const b200rk_vec* y, const b200r
   const size_t n = y->n_local;
   const int left = (c->rank + c->world - 1) % c->world, right = (c->rank + 1) % c->world;
   NCCL_TRY(c, g_nccl.GroupStart());   // same order on every rank: with world == 2 both neighbours are the same peer and the pairs match in order
-  NCCL_TRY(c, g_nccl.Send(y->d, HR, ncclDouble, left, c->comm, c->stream));
-  NCCL_TRY(c, g_nccl.Send(y->d + n - HL, HL, ncclDouble, right, c->comm, c->stream));
+  if (HR) NCCL_TRY(c, g_nccl.Send(y->d, HR, ncclDouble, left, c->comm, c->stream));     // (a one-sided stencil from source has HL or HR = 0)
+  if (HL) NCCL_TRY(c, g_nccl.Send(y->d + n - HL, HL, ncclDouble, right, c->comm, c->stream));
   if (fsal) {
-    NCCL_TRY(c, g_nccl.Send(fsal->d, HR, ncclDouble, left, c->comm, c->stream));
-    NCCL_TRY(c, g_nccl.Send(fsal->d + n - HL, HL, ncclDouble, right, c->comm, c->stream));
+    if (HR) NCCL_TRY(c, g_nccl.Send(fsal->d, HR, ncclDouble, left, c->comm, c->stream));
+    if (HL) NCCL_TRY(c, g_nccl.Send(fsal->d + n - HL, HL, ncclDouble, right, c->comm, c->stream));
   }
-  NCCL_TRY(c, g_nccl.Recv(hy + HL, HR, ncclDouble, right, c->comm, c->stream));
-  NCCL_TRY(c, g_nccl.Recv(hy, HL, ncclDouble, left, c->comm, c->stream));
+  if (HR) NCCL_TRY(c, g_nccl.Recv(hy + HL, HR, ncclDouble, right, c->comm, c->stream));
+  if (HL) NCCL_TRY(c, g_nccl.Recv(hy, HL, ncclDouble, left, c->comm, c->stream));
   if (fsal) {
-    NCCL_TRY(c, g_nccl.Recv(hk + HL, HR, ncclDouble, right, c->comm, c->stream));
-    NCCL_TRY(c, g_nccl.Recv(hk, HL, ncclDouble, left, c->comm, c->stream));
+    if (HR) NCCL_TRY(c, g_nccl.Recv(hk + HL, HR, ncclDouble, right, c->comm, c->stream));
+    if (HL) NCCL_TRY(c, g_nccl.Recv(hk, HL, ncclDouble, left, c->comm, c->stream));
   }
   NCCL_TRY(c, g_nccl.GroupEnd());
   c->collectives++;
@@ -387,9 +395,12 @@ static int l96_halo_for(b200rk_ctx* c, const MethodDef& md, const b200rk_vec* y,
 }
 
 bool l96_peer_halo_possible(const b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, size_t n_global) {
-  return c->world > 1 && c->p2p && c->fuse_stencil_attempt && c->l96_peer_halo && rhs.f == &builtin_rhs_fn &&
-         static_cast<const BuiltinRhs*>(rhs.user)->kind == B200RK_RHS_LORENZ96 && md.adaptive && md.use_fsal && method_fusable(md) &&
-         !md.rk4_final && fused_pattern_of(c, md) >= 0 && l96_attempt_shards_ok(c, n_global);
+  if (!(c->world > 1 && c->p2p && c->fuse_stencil_attempt && c->l96_peer_halo && md.adaptive && md.use_fsal && method_fusable(md) &&
+        !md.rk4_final && fused_pattern_of(c, md) >= 0))
+    return false;
+  int rl = 0, rr = 0;
+  if (jit_stencil_of(rhs, &rl, &rr)) return stencil_shards_ok(c, n_global, std::max(stencil_halo(rl, md.stages), stencil_halo(rr, md.stages)));
+  return rhs.f == &builtin_rhs_fn && static_cast<const BuiltinRhs*>(rhs.user)->kind == B200RK_RHS_LORENZ96 && l96_attempt_shards_ok(c, n_global);
 }
 
 template <int PAT, int J>
@@ -424,6 +435,41 @@ static int launch_l96_attempt_j(b200rk_ctx* c, const MethodDef& md, double F, bo
   else l96_attempt_kernel<PAT, J, kThreads, false><<<grid, kThreads, 0, c->stream>>>(a);
   CUDA_TRY(c, cudaGetLastError());
   return B200RK_OK;
+}
+
+// Whole attempt of an FSAL pair for a stencil right-hand side given as SOURCE: the NVRTC-compiled ustencil_attempt_kernel
+// (stencil_attempt.cuh) of this pattern — same tiling, same TMA prefetch, overlap from the stencil's radii.
+template <int PAT>
+static int launch_ustencil_attempt(b200rk_ctx* c, const MethodDef& md, JitRhs* jit, int rl, int rr, bool negate, double t, double dt,
+                                   const b200rk_options& o, const L96Halo& halo, const b200rk_vec* y, const b200rk_vec* fsal, b200rk_vec* y_new,
+                                   b200rk_vec* fsal_new) {
+  constexpr int S = Pattern<PAT>::S;
+  const int HL = stencil_halo(rl, S), HR = stencil_halo(rr, S), OUT = 4 * kThreads - HL - HR;
+  UStencilAttemptArgs<S> a;
+  std::memset(&a, 0, sizeof(a));
+  PwSpec pw;
+  pw.kind = PW_USER; pw.jit = jit;
+  const b200rk_vec* const* vecs = nullptr;
+  jit_describe(jit, &pw.np, &vecs, &pw.cs);
+  for (int j = 0; j < pw.np; ++j) pw.pv[j] = vecs[j];
+  TRY(check_pw_sizes(c, pw, y));
+  a.f.y = y->d; a.f.k1 = fsal->d;
+  fill_pw_args(a.f, pw, md, negate, t);
+  for (int s = 2; s <= S; ++s) row_mask(c, md.a[s], a.f.a[s - 2], S - 1);
+  row_mask(c, md.b, a.f.b, S);
+  row_mask(c, md.bhat, a.f.bh, S);
+  a.f.dt = dt; a.f.cb = dt; a.f.cbh = dt; a.f.absTol = o.absTol; a.f.relTol = o.relTol;
+  a.f.ynew = y_new->d; a.f.ks_out = fsal_new->d; a.f.n = y->n_local;
+  a.halo = halo;
+  int per_sm = 0;
+  TRY(jit_max_blocks_per_sm(c, jit, PAT, 0, &per_sm));
+  if (per_sm < 1) return fail(c, B200RK_ECUDA, "stencil attempt kernel does not fit on an SM");
+  const size_t n_tiles = (a.f.n + OUT - 1) / OUT;
+  const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>(n_tiles, (size_t)per_sm * c->sm_count));
+  TRY(ensure_partials(c, grid));
+  a.f.rs = reduce_scratch(c);
+  ProfScope ps(c, B200RK_K_FUSED, 8.0 * double(a.f.n) * (4 + pw.np));  // y, k1 (+ parameters) read; yNew, k_S written
+  return jit_launch(c, jit, PAT, 0, grid, &a, false);
 }
 
 // Warp-sized tiles (stencil_attempt.cuh: l96_warp_attempt_kernel): same argument block, persistent grid of warps.
@@ -511,8 +557,16 @@ int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, double t, co
   if (l96_attempt && !md.rk4_final)
     l96_attempt = fsal && fsal_new && y_new->d != fsal->d && fsal_new->d != y->d && fsal_new->d != fsal->d;
   if (l96_attempt && !md.rk4_final) { fused_pat = fused_pattern_of(c, md); l96_attempt = fused_pat >= 0; }
+  // a stencil right-hand side given as source: the same one-kernel attempt, compiled at run time around the expression
+  int ust_rl = 0, ust_rr = 0;
+  JitRhs* ust_jit = fused ? nullptr : jit_stencil_of(rhs, &ust_rl, &ust_rr);
+  const int ust_HL = stencil_halo(ust_rl, S), ust_HR = stencil_halo(ust_rr, S);
+  bool ust_attempt = ust_jit && c->fuse_stencil_attempt && !md.rk4_final && method_fusable(md) && fsal && fsal_new && y_new->d != y->d &&
+                     y_new->d != fsal->d && fsal_new->d != y->d && fsal_new->d != fsal->d && y->n_global >= (size_t)(ust_rl + ust_rr + 1) &&
+                     (c->world == 1 || stencil_shards_ok(c, y->n_global, std::max(ust_HL, ust_HR)));
+  if (ust_attempt) { fused_pat = fused_pattern_of(c, md); ust_attempt = fused_pat >= 0; }
   if (fused) TRY(check_pw_sizes(c, pw, y));
-  fused = fused || l96_attempt;
+  fused = fused || l96_attempt || ust_attempt;
   if (md.k1_from_fsal) {
     if (!fsal) return fail(c, B200RK_EINVAL, std::string(md.name) + ": FSAL vector required");
     TRY(check_same(c, y, fsal));
@@ -534,6 +588,7 @@ int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, double t, co
     if (md.rk4_final) TRY(l96_halo_for(c, md, y, nullptr, 8, 4, &l96_halo));
     else TRY(l96_halo_for(c, md, y, fsal, S == 9 ? StencilTile<9>::HL : StencilTile<7>::HL, S == 9 ? StencilTile<9>::HR : StencilTile<7>::HR, &l96_halo));
   }
+  if (ust_attempt) TRY(l96_halo_for(c, md, y, fsal, ust_HL, ust_HR, &l96_halo));
   double dt = dt_in, error = 0.0;
   int limitCounter = 0;
   while (true) {
@@ -555,6 +610,14 @@ int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, double t, co
           case PAT_TSIT54: TRY(launch_l96_attempt<PAT_TSIT54>(c, md, F, rhs.negate_time, dt, o, l96_halo, y, fsal, y_new, fsal_new)); break;
           case PAT_VERN65: TRY(launch_l96_attempt<PAT_VERN65>(c, md, F, rhs.negate_time, dt, o, l96_halo, y, fsal, y_new, fsal_new)); break;
           default: TRY(launch_l96_attempt<PAT_VERN65_STRICT>(c, md, F, rhs.negate_time, dt, o, l96_halo, y, fsal, y_new, fsal_new)); break;
+        }
+      } else if (ust_attempt) {
+        switch (fused_pat) {
+          case PAT_DOPRI54: TRY(launch_ustencil_attempt<PAT_DOPRI54>(c, md, ust_jit, ust_rl, ust_rr, rhs.negate_time, t, dt, o, l96_halo, y, fsal, y_new, fsal_new)); break;
+          case PAT_DOPRI54_STRICT: TRY(launch_ustencil_attempt<PAT_DOPRI54_STRICT>(c, md, ust_jit, ust_rl, ust_rr, rhs.negate_time, t, dt, o, l96_halo, y, fsal, y_new, fsal_new)); break;
+          case PAT_TSIT54: TRY(launch_ustencil_attempt<PAT_TSIT54>(c, md, ust_jit, ust_rl, ust_rr, rhs.negate_time, t, dt, o, l96_halo, y, fsal, y_new, fsal_new)); break;
+          case PAT_VERN65: TRY(launch_ustencil_attempt<PAT_VERN65>(c, md, ust_jit, ust_rl, ust_rr, rhs.negate_time, t, dt, o, l96_halo, y, fsal, y_new, fsal_new)); break;
+          default: TRY(launch_ustencil_attempt<PAT_VERN65_STRICT>(c, md, ust_jit, ust_rl, ust_rr, rhs.negate_time, t, dt, o, l96_halo, y, fsal, y_new, fsal_new)); break;
         }
       } else
       switch (fused_pat) {

@@ -55,6 +55,7 @@ struct b200rk_ctx {
   double* d_halo = nullptr;        // 3 doubles: stencil halo of the sharded Lorenz-96 right-hand side
   const PeerVecView* peer_view = nullptr;   // set by the solver that is advancing (driver.cu); null otherwise
   int* d_barrier = nullptr;                 // 1 int: payload of stream_barrier
+  double* d_halo_stencil = nullptr;  // 2 x 8 doubles: halo of a sharded stencil right-hand side given as source (jit.cu)
   double* d_halo_attempt = nullptr;  // 2 x 24 doubles: halo of y and k1 for the one-kernel Lorenz-96 attempt (stencil_attempt.cuh), sharded
   unsigned long long* h_seq = nullptr;      // pinned + mapped: sequence word of the last finished reduction
   unsigned long long* h_seq_dev = nullptr;  // device alias
@@ -333,6 +334,7 @@ void jit_describe(const JitRhs* j, int* np, const b200rk_vec* const** vecs, cons
 int jit_slot_attempt(int w);
 int jit_slot_run(int w);
 int jit_launch(b200rk_ctx* c, JitRhs* j, int pattern, int slot, unsigned grid, void* arg_block, bool cooperative);
+bool jit_is_stencil(const JitRhs* j, int* radius_left, int* radius_right);   // stencil right-hand side from source (not element-local)
 int jit_prepare(b200rk_ctx* c, JitRhs* j, int pattern);      // compile + load the base unit and (pattern >= 0) the fused unit now
 int fused_pattern_for(const b200rk_ctx* c, const MethodDef& md);   // sparsity pattern of the method's fused kernels, -1: none
 int jit_max_blocks_per_sm(b200rk_ctx* c, JitRhs* j, int pattern, int slot, int* per_sm);

@@ -13,6 +13,7 @@
 // NVRTC is bound with dlopen on first use and the driver's module API is reached through
 // cudaGetDriverEntryPoint, so libb200rk.so links neither library and still loads on a machine without them.
 #include "internal.hpp"
+#include "stencil_attempt.cuh"
 
 #include <cuda.h>
 #include <nvrtc.h>  // types only
@@ -24,6 +25,7 @@
 #include <mutex>
 
 extern "C" const char b200rk_kernels_src[];  // kernels.cuh, embedded at build time (Makefile: kernels_src.cpp)
+extern "C" const char b200rk_stencil_src[];  // stencil_attempt.cuh, likewise (stencil right-hand sides from source)
 
 namespace {
 
@@ -129,8 +131,20 @@ enum { JB_RHS_W2 = 0, JB_RHS_W4_L2 = 1, JB_RK4_W4 = 2, JB_COUNT = 3 };          
 enum { JF_ATTEMPT_W4 = 0, JF_ATTEMPT_W2 = 1, JF_RUN_W4 = 2, JF_RUN_W2 = 3, JF_COUNT = 4 };  // one unit per FusedPattern
 constexpr int kPatterns = 5;  // kernels.cuh: FusedPattern
 
-std::vector<std::string> name_expressions(int pattern) {
+// Stencil right-hand sides from source (stencil_attempt.cuh, B200RK_JIT_STENCIL): radii of the neighbourhood, 0 / 0 = element-local
+struct StencilSpec {
+  bool on = false;
+  int rl = 0, rr = 0;
+};
+enum { JS_RHS = 0 };       // stencil base unit
+enum { JS_ATTEMPT = 0 };   // stencil unit of one FusedPattern
+
+std::vector<std::string> name_expressions(int pattern, const StencilSpec& st = StencilSpec()) {
   const std::string T = std::to_string(kThreads);
+  if (st.on) {
+    if (pattern < 0) return {"b200rk::user_stencil_rhs_kernel<" + T + ">"};
+    return {"b200rk::ustencil_attempt_kernel<" + std::to_string(pattern) + ", 2, " + T + ">"};
+  }
   if (pattern < 0)
     return {"b200rk::user_rhs_kernel<2, 2, " + T + ", 0>", "b200rk::user_rhs_kernel<4, 2, " + T + ", 1>", "b200rk::user_rk4_kernel<4, " + T + ">"};
   const std::string P = std::to_string(pattern), K = std::to_string((int)PW_USER);
@@ -144,6 +158,19 @@ struct Compiled {
   std::string log;
 };
 std::map<std::string, Compiled> g_cubin_cache;  // identical (expr, np, nc, pattern) compile once per process
+
+std::string make_stencil_source(const std::string& expr, int np, int nc, const StencilSpec& st) {
+  std::string s = "#define B200RK_JIT_STENCIL 1\n#define B200RK_USER_NP " + std::to_string(np) + "\n#define B200RK_STENCIL_RL " + std::to_string(st.rl) +
+                  "\n#define B200RK_STENCIL_RR " + std::to_string(st.rr) + "\nnamespace b200rk {\n";
+  s += "__device__ __forceinline__ double user_stencil(double t, const double* b200rk_y_, const double* b200rk_p_, const double* b200rk_c_) {\n";
+  s += "  (void)t; (void)b200rk_y_; (void)b200rk_p_; (void)b200rk_c_;\n";
+  for (int j = 0; j < np; ++j) s += "  const double p" + std::to_string(j) + " = b200rk_p_[" + std::to_string(j) + "]; (void)p" + std::to_string(j) + ";\n";
+  for (int j = 0; j < nc; ++j) s += "  const double c" + std::to_string(j) + " = b200rk_c_[" + std::to_string(j) + "]; (void)c" + std::to_string(j) + ";\n";
+  // Y(d): the state at cyclic offset d; a d outside the declared radii is a compile error (negative array size)
+  s += "#define Y(d) (b200rk_y_[(d) + 0 * (int)sizeof(char[((d) >= -" + std::to_string(st.rl) + " && (d) <= " + std::to_string(st.rr) + ") ? 1 : -1])])\n";
+  s += "  return (double)(\n" + expr + "\n  );\n#undef Y\n}\n}  // namespace b200rk\n#include \"stencil_attempt.cuh\"\n";
+  return s;
+}
 
 std::string make_source(const std::string& expr, int np, int nc) {
   std::string s = "#define B200RK_JIT 1\n#define B200RK_USER_NP " + std::to_string(np) + "\nnamespace b200rk {\n";
@@ -228,9 +255,11 @@ void cache_store(const std::string& full_key, const Compiled& c) {
 }
 
 // NVRTC -> cubin for sm_100a. Compile errors are the caller's expression being wrong: B200RK_EINVAL + the log.
-int compile_unit(const b200rk_ctx* ctx, const std::string& expr, int np, int nc, int pattern, const Compiled** out) {
+int compile_unit(const b200rk_ctx* ctx, const std::string& expr, int np, int nc, int pattern, const Compiled** out,
+                 const StencilSpec& st = StencilSpec()) {
   std::lock_guard<std::mutex> lock(g_jit_mutex);
-  const std::string key = std::to_string(np) + "|" + std::to_string(nc) + "|" + std::to_string(pattern) + "|" + expr;
+  const std::string key = std::to_string(np) + "|" + std::to_string(nc) + "|" + std::to_string(pattern) + "|" +
+                          (st.on ? "stencil" + std::to_string(st.rl) + "," + std::to_string(st.rr) + "|" : "") + expr;
   auto hit = g_cubin_cache.find(key);
   if (hit != g_cubin_cache.end()) { *out = &hit->second; return B200RK_OK; }
   TRY(nvrtc_bind(ctx));
@@ -238,19 +267,20 @@ int compile_unit(const b200rk_ctx* ctx, const std::string& expr, int np, int nc,
   if (g_nvrtc.Version) g_nvrtc.Version(&vmaj, &vmin);
   char stamp[64];
   std::snprintf(stamp, sizeof(stamp), "v1|nvrtc%d.%d|%016llx|", vmaj, vmin,
-                (unsigned long long)fnv1a(b200rk_kernels_src, std::strlen(b200rk_kernels_src)));
+                (unsigned long long)fnv1a(b200rk_stencil_src, st.on ? std::strlen(b200rk_stencil_src) : 0,
+                                          fnv1a(b200rk_kernels_src, std::strlen(b200rk_kernels_src))));
   const std::string full_key = stamp + key;
   {
     Compiled cached;
     if (cache_load(full_key, &cached)) { *out = &(g_cubin_cache[key] = std::move(cached)); return B200RK_OK; }
   }
-  const std::string src = make_source(expr, np, nc);
-  const char* hdr_src[] = {b200rk_kernels_src};
-  const char* hdr_name[] = {"kernels.cuh"};
+  const std::string src = st.on ? make_stencil_source(expr, np, nc, st) : make_source(expr, np, nc);
+  const char* hdr_src[] = {b200rk_kernels_src, b200rk_stencil_src};
+  const char* hdr_name[] = {"kernels.cuh", "stencil_attempt.cuh"};
   nvrtcProgram prog = nullptr;
-  nvrtcResult r = g_nvrtc.CreateProgram(&prog, src.c_str(), "b200rk_user_rhs.cu", 1, hdr_src, hdr_name);
+  nvrtcResult r = g_nvrtc.CreateProgram(&prog, src.c_str(), "b200rk_user_rhs.cu", st.on ? 2 : 1, hdr_src, hdr_name);
   if (r != NVRTC_SUCCESS) return fail(ctx, B200RK_ECUDA, std::string("nvrtcCreateProgram: ") + g_nvrtc.GetErrorString(r));
-  const std::vector<std::string> names = name_expressions(pattern);
+  const std::vector<std::string> names = name_expressions(pattern, st);
   for (auto& n : names) {
     r = g_nvrtc.AddNameExpression(prog, n.c_str());
     if (r != NVRTC_SUCCESS) { g_nvrtc.DestroyProgram(&prog); return fail(ctx, B200RK_ECUDA, "nvrtcAddNameExpression(" + n + "): " + g_nvrtc.GetErrorString(r)); }
@@ -346,6 +376,7 @@ struct JitRhs {
   b200rk_ctx* ctx = nullptr;
   std::string expr;
   int np = 0, nc = 0;
+  StencilSpec stencil;   // on: dydt[i] depends on y[i - rl .. i + rr] (cyclic); off: element-local
   const b200rk_vec* vecs[kMaxUserVecs] = {nullptr};
   double cs[kMaxUserScalars] = {0};
   JitModule base, pat[kPatterns];
@@ -356,7 +387,7 @@ static int ensure_module(b200rk_ctx* c, JitRhs* j, int pattern, JitModule** out)
   JitModule* m = pattern < 0 ? &j->base : &j->pat[pattern];
   if (!m->mod) {
     const Compiled* cc = nullptr;
-    TRY(compile_unit(c, j->expr, j->np, j->nc, pattern, &cc));
+    TRY(compile_unit(c, j->expr, j->np, j->nc, pattern, &cc, j->stencil));
     CUDA_TRY(c, cudaSetDevice(c->device));
     CUDA_TRY(c, cudaFree(nullptr));  // the runtime's primary context is current on this thread from here on
     TRY(drv_bind(c));
@@ -415,6 +446,48 @@ static int fill_user_args(b200rk_ctx* c, const JitRhs* j, const b200rk_vec* y, U
   return B200RK_OK;
 }
 
+// Stencil right-hand side from source, plain evaluation: one launch; sharded, the rl elements before and the rr after the
+// shard travel first (one grouped ncclSend/ncclRecv with the ring neighbours on the context stream, like the built-in Lorenz-96).
+static int jit_stencil_eval(b200rk_ctx* c, JitRhs* j, double t, const b200rk_vec* y, b200rk_vec* dydt) {
+  const size_t n = y->n_local;
+  if (dydt->d == y->d) return fail(c, B200RK_EINVAL, "stencil rhs: the output must not alias the input");
+  if (y->n_global < (size_t)(j->stencil.rl + j->stencil.rr + 1)) return fail(c, B200RK_EINVAL, "stencil rhs: the vector is shorter than the stencil");
+  UStencilRhsArgs a;
+  std::memset(&a, 0, sizeof(a));
+  for (int i = 0; i < j->np; ++i) { TRY(check_same(c, y, j->vecs[i])); a.p[i] = j->vecs[i]->d; }
+  for (int i = 0; i < j->nc; ++i) a.cs[i] = j->cs[i];
+  a.y = y->d; a.t = t; a.out = dydt->d; a.n = n;
+  if (c->world > 1) {
+    const int rl = j->stencil.rl, rr = j->stencil.rr;
+    for (int r = 0; r < c->world; ++r) {   // the same verdict on every rank
+      size_t o_ = 0, l_ = 0;
+      shard_range(y->n_global, r, c->world, &o_, &l_);
+      if (l_ < (size_t)std::max(rl, rr)) return fail(c, B200RK_EINVAL, "stencil rhs: every shard must hold at least max(radius_left, radius_right) elements");
+    }
+    if (!c->d_halo_stencil) CUDA_TRY(c, cudaMalloc(&c->d_halo_stencil, 2 * kMaxStencilRadius * sizeof(double)));
+    double *hl = c->d_halo_stencil, *hr = c->d_halo_stencil + kMaxStencilRadius;
+    const int left = (c->rank + c->world - 1) % c->world, right = (c->rank + 1) % c->world;
+    NCCL_TRY(c, g_nccl.GroupStart());
+    if (rr) NCCL_TRY(c, g_nccl.Send(y->d, rr, ncclDouble, left, c->comm, c->stream));            // my head is the left neighbour's right halo
+    if (rl) NCCL_TRY(c, g_nccl.Send(y->d + n - rl, rl, ncclDouble, right, c->comm, c->stream));   // my tail is the right neighbour's left halo
+    if (rr) NCCL_TRY(c, g_nccl.Recv(hr, rr, ncclDouble, right, c->comm, c->stream));
+    if (rl) NCCL_TRY(c, g_nccl.Recv(hl, rl, ncclDouble, left, c->comm, c->stream));
+    NCCL_TRY(c, g_nccl.GroupEnd());
+    c->collectives++;
+    a.left = hl; a.right = hr;
+  }
+  if (!n) return B200RK_OK;
+  ProfScope ps(c, B200RK_K_RHS, 8.0 * double(n) * (2 + j->np));
+  const unsigned grid = (unsigned)std::min<size_t>((n + kThreads * 4 - 1) / (kThreads * 4), (size_t)c->sm_count * 16);
+  return jit_launch(c, j, -1, JS_RHS, grid, &a, false);
+}
+
+bool jit_is_stencil(const JitRhs* j, int* rl, int* rr) {
+  if (rl) *rl = j->stencil.rl;
+  if (rr) *rr = j->stencil.rr;
+  return j->stencil.on;
+}
+
 // The ODEProc itself: dydt = f(t, y), one launch (what the stage / RHS / finish pipeline calls per stage).
 int jit_rhs_fn(double t, const b200rk_vec* y, b200rk_vec* dydt, void* user) {
   JitRhs* j = static_cast<JitRhs*>(user);
@@ -422,6 +495,7 @@ int jit_rhs_fn(double t, const b200rk_vec* y, b200rk_vec* dydt, void* user) {
   TRY(check_same(c, y, dydt));
   const size_t n = y->n_local;
   if (n == 0) return B200RK_OK;
+  if (j->stencil.on) return jit_stencil_eval(c, j, t, y, dydt);
   UserRhsArgs a;
   TRY(fill_user_args(c, j, y, &a));
   a.t = t; a.out = dydt->d;
@@ -467,6 +541,30 @@ int b200rk_jit_rhs_new(b200rk_ctx* c, const char* expr, int n_vec, const b200rk_
   return B200RK_OK;
 }
 
+int b200rk_jit_stencil_rhs_new(b200rk_ctx* c, const char* expr, int radius_left, int radius_right, int n_vec, const b200rk_vec* const* vecs,
+                               int n_scalar, const double* scalars, b200rk_rhs_fn* fn, void** user) {
+  if (!c || !fn || !user) return fail(c, B200RK_EINVAL, "null argument");
+  TRY(validate(c, expr, n_vec, n_scalar));
+  if (radius_left < 0 || radius_right < 0 || radius_left > kMaxStencilRadius || radius_right > kMaxStencilRadius)
+    return fail(c, B200RK_EINVAL, "stencil rhs: radii must be in 0.." + std::to_string(kMaxStencilRadius));
+  if ((n_vec > 0 && !vecs) || (n_scalar > 0 && !scalars)) return fail(c, B200RK_EINVAL, "jit rhs: null parameter array");
+  JitRhs* j = new JitRhs;
+  j->ctx = c; j->expr = expr; j->np = n_vec; j->nc = n_scalar;
+  j->stencil.on = true; j->stencil.rl = radius_left; j->stencil.rr = radius_right;
+  for (int i = 0; i < n_vec; ++i) {
+    if (!vecs[i] || vecs[i]->ctx != c) { delete j; return fail(c, B200RK_EINVAL, "jit rhs: parameter vector belongs to another context"); }
+    if (i && vecs[i]->n_global != vecs[0]->n_global) { delete j; return fail(c, B200RK_EINVAL, "Vectors must have the same size."); }
+    j->vecs[i] = vecs[i];
+  }
+  for (int i = 0; i < n_scalar; ++i) j->cs[i] = scalars[i];
+  JitModule* m = nullptr;
+  int rc = ensure_module(c, j, -1, &m);   // a wrong expression (or a Y(d) outside the radii) is reported here with the compiler log
+  if (rc != B200RK_OK) { delete j; return rc; }
+  *fn = &jit_rhs_fn;
+  *user = j;
+  return B200RK_OK;
+}
+
 int b200rk_jit_rhs_set_scalars(void* user, int n_scalar, const double* scalars) {
   JitRhs* j = static_cast<JitRhs*>(user);
   if (!j) return fail(nullptr, B200RK_EINVAL, "null argument");
@@ -501,6 +599,31 @@ int b200rk_jit_compile_only(const char* expr, int n_vec, int n_scalar, int patte
   }
   if (cubin_bytes) *cubin_bytes = cc->cubin.size();
   if (cubin_out && cubin_cap >= cc->cubin.size()) std::memcpy(cubin_out, cc->cubin.data(), cc->cubin.size());
+  if (log && log_cap) {
+    std::string l = cc->log;
+    for (auto& n : cc->lowered) l += "\nkernel " + n;
+    std::strncpy(log, l.c_str(), log_cap - 1);
+    log[log_cap - 1] = '\0';
+  }
+  return B200RK_OK;
+}
+
+// Host only: the stencil units (pattern -1 = the dydt kernel, 0..4 = the whole-attempt kernel of that FusedPattern).
+int b200rk_jit_stencil_compile_only(const char* expr, int radius_left, int radius_right, int n_vec, int n_scalar, int pattern, size_t* cubin_bytes,
+                                    char* log, size_t log_cap) {
+  TRY(validate(nullptr, expr, n_vec, n_scalar));
+  if (pattern < -1 || pattern >= kPatterns) return fail(nullptr, B200RK_EINVAL, "jit rhs: pattern must be in -1..4");
+  if (radius_left < 0 || radius_right < 0 || radius_left > kMaxStencilRadius || radius_right > kMaxStencilRadius)
+    return fail(nullptr, B200RK_EINVAL, "stencil rhs: radii must be in 0.." + std::to_string(kMaxStencilRadius));
+  StencilSpec st;
+  st.on = true; st.rl = radius_left; st.rr = radius_right;
+  const Compiled* cc = nullptr;
+  int rc = compile_unit(nullptr, expr, n_vec, n_scalar, pattern, &cc, st);
+  if (rc != B200RK_OK) {
+    if (log && log_cap) { std::strncpy(log, thread_error().c_str(), log_cap - 1); log[log_cap - 1] = '\0'; }
+    return rc;
+  }
+  if (cubin_bytes) *cubin_bytes = cc->cubin.size();
   if (log && log_cap) {
     std::string l = cc->log;
     for (auto& n : cc->lowered) l += "\nkernel " + n;

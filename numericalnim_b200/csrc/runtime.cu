@@ -389,6 +389,7 @@ void b200rk_destroy(b200rk_ctx* c) {
   if (c->comm) g_nccl.CommDestroy(c->comm);
   cudaFree(c->d_partials); cudaFree(c->d_ticket); cudaFree(c->d_result); cudaFree(c->d_halo); cudaFreeHost(c->h_result); cudaFreeHost(c->h_seq);
   if (c->d_halo_attempt) cudaFree(c->d_halo_attempt);
+  if (c->d_halo_stencil) cudaFree(c->d_halo_stencil);
   if (c->d_barrier) cudaFree(c->d_barrier);
   if (c->d_run_state) cudaFree(c->d_run_state);
   if (c->h_run_state) cudaFreeHost(c->h_run_state);

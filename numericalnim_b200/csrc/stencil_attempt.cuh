@@ -509,4 +509,244 @@ __global__ void __launch_bounds__(THREADS) l96_rk4_kernel(const L96Rk4Args a) {
   }
 }
 
+// ===================================================================================================================
+// STENCIL RIGHT-HAND SIDES FROM SOURCE (compiled at run time only — jit.cu)
+//   dydt[i] = expr(t, Y(-RL) .. Y(+RR), p0[i] .., c0 ..)      on the cyclic index space of the state vector,
+// Y(d) = y[(i + d) mod N]. jit.cu generates
+//   __device__ double b200rk::user_stencil(double t, const double* b200rk_y_, const double* p, const double* c)
+// (with `#define Y(d) b200rk_y_[(d)]` around the caller's expression) plus B200RK_STENCIL_RL / _RR / B200RK_USER_NP and
+// compiles the two kernels below around it: the plain ODEProc evaluation every method can call through the stage / RHS /
+// finish pipeline, and the whole-attempt kernel of the FSAL pairs over overlapped tiles — the tiling of l96_attempt_kernel
+// with the overlap the stencil's radii ask for: HL = RL*(S-1), HR = RR*(S-1), rounded to 32 bytes.
+// ===================================================================================================================
+constexpr int kMaxStencilRadius = 8;   // per side; (RL + RR) * 8 evaluations must leave most of a 1024-wide tile to store
+
+struct UStencilRhsArgs {
+  const double* y;
+  const double* p[kMaxUserVecs];
+  double cs[kMaxUserScalars];
+  double t;            // the time handed to f
+  double* out;
+  size_t n;            // this rank's block of the cyclic vector
+  const double *left, *right;   // sharded: the RL elements before the block (left[0] = element -RL) and the RR after it; null on one GPU
+};
+
+template <int S>
+struct UStencilAttemptArgs {
+  FusedArgs<S> f;     // y, k1, p[], cs[], t, tsign, rhs_sign, cnode, rows, dt, tolerances, ynew, ks_out, n, rs
+  L96Halo halo;       // sharded: HL elements before / HR after the block, of y and of k1 (all null on a single GPU)
+};
+
+// overlap of the whole-attempt tiles for radii (rl, rr) and S stages, rounded to 32 bytes (host and device use the same rule)
+__host__ __device__ constexpr int stencil_halo(int radius, int S) { return ((radius * (S - 1) + 3) / 4) * 4; }
+
+#ifdef B200RK_JIT_STENCIL
+constexpr int kStencilRL = B200RK_STENCIL_RL, kStencilRR = B200RK_STENCIL_RR;
+constexpr int kStencilPadL = ((kStencilRL + 1) / 2) * 2, kStencilPadR = ((kStencilRR + 1) / 2) * 2;   // keeps every pair 16-byte aligned
+
+template <int S>
+struct UStencilTile {
+  static constexpr int HL = stencil_halo(kStencilRL, S);
+  static constexpr int HR = stencil_halo(kStencilRR, S);
+};
+
+// dydt = f(t, y): a tile of 4 * THREADS elements plus its RL + RR neighbours staged in shared memory, then one evaluation per element.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) user_stencil_rhs_kernel(const UStencilRhsArgs a) {
+  constexpr int W = 4, TILE = THREADS * W, NP = PwTraits<PW_USER>::NP, NPX = PwTraits<PW_USER>::NPX;
+  __shared__ double sh_[kStencilPadL + TILE + kStencilPadR];
+  double* sh = sh_ + kStencilPadL;
+  const size_t n = a.n;
+  for (size_t tile0 = (size_t)blockIdx.x * TILE; tile0 < n; tile0 += (size_t)gridDim.x * TILE) {
+    const size_t len = (tile0 + TILE <= n) ? (size_t)TILE : n - tile0;
+    auto at = [&](long long g) -> double {   // element g of the block, g in [-RL, n + RR)
+      if (g >= 0 && (size_t)g < n) return a.y[g];
+      if (a.left) return g < 0 ? a.left[kStencilRL + g] : a.right[(size_t)g - n];
+      return a.y[(size_t)((g % (long long)n + (long long)n) % (long long)n)];
+    };
+    const size_t i0 = tile0 + (size_t)threadIdx.x * W;
+    if (i0 + W <= n) {
+      const Pk<W> v = ld_stream<W>(a.y + i0);
+#pragma unroll
+      for (int e = 0; e < W; ++e) sh[threadIdx.x * W + e] = v.v[e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < W; ++e) sh[threadIdx.x * W + e] = (i0 + e < n) ? a.y[i0 + e] : 0.0;
+    }
+    if ((int)threadIdx.x < kStencilRL) sh[-kStencilRL + (int)threadIdx.x] = at((long long)tile0 - kStencilRL + threadIdx.x);
+    __syncthreads();
+    // the right halo goes directly behind the last valid element (a ragged last tile); written after the barrier so that it cannot
+    // race with a thread storing a padded zero into the same slot
+    if ((int)threadIdx.x < kStencilRR) sh[len + threadIdx.x] = at((long long)(tile0 + len) + threadIdx.x);
+    __syncthreads();
+    if (i0 < n) {
+      double o[W];
+#pragma unroll
+      for (int e = 0; e < W; ++e) {
+        double pe[NPX] = {};
+        if (i0 + e < n) {
+#pragma unroll
+          for (int j = 0; j < NP; ++j) pe[j] = a.p[j][i0 + e];
+          o[e] = user_stencil(a.t, sh + threadIdx.x * W + e, pe, a.cs);
+        } else o[e] = 0.0;
+      }
+      if (i0 + W <= n) {
+        Pk<W> ov;
+#pragma unroll
+        for (int e = 0; e < W; ++e) ov.v[e] = o[e];
+        st_stream<W>(a.out + i0, ov);
+      } else {
+#pragma unroll
+        for (int e = 0; e < W; ++e)
+          if (i0 + e < n) a.out[i0 + e] = o[e];
+      }
+    }
+    __syncthreads();   // the tile is rewritten by the next iteration
+  }
+}
+
+template <int PAT, int s, int J, int TW>
+struct UStencilStages {
+  template <int S>
+  __device__ __forceinline__ static void run(const double (&y)[2 * J], double (&k)[2 * J][S], double (&in)[2 * J], double (&part)[2 * J],
+                                             double (&part_bh)[2 * J], const double (&pe)[2 * J][PwTraits<PW_USER>::NPX], const int (&pos)[J],
+                                             double (*buf)[kStencilPadL + TW + kStencilPadR], const UStencilAttemptArgs<S>& a) {
+    if constexpr (s > 2) UStencilStages<PAT, s - 1, J, TW>::run(y, k, in, part, part_bh, pe, pos, buf, a);
+    double* sh = buf[s & 1] + kStencilPadL;   // the pads stay zero: their consumers are outside the stored range
+#pragma unroll
+    for (int e = 0; e < 2 * J; ++e) {
+      const double acc = const_wsum_finish<S, Pattern<PAT>::a(s - 2), s - 2>(part[e], k[e], a.f.a[s - 2]);
+      in[e] = __dadd_rn(y[e], __dmul_rn(acc, a.f.dt));                                   // stage_elem
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j) { sh[pos[j]] = in[2 * j]; sh[pos[j] + 1] = in[2 * j + 1]; }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 2 * J; ++e) {
+      if constexpr (s < S) part[e] = const_wsum_prefix<S, Pattern<PAT>::a(s - 1), s - 1>(k[e], a.f.a[s - 1]);
+      else {
+        if constexpr (!Pattern<PAT>::last) part[e] = const_wsum_prefix<S, Pattern<PAT>::b(), S - 1>(k[e], a.f.b);
+        part_bh[e] = const_wsum_prefix<S, Pattern<PAT>::bh(), S - 1>(k[e], a.f.bh);
+      }
+    }
+    // k_s = g(t + dt*c_s, stage input) with g = f forward and g(t, y) = -f(-t, y) backward (ode.nim:545): the signs are exact flips
+    const double ts = flip_sign_by(__dadd_rn(a.f.t, __dmul_rn(a.f.dt, a.f.cnode[s - 1])), a.f.tsign);
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        k[2 * j + h][s - 1] = flip_sign_by(user_stencil(ts, sh + pos[j] + h, pe[2 * j + h], a.f.cs), a.f.rhs_sign);
+  }
+};
+
+template <int PAT, int J, int THREADS>
+__global__ void __launch_bounds__(THREADS, 2) ustencil_attempt_kernel(const UStencilAttemptArgs<Pattern<PAT>::S> a) {
+  constexpr int S = Pattern<PAT>::S;
+  constexpr int E = 2 * J, TW = E * THREADS;
+  constexpr int HL = UStencilTile<S>::HL, HR = UStencilTile<S>::HR, OUT = TW - HL - HR;
+  constexpr int NP = PwTraits<PW_USER>::NP, NPX = PwTraits<PW_USER>::NPX;
+  static_assert(OUT >= TW / 2, "stencil radii too large for the tile");
+  __shared__ double buf[2][kStencilPadL + TW + kStencilPadR];
+  alignas(128) __shared__ double staged[2][TW];
+  alignas(8) __shared__ unsigned long long tile_bar;
+  const size_t n = a.f.n;
+  const size_t n_tiles = (n + OUT - 1) / OUT;
+  for (int q = threadIdx.x; q < kStencilPadL + kStencilPadR; q += THREADS) {
+    const int at = q < kStencilPadL ? q : TW + q;
+    buf[0][at] = 0.0; buf[1][at] = 0.0;
+  }
+  auto interior_tile = [&](size_t t) { const size_t t0 = t * (size_t)OUT; return t0 >= (size_t)HL && t0 - HL + TW <= n; };
+  size_t tile = blockIdx.x;
+  if (threadIdx.x == 0) {
+    tile_barrier_init(&tile_bar);
+    if (tile < n_tiles && interior_tile(tile))
+      tile_prefetch(staged[0], a.f.y + (tile * OUT - HL), staged[1], a.f.k1 + (tile * OUT - HL), TW * 8u, &tile_bar);
+  }
+  __syncthreads();
+  unsigned int phase = 0;
+  double acc = 0.0;
+  int pos[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) pos[j] = 2 * ((int)threadIdx.x + j * THREADS);
+  for (; tile < n_tiles; tile += gridDim.x) {
+    const size_t tile0 = tile * (size_t)OUT;
+    double y[E], k[E][S], in[E], pe[E][NPX];
+    const bool interior = interior_tile(tile);
+    if (interior) { tile_wait(&tile_bar, phase); phase ^= 1u; }
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int p = pos[j];
+      if (interior) {
+        const double2 yv = *reinterpret_cast<const double2*>(&staged[0][p]), kv = *reinterpret_cast<const double2*>(&staged[1][p]);
+        y[2 * j] = yv.x; y[2 * j + 1] = yv.y;
+        k[2 * j][0] = kv.x; k[2 * j + 1][0] = kv.y;
+      } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          y[2 * j + h] = l96_edge_load<HL, HR>(a.f.y, a.halo.left_y, a.halo.right_y, n, tile0, p + h);
+          k[2 * j + h][0] = l96_edge_load<HL, HR>(a.f.k1, a.halo.left_k, a.halo.right_k, n, tile0, p + h);
+        }
+      }
+      // per-element parameters of the thread's own positions (positions outside the block are never stored: any in-range value will do)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        long long g = (long long)tile0 - HL + p + h;
+        if (a.halo.left_y) g = g < 0 ? 0 : ((size_t)g >= n ? (long long)n - 1 : g);
+        else g = ((g % (long long)n) + (long long)n) % (long long)n;
+#pragma unroll
+        for (int q = 0; q < NPX; ++q) pe[2 * j + h][q] = q < NP ? a.f.p[q][g] : 0.0;
+      }
+    }
+    __syncthreads();
+    {
+      const size_t nxt = tile + gridDim.x;
+      if (threadIdx.x == 0 && nxt < n_tiles && interior_tile(nxt))
+        tile_prefetch(staged[0], a.f.y + (nxt * OUT - HL), staged[1], a.f.k1 + (nxt * OUT - HL), TW * 8u, &tile_bar);
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+#pragma unroll
+      for (int j = 1; j < S; ++j) k[e][j] = 0.0;
+    double part[E], part_bh[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) { part[e] = 0.0; part_bh[e] = 0.0; }
+    UStencilStages<PAT, S, J, TW>::run(y, k, in, part, part_bh, pe, pos, buf, a);
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int p = pos[j];
+      const size_t g = tile0 + (size_t)(p - HL);
+      const bool stored = p >= HL && p < HL + OUT && g < n;
+      double yn[2], ks[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int e = 2 * j + h;
+        ks[h] = k[e][S - 1];
+        if (Pattern<PAT>::last) yn[h] = in[e];
+        else yn[h] = __dadd_rn(y[e], __dmul_rn(const_wsum_finish<S, Pattern<PAT>::b(), S - 1>(part[e], k[e], a.f.b), a.f.cb));
+        const double lo = __dmul_rn(const_wsum_finish<S, Pattern<PAT>::bh(), S - 1>(part_bh[e], k[e], a.f.bh), a.f.cbh);
+        double err;
+        if (Pattern<PAT>::direct) err = lo;
+        else err = __dadd_rn(yn[h], -__dadd_rn(y[e], lo));
+        const double tol = __dadd_rn(a.f.absTol, __dmul_rn(fabs(yn[h]), a.f.relTol));
+        const double r = err_ratio(err, tol);
+        if (stored && g + h < n) acc = __dadd_rn(acc, __dmul_rn(r, r));
+      }
+      if (stored) {
+        if (g + 1 < n) {
+          Pk<2> o;
+          o.v[0] = yn[0]; o.v[1] = yn[1];
+          st_stream<2>(a.f.ynew + g, o);
+          o.v[0] = ks[0]; o.v[1] = ks[1];
+          st_stream<2>(a.f.ks_out + g, o);
+        } else {
+          a.f.ynew[g] = yn[0];
+          a.f.ks_out[g] = ks[0];
+        }
+      }
+    }
+  }
+  grid_sum_finish<THREADS>(acc, a.f.rs);
+}
+#endif  // B200RK_JIT_STENCIL
+
 }  // namespace b200rk

@@ -3,7 +3,7 @@
 ##
 ## STATUS: written against the C header, NOT compiled — this image has no Nim toolchain (nim, nimble and
 ## choosenim are absent; see DESIGN.md §2). There is one `importc` declaration per B200RK_API symbol of the header
-## (69; tests/test_nim_shim.py parses both files and compares names and arities), and the behaviour of every symbol
+## (71; tests/test_nim_shim.py parses both files and compares names and arities), and the behaviour of every symbol
 ## is exercised through the same ABI by the pytest suite (ctypes). Usage from reference code:
 ##
 ##   import numericalnim            # for ODEoptions, NumContext, linspace, ...
@@ -72,6 +72,10 @@ proc b200rk_solve(ctx: B200rkCtx, methodId: cint, f: RhsFn, user: pointer, y0: V
                   options: ptr COptions, tOut: ptr cdouble, yOut: ptr VecHandle, nYOut: ptr csize_t, stats: ptr CStats): cint {.importc, cdecl, dynlib: lib.}
 proc b200rk_jit_rhs_new(ctx: B200rkCtx, expr: cstring, nVec: cint, vecs: ptr VecHandle, nScalar: cint, scalars: ptr cdouble,
                         fn: ptr RhsFn, user: ptr pointer): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_jit_stencil_rhs_new(ctx: B200rkCtx, expr: cstring, radiusLeft, radiusRight, nVec: cint, vecs: ptr VecHandle, nScalar: cint, scalars: ptr cdouble,
+                                fn: ptr RhsFn, user: ptr pointer): cint {.importc, cdecl, dynlib: lib.}
+proc b200rk_jit_stencil_compile_only(expr: cstring, radiusLeft, radiusRight, nVec, nScalar, pattern: cint, cubinBytes: ptr csize_t,
+                                     log: cstring, logCap: csize_t): cint {.importc, cdecl, dynlib: lib.}
 proc b200rk_jit_rhs_set_scalars(user: pointer, nScalar: cint, scalars: ptr cdouble): cint {.importc, cdecl, dynlib: lib.}
 proc b200rk_jit_rhs_free(user: pointer): cint {.importc, cdecl, dynlib: lib.}
 proc b200rk_hermite_interpolate(ctx: B200rkCtx, x: ptr cdouble, nx: csize_t, t: ptr cdouble, nt: csize_t, y, dy: ptr VecHandle,
@@ -272,6 +276,19 @@ proc newJitRhs*(expr: string, vecs: openArray[GpuVector] = [], scalars: openArra
   var cs = @scalars
   check(b200rk_jit_rhs_new(ctx, expr.cstring, hs.len.cint, (if hs.len > 0: addr hs[0] else: nil), cs.len.cint,
                            (if cs.len > 0: cast[ptr cdouble](addr cs[0]) else: nil), addr result.fn, addr result.user), ctx)
+
+proc newJitStencilRhs*(expr: string, radiusLeft, radiusRight: int, vecs: openArray[GpuVector] = [], scalars: openArray[float] = [],
+                       ctx: B200rkCtx = b200rkContext()): JitRhs =
+  ## dydt[i] = expr(t, Y(-radiusLeft)..Y(+radiusRight), p0[i].., c0..), Y(d) = y[(i + d) mod N]; e.g.
+  ## newJitStencilRhs("((Y(1) - Y(-2)) * Y(-1) - Y(0)) + c0", 2, 1, scalars = [8.0]) is Lorenz-96. Used like a JitRhs.
+  new(result, proc(r: JitRhs) = (if not r.user.isNil: discard b200rk_jit_rhs_free(r.user)))
+  result.ctx = ctx
+  result.vecs = @vecs
+  var hs = newSeq[VecHandle](vecs.len)
+  for i in 0 ..< result.vecs.len: hs[i] = result.vecs[i].h
+  var cs = @scalars
+  check(b200rk_jit_stencil_rhs_new(ctx, expr.cstring, radiusLeft.cint, radiusRight.cint, hs.len.cint, (if hs.len > 0: addr hs[0] else: nil),
+                                   cs.len.cint, (if cs.len > 0: cast[ptr cdouble](addr cs[0]) else: nil), addr result.fn, addr result.user), ctx)
 
 proc solveODE*(f: JitRhs, y0: GpuVector, tspan: openArray[float], options: ODEoptions = newODEoptions(),
                integrator = "dopri54"): (seq[float], seq[GpuVector]) =

@@ -494,6 +494,39 @@ class JitRhs:
             pass
 
 
+class JitStencilRhs(JitRhs):
+    """Stencil right-hand side given as source (b200rk_jit_stencil_rhs_new): ``dy[i] = expr(t, Y(-rl)..Y(+rr), p0[i].., c0..)`` with
+    ``Y(d) = y[(i + d) mod N]`` (cyclic). Compiled into a plain dy = f(t, y) kernel for every method and into the one-kernel
+    attempt over overlapped tiles for DOPRI54 / Tsit54 / Vern65 (what the built-in Lorenz-96 gets)."""
+
+    def __init__(self, expr: str, radius_left: int, radius_right: int, vecs: Sequence["GpuVector"] = (), scalars: Sequence[float] = (),
+                 ctx: Context | None = None):
+        vecs = list(vecs)
+        self.ctx = ctx or (vecs[0].ctx if vecs else default_context())
+        self._vecs = vecs  # keep alive
+        self.expr, self.radius_left, self.radius_right = expr, int(radius_left), int(radius_right)
+        self.fn = capi.RHS_FN()
+        self.user = C.c_void_p()
+        cs = np.ascontiguousarray(np.asarray(list(scalars), dtype=np.float64))
+        capi.check(capi.lib().b200rk_jit_stencil_rhs_new(self.ctx.handle, expr.encode(), self.radius_left, self.radius_right, len(vecs),
+                                                         _ptr_array(vecs) if vecs else None, cs.size, cs.ctypes.data if cs.size else None,
+                                                         C.byref(self.fn), C.byref(self.user)), self.ctx.handle)
+
+
+def rhsJitStencil(expr: str, radius_left: int, radius_right: int, vecs: Sequence["GpuVector"] = (), scalars: Sequence[float] = (),
+                  ctx: Context | None = None) -> JitStencilRhs:
+    """``rhsJitStencil("((Y(1) - Y(-2)) * Y(-1) - Y(0)) + c0", 2, 1, scalars=[8.0])`` — see JitStencilRhs."""
+    return JitStencilRhs(expr, radius_left, radius_right, vecs, scalars, ctx)
+
+
+def jitStencilCompileOnly(expr: str, radius_left: int, radius_right: int, n_vec: int = 0, n_scalar: int = 0, pattern: int = -1):
+    """Host-only NVRTC compile of one stencil translation unit (no GPU needed): returns (cubin size, log with kernel names)."""
+    nb = C.c_size_t(0)
+    log = C.create_string_buffer(1 << 16)
+    capi.check(capi.lib().b200rk_jit_stencil_compile_only(expr.encode(), radius_left, radius_right, n_vec, n_scalar, pattern, C.byref(nb), log, len(log)))
+    return nb.value, log.value.decode()
+
+
 def rhsJit(expr: str, vecs: Sequence["GpuVector"] = (), scalars: Sequence[float] = (), ctx: Context | None = None) -> JitRhs:
     """``rhsJit("c0*y*(1.0 - y/p0)", vecs=[K], scalars=[r])`` — see JitRhs."""
     return JitRhs(expr, vecs, scalars, ctx)

@@ -24,11 +24,23 @@ UNITS = [  # (expression, n_vec, n_scalar, patterns)
     ("-y*exp(-c0*t) + sin(p0)", 1, 1, (-1,)),
 ]
 
+STENCIL_UNITS = [  # (expression, radius_left, radius_right, n_vec, n_scalar, patterns) — tests/test_gpu_stencil_from_source.py, bench.py
+    ("((Y(1) - Y(-2)) * Y(-1) - Y(0)) + c0", 2, 1, 0, 1, ALL),
+    ("c0*((Y(-1) - 2.0*Y(0)) + Y(1))*p0 + c1*t", 1, 1, 1, 2, (-1, 0, 2, 3)),
+    ("-(c0*(Y(0) - Y(-1)))", 1, 0, 0, 1, (-1, 0, 2, 3)),
+    ("((Y(-3) + Y(2)) - 2.0*Y(0))*c0 - Y(0)*Y(0)*Y(0)*c1", 3, 2, 0, 2, (-1, 0, 2, 3)),
+    ("Y(-2) + Y(1)", 2, 1, 0, 0, (-1,)),
+]
+
 if __name__ == "__main__":
     t0 = time.time()
     n = 0
     for expr, nv, nc, pats in UNITS:
         for p in pats:
             nn.jitCompileOnly(expr, nv, nc, p)
+            n += 1
+    for expr, rl, rr, nv, nc, pats in STENCIL_UNITS:
+        for p in pats:
+            nn.jitStencilCompileOnly(expr, rl, rr, nv, nc, p)
             n += 1
     print(f"{n} units in {time.time() - t0:.1f} s -> {os.environ['B200RK_JIT_CACHE']}")

@@ -102,8 +102,39 @@ def main():
             if not np.array_equal(ys[-1].local_numpy().view(np.uint64), np.asarray(ref4).view(np.uint64)):
                 fails.append(("lorenz96 rk4 one-kernel step bitwise", nl))
         finally:
-            ctx.set("fuse_stencil_attempt", 0)
+            ctx.set("fuse_stencil_attempt", 1)
             ctx.set("l96_peer_halo", 1)
+    # STENCIL right-hand side given as source, sharded: the plain dydt kernel exchanges radius_left / radius_right elements per evaluation,
+    # the NVRTC-compiled one-kernel attempt reads its overlap from the peer-mapped ring neighbours (or one ncclSend/ncclRecv per step)
+    nl = 100003
+    yl = 8.0 + 0.01 * np.sin(2 * np.pi * 37 * np.arange(nl) / nl)
+    Kd = 1.0 + 0.5 * np.sin(2 * np.pi * 3 * np.arange(nl) / nl)
+    for name, expr, rl, rr, pv, cs, fnp, y_init, rtol in (
+            ("lorenz96 from source", "((Y(1) - Y(-2)) * Y(-1) - Y(0)) + c0", 2, 1, [], [8.0],
+             lambda t, y: ((np.roll(y, -1) - np.roll(y, 2)) * np.roll(y, 1) - y) + 8.0, yl, 1e-7),
+            ("diffusion from source", "c0*((Y(-1) - 2.0*Y(0)) + Y(1))*p0 + c1*t", 1, 1, [Kd], [0.3, 0.05],
+             lambda t, y: 0.3 * ((np.roll(y, 1) - 2.0 * y) + np.roll(y, -1)) * Kd + 0.05 * t, 1.0 + 0.5 * np.sin(2 * np.pi * np.arange(nl) / nl), 1e-9)):
+        gs = nn.newVector(y_init, ctx)
+        lo, ll = gs.local_offset, gs.local_len
+        srhs = nn.rhsJitStencil(expr, rl, rr, [nn.newVector(p, ctx) for p in pv], cs, ctx)
+        out = gs._new_like()
+        assert srhs.fn(0.3, gs._h, out._h, srhs.user) == 0
+        if not np.array_equal(out.local_numpy().view(np.uint64), fnp(0.3, y_init)[lo:lo + ll].view(np.uint64)):
+            fails.append((name, "rhs kernel bitwise"))
+        refs = O.solve_vector("tsit54", O.rhs_callback(fnp), y_init, [0.0, 0.3], O.new_options(**kw))
+        for fuse, peer_halo in ((1, 1), (1, 0), (0, 1)):
+            ctx.set("fuse_stencil_attempt", fuse)
+            ctx.set("l96_peer_halo", peer_halo)
+            t, ys = nn.solveODE(srhs, gs, [0.0, 0.3], nn.newODEoptions(**kw), integrator="tsit54")
+            st = dict(nn.ode.last_stats)
+            got, exp = ys[-1].local_numpy(), refs.y[-1][lo:lo + ll]
+            ok = bool(np.all(np.abs(got - exp) <= rtol * np.abs(exp) + 1e-13 * np.max(np.abs(refs.y[-1])))) and st["steps"] == refs.stats.steps and st["rejected"] == refs.stats.rejected
+            if not ok:
+                fails.append((name, fuse, peer_halo, st, refs.stats.steps, float(np.max(np.abs(got - exp)))))
+            if rank == 0:
+                print(f"[multi-gpu world={world}] {name} tsit54 fuse={fuse} peer_halo={peer_halo}: steps={st['steps']} launches={st['launches']} collectives={st['collectives']} ok={ok}", flush=True)
+        ctx.set("fuse_stencil_attempt", 1)
+        ctx.set("l96_peer_halo", 1)
     # right-hand side given as SOURCE, sharded: the parameter vector shards like the state; the run-time compiled
     # attempt kernel / device loop use the same in-kernel all-reduce as the built-ins
     K = 2.0 + 3.0 * np.arange(n) / (n - 1)

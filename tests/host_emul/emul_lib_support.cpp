@@ -16,10 +16,13 @@ int jit_slot_run(int) { return 0; }
 int jit_launch(b200rk_ctx* c, JitRhs*, int, int, unsigned, void*, bool) { return unavailable(c); }
 int jit_max_blocks_per_sm(b200rk_ctx* c, JitRhs*, int, int, int*) { return unavailable(c); }
 int jit_prepare(b200rk_ctx* c, JitRhs*, int) { return unavailable(c); }
+bool jit_is_stencil(const JitRhs*, int*, int*) { return false; }
 int jit_launch_rk4(b200rk_ctx* c, JitRhs*, bool, double, double, const b200rk_vec*, b200rk_vec*) { return unavailable(c); }
 
 extern "C" {
 int b200rk_jit_rhs_new(b200rk_ctx* c, const char*, int, const b200rk_vec* const*, int, const double*, b200rk_rhs_fn*, void**) { return unavailable(c); }
+int b200rk_jit_stencil_rhs_new(b200rk_ctx* c, const char*, int, int, int, const b200rk_vec* const*, int, const double*, b200rk_rhs_fn*, void**) { return unavailable(c); }
+int b200rk_jit_stencil_compile_only(const char*, int, int, int, int, int, size_t*, char*, size_t) { return unavailable(nullptr); }
 int b200rk_jit_rhs_set_scalars(void*, int, const double*) { return unavailable(nullptr); }
 int b200rk_jit_rhs_free(void*) { return B200RK_OK; }
 int b200rk_jit_compile_only(const char*, int, int, int, void*, size_t, size_t*, char*, size_t) { return unavailable(nullptr); }

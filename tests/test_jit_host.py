@@ -158,3 +158,29 @@ def test_kernel_argument_blocks_have_the_same_size_in_both_compilations(tmp_path
             twin = name.replace(f"ILi{pat}ELi2E", f"ILi{pat}ELi1E")  # PW_USER -> PW_DIAG instance built by nvcc
             assert twin in ref, twin
             assert ref[twin] == size and size > 800, (name, size, ref[twin])
+
+
+# ---- stencil right-hand sides from source (b200rk_jit_stencil_rhs_new): the same host-only compile ----------------------
+STENCILS = [("((Y(1) - Y(-2)) * Y(-1) - Y(0)) + c0", 2, 1, 0, 1),                    # Lorenz-96
+            ("c0*((Y(-1) - 2.0*Y(0)) + Y(1))*p0 + c1*t", 1, 1, 1, 2),                # diffusion with a coefficient field and a source term
+            ("-(c0*(Y(0) - Y(-1)))", 1, 0, 0, 1),                                     # upwind advection: one-sided
+            ("(Y(-3) + Y(2)) - 2.0*Y(0)", 3, 2, 0, 0)]
+
+
+@pytest.mark.parametrize("expr,rl,rr,nv,ns", STENCILS)
+def test_stencil_units_compile_for_the_rhs_kernel_and_every_pair(expr, rl, rr, nv, ns):
+    n, log = nn.jitStencilCompileOnly(expr, rl, rr, nv, ns, -1)
+    assert n > 1000 and "user_stencil_rhs_kernel" in log
+    for pattern in (0, 2, 3):
+        n, log = nn.jitStencilCompileOnly(expr, rl, rr, nv, ns, pattern)
+        assert n > 1000 and "ustencil_attempt_kernel" in log, log
+
+
+def test_stencil_offset_outside_the_declared_radii_is_a_value_error():
+    with pytest.raises(ValueError) as e:
+        nn.jitStencilCompileOnly("Y(2) - Y(0)", 1, 1, 0, 0, -1)
+    assert "Y(2)" in str(e.value)
+    with pytest.raises(ValueError):
+        nn.jitStencilCompileOnly("Y(0)", 9, 0, 0, 0, -1)     # radii are limited to 0..8
+    with pytest.raises(ValueError):
+        nn.jitStencilCompileOnly("Y(0); y", 1, 1, 0, 0, -1)  # a single expression

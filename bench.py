@@ -427,6 +427,22 @@ def run_ours(args):
                 px, rfx = fused_roofline(pbx, rx)
                 extra[key] = summarize(pbx, rx, rfx, px)
                 extra[key]["repeats"] = {"n": len(rx["ms_all"]), "ms": rx["ms_all"]}
+                if key == "cfg3" and not args.no_jit:
+                    # the same Lorenz-96 ring handed over as a SOURCE expression (b200rk_jit_stencil_rhs_new): NVRTC compiles it into the
+                    # generic one-kernel attempt — what a user-defined stencil closure gets instead of the built-in
+                    try:
+                        srhs = nn.rhsJitStencil("((Y(1) - Y(-2)) * Y(-1) - Y(0)) + c0", 2, 1, [], [8.0], ctx)
+                        rs = timed_steps(pbx, 1, srhs)
+                        fu = rs["prof"]["fused"]
+                        extra[key]["stencil_from_source"] = {
+                            "note": "right-hand side given as the source expression ((Y(1) - Y(-2)) * Y(-1) - Y(0)) + c0 with radii 2 / 1, compiled at run time "
+                                    "into the overlapped-tile attempt kernel (bit-identical to the built-in: tests/test_gpu_stencil_from_source.py)",
+                            "value": args.steps * world / (rs["ms_max"] * 1e-3), "ms_per_step": rs["ms_max"] / args.steps, "attempts": rs["attempts"],
+                            "gpu_launches": rs["launches"], "avg_launch_us": 1e3 * fu["ms"] / max(1, fu["launches"]),
+                            "hbm_gbs": gbs(fu), "frac": gbs(fu) / peak}
+                    except Exception as e:  # noqa: BLE001
+                        extra[key]["stencil_from_source"] = {"error": str(e)[:300]}
+                        ctx.set("profile", 0)
                 pbx.free()
             except Exception as e:  # noqa: BLE001 — the headline must survive
                 extra[key] = {"error": str(e)[:400]}

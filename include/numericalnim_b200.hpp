@@ -282,6 +282,33 @@ class JitRhs {
   void* user_ = nullptr;
 };
 
+// Stencil right-hand side given as source (b200rk_jit_stencil_rhs_new): dydt[i] = expr(t, Y(-rl)..Y(+rr), p0[i].., c0..) with
+// Y(d) = y[(i + d) mod N]. E.g. JitStencilRhs(dev, "((Y(1) - Y(-2)) * Y(-1) - Y(0)) + c0", 2, 1, {}, {8.0}) is Lorenz-96: compiled
+// into a dydt kernel for every method and into the one-kernel attempt over overlapped tiles for DOPRI54 / Tsit54 / Vern65.
+class JitStencilRhs {
+ public:
+  JitStencilRhs(std::shared_ptr<Device> dev, const std::string& expr, int radiusLeft, int radiusRight, const std::vector<const GpuVector*>& vecs = {},
+                const std::vector<double>& scalars = {}) : dev_(std::move(dev)) {
+    std::vector<const b200rk_vec*> hs;
+    for (const GpuVector* v : vecs) { keep_.push_back(std::make_unique<GpuVector>(*v)); hs.push_back(keep_.back()->handle()); }
+    check(b200rk_jit_stencil_rhs_new(dev_->handle(), expr.c_str(), radiusLeft, radiusRight, (int)hs.size(), hs.empty() ? nullptr : hs.data(),
+                                     (int)scalars.size(), scalars.empty() ? nullptr : scalars.data(), &fn_, &user_), dev_->handle());
+  }
+  ~JitStencilRhs() { b200rk_jit_rhs_free(user_); }
+  JitStencilRhs(const JitStencilRhs&) = delete;
+  void setScalars(const std::vector<double>& scalars) {
+    check(b200rk_jit_rhs_set_scalars(user_, (int)scalars.size(), scalars.empty() ? nullptr : scalars.data()), dev_->handle());
+  }
+  b200rk_rhs_fn fn() const { return fn_; }
+  void* user() const { return user_; }
+
+ private:
+  std::shared_ptr<Device> dev_;
+  std::vector<std::unique_ptr<GpuVector>> keep_;
+  b200rk_rhs_fn fn_ = nullptr;
+  void* user_ = nullptr;
+};
+
 template <class DeviceRhs, class = decltype(std::declval<const DeviceRhs&>().fn()), class = decltype(std::declval<const DeviceRhs&>().user())>
 inline Solution solveODE(const DeviceRhs& f, const GpuVector& y0, const std::vector<double>& tspan, const ODEoptions& options = newODEoptions(),
                          const std::string& integrator = "dopri54") {

@@ -631,16 +631,26 @@ struct UStencilStages {
     }
     // k_s = g(t + dt*c_s, stage input) with g = f forward and g(t, y) = -f(-t, y) backward (ode.nim:545): the signs are exact flips
     const double ts = flip_sign_by(__dadd_rn(a.f.t, __dmul_rn(a.f.dt, a.f.cnode[s - 1])), a.f.tsign);
+    // the neighbourhood of a pair — positions p - RL .. p + 1 + RR — is pulled into registers once with 128-bit loads (the window
+    // starts at an even offset, every pair is 16-byte aligned) and both evaluations index it with compile-time offsets
+    constexpr int WL = kStencilPadL, WLEN = kStencilPadL + 2 + kStencilPadR;
 #pragma unroll
-    for (int j = 0; j < J; ++j)
+    for (int j = 0; j < J; ++j) {
+      double w[WLEN];
+#pragma unroll
+      for (int q = 0; q < WLEN; q += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(sh + pos[j] - WL + q);
+        w[q] = v.x; w[q + 1] = v.y;
+      }
 #pragma unroll
       for (int h = 0; h < 2; ++h)
-        k[2 * j + h][s - 1] = flip_sign_by(user_stencil(ts, sh + pos[j] + h, pe[2 * j + h], a.f.cs), a.f.rhs_sign);
+        k[2 * j + h][s - 1] = flip_sign_by(user_stencil(ts, w + WL + h, pe[2 * j + h], a.f.cs), a.f.rhs_sign);
+    }
   }
 };
 
 template <int PAT, int J, int THREADS>
-__global__ void __launch_bounds__(THREADS, 2) ustencil_attempt_kernel(const UStencilAttemptArgs<Pattern<PAT>::S> a) {
+__global__ void __launch_bounds__(THREADS, (Pattern<PAT>::S > 7 || PwTraits<PW_USER>::NP > 0) ? 2 : 3) ustencil_attempt_kernel(const UStencilAttemptArgs<Pattern<PAT>::S> a) {
   constexpr int S = Pattern<PAT>::S;
   constexpr int E = 2 * J, TW = E * THREADS;
   constexpr int HL = UStencilTile<S>::HL, HR = UStencilTile<S>::HR, OUT = TW - HL - HR;

@@ -24,8 +24,8 @@ pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None or not glob.gl
 
 
 def _device_objects():
-    """Build objects that carry device code (kernels_src.o is the embedded header text: host data only)."""
-    return [p for p in sorted(glob.glob(os.path.join(OBJ, "*.o"))) if os.path.basename(p) != "kernels_src.o"]
+    """Build objects that carry device code (kernels_src.o / stencil_src.o are the embedded header texts: host data only)."""
+    return [p for p in sorted(glob.glob(os.path.join(OBJ, "*.o"))) if os.path.basename(p) not in ("kernels_src.o", "stencil_src.o")]
 
 
 def _kernels():

@@ -193,7 +193,7 @@ B200RK_API int b200rk_jit_compile_only(const char* expr, int n_vec, int n_scalar
  *     dydt[i] = expr(t, Y(-radius_left) .. Y(+radius_right), p0[i] .., c0 ..),     Y(d) = y[(i + d) mod N]   (cyclic),
  * e.g. Lorenz-96 "((Y(1) - Y(-2)) * Y(-1) - Y(0)) + c0" with radii 2 / 1, diffusion "c0*((Y(-1) - 2.0*Y(0)) + Y(1))" with 1 / 1.
  * Radii 0..8; a Y(d) outside them is a compile error. NVRTC compiles the expression into (i) a plain dydt = f(t, y) kernel
- * every method calls through the stage / RHS / finish pipeline and (ii) — for DOPRI54 / Tsit54 / Vern65 — the ONE-KERNEL attempt
+ * every method calls through the stage / RHS / finish pipeline, (ii) a one-kernel RK4 step and (iii) — for DOPRI54 / Tsit54 / Vern65 — the ONE-KERNEL attempt
  * over overlapped tiles (the built-in Lorenz-96's kernel with the overlap the radii ask for: 4 + n_vec vector passes per attempt
  * instead of ~55). Sharded, the halo travels once per step (or is read in place from the peer-mapped ring neighbours inside a
  * solver). Everything else as for b200rk_jit_rhs_new; freed with b200rk_jit_rhs_free. */

@@ -565,8 +565,12 @@ int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, double t, co
                      y_new->d != fsal->d && fsal_new->d != y->d && fsal_new->d != fsal->d && y->n_global >= (size_t)(ust_rl + ust_rr + 1) &&
                      (c->world == 1 || stencil_shards_ok(c, y->n_global, std::max(ust_HL, ust_HR)));
   if (ust_attempt) { fused_pat = fused_pattern_of(c, md); ust_attempt = fused_pat >= 0; }
+  // ... and a whole RK4 step in one kernel (4 evaluations: overlap 4 * radius)
+  const int rk4_HL = stencil_halo(ust_rl, 5), rk4_HR = stencil_halo(ust_rr, 5);
+  const bool ust_rk4 = ust_jit && c->fuse_stencil_attempt && md.rk4_final && y_new->d != y->d && y->n_global >= (size_t)(ust_rl + ust_rr + 1) &&
+                       (c->world == 1 || stencil_shards_ok(c, y->n_global, std::max(rk4_HL, rk4_HR)));
   if (fused) TRY(check_pw_sizes(c, pw, y));
-  fused = fused || l96_attempt || ust_attempt;
+  fused = fused || l96_attempt || ust_attempt || ust_rk4;
   if (md.k1_from_fsal) {
     if (!fsal) return fail(c, B200RK_EINVAL, std::string(md.name) + ": FSAL vector required");
     TRY(check_same(c, y, fsal));
@@ -589,6 +593,7 @@ int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, double t, co
     else TRY(l96_halo_for(c, md, y, fsal, S == 9 ? StencilTile<9>::HL : StencilTile<7>::HL, S == 9 ? StencilTile<9>::HR : StencilTile<7>::HR, &l96_halo));
   }
   if (ust_attempt) TRY(l96_halo_for(c, md, y, fsal, ust_HL, ust_HR, &l96_halo));
+  if (ust_rk4) TRY(l96_halo_for(c, md, y, nullptr, rk4_HL, rk4_HR, &l96_halo));
   double dt = dt_in, error = 0.0;
   int limitCounter = 0;
   while (true) {
@@ -599,6 +604,7 @@ int do_step(b200rk_ctx* c, const MethodDef& md, const RhsCall& rhs, double t, co
       if (rhs.evals) *rhs.evals += md.rk4_final ? 4 : (S - 1);
       if (md.rk4_final) {
         if (l96_attempt) TRY(launch_l96_rk4(c, static_cast<const BuiltinRhs*>(rhs.user)->scalar, rhs.negate_time, dt, l96_halo, y, y_new));
+        else if (ust_rk4) TRY(jit_launch_stencil_rk4(c, ust_jit, rhs.negate_time, t, dt, l96_halo, y, y_new));
         else TRY(launch_fused_rk4(c, pw, rhs.negate_time, t, dt, y, y_new));
         break;
       }

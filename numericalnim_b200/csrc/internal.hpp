@@ -334,7 +334,9 @@ void jit_describe(const JitRhs* j, int* np, const b200rk_vec* const** vecs, cons
 int jit_slot_attempt(int w);
 int jit_slot_run(int w);
 int jit_launch(b200rk_ctx* c, JitRhs* j, int pattern, int slot, unsigned grid, void* arg_block, bool cooperative);
-bool jit_is_stencil(const JitRhs* j, int* radius_left, int* radius_right);   // stencil right-hand side from source (not element-local)
+bool jit_is_stencil(const JitRhs* j, int* radius_left, int* radius_right);
+namespace b200rk { struct L96Halo; }   // stencil_attempt.cuh
+int jit_launch_stencil_rk4(b200rk_ctx* c, JitRhs* j, bool negate, double t, double dt, const b200rk::L96Halo& halo, const b200rk_vec* y, b200rk_vec* y_new);   // stencil right-hand side from source (not element-local)
 int jit_prepare(b200rk_ctx* c, JitRhs* j, int pattern);      // compile + load the base unit and (pattern >= 0) the fused unit now
 int fused_pattern_for(const b200rk_ctx* c, const MethodDef& md);   // sparsity pattern of the method's fused kernels, -1: none
 int jit_max_blocks_per_sm(b200rk_ctx* c, JitRhs* j, int pattern, int slot, int* per_sm);

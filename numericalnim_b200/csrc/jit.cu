@@ -136,13 +136,13 @@ struct StencilSpec {
   bool on = false;
   int rl = 0, rr = 0;
 };
-enum { JS_RHS = 0 };       // stencil base unit
+enum { JS_RHS = 0, JS_RK4 = 1 };   // stencil base unit
 enum { JS_ATTEMPT = 0 };   // stencil unit of one FusedPattern
 
 std::vector<std::string> name_expressions(int pattern, const StencilSpec& st = StencilSpec()) {
   const std::string T = std::to_string(kThreads);
   if (st.on) {
-    if (pattern < 0) return {"b200rk::user_stencil_rhs_kernel<" + T + ">"};
+    if (pattern < 0) return {"b200rk::user_stencil_rhs_kernel<" + T + ">", "b200rk::ustencil_rk4_kernel<2, " + T + ">"};
     return {"b200rk::ustencil_attempt_kernel<" + std::to_string(pattern) + ", 2, " + T + ">"};
   }
   if (pattern < 0)
@@ -480,6 +480,23 @@ static int jit_stencil_eval(b200rk_ctx* c, JitRhs* j, double t, const b200rk_vec
   ProfScope ps(c, B200RK_K_RHS, 8.0 * double(n) * (2 + j->np));
   const unsigned grid = (unsigned)std::min<size_t>((n + kThreads * 4 - 1) / (kThreads * 4), (size_t)c->sm_count * 16);
   return jit_launch(c, j, -1, JS_RHS, grid, &a, false);
+}
+
+// One RK4 step of a stencil right-hand side from source in one kernel (stencil_attempt.cuh: ustencil_rk4_kernel).
+int jit_launch_stencil_rk4(b200rk_ctx* c, JitRhs* j, bool negate, double t, double dt, const L96Halo& halo, const b200rk_vec* y, b200rk_vec* y_new) {
+  const size_t n = y->n_local;
+  if (!n) return B200RK_OK;
+  UStencilRk4Args a;
+  std::memset(&a, 0, sizeof(a));
+  for (int i = 0; i < j->np; ++i) { TRY(check_same(c, y, j->vecs[i])); a.p[i] = j->vecs[i]->d; }
+  for (int i = 0; i < j->nc; ++i) a.cs[i] = j->cs[i];
+  a.y = y->d; a.ynew = y_new->d; a.n = n;
+  a.t = t; a.tsign = negate ? -1.0 : 1.0; a.rsign = negate ? -1.0 : 1.0;
+  a.hdt = 0.5 * dt; a.dt = dt; a.c6 = dt / 6.0;   // same host scalars as launch_fused_rk4 / launch_rk4_final
+  a.halo = halo;
+  const int OUT = 4 * kThreads - stencil_halo(j->stencil.rl, 5) - stencil_halo(j->stencil.rr, 5);
+  ProfScope ps(c, B200RK_K_FUSED, 8.0 * double(n) * (2 + j->np));
+  return jit_launch(c, j, -1, JS_RK4, (unsigned)((n + OUT - 1) / OUT), &a, false);
 }
 
 bool jit_is_stencil(const JitRhs* j, int* rl, int* rr) {

@@ -537,6 +537,17 @@ struct UStencilAttemptArgs {
   L96Halo halo;       // sharded: HL elements before / HR after the block, of y and of k1 (all null on a single GPU)
 };
 
+struct UStencilRk4Args {   // one RK4 step (ode.nim:180-189) of a stencil right-hand side from source in one kernel
+  const double* y;
+  double* ynew;
+  size_t n;
+  const double* p[kMaxUserVecs];
+  double cs[kMaxUserScalars];
+  double t, tsign, rsign;   // step start time (solver coordinates); -1 / -1 for the backward pass g(t, y) = -f(-t, y)
+  double hdt, dt, c6;       // 0.5*dt, dt, dt/6.0 computed by the host
+  L96Halo halo;             // sharded: left_y = the 4*RL (rounded) elements before the block, right_y = the 4*RR after it
+};
+
 // overlap of the whole-attempt tiles for radii (rl, rr) and S stages, rounded to 32 bytes (host and device use the same rule)
 __host__ __device__ constexpr int stencil_halo(int radius, int S) { return ((radius * (S - 1) + 3) / 4) * 4; }
 
@@ -756,6 +767,80 @@ __global__ void __launch_bounds__(THREADS, (Pattern<PAT>::S > 7 || PwTraits<PW_U
     }
   }
   grid_sum_finish<THREADS>(acc, a.f.rs);
+}
+// A whole RK4 step in one kernel, same tiling: four evaluations (k1 = f(t, y) included: RK4 has no FSAL) -> overlap 4*RL left /
+// 4*RR right; reads y (+ parameters), writes yNew. Stage inputs and the final combine are fused_rk4_elem / rk4_elem, stage times
+// those of user_rk4_elem.
+template <int J, int THREADS>
+__global__ void __launch_bounds__(THREADS) ustencil_rk4_kernel(const UStencilRk4Args a) {
+  constexpr int E = 2 * J, TW = E * THREADS, HL = stencil_halo(kStencilRL, 5), HR = stencil_halo(kStencilRR, 5), OUT = TW - HL - HR;
+  constexpr int NP = PwTraits<PW_USER>::NP, NPX = PwTraits<PW_USER>::NPX;
+  __shared__ double buf[2][kStencilPadL + TW + kStencilPadR];
+  const size_t n = a.n;
+  const size_t tile0 = (size_t)blockIdx.x * OUT;
+  for (int q = threadIdx.x; q < kStencilPadL + kStencilPadR; q += THREADS) {
+    const int at = q < kStencilPadL ? q : TW + q;
+    buf[0][at] = 0.0; buf[1][at] = 0.0;
+  }
+  double y[E], k[4][E], in[E], pe[E][NPX];
+  int pos[J];
+  const bool interior = tile0 >= (size_t)HL && tile0 - HL + TW <= n;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int p = 2 * ((int)threadIdx.x + j * THREADS);
+    pos[j] = p;
+    if (interior) {
+      const Pk<2> yv = ld_stream<2>(a.y + (tile0 - HL + p));
+      y[2 * j] = yv.v[0]; y[2 * j + 1] = yv.v[1];
+    } else {
+      y[2 * j] = l96_edge_load<HL, HR>(a.y, a.halo.left_y, a.halo.right_y, n, tile0, p);
+      y[2 * j + 1] = l96_edge_load<HL, HR>(a.y, a.halo.left_y, a.halo.right_y, n, tile0, p + 1);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      long long g = (long long)tile0 - HL + p + h;
+      if (a.halo.left_y) g = g < 0 ? 0 : ((size_t)g >= n ? (long long)n - 1 : g);
+      else g = ((g % (long long)n) + (long long)n) % (long long)n;
+#pragma unroll
+      for (int q = 0; q < NPX; ++q) pe[2 * j + h][q] = q < NP ? a.p[q][g] : 0.0;
+    }
+  }
+  const double tm = __dadd_rn(a.t, __dmul_rn(a.dt, 0.5)), te = __dadd_rn(a.t, __dmul_rn(a.dt, 1.0));   // ode.nim:185-187
+  constexpr int WL = kStencilPadL, WLEN = kStencilPadL + 2 + kStencilPadR;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {   // stage s + 1: its input, published; then k_{s+1} from the neighbourhood
+    double* sh = buf[s & 1] + kStencilPadL;
+    const double c = (s == 3) ? a.dt : a.hdt;
+    const double ts = flip_sign_by(s == 0 ? a.t : (s == 3 ? te : tm), a.tsign);
+#pragma unroll
+    for (int e = 0; e < E; ++e) in[e] = (s == 0) ? y[e] : __dadd_rn(y[e], __dmul_rn(k[s - 1 < 0 ? 0 : s - 1][e], c));
+#pragma unroll
+    for (int j = 0; j < J; ++j) { sh[pos[j]] = in[2 * j]; sh[pos[j] + 1] = in[2 * j + 1]; }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      double w[WLEN];
+#pragma unroll
+      for (int q = 0; q < WLEN; q += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(sh + pos[j] - WL + q);
+        w[q] = v.x; w[q + 1] = v.y;
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) k[s][2 * j + h] = flip_sign_by(user_stencil(ts, w + WL + h, pe[2 * j + h], a.cs), a.rsign);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int p = pos[j];
+    const size_t g = tile0 + (size_t)(p - HL);
+    if (p >= HL && p < HL + OUT && g < n) {
+      Pk<2> o;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) o.v[h] = rk4_elem(y[2 * j + h], k[0][2 * j + h], k[1][2 * j + h], k[2][2 * j + h], k[3][2 * j + h], a.c6);
+      if (g + 1 < n) st_stream<2>(a.ynew + g, o);
+      else a.ynew[g] = o.v[0];
+    }
+  }
 }
 #endif  // B200RK_JIT_STENCIL
 

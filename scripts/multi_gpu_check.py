@@ -135,6 +135,15 @@ def main():
                 print(f"[multi-gpu world={world}] {name} tsit54 fuse={fuse} peer_halo={peer_halo}: steps={st['steps']} launches={st['launches']} collectives={st['collectives']} ok={ok}", flush=True)
         ctx.set("fuse_stencil_attempt", 1)
         ctx.set("l96_peer_halo", 1)
+        # RK4 of the same stencil: one kernel per step, the 4 * radius halo by one ncclSend/ncclRecv per step; bit-identical to the oracle
+        t, ys = nn.solveODE(srhs, gs, [0.0, 0.02], nn.newODEoptions(dt=2e-3), integrator="rk4")
+        st = dict(nn.ode.last_stats)
+        ref4 = O.solve_vector("rk4", O.rhs_callback(fnp), y_init, [0.0, 0.02], O.new_options(dt=2e-3)).y[-1][lo:lo + ll]
+        ok4 = np.array_equal(ys[-1].local_numpy().view(np.uint64), np.asarray(ref4).view(np.uint64))
+        if not ok4:
+            fails.append((name, "rk4 one-kernel step bitwise"))
+        if rank == 0:
+            print(f"[multi-gpu world={world}] {name} rk4 one-kernel step: steps={st['steps']} launches={st['launches']} collectives={st['collectives']} ok={ok4}", flush=True)
     # right-hand side given as SOURCE, sharded: the parameter vector shards like the state; the run-time compiled
     # attempt kernel / device loop use the same in-kernel all-reduce as the built-ins
     K = 2.0 + 3.0 * np.arange(n) / (n - 1)

@@ -17,6 +17,7 @@ int jit_launch(b200rk_ctx* c, JitRhs*, int, int, unsigned, void*, bool) { return
 int jit_max_blocks_per_sm(b200rk_ctx* c, JitRhs*, int, int, int*) { return unavailable(c); }
 int jit_prepare(b200rk_ctx* c, JitRhs*, int) { return unavailable(c); }
 bool jit_is_stencil(const JitRhs*, int*, int*) { return false; }
+int jit_launch_stencil_rk4(b200rk_ctx* c, JitRhs*, bool, double, double, const b200rk::L96Halo&, const b200rk_vec*, b200rk_vec*) { return unavailable(c); }
 int jit_launch_rk4(b200rk_ctx* c, JitRhs*, bool, double, double, const b200rk_vec*, b200rk_vec*) { return unavailable(c); }
 
 extern "C" {

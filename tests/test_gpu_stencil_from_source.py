@@ -138,6 +138,39 @@ def test_adaptive_solve_with_dense_output_and_backward_time(nn, name, method):
         assert np.all(np.abs(g - e) <= rtol * np.abs(e) + 1e-13 * np.max(np.abs(e))), float(np.max(np.abs(g - e)))
 
 
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_rk4_step_in_one_kernel_is_bit_identical(nn, name):
+    """RK4 (ode.nim:180-189) of a stencil from source: k1..k4 and the final combine in ONE kernel over tiles that overlap by 4 * radius —
+    bit-identical to the stage / RHS pipeline and to the oracle, around the tile seams, with dense output and a backward pass."""
+    ctx = nn.default_context()
+    rng = np.random.default_rng(23)
+    try:
+        for n in (9, 11, 1003, 1011, 1012, 1013, 1024, 2023, 2024, 4099, 65536 + 3):
+            rhs, orhs, pvals = make(nn, name, n, rng)
+            y = 8.0 + rng.uniform(-1, 1, n)
+            gy = nn.newVector(y)
+            res = {}
+            for fuse in (1, 0):
+                ctx.set("fuse_stencil_attempt", fuse)
+                l0 = ctx.stats()["launches"]
+                yn, fn, dt_used, err = nn.integratorStep("rk4", rhs, 0.4, gy, gy, 2e-3, nn.newODEoptions(dt=2e-3))
+                res[fuse] = (yn.to_numpy(), ctx.stats()["launches"] - l0)
+            assert_bitwise_equal(res[1][0], res[0][0], f"{name} rk4 n={n}")
+            assert res[1][1] <= 2 and res[0][1] >= 8, (res[1][1], res[0][1])
+            yn_ref, *_ = O.step_vector("rk4", orhs, 0.4, y, y, 2e-3, O.new_options(dt=2e-3))
+            assert_bitwise_equal(res[1][0], yn_ref, f"{name} rk4 vs oracle n={n}")
+        ctx.set("fuse_stencil_attempt", 1)
+        n = 3001
+        rhs, orhs, pvals = make(nn, name, n, rng)
+        y0 = 1.0 + 0.5 * np.sin(2 * np.pi * np.arange(n) / n)
+        ts = nn.linspace(-0.02, 0.03, 7)
+        t, ys = nn.solveODE(rhs, nn.newVector(y0), ts, nn.newODEoptions(dt=2e-3), integrator="rk4")
+        ref = O.solve_vector("rk4", orhs, y0, ts, O.new_options(dt=2e-3))
+        assert_bitwise_equal(np.array([v.to_numpy() for v in ys]), ref.y, f"{name} rk4 trajectory (dense output, backward pass)")
+    finally:
+        ctx.set("fuse_stencil_attempt", 1)
+
+
 @pytest.mark.parametrize("method", ["rk4", "bs32", "heun2", "ssprk3"])
 def test_methods_without_a_fused_form_run_the_pipeline_bit_identically(nn, method):
     rng = np.random.default_rng(19)

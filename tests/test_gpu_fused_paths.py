@@ -139,7 +139,7 @@ def test_cumsimpson_fn_streams_a_fine_grid_by_itself(nn):
 
 
 # ---- knob fuse_stencil_attempt: a whole attempt of the built-in Lorenz-96 right-hand side in one kernel ---------------
-@pytest.mark.parametrize("pairs", [2, 1])
+@pytest.mark.parametrize("pairs", [2, 1, 0])   # 0: the warp-tile variant (knob l96_warp_tiles: shuffles, no shared memory, 128-position tiles)
 @pytest.mark.parametrize("method,stages", [("dopri54", 7), ("tsit54", 7), ("vern65", 9)])
 def test_l96_attempt_kernel_bitwise_equals_pipeline(nn, method, stages, pairs):
     """l96_attempt_kernel (stencil_attempt.cuh: overlapped tiles, stage inputs through shared memory): yNew and the new
@@ -151,7 +151,7 @@ def test_l96_attempt_kernel_bitwise_equals_pipeline(nn, method, stages, pairs):
     import oracle as O
     ctx = nn.default_context()
     rng = np.random.default_rng(17)
-    out_per_tile = 512 * pairs - (12 + 8 if stages == 7 else 16 + 8)
+    out_per_tile = (512 * pairs if pairs else 128) - (12 + 8 if stages == 7 else 16 + 8)
     sizes = [4, 5, 7, 19, 21, out_per_tile - 1, out_per_tile, out_per_tile + 1, 1023, 1024, 1025, 2 * out_per_tile - 1, 2 * out_per_tile,
              2 * out_per_tile + 2, 3 * out_per_tile + 13]
     if not os.environ.get("B200RK_TEST_HOST_EMULATION"):
@@ -162,7 +162,8 @@ def test_l96_attempt_kernel_bitwise_equals_pipeline(nn, method, stages, pairs):
     o = nn.newODEoptions(**opts)
     rhs = nn.rhsLorenz96(8.0)
     try:
-        ctx.set("l96_attempt_pairs", pairs)
+        ctx.set("l96_attempt_pairs", pairs or 2)
+        ctx.set("l96_warp_tiles", 1 if pairs == 0 else 0)
         for strict in (0, 1):
             ctx.set("strict_zeros", strict)
             for n in (sizes if not strict else sizes[5:9] if not LIGHT else sizes[2:3]):
@@ -189,6 +190,7 @@ def test_l96_attempt_kernel_bitwise_equals_pipeline(nn, method, stages, pairs):
         ctx.set("strict_zeros", 0)
         ctx.set("fuse_stencil_attempt", 1)
         ctx.set("l96_attempt_pairs", 2)
+        ctx.set("l96_warp_tiles", 0)
 
 
 @pytest.mark.parametrize("method", ["tsit54", "vern65"])
@@ -289,3 +291,41 @@ def test_l96_rk4_step_in_one_kernel_is_bit_identical(nn):
         assert np.array_equal(out[1].view(np.uint64), np.asarray(want).view(np.uint64))
     finally:
         ctx.set("fuse_stencil_attempt", 1)
+
+
+def test_round2_knobs_and_host_side_tstart_copy(nn):
+    """Knobs added in round 2 are readable / writable, and solve_host returns the same bits whichever way the tStart slot is filled
+    (D2H on a second stream, or a host-side copy of y0 by helper threads)."""
+    import ctypes as C
+
+    from numericalnim_b200 import _capi
+    ctx = nn.default_context()
+    for key, val in (("peer_timeout_s", 30), ("l96_ctas_per_sm", 2), ("l96_warp_tiles", 1), ("tstart_copy", 1)):
+        old = ctx.get(key)
+        ctx.set(key, val)
+        assert ctx.get(key) == val
+        ctx.set(key, old)
+    with pytest.raises(ValueError):
+        ctx.set("peer_timeout_s", 0)
+    n = 70001
+    lam = 0.1 + 9.9 * np.arange(n) / (n - 1)
+    y0 = 1.0 + 0.5 * np.sin(2 * np.pi * np.arange(n) / n)
+    rhs = nn.rhsDiagLinear(nn.newVector(lam))
+    ts = np.array([0.0, 0.5])
+    opts = nn.newODEoptions(absTol=1e-6, relTol=1e-6, dtMax=1.0, dtMin=1e-8)
+    outs = {}
+    try:
+        for mode in (0, 1):
+            ctx.set("tstart_copy", mode)
+            out = np.empty((2, n))
+            t_out = np.empty(2)
+            n_out = C.c_size_t(0)
+            st = _capi.Stats()
+            _capi.check(_capi.lib().b200rk_solve_host(ctx.handle, nn.ode.method_id("dopri54"), rhs.fn, rhs.user, n, y0.ctypes.data, ts.ctypes.data, 2,
+                                                      C.byref(opts), t_out.ctypes.data, out.ctypes.data, C.byref(n_out), C.byref(st)), ctx.handle)
+            assert n_out.value == 2 and list(t_out) == [0.0, 0.5]
+            outs[mode] = out
+        assert np.array_equal(outs[0].view(np.uint64), outs[1].view(np.uint64))
+        assert np.array_equal(outs[0][0].view(np.uint64), y0.view(np.uint64))
+    finally:
+        ctx.set("tstart_copy", 0)

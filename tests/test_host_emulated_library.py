@@ -29,7 +29,7 @@ def test_gpu_suites_pass_under_host_emulation():
     counts = {k: int(v) for v, k in re.findall(r"(\d+) (passed|failed|error|errors|xpassed|xfailed|skipped)", tail)}
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
     assert counts.get("failed", 0) == 0 and counts.get("error", 0) == 0 and counts.get("errors", 0) == 0, tail
-    assert counts.get("passed", 0) >= 221, tail            # parity 147 + fuzz 3 + quadrature 40 + device loop 9 + fused paths 22
+    assert counts.get("passed", 0) >= 225, tail            # parity 147 + fuzz 3 + quadrature 40 + device loop 9 + fused paths 26
     assert counts.get("xpassed", 0) + counts.get("xfailed", 0) == 0, tail
 
 

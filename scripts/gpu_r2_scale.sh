@@ -10,7 +10,7 @@ print("N", d["n_gpus"], "value", round(d["value"],1), "per gpu", round(d["value"
 print("  parity", d["parity_check"]["ok"], d["parity_check"]["cases"], d["parity_check"]["max_rel"], "pipeline", round(d["pipeline"]["value"],1))
 for k in ("cfg3","cfg4"):
     c=d.get(k) or {}
-    if c: print("  ", k, round(c.get("value",0),1), "frac", round((c.get("roofline") or {}).get("frac",0),3), "collectives", c.get("collectives"), "attempts", c.get("attempts"), c.get("error"))
+    if c: print("  ", k, round(c.get("value",0),1), "frac", round((c.get("roofline") or {}).get("frac",0),3), "collectives", c.get("collectives"), "attempts", c.get("attempts"), c.get("error"), "from source", (c.get("stencil_from_source") or {}).get("value"))
 print("  e2e", round(e["value"],1), "ms/solve", round(e["ms_per_solve"],3), "resident", round(e.get("rhs_resident",{}).get("value",0),1), "alt tstart", e.get("tstart_slot",{}).get("alternative_value"), "pcie", e.get("pcie"))
 print("  clocks", d["clocks"])'
 if [ "$N" = "1" ]; then
@@ -24,4 +24,4 @@ d = json.loads(sys.stdin.read())
 print('cfg3 N', d['n_gpus'], 'value', round(d['value'], 1), 'per gpu', round(d['value'] / d['n_gpus'], 1), 'frac', round(d['roofline']['frac'], 3), 'collectives', d['collectives'], 'attempts', d['attempts'])"
 fi
 tail -2 gpurun_out/scale_r2_n$N.err | cut -c1-200
-if [ "$N" = "8" ]; then bash scripts/gpu_r2_sweep.sh 8; fi
+if [ "$N" = "8" ] && [ "${2:-}" = "sweep" ]; then bash scripts/gpu_r2_sweep.sh 8; fi

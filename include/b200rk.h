@@ -99,7 +99,7 @@ B200RK_API int b200rk_world(const b200rk_ctx* ctx);
  * kernel; 0 = always the stage / RHS / finish pipeline), "fuse_stencil" (built-in Lorenz-96: stage accumulate + stencil
  * in one kernel), "device_loop" (-1 auto | 0 | 1: the whole adaptive loop in one persistent kernel), "spin_readback",
  * "l2_hints" (-1 auto | 0 | 1: producer/consumer hand-off through the L2), "fuse_simpson" (default 1: cumsimpson as one kernel), "fuse_stencil_attempt" (default 1: a whole attempt of the built-in Lorenz-96 right-hand side in one
- * kernel, with "l96_attempt_pairs" 1|2 = 512- or 1024-wide tiles, "l96_ctas_per_sm" (0 = occupancy), "l96_warp_tiles" (default 0: warp-sized tiles exchanged by shuffle — measured slower) and,
+ * kernel, with "l96_attempt_pairs" 1|2 = 512- or 1024-wide tiles, "l96_ctas_per_sm" (0 = occupancy), "l96_warp_tiles" (default 0; 8 | 4 = warp-sized tiles exchanged by shuffle with that many elements per lane — measured slower) and,
  * sharded, "l96_peer_halo" 1|0 = halo read in place from the peer-mapped ring neighbours | one ncclSend/ncclRecv per step), "finish_prefetch" (default 0: measured, no gain),
  * "tstart_copy" (solve_host: 0 = the tStart state returns by D2H on a second stream, 1 = host-side copy), "peer_timeout_s" (how long a kernel waits for a peer's partial sum, default 120), "profile" (0|1), "pool_budget_mb" (bytes of freed vectors the context keeps for reuse;
  * 0 = release everything now). Read-only: "p2p", "sm_count". */

@@ -472,12 +472,12 @@ static int launch_ustencil_attempt(b200rk_ctx* c, const MethodDef& md, JitRhs* j
   return jit_launch(c, jit, PAT, 0, grid, &a, false);
 }
 
-// Warp-sized tiles (stencil_attempt.cuh: l96_warp_attempt_kernel): same argument block, persistent grid of warps.
-template <int PAT>
-static int launch_l96_warp(b200rk_ctx* c, const MethodDef& md, double F, bool negate, double dt, const b200rk_options& o,
-                           const L96Halo& halo, const b200rk_vec* y, const b200rk_vec* fsal, b200rk_vec* y_new, b200rk_vec* fsal_new) {
+// Warp-sized tiles (stencil_attempt.cuh: l96_warp_attempt_kernel): same argument block, persistent grid of warps; E elements per lane.
+template <int PAT, int E>
+static int launch_l96_warp_e(b200rk_ctx* c, const MethodDef& md, double F, bool negate, double dt, const b200rk_options& o,
+                             const L96Halo& halo, const b200rk_vec* y, const b200rk_vec* fsal, b200rk_vec* y_new, b200rk_vec* fsal_new) {
   constexpr int S = Pattern<PAT>::S;
-  constexpr int OUT = WarpTile<S>::OUT, WPB = kThreads / 32;
+  constexpr int OUT = WarpTile<S, E>::OUT, WPB = kThreads / 32;
   L96AttemptArgs<S> a;
   std::memset(&a, 0, sizeof(a));
   a.f.y = y->d; a.f.k1 = fsal->d;
@@ -490,7 +490,7 @@ static int launch_l96_warp(b200rk_ctx* c, const MethodDef& md, double F, bool ne
   a.halo = halo;
   static int per_sm = 0;   // per instantiation
   if (per_sm == 0) {
-    CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l96_warp_attempt_kernel<PAT, kThreads, false>, kThreads, 0));
+    CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l96_warp_attempt_kernel<PAT, E, kThreads, false>, kThreads, 0));
     if (per_sm < 1) per_sm = 1;
   }
   const size_t n_tiles = (a.f.n + OUT - 1) / OUT;
@@ -499,10 +499,16 @@ static int launch_l96_warp(b200rk_ctx* c, const MethodDef& md, double F, bool ne
   TRY(ensure_partials(c, grid));
   a.f.rs = reduce_scratch(c);
   ProfScope ps(c, B200RK_K_FUSED, 8.0 * double(a.f.n) * 4);  // y, k1 read; yNew, k_S written
-  if (negate) l96_warp_attempt_kernel<PAT, kThreads, true><<<grid, kThreads, 0, c->stream>>>(a);
-  else l96_warp_attempt_kernel<PAT, kThreads, false><<<grid, kThreads, 0, c->stream>>>(a);
+  if (negate) l96_warp_attempt_kernel<PAT, E, kThreads, true><<<grid, kThreads, 0, c->stream>>>(a);
+  else l96_warp_attempt_kernel<PAT, E, kThreads, false><<<grid, kThreads, 0, c->stream>>>(a);
   CUDA_TRY(c, cudaGetLastError());
   return B200RK_OK;
+}
+template <int PAT>
+static int launch_l96_warp(b200rk_ctx* c, const MethodDef& md, double F, bool negate, double dt, const b200rk_options& o,
+                           const L96Halo& halo, const b200rk_vec* y, const b200rk_vec* fsal, b200rk_vec* y_new, b200rk_vec* fsal_new) {
+  if (c->l96_warp_tiles == 4) return launch_l96_warp_e<PAT, 4>(c, md, F, negate, dt, o, halo, y, fsal, y_new, fsal_new);
+  return launch_l96_warp_e<PAT, 8>(c, md, F, negate, dt, o, halo, y, fsal, y_new, fsal_new);
 }
 
 // Tile width = 512 * J positions (knob "l96_attempt_pairs": 2 = 1024-wide tiles, 2 % overlap, 80-98 registers; 1 = 512-wide,

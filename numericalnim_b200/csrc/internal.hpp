@@ -89,7 +89,7 @@ struct b200rk_ctx {
   bool fuse_stencil = true;    // built-in Lorenz-96 (single GPU): stage accumulate + stencil RHS in one kernel
   bool fuse_stencil_attempt = true;  // built-in Lorenz-96: a whole attempt in one kernel over overlapped tiles (default since round 2: 914 -> 3939 steps/s on config 3, profiles/r02_*)
   bool l96_peer_halo = true;   // sharded one-kernel Lorenz-96 attempt inside a solver: read the halo in place from the peer-mapped neighbours (false: ncclSend/ncclRecv)
-  bool l96_warp_tiles = false; // one-kernel Lorenz-96 attempt over warp-sized tiles (shuffles, no block barrier) instead of CTA-sized tiles: measured slower (164-185 vs 154 us), kept as an A/B knob
+  int l96_warp_tiles = 0;      // one-kernel Lorenz-96 attempt over warp-sized tiles (shuffles, no block barrier) instead of CTA-sized tiles: 0 off, 8 (or 1) = 8 elements per lane, 4 = 4 per lane
   int l96_ctas_per_sm = 0;     // l96_attempt_kernel's persistent grid: CTAs per SM, 0 = what the occupancy calculator allows
   int l96_attempt_pairs = 2;   // l96_attempt_kernel: 128-bit pairs per thread (tile = 512 * pairs positions); 1 or 2
   bool finish_prefetch = false; // register-prefetching finish kernel: measured on the B200 in round 2 — no gain (88.5 vs 90.1-91.8 us), stays off

@@ -324,7 +324,7 @@ static int ctx_common_init(b200rk_ctx* c) {
   if (const char* e = getenv("B200RK_FUSE_POINTWISE")) c->fuse_pointwise = atoi(e) != 0;
   if (const char* e = getenv("B200RK_FUSE_STENCIL")) c->fuse_stencil = atoi(e) != 0;
   if (const char* e = getenv("B200RK_TSTART_COPY")) c->tstart_copy = atoi(e) != 0;
-  if (const char* e = getenv("B200RK_L96_WARP_TILES")) c->l96_warp_tiles = atoi(e) != 0;
+  if (const char* e = getenv("B200RK_L96_WARP_TILES")) c->l96_warp_tiles = (atoi(e) == 4) ? 4 : (atoi(e) != 0 ? 8 : 0);
   if (const char* e = getenv("B200RK_L96_CTAS_PER_SM")) c->l96_ctas_per_sm = std::max(0, std::min(32, atoi(e)));
   if (const char* e = getenv("B200RK_FUSE_STENCIL_ATTEMPT")) c->fuse_stencil_attempt = atoi(e) != 0;
   if (const char* e = getenv("B200RK_L96_PEER_HALO")) c->l96_peer_halo = atoi(e) != 0;
@@ -423,7 +423,7 @@ int b200rk_set(b200rk_ctx* c, const char* key, int64_t v) {
   else if (k == "fuse_stencil_attempt") c->fuse_stencil_attempt = v != 0;
   else if (k == "l96_peer_halo") c->l96_peer_halo = v != 0;
   else if (k == "tstart_copy") c->tstart_copy = v != 0;
-  else if (k == "l96_warp_tiles") c->l96_warp_tiles = v != 0;
+  else if (k == "l96_warp_tiles") c->l96_warp_tiles = (v == 4) ? 4 : (v != 0 ? 8 : 0);
   else if (k == "l96_ctas_per_sm") { if (v < 0 || v > 32) return fail(c, B200RK_EINVAL, "l96_ctas_per_sm must be in 0..32"); c->l96_ctas_per_sm = (int)v; }
   else if (k == "l96_attempt_pairs") { if (v != 1 && v != 2) return fail(c, B200RK_EINVAL, "l96_attempt_pairs must be 1 or 2"); c->l96_attempt_pairs = (int)v; }
   else if (k == "fuse_simpson") c->fuse_simpson = v != 0;

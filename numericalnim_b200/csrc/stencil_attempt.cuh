@@ -305,124 +305,142 @@ __global__ void __launch_bounds__(THREADS, (Pattern<PAT>::S > 7 || J > 2) ? 2 : 
 // the arithmetic of the others, as in the element-local fused kernel. The price is a larger overlap: HL + HR of 128
 // positions (16 % for the 7-stage pairs, 19 % for Vern65) instead of 2 % of a 1024-wide tile. Per-element arithmetic is the
 // CTA-tile kernel's (const_wsum rows, l96_pair's operation order, err_ratio): yNew and k_S are bit-identical.
-// MEASURED (B200, Tsit54, 2^24; profiles/r02_l96_attempt_variants.md): 164 us per attempt with plain register loads (fp64 pipe
-// 68 % busy, a quarter of the stall samples on the tile's own loads), 182 us with the cp.async prefetch below at 80 registers
-// (88 bytes of spills), 185 us at 124 registers / 2 CTAs per SM — against 154 us for the CTA-tile kernel, whose 2 % overlap
-// outweighs its barriers. The kernel therefore stays behind knob "l96_warp_tiles" (default 0) as the measured alternative.
+// MEASURED (B200, Tsit54, 2^24; profiles/r02_l96_attempt_variants.md): 4 elements per lane — 164 us per attempt with plain register
+// loads (fp64 pipe 68 % busy, a quarter of the stall samples on the tile's own loads), 182-188 us with the cp.async prefetch at 80
+// registers (spills), 185 us at 124 registers / 2 CTAs per SM; 8 elements per lane (211 registers, 1 CTA per SM, half the overlap and
+// shuffles) — 170 us; against 154 us for the CTA-tile kernel. The kernel therefore stays behind knob "l96_warp_tiles" (default 0;
+// 8 or 4 = elements per lane) as the measured alternative.
 // Positions whose neighbours lie outside the tile read another lane's value through the shuffle's clamping; they are
 // in the overlap and never stored (lane 0's left inputs and lane 31's right input go bad first: 2 resp. 1 position per stage).
 // ---------------------------------------------------------------------------------------------------
-template <int S>
+template <int S, int E>
 struct WarpTile {
-  static constexpr int E = 4, TW = 32 * E;
+  static constexpr int TW = 32 * E;
   static constexpr int HL = StencilTile<S>::HL, HR = StencilTile<S>::HR, OUT = TW - HL - HR;
 };
 
-template <int PAT, int s, bool NEG>
+// Stencil at the lane's E adjacent positions: k[i] = ((in[i+1] - in[i-2]) * in[i-1] - in[i]) + F in l96_pair's operation order; in[-2],
+// in[-1] come from lane l-1 (its last two inputs), in[E] from lane l+1 (its first).
+template <int PAT, int s, int E, bool NEG>
 struct L96WarpStages {
   template <int S>
-  __device__ __forceinline__ static void run(const double (&y)[4], double (&k)[4][S], double (&in)[4], const L96AttemptArgs<S>& a) {
-    if constexpr (s > 2) L96WarpStages<PAT, s - 1, NEG>::run(y, k, in, a);
+  __device__ __forceinline__ static void run(const double (&y)[E], double (&k)[E][S], double (&in)[E], const L96AttemptArgs<S>& a) {
+    if constexpr (s > 2) L96WarpStages<PAT, s - 1, E, NEG>::run(y, k, in, a);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < E; ++e) {
       const double acc = const_wsum<S, Pattern<PAT>::a(s - 2)>(k[e], a.f.a[s - 2]);
       in[e] = __dadd_rn(y[e], __dmul_rn(acc, a.f.dt));                                   // stage_elem
     }
-    const double m2 = __shfl_up_sync(0xffffffffu, in[2], 1), m1 = __shfl_up_sync(0xffffffffu, in[3], 1);   // positions -2, -1
-    const double p4 = __shfl_down_sync(0xffffffffu, in[0], 1);                                            // position +4
-    l96_pair<NEG>(m2, m1, in[2], in[0], in[1], a.F, k[0][s - 1], k[1][s - 1]);
-    l96_pair<NEG>(in[0], in[1], p4, in[2], in[3], a.F, k[2][s - 1], k[3][s - 1]);
+    double w[E + 3];   // w[i] = in[i - 2]
+    w[0] = __shfl_up_sync(0xffffffffu, in[E - 2], 1);
+    w[1] = __shfl_up_sync(0xffffffffu, in[E - 1], 1);
+    w[E + 2] = __shfl_down_sync(0xffffffffu, in[0], 1);
+#pragma unroll
+    for (int e = 0; e < E; ++e) w[e + 2] = in[e];
+#pragma unroll
+    for (int e = 0; e < E; e += 2)
+      l96_pair<NEG>(w[e], w[e + 1], w[e + 4], w[e + 2], w[e + 3], a.F, k[e][s - 1], k[e + 1][s - 1]);
   }
 };
 
-// Register-free prefetch of a lane's own 2 x 32 bytes of the next tile: cp.async (LDGSTS) into a per-warp staging area.
+// Register-free prefetch of a lane's own bytes of the next tile: cp.async (LDGSTS) into a per-thread staging area.
 // A lane later reads back exactly the bytes it copied itself, so no warp- or block-level synchronisation is involved —
 // cp.async.wait_group on the issuing thread is all the ordering there is.
 #ifndef B200RK_HOST_EMULATION
-__device__ __forceinline__ void lane_prefetch32(double* dst_lo, double* dst_hi, const double* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned int)__cvta_generic_to_shared(dst_lo)), "l"(src) : "memory");
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned int)__cvta_generic_to_shared(dst_hi)), "l"(src + 2) : "memory");
+__device__ __forceinline__ void lane_prefetch16(double* dst, const double* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned int)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void lane_prefetch_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void lane_prefetch_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 #else
-inline void lane_prefetch32(double* dst_lo, double* dst_hi, const double* src) { dst_lo[0] = src[0]; dst_lo[1] = src[1]; dst_hi[0] = src[2]; dst_hi[1] = src[3]; }
+inline void lane_prefetch16(double* dst, const double* src) { dst[0] = src[0]; dst[1] = src[1]; }
 inline void lane_prefetch_commit() {}
 inline void lane_prefetch_wait() {}
 #endif
 
-template <int PAT, int THREADS, bool NEG>
-__global__ void __launch_bounds__(THREADS, Pattern<PAT>::S > 7 ? 2 : 3) l96_warp_attempt_kernel(const L96AttemptArgs<Pattern<PAT>::S> a) {
+// E = 8 elements per lane (256-position tiles, 8-9 % overlap, ~170-200 registers: ONE CTA per SM — the fp64 pipe of a scheduler is
+// saturated by a single warp once it has 4 independent chains in flight (measured: 8-cycle dependent latency, 2 cycles per issue), so
+// two warps of 8 chains per scheduler are enough, and wider lanes halve both the overlap and the shuffles per element).
+// E = 4: 128-position tiles, 16-19 % overlap, 80 registers, 3 CTAs per SM.
+template <int PAT, int E, int THREADS, bool NEG>
+__global__ void __launch_bounds__(THREADS, E >= 8 ? 1 : (Pattern<PAT>::S > 7 ? 2 : 3)) l96_warp_attempt_kernel(const L96AttemptArgs<Pattern<PAT>::S> a) {
   constexpr int S = Pattern<PAT>::S;
-  using T = WarpTile<S>;
+  using T = WarpTile<S, E>;
   constexpr int HL = T::HL, HR = T::HR, OUT = T::OUT, TW = T::TW;
+  static_assert(E % 4 == 0, "a lane stores whole 32-byte groups");
   const size_t n = a.f.n;
   const size_t n_tiles = (n + OUT - 1) / OUT;
   const int lane = threadIdx.x & 31;
   const size_t warp = (size_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5), n_warps = (size_t)gridDim.x * (THREADS / 32);
-  const int p = 4 * lane;                                   // first of the lane's 4 positions
-  const bool lane_stores = p >= HL && p < HL + OUT;         // HL, OUT multiples of 4: a lane stores all 4 positions or none
+  const int p = E * lane;                                   // first of the lane's E positions
   double acc = 0.0;
-  alignas(16) __shared__ double staged[2][2][THREADS][2];   // [y | k1][low / high pair][thread][2]: each lane's own slots (16 bytes apart across lanes: conflict-free), written by cp.async
+  alignas(16) __shared__ double staged[2][E / 2][THREADS][2];   // [y | k1][pair][thread][2]: a lane's pairs lie 16 bytes apart across lanes (conflict-free); written by cp.async
   auto interior_tile = [&](size_t t) { const size_t t0 = t * (size_t)OUT; return t0 >= (size_t)HL && t0 - HL + TW <= n; };
-  if (warp < n_tiles && interior_tile(warp)) {
-    lane_prefetch32(staged[0][0][threadIdx.x], staged[0][1][threadIdx.x], a.f.y + (warp * OUT - HL + p));
-    lane_prefetch32(staged[1][0][threadIdx.x], staged[1][1][threadIdx.x], a.f.k1 + (warp * OUT - HL + p));
-  }
+  auto prefetch = [&](size_t t) {
+    const size_t g = t * (size_t)OUT - HL + p;
+#pragma unroll
+    for (int q = 0; q < E / 2; ++q) {
+      lane_prefetch16(staged[0][q][threadIdx.x], a.f.y + g + 2 * q);
+      lane_prefetch16(staged[1][q][threadIdx.x], a.f.k1 + g + 2 * q);
+    }
+  };
+  if (warp < n_tiles && interior_tile(warp)) prefetch(warp);
   lane_prefetch_commit();
   for (size_t tile = warp; tile < n_tiles; tile += n_warps) {
     const size_t tile0 = tile * (size_t)OUT;                // first stored element of this tile
-    double y[4], k[4][S], in[4];
+    double y[E], k[E][S], in[E];
     const bool interior = interior_tile(tile);
-    if (interior) {                                         // the lane's 2 x 32 bytes were prefetched while the previous tile was evaluated
+    if (interior) {                                         // the lane's bytes were prefetched while the previous tile was evaluated
       lane_prefetch_wait();
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { y[e] = staged[0][e >> 1][threadIdx.x][e & 1]; k[e][0] = staged[1][e >> 1][threadIdx.x][e & 1]; }
+      for (int e = 0; e < E; ++e) { y[e] = staged[0][e >> 1][threadIdx.x][e & 1]; k[e][0] = staged[1][e >> 1][threadIdx.x][e & 1]; }
     }
     {
       const size_t nxt = tile + n_warps;
-      if (nxt < n_tiles && interior_tile(nxt)) {
-        lane_prefetch32(staged[0][0][threadIdx.x], staged[0][1][threadIdx.x], a.f.y + (nxt * OUT - HL + p));
-        lane_prefetch32(staged[1][0][threadIdx.x], staged[1][1][threadIdx.x], a.f.k1 + (nxt * OUT - HL + p));
-      }
+      if (nxt < n_tiles && interior_tile(nxt)) prefetch(nxt);
       lane_prefetch_commit();
     }
-    if (!interior) {                                                // first / last tiles: around the ring, or into the neighbouring shards
+    if (!interior) {                                        // first / last tiles: around the ring, or into the neighbouring shards
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
+      for (int e = 0; e < E; ++e) {
         y[e] = l96_edge_load<HL, HR>(a.f.y, a.halo.left_y, a.halo.right_y, n, tile0, p + e);
         k[e][0] = l96_edge_load<HL, HR>(a.f.k1, a.halo.left_k, a.halo.right_k, n, tile0, p + e);
       }
     }
 #pragma unroll
-    for (int e = 0; e < 4; ++e)
+    for (int e = 0; e < E; ++e)
 #pragma unroll
       for (int j = 1; j < S; ++j) k[e][j] = 0.0;
-    L96WarpStages<PAT, S, NEG>::run(y, k, in, a);
-    const size_t g = tile0 + (size_t)(p - HL);              // meaningful when lane_stores
-    const bool stored = lane_stores && g < n;
-    Pk<4> yo, ko;
+    L96WarpStages<PAT, S, E, NEG>::run(y, k, in, a);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      ko.v[e] = k[e][S - 1];
-      if (Pattern<PAT>::last) yo.v[e] = in[e];
-      else yo.v[e] = __dadd_rn(y[e], __dmul_rn(const_wsum<S, Pattern<PAT>::b()>(k[e], a.f.b), a.f.cb));
-      const double lo = __dmul_rn(const_wsum<S, Pattern<PAT>::bh()>(k[e], a.f.bh), a.f.cbh);
-      double err;
-      if (Pattern<PAT>::direct) err = lo;
-      else err = __dadd_rn(yo.v[e], -__dadd_rn(y[e], lo));
-      const double tol = __dadd_rn(a.f.absTol, __dmul_rn(fabs(yo.v[e]), a.f.relTol));
-      const double r = err_ratio(err, tol);
-      if (stored && g + e < n) acc = __dadd_rn(acc, __dmul_rn(r, r));
-    }
-    if (stored) {
-      if (g + 4 <= n) {
-        st_stream<4>(a.f.ynew + g, yo);
-        st_stream<4>(a.f.ks_out + g, ko);
-      } else {
+    for (int h = 0; h < E / 4; ++h) {                       // HL, OUT multiples of 4: a group of 4 positions is stored whole or not at all (up to n)
+      const int ph = p + 4 * h;
+      const size_t g = tile0 + (size_t)(ph - HL);           // meaningful when the group is stored
+      const bool stored = ph >= HL && ph < HL + OUT && g < n;
+      Pk<4> yo, ko;
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (g + e < n) { a.f.ynew[g + e] = yo.v[e]; a.f.ks_out[g + e] = ko.v[e]; }
+      for (int q = 0; q < 4; ++q) {
+        const int e = 4 * h + q;
+        ko.v[q] = k[e][S - 1];
+        if (Pattern<PAT>::last) yo.v[q] = in[e];
+        else yo.v[q] = __dadd_rn(y[e], __dmul_rn(const_wsum<S, Pattern<PAT>::b()>(k[e], a.f.b), a.f.cb));
+        const double lo = __dmul_rn(const_wsum<S, Pattern<PAT>::bh()>(k[e], a.f.bh), a.f.cbh);
+        double err;
+        if (Pattern<PAT>::direct) err = lo;
+        else err = __dadd_rn(yo.v[q], -__dadd_rn(y[e], lo));
+        const double tol = __dadd_rn(a.f.absTol, __dmul_rn(fabs(yo.v[q]), a.f.relTol));
+        const double r = err_ratio(err, tol);
+        if (stored && g + q < n) acc = __dadd_rn(acc, __dmul_rn(r, r));
+      }
+      if (stored) {
+        if (g + 4 <= n) {
+          st_stream<4>(a.f.ynew + g, yo);
+          st_stream<4>(a.f.ks_out + g, ko);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (g + q < n) { a.f.ynew[g + q] = yo.v[q]; a.f.ks_out[g + q] = ko.v[q]; }
+        }
       }
     }
   }

@@ -139,7 +139,7 @@ def test_cumsimpson_fn_streams_a_fine_grid_by_itself(nn):
 
 
 # ---- knob fuse_stencil_attempt: a whole attempt of the built-in Lorenz-96 right-hand side in one kernel ---------------
-@pytest.mark.parametrize("pairs", [2, 1, 0])   # 0: the warp-tile variant (knob l96_warp_tiles: shuffles, no shared memory, 128-position tiles)
+@pytest.mark.parametrize("pairs", [2, 1, 0, -4])   # 0 / -4: the warp-tile variant (knob l96_warp_tiles: shuffles, no shared-memory exchange; 8 / 4 elements per lane = 256- / 128-position tiles)
 @pytest.mark.parametrize("method,stages", [("dopri54", 7), ("tsit54", 7), ("vern65", 9)])
 def test_l96_attempt_kernel_bitwise_equals_pipeline(nn, method, stages, pairs):
     """l96_attempt_kernel (stencil_attempt.cuh: overlapped tiles, stage inputs through shared memory): yNew and the new
@@ -151,7 +151,7 @@ def test_l96_attempt_kernel_bitwise_equals_pipeline(nn, method, stages, pairs):
     import oracle as O
     ctx = nn.default_context()
     rng = np.random.default_rng(17)
-    out_per_tile = (512 * pairs if pairs else 128) - (12 + 8 if stages == 7 else 16 + 8)
+    out_per_tile = (512 * pairs if pairs > 0 else (256 if pairs == 0 else 128)) - (12 + 8 if stages == 7 else 16 + 8)
     sizes = [4, 5, 7, 19, 21, out_per_tile - 1, out_per_tile, out_per_tile + 1, 1023, 1024, 1025, 2 * out_per_tile - 1, 2 * out_per_tile,
              2 * out_per_tile + 2, 3 * out_per_tile + 13]
     if not os.environ.get("B200RK_TEST_HOST_EMULATION"):
@@ -162,8 +162,8 @@ def test_l96_attempt_kernel_bitwise_equals_pipeline(nn, method, stages, pairs):
     o = nn.newODEoptions(**opts)
     rhs = nn.rhsLorenz96(8.0)
     try:
-        ctx.set("l96_attempt_pairs", pairs or 2)
-        ctx.set("l96_warp_tiles", 1 if pairs == 0 else 0)
+        ctx.set("l96_attempt_pairs", pairs if pairs > 0 else 2)
+        ctx.set("l96_warp_tiles", 8 if pairs == 0 else (4 if pairs == -4 else 0))
         for strict in (0, 1):
             ctx.set("strict_zeros", strict)
             for n in (sizes if not strict else sizes[5:9] if not LIGHT else sizes[2:3]):
@@ -300,7 +300,7 @@ def test_round2_knobs_and_host_side_tstart_copy(nn):
 
     from numericalnim_b200 import _capi
     ctx = nn.default_context()
-    for key, val in (("peer_timeout_s", 30), ("l96_ctas_per_sm", 2), ("l96_warp_tiles", 1), ("tstart_copy", 1)):
+    for key, val in (("peer_timeout_s", 30), ("l96_ctas_per_sm", 2), ("l96_warp_tiles", 4), ("tstart_copy", 1)):
         old = ctx.get(key)
         ctx.set(key, val)
         assert ctx.get(key) == val

@@ -403,11 +403,12 @@ bool l96_peer_halo_possible(const b200rk_ctx* c, const MethodDef& md, const RhsC
   return rhs.f == &builtin_rhs_fn && static_cast<const BuiltinRhs*>(rhs.user)->kind == B200RK_RHS_LORENZ96 && l96_attempt_shards_ok(c, n_global);
 }
 
-template <int PAT, int J>
+template <int PAT, int J, bool HALF = false>   // HALF: 128-thread CTAs (half-width tiles, twice the CTAs per SM, barrier domains of 4 warps)
 static int launch_l96_attempt_j(b200rk_ctx* c, const MethodDef& md, double F, bool negate, double dt, const b200rk_options& o,
                                 const L96Halo& halo, const b200rk_vec* y, const b200rk_vec* fsal, b200rk_vec* y_new, b200rk_vec* fsal_new) {
   constexpr int S = Pattern<PAT>::S;
-  constexpr int OUT = 2 * J * kThreads - StencilTile<S>::HL - StencilTile<S>::HR;
+  constexpr int T = HALF ? kThreads / 2 : kThreads;
+  constexpr int OUT = 2 * J * T - StencilTile<S>::HL - StencilTile<S>::HR;
   L96AttemptArgs<S> a;
   std::memset(&a, 0, sizeof(a));
   a.f.y = y->d; a.f.k1 = fsal->d;
@@ -422,7 +423,7 @@ static int launch_l96_attempt_j(b200rk_ctx* c, const MethodDef& md, double F, bo
   // its share of the tiles with the next tile's bulk copies in flight
   static int per_sm = 0;   // per instantiation
   if (per_sm == 0) {
-    CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l96_attempt_kernel<PAT, J, kThreads, false>, kThreads, 0));
+    CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l96_attempt_kernel<PAT, J, T, false>, T, 0));
     if (per_sm < 1) per_sm = 1;
   }
   const size_t n_tiles = (a.f.n + OUT - 1) / OUT;
@@ -431,8 +432,13 @@ static int launch_l96_attempt_j(b200rk_ctx* c, const MethodDef& md, double F, bo
   TRY(ensure_partials(c, grid));
   a.f.rs = reduce_scratch(c);
   ProfScope ps(c, B200RK_K_FUSED, 8.0 * double(a.f.n) * 4);  // y, k1 read; yNew, k_S written
-  if (negate) l96_attempt_kernel<PAT, J, kThreads, true><<<grid, kThreads, 0, c->stream>>>(a);
-  else l96_attempt_kernel<PAT, J, kThreads, false><<<grid, kThreads, 0, c->stream>>>(a);
+  if constexpr (HALF) {
+    if (negate) l96_attempt_kernel<PAT, J, kThreads / 2, true><<<grid, kThreads / 2, 0, c->stream>>>(a);
+    else l96_attempt_kernel<PAT, J, kThreads / 2, false><<<grid, kThreads / 2, 0, c->stream>>>(a);
+  } else {
+    if (negate) l96_attempt_kernel<PAT, J, kThreads, true><<<grid, kThreads, 0, c->stream>>>(a);
+    else l96_attempt_kernel<PAT, J, kThreads, false><<<grid, kThreads, 0, c->stream>>>(a);
+  }
   CUDA_TRY(c, cudaGetLastError());
   return B200RK_OK;
 }
@@ -517,6 +523,7 @@ template <int PAT>
 static int launch_l96_attempt(b200rk_ctx* c, const MethodDef& md, double F, bool negate, double dt, const b200rk_options& o,
                               const L96Halo& halo, const b200rk_vec* y, const b200rk_vec* fsal, b200rk_vec* y_new, b200rk_vec* fsal_new) {
   if (c->l96_warp_tiles) return launch_l96_warp<PAT>(c, md, F, negate, dt, o, halo, y, fsal, y_new, fsal_new);
+  if (c->l96_attempt_threads == 128) return launch_l96_attempt_j<PAT, 2, true>(c, md, F, negate, dt, o, halo, y, fsal, y_new, fsal_new);
   if (c->l96_attempt_pairs == 1) return launch_l96_attempt_j<PAT, 1>(c, md, F, negate, dt, o, halo, y, fsal, y_new, fsal_new);
   return launch_l96_attempt_j<PAT, 2>(c, md, F, negate, dt, o, halo, y, fsal, y_new, fsal_new);
 }

@@ -91,6 +91,7 @@ struct b200rk_ctx {
   bool l96_peer_halo = true;   // sharded one-kernel Lorenz-96 attempt inside a solver: read the halo in place from the peer-mapped neighbours (false: ncclSend/ncclRecv)
   int l96_warp_tiles = 0;      // one-kernel Lorenz-96 attempt over warp-sized tiles (shuffles, no block barrier) instead of CTA-sized tiles: 0 off, 8 (or 1) = 8 elements per lane, 4 = 4 per lane
   int l96_ctas_per_sm = 0;     // l96_attempt_kernel's persistent grid: CTAs per SM, 0 = what the occupancy calculator allows
+  int l96_attempt_threads = 128;   // l96_attempt_kernel: threads per CTA: 128 = 512-position tiles, 6 CTAs per SM, barrier domains of 4 warps (measured 150 vs 155 us for 256)
   int l96_attempt_pairs = 2;   // l96_attempt_kernel: 128-bit pairs per thread (tile = 512 * pairs positions); 1 or 2
   bool finish_prefetch = false; // register-prefetching finish kernel: measured on the B200 in round 2 — no gain (88.5 vs 90.1-91.8 us), stays off
   int stream_simpson = -1;     // cumsimpson(f, X, dx): -1 = stream the grid only when the composed form would not fit, 0 never, 1 always

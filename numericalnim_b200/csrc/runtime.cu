@@ -324,6 +324,7 @@ static int ctx_common_init(b200rk_ctx* c) {
   if (const char* e = getenv("B200RK_FUSE_POINTWISE")) c->fuse_pointwise = atoi(e) != 0;
   if (const char* e = getenv("B200RK_FUSE_STENCIL")) c->fuse_stencil = atoi(e) != 0;
   if (const char* e = getenv("B200RK_TSTART_COPY")) c->tstart_copy = atoi(e) != 0;
+  if (const char* e = getenv("B200RK_L96_ATTEMPT_THREADS")) c->l96_attempt_threads = atoi(e) == 128 ? 128 : 256;
   if (const char* e = getenv("B200RK_L96_WARP_TILES")) c->l96_warp_tiles = (atoi(e) == 4) ? 4 : (atoi(e) != 0 ? 8 : 0);
   if (const char* e = getenv("B200RK_L96_CTAS_PER_SM")) c->l96_ctas_per_sm = std::max(0, std::min(32, atoi(e)));
   if (const char* e = getenv("B200RK_FUSE_STENCIL_ATTEMPT")) c->fuse_stencil_attempt = atoi(e) != 0;
@@ -424,6 +425,7 @@ int b200rk_set(b200rk_ctx* c, const char* key, int64_t v) {
   else if (k == "l96_peer_halo") c->l96_peer_halo = v != 0;
   else if (k == "tstart_copy") c->tstart_copy = v != 0;
   else if (k == "l96_warp_tiles") c->l96_warp_tiles = (v == 4) ? 4 : (v != 0 ? 8 : 0);
+  else if (k == "l96_attempt_threads") { if (v != 128 && v != 256) return fail(c, B200RK_EINVAL, "l96_attempt_threads must be 128 or 256"); c->l96_attempt_threads = (int)v; }
   else if (k == "l96_ctas_per_sm") { if (v < 0 || v > 32) return fail(c, B200RK_EINVAL, "l96_ctas_per_sm must be in 0..32"); c->l96_ctas_per_sm = (int)v; }
   else if (k == "l96_attempt_pairs") { if (v != 1 && v != 2) return fail(c, B200RK_EINVAL, "l96_attempt_pairs must be 1 or 2"); c->l96_attempt_pairs = (int)v; }
   else if (k == "fuse_simpson") c->fuse_simpson = v != 0;
@@ -473,6 +475,7 @@ int b200rk_get(const b200rk_ctx* c, const char* key, int64_t* v) {
   else if (k == "l96_ctas_per_sm") *v = c->l96_ctas_per_sm;
   else if (k == "tstart_copy") *v = c->tstart_copy;
   else if (k == "l96_warp_tiles") *v = c->l96_warp_tiles;
+  else if (k == "l96_attempt_threads") *v = c->l96_attempt_threads;
   else if (k == "peer_timeout_s") *v = c->peer_timeout_s;
   else return fail(c, B200RK_EINVAL, "unknown knob " + k);
   return B200RK_OK;

@@ -170,19 +170,23 @@ inline void tile_prefetch(double* dst_y, const double* src_y, double* dst_k, con
 inline void tile_wait(unsigned long long*, unsigned int) {}
 #endif
 
+#ifndef L96_PREFETCH_DEPTH
+#define L96_PREFETCH_DEPTH 1
+#endif
 // Persistent grid: a CTA walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ...; while it evaluates the S - 1 stages of
 // one tile the next tile's y and k1 are already on their way into shared memory (tile_prefetch), so the HBM latency of a
 // tile hides under the ~500 fp64 instructions per warp of the previous one instead of idling the CTA (first measured form,
 // one tile per CTA and register loads: 188 us per attempt at 2^24 with the fp64 pipe 55 % busy and 17 % of the warp
 // stalls on the tile's loads).
 template <int PAT, int J, int THREADS, bool NEG>
-__global__ void __launch_bounds__(THREADS, (Pattern<PAT>::S > 7 || J > 2) ? 2 : 3) l96_attempt_kernel(const L96AttemptArgs<Pattern<PAT>::S> a) {
+__global__ void __launch_bounds__(THREADS, ((Pattern<PAT>::S > 7 || J > 2) ? 2 : 3) * (256 / THREADS)) l96_attempt_kernel(const L96AttemptArgs<Pattern<PAT>::S> a) {
   constexpr int S = Pattern<PAT>::S;
   constexpr int E = 2 * J, TW = E * THREADS;
   constexpr int HL = StencilTile<S>::HL, HR = StencilTile<S>::HR, OUT = TW - HL - HR;
+  constexpr int NST = (TW <= 512) ? L96_PREFETCH_DEPTH : 1;   // tiles in flight ahead of the one being evaluated (static shared memory: 48 KB)
   __shared__ double buf[2][TW + 4];
-  alignas(128) __shared__ double staged[2][TW];   // [0]: the tile's y, [1]: its k1 (FSAL) — written by the bulk copies
-  alignas(8) __shared__ unsigned long long tile_bar;
+  alignas(128) __shared__ double staged[NST][2][TW];   // ring: [.][0] a tile's y, [.][1] its k1 (FSAL) — written by the bulk copies
+  alignas(8) __shared__ unsigned long long tile_bar[NST];
   const size_t n = a.f.n;
   const size_t n_tiles = (n + OUT - 1) / OUT;
   if (threadIdx.x < 3) {
@@ -194,12 +198,16 @@ __global__ void __launch_bounds__(THREADS, (Pattern<PAT>::S > 7 || J > 2) ? 2 : 
   auto interior_tile = [&](size_t t) { const size_t t0 = t * (size_t)OUT; return t0 >= (size_t)HL && t0 - HL + TW <= n; };
   size_t tile = blockIdx.x;
   if (threadIdx.x == 0) {
-    tile_barrier_init(&tile_bar);
-    if (tile < n_tiles && interior_tile(tile))
-      tile_prefetch(staged[0], a.f.y + (tile * OUT - HL), staged[1], a.f.k1 + (tile * OUT - HL), TW * 8u, &tile_bar);
+    for (int q = 0; q < NST; ++q) {
+      tile_barrier_init(&tile_bar[q]);
+      const size_t t = tile + (size_t)q * gridDim.x;
+      if (t < n_tiles && interior_tile(t))
+        tile_prefetch(staged[q][0], a.f.y + (t * OUT - HL), staged[q][1], a.f.k1 + (t * OUT - HL), TW * 8u, &tile_bar[q]);
+    }
   }
   __syncthreads();
-  unsigned int phase = 0;
+  unsigned int phase_bits = 0;   // bit q: parity of the next completion of ring slot q
+  int slot = 0;
   double acc = 0.0;
   int pos[J];   // first position of each pair the thread owns
 #pragma unroll
@@ -208,12 +216,12 @@ __global__ void __launch_bounds__(THREADS, (Pattern<PAT>::S > 7 || J > 2) ? 2 : 
   const size_t tile0 = tile * (size_t)OUT;          // first stored element of this tile
   double y[E], k[E][S], in[E];
   const bool interior = interior_tile(tile);
-  if (interior) { tile_wait(&tile_bar, phase); phase ^= 1u; }
+  if (interior) { tile_wait(&tile_bar[slot], (phase_bits >> slot) & 1u); phase_bits ^= 1u << slot; }
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     const int p = pos[j];
     if (interior) {
-      const double2 yv = *reinterpret_cast<const double2*>(&staged[0][p]), kv = *reinterpret_cast<const double2*>(&staged[1][p]);   // LDS.128, conflict-free
+      const double2 yv = *reinterpret_cast<const double2*>(&staged[slot][0][p]), kv = *reinterpret_cast<const double2*>(&staged[slot][1][p]);   // LDS.128, conflict-free
       y[2 * j] = yv.x; y[2 * j + 1] = yv.y;
       k[2 * j][0] = kv.x; k[2 * j + 1][0] = kv.y;
     } else {
@@ -226,9 +234,10 @@ __global__ void __launch_bounds__(THREADS, (Pattern<PAT>::S > 7 || J > 2) ? 2 : 
   }
   __syncthreads();   // every thread holds its part of the tile: the staging buffers (and the previous tile's last stage buffer) are free
   {
-    const size_t nxt = tile + gridDim.x;
+    const size_t nxt = tile + (size_t)NST * gridDim.x;   // the ring slot just emptied receives the tile NST rounds ahead
     if (threadIdx.x == 0 && nxt < n_tiles && interior_tile(nxt))
-      tile_prefetch(staged[0], a.f.y + (nxt * OUT - HL), staged[1], a.f.k1 + (nxt * OUT - HL), TW * 8u, &tile_bar);
+      tile_prefetch(staged[slot][0], a.f.y + (nxt * OUT - HL), staged[slot][1], a.f.k1 + (nxt * OUT - HL), TW * 8u, &tile_bar[slot]);
+    slot = (slot + 1 == NST) ? 0 : slot + 1;
   }
 #pragma unroll
   for (int e = 0; e < E; ++e)

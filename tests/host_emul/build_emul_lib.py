@@ -22,7 +22,7 @@ OUT = os.path.join(HERE, "_build", "libb200rk_emul.so")
 SOURCES = ["runtime.cu", "launch.cu", "executor.cu", "driver.cu", "capi.cu", "quadrature.cu"]
 THREADED = ("stage_l96_kernel", "l96_attempt_kernel", "l96_warp_attempt_kernel", "l96_rk4_kernel")   # shared-memory tile + __syncthreads (the cooperative loop goes through cudaLaunchCooperativeKernel)
 
-LAUNCH = re.compile(r"(?P<kernel>\b\w+<[^;<>]*(?:<[^;<>]*>[^;<>]*)*>)<<<(?P<grid>.+?), kThreads, 0, c->stream>>>\((?P<args>.*)\);(?P<tail>\s*(//.*)?)$")
+LAUNCH = re.compile(r"(?P<kernel>\b\w+<[^;<>]*(?:<[^;<>]*>[^;<>]*)*>)<<<(?P<grid>.+?), (?P<threads>kThreads(?: / 2)?), 0, c->stream>>>\((?P<args>.*)\);(?P<tail>\s*(//.*)?)$")
 
 
 def transform(text: str, name: str) -> str:
@@ -32,8 +32,8 @@ def transform(text: str, name: str) -> str:
         if m:
             kernel, grid, args = m.group("kernel"), m.group("grid"), m.group("args")
             fn = "emul_launch_threaded" if kernel.split("<")[0] in THREADED else "emul_launch_serial"
-            body = ("{ auto emul_args_ = std::make_tuple(%s); %s((%s), kThreads, [&] { std::apply([](auto&... x_) { %s(x_...); }, emul_args_); }); }%s"
-                    % (args, fn, grid, kernel, m.group("tail")))
+            body = ("{ auto emul_args_ = std::make_tuple(%s); %s((%s), %s, [&] { std::apply([](auto&... x_) { %s(x_...); }, emul_args_); }); }%s"
+                    % (args, fn, grid, m.group("threads"), kernel, m.group("tail")))
             line = line[: m.start()] + body
             n += 1
         line = line.replace("cudaLaunchCooperativeKernel((void*)kernel,", "cudaLaunchCooperativeKernel(kernel,")

@@ -139,7 +139,7 @@ def test_cumsimpson_fn_streams_a_fine_grid_by_itself(nn):
 
 
 # ---- knob fuse_stencil_attempt: a whole attempt of the built-in Lorenz-96 right-hand side in one kernel ---------------
-@pytest.mark.parametrize("pairs", [2, 1, 0, -4])   # 0 / -4: the warp-tile variant (knob l96_warp_tiles: shuffles, no shared-memory exchange; 8 / 4 elements per lane = 256- / 128-position tiles)
+@pytest.mark.parametrize("pairs", [2, 1, 0, -4, -128])   # -128: the CTA-tile kernel with 128-thread CTAs (knob l96_attempt_threads)   # 0 / -4: the warp-tile variant (knob l96_warp_tiles: shuffles, no shared-memory exchange; 8 / 4 elements per lane = 256- / 128-position tiles)
 @pytest.mark.parametrize("method,stages", [("dopri54", 7), ("tsit54", 7), ("vern65", 9)])
 def test_l96_attempt_kernel_bitwise_equals_pipeline(nn, method, stages, pairs):
     """l96_attempt_kernel (stencil_attempt.cuh: overlapped tiles, stage inputs through shared memory): yNew and the new
@@ -151,7 +151,7 @@ def test_l96_attempt_kernel_bitwise_equals_pipeline(nn, method, stages, pairs):
     import oracle as O
     ctx = nn.default_context()
     rng = np.random.default_rng(17)
-    out_per_tile = (512 * pairs if pairs > 0 else (256 if pairs == 0 else 128)) - (12 + 8 if stages == 7 else 16 + 8)
+    out_per_tile = (512 * pairs if pairs > 0 else (256 if pairs == 0 else (512 if pairs == -128 else 128))) - (12 + 8 if stages == 7 else 16 + 8)
     sizes = [4, 5, 7, 19, 21, out_per_tile - 1, out_per_tile, out_per_tile + 1, 1023, 1024, 1025, 2 * out_per_tile - 1, 2 * out_per_tile,
              2 * out_per_tile + 2, 3 * out_per_tile + 13]
     if not os.environ.get("B200RK_TEST_HOST_EMULATION"):
@@ -164,6 +164,7 @@ def test_l96_attempt_kernel_bitwise_equals_pipeline(nn, method, stages, pairs):
     try:
         ctx.set("l96_attempt_pairs", pairs if pairs > 0 else 2)
         ctx.set("l96_warp_tiles", 8 if pairs == 0 else (4 if pairs == -4 else 0))
+        ctx.set("l96_attempt_threads", 128 if pairs == -128 else 256)   # (128 is the default; the 256-thread geometry is what pairs = 2 / 1 test)
         for strict in (0, 1):
             ctx.set("strict_zeros", strict)
             for n in (sizes if not strict else sizes[5:9] if not LIGHT else sizes[2:3]):
@@ -191,6 +192,7 @@ def test_l96_attempt_kernel_bitwise_equals_pipeline(nn, method, stages, pairs):
         ctx.set("fuse_stencil_attempt", 1)
         ctx.set("l96_attempt_pairs", 2)
         ctx.set("l96_warp_tiles", 0)
+        ctx.set("l96_attempt_threads", 128)
 
 
 @pytest.mark.parametrize("method", ["tsit54", "vern65"])

@@ -63,3 +63,7 @@ def test_c_extras_demo_runs(tmp_path):
     line = [l for l in r.stdout.splitlines() if l.startswith("steps=")][0]
     vals = dict(kv.split("=") for kv in line.split())
     assert float(vals["err_solution"]) < 1e-6 and float(vals["err_integral"]) < 1e-5 and float(vals["err_interpolated"]) < 1e-5
+    # the heat equation on a ring given as a stencil expression: one kernel per attempt, exact decay of a Fourier mode
+    assert "bad_stencil_rc=1 is_einval=1" in r.stdout
+    sv = dict(kv.split("=") for kv in [l for l in r.stdout.splitlines() if l.startswith("stencil_attempts=")][0].split())
+    assert float(sv["err_stencil"]) < 1e-7 and int(sv["stencil_launches"]) <= int(sv["stencil_attempts"]) + 8

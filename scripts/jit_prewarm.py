@@ -30,6 +30,10 @@ STENCIL_UNITS = [  # (expression, radius_left, radius_right, n_vec, n_scalar, pa
     ("-(c0*(Y(0) - Y(-1)))", 1, 0, 0, 1, (-1, 0, 2, 3)),
     ("((Y(-3) + Y(2)) - 2.0*Y(0))*c0 - Y(0)*Y(0)*Y(0)*c1", 3, 2, 0, 2, (-1, 0, 2, 3)),
     ("Y(-2) + Y(1)", 2, 1, 0, 0, (-1,)),
+    ("c0*(Y(3) - Y(0))", 0, 3, 0, 1, (-1, 0, 2, 3)),
+    ("((Y(-8) + Y(8)) - 2.0*Y(0))*c0", 8, 8, 0, 1, (-1, 0, 2, 3)),
+    ("c0*Y(0) + c1*t", 0, 0, 0, 2, (-1, 0, 2, 3)),
+    ("c0*((Y(-1) - 2.0*Y(0)) + Y(1))", 1, 1, 0, 1, (-1, 2)),          # examples/c_extras_demo.c
 ]
 
 if __name__ == "__main__":

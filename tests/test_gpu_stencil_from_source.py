@@ -32,7 +32,13 @@ CASES = {
     "wide": dict(expr="((Y(-3) + Y(2)) - 2.0*Y(0))*c0 - Y(0)*Y(0)*Y(0)*c1", rl=3, rr=2, cs=[0.2, 0.01],
                  f=lambda t, y, p, c: ((Yr(y, -3) + Yr(y, 2)) - 2.0 * y) * c[0] - y * y * y * c[1]),
 }
-SIZES = [7, 9, 1003, 1004, 1005, 1023, 1024, 1025, 2009, 4099, 65536 + 3]
+# extreme radii: right-only (HL = 0), the maximum 8 / 8 (overlap 48 + 48 of a 1024-wide tile for the 7-stage pairs), and 0 / 0 (element-local)
+CASES.update({
+    "right_only": dict(expr="c0*(Y(3) - Y(0))", rl=0, rr=3, cs=[0.4], f=lambda t, y, p, c: c[0] * (Yr(y, 3) - y)),
+    "radius8": dict(expr="((Y(-8) + Y(8)) - 2.0*Y(0))*c0", rl=8, rr=8, cs=[0.05], f=lambda t, y, p, c: ((Yr(y, -8) + Yr(y, 8)) - 2.0 * y) * c[0]),
+    "radius0": dict(expr="c0*Y(0) + c1*t", rl=0, rr=0, cs=[-0.3, 0.1], f=lambda t, y, p, c: c[0] * y + c[1] * t),
+})
+SIZES = [17, 19, 1003, 1004, 1005, 1023, 1024, 1025, 2009, 4099, 65536 + 3]
 
 
 def make(nn, name, n, rng):
@@ -91,14 +97,14 @@ def test_lorenz96_from_source_equals_the_builtin_bit_for_bit(nn, method):
 
 
 @pytest.mark.parametrize("method", ["dopri54", "tsit54", "vern65"])
-@pytest.mark.parametrize("name", ["diffusion", "upwind", "wide"])
+@pytest.mark.parametrize("name", ["diffusion", "upwind", "wide", "right_only", "radius8", "radius0"])
 def test_one_step_of_a_user_stencil_is_bit_identical_to_the_oracle(nn, name, method):
     """Parameter vectors, explicit time dependence, one-sided and wide neighbourhoods: one IntegratorProc call, fused vs pipeline vs oracle."""
     ctx = nn.default_context()
     rng = np.random.default_rng(13)
     kw = dict(absTol=1e-2, relTol=1e-2, dtMax=1.0, dtMin=1e-8, dt=0.01)
     try:
-        for n in (9, 1004, 1025, 4099):
+        for n in (19, 1004, 1025, 4099):
             rhs, orhs, pvals = make(nn, name, n, rng)
             y = 1.0 + 0.5 * rng.uniform(-1, 1, n)
             fs = CASES[name]["f"](0.25, y, pvals, CASES[name]["cs"])
@@ -145,7 +151,7 @@ def test_rk4_step_in_one_kernel_is_bit_identical(nn, name):
     ctx = nn.default_context()
     rng = np.random.default_rng(23)
     try:
-        for n in (9, 11, 1003, 1011, 1012, 1013, 1024, 2023, 2024, 4099, 65536 + 3):
+        for n in (19, 21, 1003, 1011, 1012, 1013, 1024, 2023, 2024, 4099, 65536 + 3):
             rhs, orhs, pvals = make(nn, name, n, rng)
             y = 8.0 + rng.uniform(-1, 1, n)
             gy = nn.newVector(y)

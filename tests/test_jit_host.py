@@ -164,7 +164,8 @@ def test_kernel_argument_blocks_have_the_same_size_in_both_compilations(tmp_path
 STENCILS = [("((Y(1) - Y(-2)) * Y(-1) - Y(0)) + c0", 2, 1, 0, 1),                    # Lorenz-96
             ("c0*((Y(-1) - 2.0*Y(0)) + Y(1))*p0 + c1*t", 1, 1, 1, 2),                # diffusion with a coefficient field and a source term
             ("-(c0*(Y(0) - Y(-1)))", 1, 0, 0, 1),                                     # upwind advection: one-sided
-            ("(Y(-3) + Y(2)) - 2.0*Y(0)", 3, 2, 0, 0)]
+            ("(Y(-3) + Y(2)) - 2.0*Y(0)", 3, 2, 0, 0),
+            ("c0*(Y(3) - Y(0))", 0, 3, 0, 1), ("((Y(-8) + Y(8)) - 2.0*Y(0))*c0", 8, 8, 0, 1), ("c0*Y(0) + c1*t", 0, 0, 0, 2)]   # right-only, maximum radii, element-local
 
 
 @pytest.mark.parametrize("expr,rl,rr,nv,ns", STENCILS)
